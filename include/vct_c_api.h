@@ -1,0 +1,134 @@
+/*
+ * vct_c_api.h -- C ABI of libvct_b200.so, the B200 (sm_100a) implementation of the hot path of
+ * AlerianEmperor/Voxel-Cone-Tracing: shadow map -> voxelisation with PCF light injection -> 3D mip
+ * pyramid -> per-pixel cone tracing.
+ *
+ * Every entry point replaces a piece of the reference's OpenGL pipeline; the reference location is
+ * cited as file:line relative to /root/reference/Voxel_Cone_Tracing_Final/.  Plain pointers and sizes
+ * only: no C++ or torch types cross this boundary.  All functions return 0 on success and a negative
+ * vct_status otherwise; vct_last_error() gives the message.  A handle is not thread-safe (the
+ * reference is single threaded: one GL context, main.cpp:44).  There is NO CPU fallback: creating a
+ * context without a CUDA device fails with VCT_ERR_CUDA.
+ */
+#ifndef VCT_C_API_H_
+#define VCT_C_API_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vct_context* vct_handle;
+
+typedef enum vct_status {
+  VCT_OK = 0,
+  VCT_ERR_INVALID = -1,     /* bad argument / unknown uniform name (GL silently ignores location -1) */
+  VCT_ERR_CUDA = -2,        /* a CUDA runtime call failed, or no device */
+  VCT_ERR_STATE = -3,       /* pass called before its inputs exist (no mesh, no shadow map, ...) */
+  VCT_ERR_OVERFLOW = -4     /* a device work queue overflowed; raise MaxFragments / MaxTileItems */
+} vct_status;
+
+/* pass identifiers for vct_pass_time_us */
+typedef enum vct_pass {
+  VCT_PASS_DEPTH = 0,       /* DrawDepthTexture                         Voxel_Cone_Tracing.h:192-211 */
+  VCT_PASS_VOX_CLEAR = 1,   /* (reference never clears: texture zeroed once, :115-121)              */
+  VCT_PASS_VOX_COVER = 2,   /* Voxelization.vs/.gs + rasteriser         Shader/Voxelization.gs:22-51 */
+  VCT_PASS_VOX_SHADE = 3,   /* Voxelization.fs (albedo, PCF, store)     Shader/Voxelization.fs:54-89 */
+  VCT_PASS_RESOLVE = 4,     /* accumulator -> RGBA8 level 0 (imageStore's unorm8 conversion)        */
+  VCT_PASS_MIP = 5,         /* glGenerateMipmap(GL_TEXTURE_3D)          Voxel_Cone_Tracing.h:246-248 */
+  VCT_PASS_VISIBILITY = 6,  /* VoxelConeTracing.vs + raster + depth test + discard                  */
+  VCT_PASS_CONE = 7,        /* VoxelConeTracing.fs                      Shader/VoxelConeTracing.fs:165-229 */
+  VCT_PASS_FRAME = 8,       /* whole vct_frame() call                                               */
+  VCT_PASS_REINJECT = 9,    /* Bounces >= 3 extension                                               */
+  VCT_PASS_COUNT = 10
+} vct_pass;
+
+/* ---- lifetime.  Replaces Voxel_Cone_Tracing::Voxel_Cone_Tracing + init_voxel_cone_tracing resource
+ * creation (Voxel_Cone_Tracing.h:57-136: FBO, depth texture, 3D texture).  Defaults are the
+ * reference's constants (VoxelDimensions 128, VoxelGridWorldSize 150, ShadowMapSize 4096, 1280x720). */
+int vct_create(int cuda_device, vct_handle* out);
+int vct_destroy(vct_handle h);
+const char* vct_last_error(vct_handle h);     /* h may be NULL: error of the last failed vct_create */
+const char* vct_version(void);
+
+/* ---- uniforms.  Replace Shader::setInt/setFloat/setVec3/setMat4 (Shader.h:362-417) with the same
+ * string keys the reference passes (Voxel_Cone_Tracing.h:167-187,224-243):
+ *   int   : VoxelDimensions ShadowMapSize screen_width screen_height PcfRadius CoveragePolicy
+ *           Bounces NumDiffuseCones GridFormat MaxFragments MaxTileItems DenseResolve Profile
+ *           ShadowMap VoxelTexture (texture-unit numbers: accepted and ignored)
+ *   float : VoxelGridWorldSize ambientFactor DiffuseTanHalfAngle SpecularTanHalfAngle StepMultiplier
+ *           MaxDistance MaxAlpha ShadowBias
+ *   vec3  : CameraPosition LightDirection
+ *   mat4  : ModelMatrix ModelViewMatrix ProjectionMatrix DepthModelViewProjectionMatrix ProjX ProjY ProjZ
+ *           (16 floats, column-major, i.e. glm memory order with transpose = GL_FALSE)             */
+int vct_set_i(vct_handle h, const char* name, int v);
+int vct_set_f(vct_handle h, const char* name, float v);
+int vct_set_3f(vct_handle h, const char* name, float x, float y, float z);
+int vct_set_mat4(vct_handle h, const char* name, const float* colmajor16);
+int vct_get_i(vct_handle h, const char* name, int* v);
+int vct_get_f(vct_handle h, const char* name, float* v);
+/* Cone_Directions / Cone_Weights tables (VoxelConeTracing.fs:48-57); n <= 16 */
+int vct_set_cones(vct_handle h, int n, const float* directions_xyz, const float* weights);
+
+/* ---- scene.  Replace Model/Mesh upload (Mesh.h:49-82 glBufferData; Model.h:141-186 glTexImage2D +
+ * glGenerateMipmap) and the per-mesh sampler binding (Mesh.h:84-111).  Host arrays stay owned by the
+ * caller; the library copies them to the device. */
+int vct_upload_texture(vct_handle h, int tex_id, int width, int height, int channels /*1,3,4*/,
+                       const uint8_t* pixels);
+int vct_set_material(vct_handle h, int material_id, int diffuse_tex, int specular_tex, int height_tex,
+                     float shininess /* Mesh.h:86: 20 */);
+/* verts14 = struct Vertex (Mesh.h:12-19): Position3 Normal3 TexCoords2 Tangents3 Bi_Tangents3 */
+int vct_upload_mesh(vct_handle h, const float* verts14, size_t n_verts, const uint32_t* indices,
+                    size_t n_tris, const uint16_t* tri_material /* may be NULL */);
+/* dynamic meshes: overwrite Position of every vertex; src is n_verts*3 floats on the host or, with
+ * on_device != 0, a device pointer on the context's device (copied on the context's stream) */
+int vct_update_positions(vct_handle h, const float* xyz, size_t n_verts, int on_device);
+
+/* ---- passes.  One per reference method. */
+int vct_draw_depth(vct_handle h);        /* DrawDepthTexture   Voxel_Cone_Tracing.h:192-211 */
+int vct_draw_voxels(vct_handle h);       /* DrawVoxelTexture   Voxel_Cone_Tracing.h:213-250 (clear+voxelise+resolve+mip) */
+/* Render, Voxel_Cone_Tracing.h:146-190.  host_rgba (H*W*4 bytes, row 0 = bottom row as in GL window
+ * coordinates) may be NULL: then the frame stays on the device and the call is asynchronous. */
+int vct_render(vct_handle h, uint8_t* host_rgba);
+/* vct_draw_voxels + vct_render as one call (what the metric "full frames/s" times) */
+int vct_frame(vct_handle h, uint8_t* host_rgba);
+
+/* split form of vct_draw_voxels for triangle-sharded voxelisation across GPUs: accumulate a triangle
+ * range into the integer accumulator, exchange (all-reduce the buffer returned by vct_accum_buffer as
+ * uint32 sum), then resolve + mip.  clear_first zeroes the accumulator. */
+int vct_voxelize_range(vct_handle h, size_t tri_begin, size_t tri_end, int clear_first);
+int vct_accum_buffer(vct_handle h, void** device_ptr, size_t* n_uint32);
+int vct_resolve_and_mip(vct_handle h);   /* dense resolve of the whole accumulator, then mip */
+
+/* ---- read-back (the reference reads nothing back; these exist for parity checks and hosts) */
+int vct_readback_depth(vct_handle h, uint32_t* d24 /* S*S */);
+int vct_readback_counts(vct_handle h, uint32_t* counts /* V^3, (z*V+y)*V+x */);
+int vct_readback_sums(vct_handle h, uint32_t* rgb /* V^3*3 */);
+int vct_readback_grid(vct_handle h, int level, uint8_t* rgba /* (V>>level)^3*4 */);
+int vct_upload_grid_level0(vct_handle h, const uint8_t* rgba);   /* then vct_build_mips */
+int vct_build_mips(vct_handle h);
+int vct_readback_visibility(vct_handle h, uint32_t* tri_id /* H*W, 0xFFFFFFFF = background */);
+int vct_readback_frame(vct_handle h, uint8_t* rgba /* H*W*4 */);
+int vct_frame_buffer(vct_handle h, void** device_ptr, size_t* n_bytes);
+int vct_cone_samples(vct_handle h, uint64_t* n);       /* textureLod calls of the last vct_render */
+int vct_fragment_count(vct_handle h, uint64_t* n);     /* fragments of the last voxelisation */
+int vct_occupied_voxels(vct_handle h, uint64_t* n);
+
+/* ---- execution control */
+int vct_set_stream(vct_handle h, void* cuda_stream);   /* run on the caller's stream (e.g. torch's) */
+int vct_sync(vct_handle h);
+int vct_pass_time_us(vct_handle h, int pass, float* us);   /* CUDA-event time of the last run of a pass */
+int vct_kernel_launches(vct_handle h, uint64_t* n);        /* kernels launched by this context so far */
+
+/* ---- micro-benchmarks used for the roofline denominators (DESIGN.md "Rooflines") */
+/* trilinear+mip-linear tex3DLod throughput on a V^3 RGBA8 pyramid: n_samples per launch, pattern 0 =
+ * coherent cone-like walks, 1 = random.  Returns giga-samples/s. */
+int vct_bench_tex3d(vct_handle h, int V, uint64_t n_samples, int pattern, float lod, int iters,
+                    float* gsamples_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VCT_C_API_H_ */

@@ -1,0 +1,794 @@
+// vct_api.cu -- the C ABI of include/vct_c_api.h: context, uniforms, scene upload, resources, read-back.
+#include <cstdio>
+#include <cstring>
+
+#include "vct_internal.h"
+
+namespace vct {
+
+static thread_local std::string g_create_error;
+
+int set_error(vct_context* c, int code, const std::string& msg) {
+  if (c) c->err = msg; else g_create_error = msg;
+  return code;
+}
+
+int check_cuda(vct_context* c, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return VCT_OK;
+  return set_error(c, VCT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+int readback_accum(vct_context* c, uint32_t* counts, uint32_t* sums);
+
+// ------------------------------------------------------------------------------------------ helpers
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+static void set_identity(float* m) {
+  std::memset(m, 0, 16 * sizeof(float));
+  m[0] = m[5] = m[10] = m[15] = 1.0f;
+}
+
+static void default_params(Params& P) {
+  std::memset(&P, 0, sizeof(P));
+  P.V = 128; P.levels = 8; P.grid_world = 150.0f; P.S = 4096; P.W = 1280; P.H = 720;   // Voxel_Cone_Tracing.h:16-17,24-25,35
+  float* mats[] = {P.model, P.model_view, P.proj, P.depth_mvp, P.projx, P.projy, P.projz};
+  for (float* m : mats) set_identity(m);
+  P.cam[1] = 4.0f;                                       // Voxel_Cone_Tracing.h:8
+  P.light[1] = 1.0f; P.light[2] = 0.25f;                 // :14
+  P.ambient = 0.1f;                                      // :53
+  static const float dirs[18] = {0, 0, 1, 0, 0.866025f, 0.5f, 0.823639f, 0.267617f, 0.5f,
+                                 0.509037f, -0.700629f, 0.5f, -0.509037f, -0.700629f, 0.5f,
+                                 -0.823639f, 0.267617f, 0.5f};           // VoxelConeTracing.fs:49-57
+  static const float wts[6] = {0.25f, 0.15f, 0.15f, 0.15f, 0.15f, 0.15f};  // :48
+  P.n_cones = 6;
+  std::memcpy(P.cone_dir, dirs, sizeof(dirs));
+  std::memcpy(P.cone_w, wts, sizeof(wts));
+  P.diffuse_tan = 0.577f; P.spec_tan = 0.07f; P.step_mult = 1.0f;   // :198, :218
+  P.max_dist = 75.0f; P.max_alpha = 0.95f;                          // :43-44
+  P.pcf_radius = 2; P.shadow_bias = 0.002f;                         // Voxelization.fs:26,88
+  P.coverage = 1;                                                   // 4x MSAA window, main.cpp:30
+  P.bounces = 2;
+}
+
+// ------------------------------------------------------------------------------------------ resources
+__global__ void zero_u64(unsigned long long* p, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += st) p[i] = 0ull;
+}
+
+static void free_grid(vct_context* c) {
+  if (c->grid_tex) cudaDestroyTextureObject(c->grid_tex);
+  for (auto s : c->grid_surf) cudaDestroySurfaceObject(s);
+  c->grid_surf.clear();
+  if (c->grid_array) cudaFreeMipmappedArray(c->grid_array);
+  cudaFree(c->d_accum); cudaFree(c->d_touched);
+  c->grid_tex = 0; c->grid_array = nullptr; c->d_accum = nullptr; c->d_touched = nullptr; c->grid_V = 0;
+}
+
+int ensure_grid(vct_context* c) {
+  const int V = c->P.V;
+  if (c->grid_V == V) return VCT_OK;
+  free_grid(c);
+  const size_t n = (size_t)V * V * V;
+  VCT_CUDA(c, cudaMalloc(&c->d_accum, n * 16));
+  VCT_CUDA(c, cudaMalloc(&c->d_touched, n * 4));
+  c->touched_cap = n;
+  cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
+  VCT_CUDA(c, cudaMallocMipmappedArray(&c->grid_array, &desc, make_cudaExtent(V, V, V), c->P.levels,
+                                       cudaArraySurfaceLoadStore));
+  for (int l = 0; l < c->P.levels; ++l) {
+    cudaArray_t lvl;
+    VCT_CUDA(c, cudaGetMipmappedArrayLevel(&lvl, c->grid_array, l));
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = lvl;
+    cudaSurfaceObject_t s;
+    VCT_CUDA(c, cudaCreateSurfaceObject(&s, &rd));
+    c->grid_surf.push_back(s);
+  }
+  // sampler state of the reference's voxel texture: MIN = LINEAR_MIPMAP_LINEAR, MAG = LINEAR
+  // (Voxel_Cone_Tracing.h:112-113), wrap never set => GL_REPEAT on s,t,r.
+  cudaResourceDesc rd{};
+  rd.resType = cudaResourceTypeMipmappedArray;
+  rd.res.mipmap.mipmap = c->grid_array;
+  cudaTextureDesc td{};
+  td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeWrap;
+  td.filterMode = cudaFilterModeLinear;
+  td.mipmapFilterMode = cudaFilterModeLinear;
+  td.readMode = cudaReadModeNormalizedFloat;
+  td.normalizedCoords = 1;
+  td.minMipmapLevelClamp = 0.0f;
+  td.maxMipmapLevelClamp = (float)(c->P.levels - 1);
+  VCT_CUDA(c, cudaCreateTextureObject(&c->grid_tex, &rd, &td, nullptr));
+  c->grid_V = V;
+  // zero everything: accumulator, touched list, and all mip levels (the reference uploads a zeroed
+  // texture and calls glGenerateMipmap, Voxel_Cone_Tracing.h:115-126)
+  VCT_CUDA(c, cudaMemsetAsync(c->d_accum, 0, n * 16, c->stream));
+  VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_touched, 0, sizeof(unsigned int), c->stream));
+  c->accum_dense_dirty = false;
+  int rc = launch_resolve(c, true); if (rc) return rc;
+  rc = launch_mip(c); if (rc) return rc;
+  return VCT_OK;
+}
+
+int ensure_shadow(vct_context* c) {
+  if (c->depth_S == c->P.S && c->d_depth) return VCT_OK;
+  cudaFree(c->d_depth); c->d_depth = nullptr; c->depth_valid = false;
+  VCT_CUDA(c, cudaMalloc(&c->d_depth, (size_t)c->P.S * c->P.S * 4));
+  c->depth_S = c->P.S;
+  return VCT_OK;
+}
+
+int ensure_frame(vct_context* c) {
+  if (c->frame_W == c->P.W && c->frame_H == c->P.H && c->d_frame) return VCT_OK;
+  cudaFree(c->d_vis); cudaFree(c->d_frame);
+  c->d_vis = nullptr; c->d_frame = nullptr;
+  const size_t n = (size_t)c->P.W * c->P.H;
+  VCT_CUDA(c, cudaMalloc(&c->d_vis, n * 8));
+  VCT_CUDA(c, cudaMalloc(&c->d_frame, n * 4));
+  c->frame_W = c->P.W; c->frame_H = c->P.H;
+  return VCT_OK;
+}
+
+int ensure_queues(vct_context* c) {
+  if (c->frags_cap != c->max_fragments || !c->d_frags) {
+    cudaFree(c->d_frags); c->d_frags = nullptr;
+    VCT_CUDA(c, cudaMalloc(&c->d_frags, c->max_fragments * sizeof(uint2)));
+    c->frags_cap = c->max_fragments;
+  }
+  if (c->items_cap != c->max_items || !c->d_items) {
+    cudaFree(c->d_items); c->d_items = nullptr;
+    VCT_CUDA(c, cudaMalloc(&c->d_items, c->max_items * sizeof(TileItem)));
+    c->items_cap = c->max_items;
+  }
+  return VCT_OK;
+}
+
+int check_overflow(vct_context* c) {
+  unsigned int ov = 0;
+  VCT_CUDA(c, cudaMemcpyAsync(&ov, &c->d_counters->overflow, 4, cudaMemcpyDeviceToHost, c->stream));
+  VCT_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (ov) {
+    cudaMemsetAsync(&c->d_counters->overflow, 0, 4, c->stream);
+    return set_error(c, VCT_ERR_OVERFLOW, "device work queue overflow: raise MaxFragments / MaxTileItems");
+  }
+  return VCT_OK;
+}
+
+// ---- material textures: glTexImage2D + glGenerateMipmap(GL_TEXTURE_2D), Model.h:159-175
+__global__ void expand_rgba(const uint8_t* __restrict__ src, uchar4* __restrict__ dst, size_t n, int ch,
+                            unsigned int* has_alpha) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uchar4 o;
+  o.x = src[i * ch];
+  o.y = ch >= 3 ? src[i * ch + 1] : 0;     // GL_RED samples (r,0,0,1); GL_RGB samples alpha 1
+  o.z = ch >= 3 ? src[i * ch + 2] : 0;
+  o.w = ch == 4 ? src[i * ch + 3] : 255;
+  dst[i] = o;
+  if (o.w != 255) *has_alpha = 1u;
+}
+
+__global__ void mip2d(const uchar4* __restrict__ src, int pw, int ph, uchar4* __restrict__ dst, int nw, int nh) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= nw || y >= nh) return;
+  int x0 = min(2 * x, pw - 1), x1 = min(2 * x + 1, pw - 1), y0 = min(2 * y, ph - 1), y1 = min(2 * y + 1, ph - 1);
+  uchar4 a = src[(size_t)y0 * pw + x0], b = src[(size_t)y0 * pw + x1], c = src[(size_t)y1 * pw + x0], d = src[(size_t)y1 * pw + x1];
+  uchar4 o;
+  o.x = (unsigned char)((a.x + b.x + c.x + d.x + 2) >> 2);
+  o.y = (unsigned char)((a.y + b.y + c.y + d.y + 2) >> 2);
+  o.z = (unsigned char)((a.z + b.z + c.z + d.z + 2) >> 2);
+  o.w = (unsigned char)((a.w + b.w + c.w + d.w + 2) >> 2);
+  dst[(size_t)y * nw + x] = o;
+}
+
+static void free_texture(TextureEntry& t) {
+  if (t.tex) cudaDestroyTextureObject(t.tex);
+  if (t.array) cudaFreeMipmappedArray(t.array);
+  t = TextureEntry();
+}
+
+static int make_texture(vct_context* c, TextureEntry& out, int w, int h, int ch, const uint8_t* pixels) {
+  int levels = 1;
+  for (int a = w, b = h; a > 1 || b > 1; a = a > 1 ? a / 2 : 1, b = b > 1 ? b / 2 : 1) ++levels;
+  const size_t n = (size_t)w * h;
+  uint8_t* d_src = nullptr; uchar4 *d_a = nullptr, *d_b = nullptr; unsigned int* d_flag = nullptr;
+  VCT_CUDA(c, cudaMalloc(&d_src, n * ch));
+  VCT_CUDA(c, cudaMalloc(&d_a, n * 4));
+  VCT_CUDA(c, cudaMalloc(&d_b, (n / 2 + 4) * 4));
+  VCT_CUDA(c, cudaMalloc(&d_flag, 4));
+  VCT_CUDA(c, cudaMemsetAsync(d_flag, 0, 4, c->stream));
+  VCT_CUDA(c, cudaMemcpyAsync(d_src, pixels, n * ch, cudaMemcpyHostToDevice, c->stream));
+  expand_rgba<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_src, d_a, n, ch, d_flag);
+  cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
+  VCT_CUDA(c, cudaMallocMipmappedArray(&out.array, &desc, make_cudaExtent(w, h, 0), levels));
+  int pw = w, ph = h;
+  uchar4 *cur = d_a, *nxt = d_b;
+  for (int l = 0; l < levels; ++l) {
+    cudaArray_t lvl;
+    VCT_CUDA(c, cudaGetMipmappedArrayLevel(&lvl, out.array, l));
+    VCT_CUDA(c, cudaMemcpy2DToArrayAsync(lvl, 0, 0, cur, (size_t)pw * 4, (size_t)pw * 4, ph, cudaMemcpyDeviceToDevice, c->stream));
+    if (l + 1 < levels) {
+      int nw = pw > 1 ? pw / 2 : 1, nh = ph > 1 ? ph / 2 : 1;
+      dim3 b(16, 16), g((nw + 15) / 16, (nh + 15) / 16);
+      mip2d<<<g, b, 0, c->stream>>>(cur, pw, ph, nxt, nw, nh);
+      uchar4* t = cur; cur = nxt; nxt = t;
+      pw = nw; ph = nh;
+    }
+  }
+  c->launches += levels;
+  unsigned int flag = 0;
+  VCT_CUDA(c, cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, c->stream));
+  VCT_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaFree(d_src); cudaFree(d_a); cudaFree(d_b); cudaFree(d_flag);
+  // sampler state: REPEAT, MIN = LINEAR_MIPMAP_LINEAR, MAG = LINEAR (Model.h:172-175)
+  cudaResourceDesc rd{};
+  rd.resType = cudaResourceTypeMipmappedArray;
+  rd.res.mipmap.mipmap = out.array;
+  cudaTextureDesc td{};
+  td.addressMode[0] = td.addressMode[1] = cudaAddressModeWrap;
+  td.filterMode = cudaFilterModeLinear;
+  td.mipmapFilterMode = cudaFilterModeLinear;
+  td.readMode = cudaReadModeNormalizedFloat;
+  td.normalizedCoords = 1;
+  td.maxMipmapLevelClamp = (float)(levels - 1);
+  VCT_CUDA(c, cudaCreateTextureObject(&out.tex, &rd, &td, nullptr));
+  out.w = w; out.h = h; out.has_alpha = flag != 0;
+  return VCT_OK;
+}
+
+int sync_materials(vct_context* c) {
+  if (!c->materials_dirty && c->d_materials) return VCT_OK;
+  if (!c->white_tex) {
+    TextureEntry t;
+    const uint8_t white[4] = {255, 255, 255, 255};
+    int rc = make_texture(c, t, 1, 1, 4, white); if (rc) return rc;
+    c->white_tex = t.tex; c->white_arr = t.array;
+  }
+  size_t n = c->materials.size();
+  if (n == 0) { c->materials.resize(1); n = 1; }
+  std::vector<MaterialDev> host(n);
+  for (size_t i = 0; i < n; ++i) {
+    const MaterialHost& m = c->materials[i];
+    auto pick = [&](int id, cudaTextureObject_t& t, int& w, int& h, bool* alpha) {
+      if (id >= 0 && id < (int)c->textures.size() && c->textures[id].tex) {
+        t = c->textures[id].tex; w = c->textures[id].w; h = c->textures[id].h;
+        if (alpha) *alpha = c->textures[id].has_alpha;
+      } else { t = c->white_tex; w = 1; h = 1; if (alpha) *alpha = false; }
+    };
+    bool alpha = false;
+    pick(m.d, host[i].diffuse, host[i].dw, host[i].dh, &alpha);
+    pick(m.s, host[i].specular, host[i].sw, host[i].sh, nullptr);
+    pick(m.h, host[i].height, host[i].hw, host[i].hh, nullptr);
+    host[i].shininess = m.shininess;
+    host[i].alpha_test = alpha ? 1 : 0;
+  }
+  if (c->n_materials_dev < n) {
+    cudaFree(c->d_materials); c->d_materials = nullptr;
+    VCT_CUDA(c, cudaMalloc(&c->d_materials, n * sizeof(MaterialDev)));
+    c->n_materials_dev = n;
+  }
+  VCT_CUDA(c, cudaMemcpyAsync(c->d_materials, host.data(), n * sizeof(MaterialDev), cudaMemcpyHostToDevice, c->stream));
+  VCT_CUDA(c, cudaStreamSynchronize(c->stream));   // `host` goes out of scope
+  c->materials_dirty = false;
+  return VCT_OK;
+}
+
+// ------------------------------------------------------------------------------------------ tex bench
+__global__ void fill_level_random(cudaSurfaceObject_t s, int n, unsigned seed) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, z = blockIdx.z;
+  if (x >= n || y >= n) return;
+  unsigned h = (unsigned)(x * 73856093) ^ (unsigned)(y * 19349663) ^ (unsigned)(z * 83492791) ^ seed;
+  h ^= h >> 13; h *= 0x5bd1e995u; h ^= h >> 15;
+  surf3Dwrite(h, s, x * 4, y, z);
+}
+
+// each thread marches `steps` samples; a warp covers an 8x4 patch of start points (as cone_trace does)
+__global__ void __launch_bounds__(256) tex3d_bench(cudaTextureObject_t tex, int steps, float lod, int pattern,
+                                                   float step_len, float4* sink, int W) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+  const int j = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+  float u = (i + 0.5f) / (float)W, v = (j + 0.5f) / (float)W, w = 0.37f;
+  float du = 0.57f * step_len, dv = 0.31f * step_len, dw = 0.76f * step_len;
+  unsigned rng = (unsigned)(i * 9781 + j * 6271) | 1u;
+  float4 acc = make_float4(0, 0, 0, 0);
+  for (int s = 0; s < steps; ++s) {
+    if (pattern == 1) {
+      rng ^= rng << 13; rng ^= rng >> 17; rng ^= rng << 5;
+      u = (rng & 0xFFFF) * (1.0f / 65536.0f); v = ((rng >> 8) & 0xFFFF) * (1.0f / 65536.0f); w = (rng >> 16) * (1.0f / 65536.0f);
+    } else { u += du; v += dv; w += dw; }
+    float4 t = tex3DLod<float4>(tex, u, v, w, lod);
+    acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+  }
+  if (acc.x == -1.0f) sink[0] = acc;   // never true: keeps the loop alive
+}
+
+}  // namespace vct
+
+using namespace vct;
+
+// =========================================================================================== C ABI
+extern "C" {
+
+const char* vct_version(void) { return "vct_b200 0.1 (sm_100a)"; }
+
+int vct_create(int device, vct_handle* out) {
+  if (!out) return VCT_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return set_error(nullptr, VCT_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") +
+                                                (e == cudaSuccess ? "device count 0" : cudaGetErrorString(e)));
+  if (device < 0 || device >= n) return set_error(nullptr, VCT_ERR_INVALID, "bad device index");
+  vct_context* c = new vct_context();
+  c->device = device;
+  default_params(c->P);
+  c->materials.resize(1);
+  auto fail = [&](int rc) { g_create_error = c->err; delete c; return rc; };
+  if (int rc = check_cuda(c, cudaSetDevice(device), "cudaSetDevice")) return fail(rc);
+  if (int rc = check_cuda(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return fail(rc);
+  for (int p = 0; p < VCT_PASS_COUNT; ++p) {
+    cudaEventCreate(&c->ev_begin[p]);
+    cudaEventCreate(&c->ev_end[p]);
+  }
+  if (int rc = check_cuda(c, cudaMalloc(&c->d_counters, sizeof(Counters)), "cudaMalloc counters")) return fail(rc);
+  cudaMemset(c->d_counters, 0, sizeof(Counters));
+  *out = c;
+  return VCT_OK;
+}
+
+int vct_destroy(vct_handle c) {
+  if (!c) return VCT_ERR_INVALID;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  free_grid(c);
+  for (auto& t : c->textures) free_texture(t);
+  if (c->white_tex) cudaDestroyTextureObject(c->white_tex);
+  if (c->white_arr) cudaFreeMipmappedArray(c->white_arr);
+  cudaFree(c->d_verts); cudaFree(c->d_idx); cudaFree(c->d_trimat); cudaFree(c->d_materials);
+  cudaFree(c->d_depth); cudaFree(c->d_frags); cudaFree(c->d_items); cudaFree(c->d_counters);
+  cudaFree(c->d_vis); cudaFree(c->d_frame);
+  for (int p = 0; p < VCT_PASS_COUNT; ++p) { cudaEventDestroy(c->ev_begin[p]); cudaEventDestroy(c->ev_end[p]); }
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return VCT_OK;
+}
+
+const char* vct_last_error(vct_handle c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+#define NEED(c) do { if (!(c)) return VCT_ERR_INVALID; cudaSetDevice((c)->device); } while (0)
+
+int vct_set_i(vct_handle c, const char* name, int v) {
+  NEED(c);
+  if (!name) return set_error(c, VCT_ERR_INVALID, "null uniform name");
+  std::string k(name);
+  Params& P = c->P;
+  if (k == "VoxelDimensions") {
+    if (v < 2 || v > 1024 || (v & (v - 1))) return set_error(c, VCT_ERR_INVALID, "VoxelDimensions must be a power of two in [2,1024]");
+    P.V = v; P.levels = ilog2(v) + 1;
+  } else if (k == "ShadowMapSize") {
+    if (v < 1 || v > 16384) return set_error(c, VCT_ERR_INVALID, "ShadowMapSize out of range");
+    if (v != P.S) c->depth_valid = false;
+    P.S = v;
+  } else if (k == "screen_width") { if (v < 1 || v > 16384) return set_error(c, VCT_ERR_INVALID, "screen_width out of range"); P.W = v; }
+  else if (k == "screen_height") { if (v < 1 || v > 16384) return set_error(c, VCT_ERR_INVALID, "screen_height out of range"); P.H = v; }
+  else if (k == "PcfRadius") { if (v < 0 || v > 8) return set_error(c, VCT_ERR_INVALID, "PcfRadius out of range"); P.pcf_radius = v; }
+  else if (k == "CoveragePolicy") { if (v < 0 || v > 2) return set_error(c, VCT_ERR_INVALID, "CoveragePolicy must be 0,1,2"); P.coverage = v; }
+  else if (k == "Bounces") { if (v < 1 || v > 8) return set_error(c, VCT_ERR_INVALID, "Bounces out of range"); P.bounces = v; }
+  else if (k == "NumDiffuseCones") { if (v < 0 || v > VCT_MAX_CONES) return set_error(c, VCT_ERR_INVALID, "NumDiffuseCones out of range"); P.n_cones = v; }
+  else if (k == "GridFormat") { if (v != 0) return set_error(c, VCT_ERR_INVALID, "GridFormat: only 0 (RGBA8) is implemented"); c->grid_format = v; }
+  else if (k == "MaxFragments") { if (v < 1024) return set_error(c, VCT_ERR_INVALID, "MaxFragments too small"); c->max_fragments = (size_t)v; }
+  else if (k == "MaxTileItems") { if (v < 1024) return set_error(c, VCT_ERR_INVALID, "MaxTileItems too small"); c->max_items = (size_t)v; }
+  else if (k == "DenseResolve") c->dense_resolve = v != 0;
+  else if (k == "Profile") c->profile = v != 0;
+  else if (k == "ShadowMap" || k == "VoxelTexture") { /* texture unit numbers: meaningless here */ }
+  else return set_error(c, VCT_ERR_INVALID, "unknown int uniform '" + k + "'");
+  return VCT_OK;
+}
+
+int vct_get_i(vct_handle c, const char* name, int* v) {
+  NEED(c);
+  if (!name || !v) return VCT_ERR_INVALID;
+  std::string k(name);
+  const Params& P = c->P;
+  if (k == "VoxelDimensions") *v = P.V; else if (k == "ShadowMapSize") *v = P.S;
+  else if (k == "screen_width") *v = P.W; else if (k == "screen_height") *v = P.H;
+  else if (k == "PcfRadius") *v = P.pcf_radius; else if (k == "CoveragePolicy") *v = P.coverage;
+  else if (k == "Bounces") *v = P.bounces; else if (k == "NumDiffuseCones") *v = P.n_cones;
+  else if (k == "GridFormat") *v = c->grid_format; else if (k == "MipLevels") *v = P.levels;
+  else if (k == "MaxFragments") *v = (int)c->max_fragments; else if (k == "MaxTileItems") *v = (int)c->max_items;
+  else if (k == "DenseResolve") *v = c->dense_resolve; else if (k == "Profile") *v = c->profile;
+  else return set_error(c, VCT_ERR_INVALID, "unknown int uniform '" + k + "'");
+  return VCT_OK;
+}
+
+static float* float_slot(Params& P, const std::string& k) {
+  if (k == "VoxelGridWorldSize") return &P.grid_world;
+  if (k == "ambientFactor") return &P.ambient;
+  if (k == "DiffuseTanHalfAngle") return &P.diffuse_tan;
+  if (k == "SpecularTanHalfAngle") return &P.spec_tan;
+  if (k == "StepMultiplier") return &P.step_mult;
+  if (k == "MaxDistance") return &P.max_dist;
+  if (k == "MaxAlpha") return &P.max_alpha;
+  if (k == "ShadowBias") return &P.shadow_bias;
+  return nullptr;
+}
+
+int vct_set_f(vct_handle c, const char* name, float v) {
+  NEED(c);
+  if (!name) return VCT_ERR_INVALID;
+  float* s = float_slot(c->P, name);
+  if (!s) return set_error(c, VCT_ERR_INVALID, std::string("unknown float uniform '") + name + "'");
+  if (!(v == v)) return set_error(c, VCT_ERR_INVALID, "NaN uniform");
+  if (std::string(name) == "StepMultiplier" && !(v > 0.0f)) return set_error(c, VCT_ERR_INVALID, "StepMultiplier must be > 0");
+  if (std::string(name) == "VoxelGridWorldSize" && !(v > 0.0f)) return set_error(c, VCT_ERR_INVALID, "VoxelGridWorldSize must be > 0");
+  *s = v;
+  return VCT_OK;
+}
+
+int vct_get_f(vct_handle c, const char* name, float* v) {
+  NEED(c);
+  if (!name || !v) return VCT_ERR_INVALID;
+  float* s = float_slot(c->P, name);
+  if (!s) return set_error(c, VCT_ERR_INVALID, std::string("unknown float uniform '") + name + "'");
+  *v = *s;
+  return VCT_OK;
+}
+
+int vct_set_3f(vct_handle c, const char* name, float x, float y, float z) {
+  NEED(c);
+  if (!name) return VCT_ERR_INVALID;
+  std::string k(name);
+  float* d = k == "CameraPosition" ? c->P.cam : k == "LightDirection" ? c->P.light : nullptr;
+  if (!d) return set_error(c, VCT_ERR_INVALID, "unknown vec3 uniform '" + k + "'");
+  d[0] = x; d[1] = y; d[2] = z;
+  return VCT_OK;
+}
+
+int vct_set_mat4(vct_handle c, const char* name, const float* m) {
+  NEED(c);
+  if (!name || !m) return VCT_ERR_INVALID;
+  std::string k(name);
+  Params& P = c->P;
+  float* d = k == "ModelMatrix" ? P.model : k == "ModelViewMatrix" ? P.model_view : k == "ProjectionMatrix" ? P.proj
+           : k == "DepthModelViewProjectionMatrix" ? P.depth_mvp : k == "ProjX" ? P.projx : k == "ProjY" ? P.projy
+           : k == "ProjZ" ? P.projz : nullptr;
+  if (!d) return set_error(c, VCT_ERR_INVALID, "unknown mat4 uniform '" + k + "'");
+  std::memcpy(d, m, 16 * sizeof(float));
+  return VCT_OK;
+}
+
+int vct_set_cones(vct_handle c, int n, const float* dirs, const float* w) {
+  NEED(c);
+  if (n < 0 || n > VCT_MAX_CONES || (n && (!dirs || !w))) return set_error(c, VCT_ERR_INVALID, "vct_set_cones: bad arguments");
+  c->P.n_cones = n;
+  std::memcpy(c->P.cone_dir, dirs, (size_t)n * 3 * sizeof(float));
+  std::memcpy(c->P.cone_w, w, (size_t)n * sizeof(float));
+  return VCT_OK;
+}
+
+int vct_upload_texture(vct_handle c, int id, int w, int h, int ch, const uint8_t* px) {
+  NEED(c);
+  if (id < 0 || id > 65535 || w < 1 || h < 1 || w > 32768 || h > 32768 || (ch != 1 && ch != 3 && ch != 4) || !px)
+    return set_error(c, VCT_ERR_INVALID, "vct_upload_texture: bad arguments");
+  if ((int)c->textures.size() <= id) c->textures.resize(id + 1);
+  free_texture(c->textures[id]);
+  c->materials_dirty = true;
+  return make_texture(c, c->textures[id], w, h, ch, px);
+}
+
+int vct_set_material(vct_handle c, int mat, int d, int s, int h, float shininess) {
+  NEED(c);
+  if (mat < 0 || mat > 65535) return set_error(c, VCT_ERR_INVALID, "vct_set_material: bad material id");
+  if ((int)c->materials.size() <= mat) c->materials.resize(mat + 1);
+  c->materials[mat].d = d; c->materials[mat].s = s; c->materials[mat].h = h; c->materials[mat].shininess = shininess;
+  c->materials_dirty = true;
+  return VCT_OK;
+}
+
+int vct_upload_mesh(vct_handle c, const float* verts, size_t nv, const uint32_t* idx, size_t nt, const uint16_t* tm) {
+  NEED(c);
+  if (!verts || !idx || nv == 0 || nt == 0 || nt > 0x7FFFFFFFull / 3) return set_error(c, VCT_ERR_INVALID, "vct_upload_mesh: bad arguments");
+  uint16_t max_mat = 0;
+  for (size_t i = 0; i < nt * 3; ++i)
+    if (idx[i] >= nv) return set_error(c, VCT_ERR_INVALID, "vct_upload_mesh: index out of range");
+  if (tm) for (size_t i = 0; i < nt; ++i) max_mat = tm[i] > max_mat ? tm[i] : max_mat;
+  cudaFree(c->d_verts); cudaFree(c->d_idx); cudaFree(c->d_trimat);
+  c->d_verts = nullptr; c->d_idx = nullptr; c->d_trimat = nullptr; c->nv = c->nt = 0;
+  VCT_CUDA(c, cudaMalloc(&c->d_verts, nv * 14 * sizeof(float)));
+  VCT_CUDA(c, cudaMalloc(&c->d_idx, nt * 3 * sizeof(uint32_t)));
+  VCT_CUDA(c, cudaMemcpyAsync(c->d_verts, verts, nv * 14 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  VCT_CUDA(c, cudaMemcpyAsync(c->d_idx, idx, nt * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  if (tm) {
+    VCT_CUDA(c, cudaMalloc(&c->d_trimat, nt * sizeof(uint16_t)));
+    VCT_CUDA(c, cudaMemcpyAsync(c->d_trimat, tm, nt * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+    if (c->materials.size() <= max_mat) { c->materials.resize((size_t)max_mat + 1); c->materials_dirty = true; }
+  }
+  VCT_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->nv = nv; c->nt = nt;
+  c->depth_valid = false;
+  return VCT_OK;
+}
+
+__global__ void scatter_positions(const float* __restrict__ xyz, float* __restrict__ verts, size_t nv) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nv) return;
+  verts[i * 14 + 0] = xyz[i * 3 + 0];
+  verts[i * 14 + 1] = xyz[i * 3 + 1];
+  verts[i * 14 + 2] = xyz[i * 3 + 2];
+}
+
+int vct_update_positions(vct_handle c, const float* xyz, size_t nv, int on_device) {
+  NEED(c);
+  if (!xyz || nv != c->nv) return set_error(c, VCT_ERR_INVALID, "vct_update_positions: vertex count mismatch");
+  const float* src = xyz;
+  float* tmp = nullptr;
+  if (!on_device) {
+    VCT_CUDA(c, cudaMalloc(&tmp, nv * 12));
+    VCT_CUDA(c, cudaMemcpyAsync(tmp, xyz, nv * 12, cudaMemcpyHostToDevice, c->stream));
+    src = tmp;
+  }
+  scatter_positions<<<(unsigned)((nv + 255) / 256), 256, 0, c->stream>>>(src, c->d_verts, nv);
+  c->launches += 1;
+  if (tmp) { cudaStreamSynchronize(c->stream); cudaFree(tmp); }
+  c->depth_valid = false;
+  return check_cuda(c, cudaGetLastError(), "scatter_positions");
+}
+
+// ---- passes
+int vct_draw_depth(vct_handle c) { NEED(c); return launch_shadow(c); }
+
+int vct_draw_voxels(vct_handle c) {
+  NEED(c);
+  int rc = launch_voxel_clear(c); if (rc) return rc;
+  rc = launch_voxelize(c, 0, c->nt); if (rc) return rc;
+  rc = launch_resolve(c, c->dense_resolve != 0); if (rc) return rc;
+  rc = launch_mip(c); if (rc) return rc;
+  for (int b = 3; b <= c->P.bounces; ++b) {
+    rc = launch_reinject(c); if (rc) return rc;
+    rc = launch_mip(c); if (rc) return rc;
+  }
+  return VCT_OK;
+}
+
+int vct_voxelize_range(vct_handle c, size_t tb, size_t te, int clear_first) {
+  NEED(c);
+  int rc = ensure_grid(c); if (rc) return rc;
+  if (clear_first) {
+    c->accum_dense_dirty = true;   // force the dense clear path: after an all-reduce the touched list is stale
+    rc = launch_voxel_clear(c); if (rc) return rc;
+  }
+  c->accum_dense_dirty = true;
+  return launch_voxelize(c, tb, te);
+}
+
+int vct_accum_buffer(vct_handle c, void** p, size_t* n) {
+  NEED(c);
+  int rc = ensure_grid(c); if (rc) return rc;
+  if (p) *p = c->d_accum;
+  if (n) *n = (size_t)c->P.V * c->P.V * c->P.V * 4;
+  return VCT_OK;
+}
+
+int vct_resolve_and_mip(vct_handle c) {
+  NEED(c);
+  int rc = launch_resolve(c, true); if (rc) return rc;
+  rc = launch_mip(c); if (rc) return rc;
+  for (int b = 3; b <= c->P.bounces; ++b) {
+    rc = launch_reinject(c); if (rc) return rc;
+    rc = launch_mip(c); if (rc) return rc;
+  }
+  return VCT_OK;
+}
+
+int vct_render(vct_handle c, uint8_t* host_rgba) {
+  NEED(c);
+  int rc = launch_visibility(c); if (rc) return rc;
+  rc = launch_cone(c); if (rc) return rc;
+  if (host_rgba) {
+    VCT_CUDA(c, cudaMemcpyAsync(host_rgba, c->d_frame, (size_t)c->P.W * c->P.H * 4, cudaMemcpyDeviceToHost, c->stream));
+    VCT_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return VCT_OK;
+}
+
+int vct_frame(vct_handle c, uint8_t* host_rgba) {
+  NEED(c);
+  if (c->profile) cudaEventRecord(c->ev_begin[VCT_PASS_FRAME], c->stream);
+  int rc = vct_draw_voxels(c); if (rc) return rc;
+  rc = launch_visibility(c); if (rc) return rc;
+  rc = launch_cone(c); if (rc) return rc;
+  if (c->profile) { cudaEventRecord(c->ev_end[VCT_PASS_FRAME], c->stream); c->ev_recorded[VCT_PASS_FRAME] = true; }
+  if (host_rgba) {
+    VCT_CUDA(c, cudaMemcpyAsync(host_rgba, c->d_frame, (size_t)c->P.W * c->P.H * 4, cudaMemcpyDeviceToHost, c->stream));
+    VCT_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return VCT_OK;
+}
+
+// ---- read-back
+int vct_readback_depth(vct_handle c, uint32_t* d) {
+  NEED(c);
+  if (!d || !c->d_depth || !c->depth_valid) return set_error(c, VCT_ERR_STATE, "no shadow map");
+  VCT_CUDA(c, cudaMemcpyAsync(d, c->d_depth, (size_t)c->P.S * c->P.S * 4, cudaMemcpyDeviceToHost, c->stream));
+  return check_cuda(c, cudaStreamSynchronize(c->stream), "sync");
+}
+int vct_readback_counts(vct_handle c, uint32_t* counts) { NEED(c); return readback_accum(c, counts, nullptr); }
+int vct_readback_sums(vct_handle c, uint32_t* sums) { NEED(c); return readback_accum(c, nullptr, sums); }
+
+int vct_readback_grid(vct_handle c, int level, uint8_t* rgba) {
+  NEED(c);
+  int rc = ensure_grid(c); if (rc) return rc;
+  if (level < 0 || level >= c->P.levels || !rgba) return set_error(c, VCT_ERR_INVALID, "bad mip level");
+  const int n = c->P.V >> level;
+  cudaArray_t lvl;
+  VCT_CUDA(c, cudaGetMipmappedArrayLevel(&lvl, c->grid_array, level));
+  cudaMemcpy3DParms p{};
+  p.srcArray = lvl;
+  p.dstPtr = make_cudaPitchedPtr(rgba, (size_t)n * 4, n, n);
+  p.extent = make_cudaExtent(n, n, n);
+  p.kind = cudaMemcpyDeviceToHost;
+  VCT_CUDA(c, cudaMemcpy3DAsync(&p, c->stream));
+  return check_cuda(c, cudaStreamSynchronize(c->stream), "sync");
+}
+
+int vct_upload_grid_level0(vct_handle c, const uint8_t* rgba) {
+  NEED(c);
+  int rc = ensure_grid(c); if (rc) return rc;
+  const int n = c->P.V;
+  cudaArray_t lvl;
+  VCT_CUDA(c, cudaGetMipmappedArrayLevel(&lvl, c->grid_array, 0));
+  cudaMemcpy3DParms p{};
+  p.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(rgba), (size_t)n * 4, n, n);
+  p.dstArray = lvl;
+  p.extent = make_cudaExtent(n, n, n);
+  p.kind = cudaMemcpyHostToDevice;
+  VCT_CUDA(c, cudaMemcpy3DAsync(&p, c->stream));
+  c->accum_dense_dirty = true;   // level 0 no longer matches the touched list
+  return check_cuda(c, cudaStreamSynchronize(c->stream), "sync");
+}
+
+int vct_build_mips(vct_handle c) { NEED(c); return launch_mip(c); }
+
+__global__ void vis_to_tri(const unsigned long long* __restrict__ vis, uint32_t* __restrict__ tri, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) tri[i] = vis[i] == ~0ull ? 0xFFFFFFFFu : (uint32_t)vis[i];
+}
+
+int vct_readback_visibility(vct_handle c, uint32_t* tri) {
+  NEED(c);
+  if (!c->d_vis || !tri) return set_error(c, VCT_ERR_STATE, "no frame rendered");
+  const size_t n = (size_t)c->P.W * c->P.H;
+  uint32_t* d = nullptr;
+  VCT_CUDA(c, cudaMalloc(&d, n * 4));
+  vis_to_tri<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_vis, d, n);
+  c->launches += 1;
+  cudaError_t e = cudaMemcpyAsync(tri, d, n * 4, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d);
+  return check_cuda(c, e, "vct_readback_visibility");
+}
+
+int vct_readback_frame(vct_handle c, uint8_t* rgba) {
+  NEED(c);
+  if (!c->d_frame || !rgba) return set_error(c, VCT_ERR_STATE, "no frame rendered");
+  VCT_CUDA(c, cudaMemcpyAsync(rgba, c->d_frame, (size_t)c->P.W * c->P.H * 4, cudaMemcpyDeviceToHost, c->stream));
+  return check_cuda(c, cudaStreamSynchronize(c->stream), "sync");
+}
+
+int vct_frame_buffer(vct_handle c, void** p, size_t* n) {
+  NEED(c);
+  int rc = ensure_frame(c); if (rc) return rc;
+  if (p) *p = c->d_frame;
+  if (n) *n = (size_t)c->P.W * c->P.H * 4;
+  return VCT_OK;
+}
+
+static int read_counter(vct_context* c, const void* dptr, void* out, size_t bytes) {
+  VCT_CUDA(c, cudaMemcpyAsync(out, dptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+  return check_cuda(c, cudaStreamSynchronize(c->stream), "sync");
+}
+int vct_cone_samples(vct_handle c, uint64_t* n) {
+  NEED(c);
+  unsigned long long v = 0;
+  int rc = read_counter(c, &c->d_counters->cone_samples, &v, 8);
+  if (n) *n = v;
+  return rc;
+}
+int vct_fragment_count(vct_handle c, uint64_t* n) {
+  NEED(c);
+  unsigned int v = 0;
+  int rc = read_counter(c, &c->d_counters->n_fragments, &v, 4);
+  if (n) *n = v;
+  return rc;
+}
+int vct_occupied_voxels(vct_handle c, uint64_t* n) {
+  NEED(c);
+  unsigned int v = 0;
+  int rc = read_counter(c, &c->d_counters->n_touched, &v, 4);
+  if (n) *n = v;
+  return rc;
+}
+
+// ---- execution control
+int vct_set_stream(vct_handle c, void* s) {
+  NEED(c);
+  cudaStreamSynchronize(c->stream);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  if (s) { c->stream = (cudaStream_t)s; c->own_stream = false; }
+  else { VCT_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  return VCT_OK;
+}
+
+int vct_sync(vct_handle c) {
+  NEED(c);
+  int rc = check_cuda(c, cudaStreamSynchronize(c->stream), "cudaStreamSynchronize");
+  if (rc) return rc;
+  return check_overflow(c);
+}
+
+int vct_pass_time_us(vct_handle c, int pass, float* us) {
+  NEED(c);
+  if (pass < 0 || pass >= VCT_PASS_COUNT || !us) return VCT_ERR_INVALID;
+  if (!c->ev_recorded[pass]) return set_error(c, VCT_ERR_STATE, "pass has not run (or Profile = 0)");
+  VCT_CUDA(c, cudaEventSynchronize(c->ev_end[pass]));
+  float ms = 0.0f;
+  VCT_CUDA(c, cudaEventElapsedTime(&ms, c->ev_begin[pass], c->ev_end[pass]));
+  *us = ms * 1000.0f;
+  return VCT_OK;
+}
+
+int vct_kernel_launches(vct_handle c, uint64_t* n) { NEED(c); if (n) *n = c->launches; return VCT_OK; }
+
+int vct_bench_tex3d(vct_handle c, int V, uint64_t n_samples, int pattern, float lod, int iters, float* gsps) {
+  NEED(c);
+  if (V < 8 || V > 1024 || (V & (V - 1)) || iters < 1 || !gsps) return set_error(c, VCT_ERR_INVALID, "vct_bench_tex3d: bad arguments");
+  const int levels = ilog2(V) + 1;
+  cudaMipmappedArray_t arr = nullptr;
+  cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
+  VCT_CUDA(c, cudaMallocMipmappedArray(&arr, &desc, make_cudaExtent(V, V, V), levels, cudaArraySurfaceLoadStore));
+  for (int l = 0; l < levels; ++l) {
+    cudaArray_t lvl;
+    cudaGetMipmappedArrayLevel(&lvl, arr, l);
+    cudaResourceDesc rd{}; rd.resType = cudaResourceTypeArray; rd.res.array.array = lvl;
+    cudaSurfaceObject_t s;
+    cudaCreateSurfaceObject(&s, &rd);
+    int n = V >> l;
+    dim3 b(32, 8), g((n + 31) / 32, (n + 7) / 8, n);
+    fill_level_random<<<g, b, 0, c->stream>>>(s, n, 1234u + l);
+    cudaStreamSynchronize(c->stream);
+    cudaDestroySurfaceObject(s);
+  }
+  cudaResourceDesc rd{}; rd.resType = cudaResourceTypeMipmappedArray; rd.res.mipmap.mipmap = arr;
+  cudaTextureDesc td{};
+  td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeWrap;
+  td.filterMode = cudaFilterModeLinear; td.mipmapFilterMode = cudaFilterModeLinear;
+  td.readMode = cudaReadModeNormalizedFloat; td.normalizedCoords = 1; td.maxMipmapLevelClamp = (float)(levels - 1);
+  cudaTextureObject_t tex;
+  VCT_CUDA(c, cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+  const int Wp = 1920, Hp = 1080, steps = (int)((n_samples + (uint64_t)Wp * Hp - 1) / ((uint64_t)Wp * Hp));
+  float4* sink; VCT_CUDA(c, cudaMalloc(&sink, 16));
+  dim3 b(256), g((Wp + 31) / 32, (Hp + 7) / 8);
+  const float step_len = 1.0f / (float)(V >> (int)lod);   // one texel of the sampled level per step
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  tex3d_bench<<<g, b, 0, c->stream>>>(tex, steps, lod, pattern, step_len, sink, Wp);   // warm-up
+  float best = 1e30f;
+  for (int it = 0; it < iters; ++it) {
+    cudaEventRecord(e0, c->stream);
+    tex3d_bench<<<g, b, 0, c->stream>>>(tex, steps, lod, pattern, step_len, sink, Wp);
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    best = ms < best ? ms : best;
+  }
+  c->launches += iters + 1 + levels;
+  const double total = (double)g.x * 32 * g.y * 8 * steps;
+  *gsps = (float)(total / (best * 1e-3) * 1e-9);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaDestroyTextureObject(tex); cudaFreeMipmappedArray(arr); cudaFree(sink);
+  return check_cuda(c, cudaGetLastError(), "vct_bench_tex3d");
+}
+
+}  // extern "C"

@@ -1,0 +1,461 @@
+// vct_cone.cu -- S2 + C1..C6: primary visibility and per-pixel cone tracing.
+// Replaces Render() (Voxel_Cone_Tracing.h:146-190) and Shader/VoxelConeTracing.{vs,fs}.
+//
+// The reference is a forward renderer: the cone-trace fragment shader runs on rasterised scene geometry
+// with the hardware depth test and `discard` on alpha < 0.5, and shades overdrawn fragments.  Here the
+// work is split into
+//   visibility (raster_small / raster_tiles): VoxelConeTracing.vs:25 + viewport + back-face cull + depth
+//        LESS + alpha discard, as 2D homogeneous rasterisation (no clipping; the near plane is enforced
+//        per fragment).  Output: 64-bit atomicMin of (depth bits << 32 | triangle id) per pixel.
+//   cone_trace: one thread per pixel, one warp per 8x4 screen tile; rebuilds the interpolated varyings
+//        of the winning triangle and evaluates VoxelConeTracing.fs:165-229 exactly once per pixel.
+//        Voxel fetches are hardware trilinear tex3DLod on the mipmapped cudaArray (wrap = REPEAT).
+#include "vct_raster.cuh"
+
+namespace vct {
+
+struct HVert { float X, Y, w, zc; };
+struct HEdge { float A, B, C; };
+
+__device__ __forceinline__ HEdge hcross(const HVert& a, const HVert& b) {
+  HEdge e;
+  e.A = a.Y * b.w - b.Y * a.w;
+  e.B = b.X * a.w - a.X * b.w;
+  e.C = a.X * b.Y - b.X * a.Y;
+  return e;
+}
+__device__ __forceinline__ float heval(const HEdge& e, float px, float py) { return (e.A * px + e.B * py) + e.C; }
+__device__ __forceinline__ bool hinside(const HEdge& e, float v) {
+  return v > 0.0f || (v == 0.0f && (e.A > 0.0f || (e.A == 0.0f && e.B > 0.0f)));
+}
+
+struct HTri {
+  HVert c[3];
+  HEdge e[3];   // e[i] opposite vertex i
+};
+
+// VoxelConeTracing.vs:25 + viewport transform + GL_CULL_FACE(GL_BACK) as homogeneous set-up
+template <bool WITH_BBOX>
+__device__ __forceinline__ bool setup_htri(const Params& P, const float* __restrict__ verts,
+                                           const uint32_t* __restrict__ idx, uint32_t tri, HTri& t, int& i0,
+                                           int& i1, int& j0, int& j1) {
+  const float W = (float)P.W, H = (float)P.H;
+  bool in_near[3];
+  bool any_near = false;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float* v = verts + (size_t)__ldg(&idx[tri * 3 + k]) * 14;
+    F4 e = mul_mat_vec(P.model_view, __ldg(v), __ldg(v + 1), __ldg(v + 2), 1.0f);
+    F4 c = mul_mat_vec(P.proj, e.x, e.y, e.z, e.w);
+    if (!isfinite(c.x) || !isfinite(c.y) || !isfinite(c.z) || !isfinite(c.w)) return false;
+    t.c[k].X = (c.x + c.w) * (0.5f * W);
+    t.c[k].Y = (c.y + c.w) * (0.5f * H);
+    t.c[k].w = c.w;
+    t.c[k].zc = c.z;
+    in_near[k] = (c.z >= -c.w) && (c.w > 0.0f);
+    any_near |= in_near[k];
+  }
+  if (!any_near) return false;
+  t.e[0] = hcross(t.c[1], t.c[2]);
+  t.e[1] = hcross(t.c[2], t.c[0]);
+  t.e[2] = hcross(t.c[0], t.c[1]);
+  float det = (t.c[0].X * t.e[0].A + t.c[0].Y * t.e[0].B) + t.c[0].w * t.e[0].C;
+  if (!(det > 0.0f)) return false;
+  if (!WITH_BBOX) return true;
+
+  float minx = INFINITY, maxx = -INFINITY, miny = INFINITY, maxy = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int n = (k + 1) % 3;
+    if (in_near[k]) {
+      float x = t.c[k].X / t.c[k].w, y = t.c[k].Y / t.c[k].w;
+      minx = fminf(minx, x); maxx = fmaxf(maxx, x); miny = fminf(miny, y); maxy = fmaxf(maxy, y);
+    }
+    if (in_near[k] != in_near[n]) {
+      float da = t.c[k].zc + t.c[k].w, db = t.c[n].zc + t.c[n].w;
+      float s = da / (da - db);
+      float X = t.c[k].X + s * (t.c[n].X - t.c[k].X);
+      float Y = t.c[k].Y + s * (t.c[n].Y - t.c[k].Y);
+      float w = t.c[k].w + s * (t.c[n].w - t.c[k].w);
+      if (w > 0.0f) {
+        float x = X / w, y = Y / w;
+        minx = fminf(minx, x); maxx = fmaxf(maxx, x); miny = fminf(miny, y); maxy = fmaxf(maxy, y);
+      } else {
+        minx = miny = -1e30f; maxx = maxy = 1e30f;
+      }
+    }
+  }
+  if (!(minx <= maxx)) return false;
+  float fx0 = fmaxf(floorf(minx) - 1.0f, 0.0f), fx1 = fminf(ceilf(maxx) + 1.0f, W - 1.0f);
+  float fy0 = fmaxf(floorf(miny) - 1.0f, 0.0f), fy1 = fminf(ceilf(maxy) + 1.0f, H - 1.0f);
+  if (!(fx0 <= fx1) || !(fy0 <= fy1)) return false;
+  i0 = (int)fx0; i1 = (int)fx1; j0 = (int)fy0; j1 = (int)fy1;
+  return true;
+}
+
+template <bool TEST>
+__device__ __forceinline__ bool hbary(const HTri& t, float px, float py, float b[3]) {
+  float e0 = heval(t.e[0], px, py), e1 = heval(t.e[1], px, py), e2 = heval(t.e[2], px, py);
+  if (TEST && !(hinside(t.e[0], e0) && hinside(t.e[1], e1) && hinside(t.e[2], e2))) return false;
+  float s = (e0 + e1) + e2;
+  if (TEST && !(s > 0.0f)) return false;
+  b[0] = e0 / s; b[1] = e1 / s; b[2] = e2 / s;
+  return true;
+}
+
+__device__ __forceinline__ float bary3(const float b[3], float a0, float a1, float a2) {
+  return (b[0] * a0 + b[1] * a1) + b[2] * a2;
+}
+
+struct PixelUV { float u, v, dudx, dvdx, dudy, dvdy; };
+
+__device__ __forceinline__ PixelUV pixel_uv(const float* __restrict__ verts, const uint32_t* __restrict__ idx,
+                                            uint32_t tri, const HTri& t, float px, float py, const float b[3]) {
+  const float* v0 = verts + (size_t)__ldg(&idx[tri * 3 + 0]) * 14;
+  const float* v1 = verts + (size_t)__ldg(&idx[tri * 3 + 1]) * 14;
+  const float* v2 = verts + (size_t)__ldg(&idx[tri * 3 + 2]) * 14;
+  const float u0 = __ldg(v0 + 6), u1 = __ldg(v1 + 6), u2 = __ldg(v2 + 6);
+  const float w0 = __ldg(v0 + 7), w1 = __ldg(v1 + 7), w2 = __ldg(v2 + 7);
+  PixelUV r;
+  r.u = bary3(b, u0, u1, u2);
+  r.v = bary3(b, w0, w1, w2);
+  float bx[3], by[3];
+  hbary<false>(t, px + 1.0f, py, bx);
+  hbary<false>(t, px, py + 1.0f, by);
+  r.dudx = bary3(bx, u0, u1, u2) - r.u;
+  r.dvdx = bary3(bx, w0, w1, w2) - r.v;
+  r.dudy = bary3(by, u0, u1, u2) - r.u;
+  r.dvdy = bary3(by, w0, w1, w2) - r.v;
+  return r;
+}
+
+__device__ __forceinline__ float4 sample_mat(cudaTextureObject_t tex, int w, int h, const PixelUV& q, float du, float dv) {
+  float lod = lod_from_derivs(q.dudx, q.dvdx, q.dudy, q.dvdy, w, h);
+  return sample_material(tex, q.u + du, q.v + dv, lod);
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct VisibilityPass {
+  Params P;
+  const float* verts; const uint32_t* idx; const uint16_t* trimat; const MaterialDev* mats;
+  unsigned long long* vis;
+
+  struct Setup { HTri t; };
+
+  __device__ __forceinline__ bool setup(uint32_t tri, Setup& s, int& i0, int& i1, int& j0, int& j1) const {
+    return setup_htri<true>(P, verts, idx, tri, s.t, i0, i1, j0, j1);
+  }
+  __device__ __forceinline__ bool tile_may_cover(const Setup&, int, int, int, int) const { return true; }
+
+  __device__ __forceinline__ void shade(const Setup& s, uint32_t tri, int i, int j) const {
+    const float px = (float)i + 0.5f, py = (float)j + 0.5f;
+    float b[3];
+    if (!hbary<true>(s.t, px, py, b)) return;
+    float zc = bary3(b, s.t.c[0].zc, s.t.c[1].zc, s.t.c[2].zc);
+    float w = bary3(b, s.t.c[0].w, s.t.c[1].w, s.t.c[2].w);
+    float zw = (zc / w) * 0.5f + 0.5f;
+    if (!(zw >= 0.0f) || zw > 1.0f) return;                 // near / far clip
+    const MaterialDev& m = mats[trimat ? trimat[tri] : 0];
+    if (m.alpha_test) {                                     // discard, VoxelConeTracing.fs:167-172
+      PixelUV q = pixel_uv(verts, idx, tri, s.t, px, py, b);
+      float4 c = sample_mat(m.diffuse, m.dw, m.dh, q, 0.0f, 0.0f);
+      if (c.w < 0.5f) return;
+    }
+    unsigned long long key = ((unsigned long long)__float_as_uint(zw) << 32) | tri;
+    atomicMin(&vis[(size_t)j * P.W + i], key);
+  }
+  __device__ __forceinline__ void small(const Setup& s, uint32_t tri, bool active, int i0, int i1, int j0, int j1) const {
+    if (!active) return;
+    for (int j = j0; j <= j1; ++j)
+      for (int i = i0; i <= i1; ++i) shade(s, tri, i, j);
+  }
+  __device__ __forceinline__ void pixel(const Setup& s, uint32_t tri, int i, int j, bool in_bbox) const {
+    if (in_bbox) shade(s, tri, i, j);
+  }
+};
+
+__global__ void fill_u64(unsigned long long* p, size_t n, unsigned long long v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
+int launch_visibility(vct_context* c) {
+  if (!c->nt) return set_error(c, VCT_ERR_STATE, "vct_render: no mesh uploaded");
+  int rc = ensure_frame(c); if (rc) return rc;
+  rc = ensure_queues(c); if (rc) return rc;
+  rc = sync_materials(c); if (rc) return rc;
+  PassTimer timer(c, VCT_PASS_VISIBILITY);
+  const size_t n = (size_t)c->P.W * c->P.H;
+  fill_u64<<<148 * 4, 256, 0, c->stream>>>(c->d_vis, n, ~0ull);
+  VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_items, 0, sizeof(unsigned int), c->stream));
+  VisibilityPass pass{c->P, c->d_verts, c->d_idx, c->d_trimat, c->d_materials, c->d_vis};
+  const uint32_t nt = (uint32_t)c->nt;
+  raster_small<VisibilityPass><<<(nt + 127) / 128, 128, 0, c->stream>>>(pass, 0, nt, c->d_items,
+                                                                        (uint32_t)c->items_cap, c->d_counters);
+  raster_tiles<VisibilityPass><<<148 * 4, 256, 0, c->stream>>>(pass, c->d_items, (uint32_t)c->items_cap, c->d_counters);
+  c->launches += 3;
+  VCT_CUDA(c, cudaGetLastError());
+  return VCT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 vadd(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 vsub(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 vscale(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float vdot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ V3 vcross(V3 a, V3 b) {
+  return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ V3 vnormalize(V3 a) {
+  float l = sqrtf(vdot(a, a));
+  return v3(a.x / l, a.y / l, a.z / l);
+}
+
+struct ConeConsts { float vws, inv_half, max_lod; };
+
+// Voxel_Cone_Tracing(direction, tanHalfAngle), VoxelConeTracing.fs:82-107.  SampleVoxels (:59-66) folded in:
+// uvw = pos / (G/2) * 0.5 + 0.5; textureLod clamps lod to [0, log2 V] in hardware (maxMipmapLevelClamp).
+__device__ __forceinline__ float4 cone_march(cudaTextureObject_t grid, const Params& P, const ConeConsts& k,
+                                             V3 start, V3 dir, float tanHalf, unsigned& samples) {
+  float cr = 0.0f, cg = 0.0f, cb = 0.0f, alpha = 0.0f, occ = 0.0f;
+  float dist = k.vws;
+  const float two_tan = 2.0f * tanHalf;
+  while (dist < P.max_dist && alpha < P.max_alpha) {
+    float diameter = fmaxf(k.vws, two_tan * dist);
+    float lod = log2f(diameter / k.vws);
+    float u = ((start.x + dist * dir.x) / k.inv_half) * 0.5f + 0.5f;
+    float v = ((start.y + dist * dir.y) / k.inv_half) * 0.5f + 0.5f;
+    float w = ((start.z + dist * dir.z) / k.inv_half) * 0.5f + 0.5f;
+    float4 s = tex3DLod<float4>(grid, u, v, w, lod);
+    float t = 1.0f - alpha;
+    cr += t * s.x; cg += t * s.y; cb += t * s.z;
+    occ += (t * s.w) / (1.0f + 0.03f * diameter);
+    alpha += t * s.w;
+    dist += diameter * P.step_mult;
+    ++samples;
+  }
+  return make_float4(cr, cg, cb, occ);
+}
+
+__device__ __forceinline__ unsigned char to_unorm8(float x) {
+  x = fminf(fmaxf(x, 0.0f), 1.0f);
+  if (!(x == x)) x = 0.0f;
+  return (unsigned char)__float2int_rn(x * 255.0f);
+}
+
+// one warp = 8x4 pixels; block = 8 warps = 32x8 pixels
+__global__ void __launch_bounds__(256) cone_trace(Params P, const float* __restrict__ verts,
+                                                  const uint32_t* __restrict__ idx,
+                                                  const uint16_t* __restrict__ trimat,
+                                                  const MaterialDev* __restrict__ mats,
+                                                  const uint32_t* __restrict__ depth,
+                                                  const unsigned long long* __restrict__ vis,
+                                                  cudaTextureObject_t grid, uchar4* __restrict__ frame,
+                                                  Counters* __restrict__ ctr, int y_begin, int y_end) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+  const int j = y_begin + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+  unsigned samples = 0;
+  if (i < P.W && j < y_end) {
+    const unsigned long long key = vis[(size_t)j * P.W + i];
+    uchar4 out;
+    if (key == ~0ull) {
+      // glClearColor, Voxel_Cone_Tracing.h:156-159
+      unsigned char bg = to_unorm8(P.ambient < 0.5f ? 0.5f : 1.0f);
+      out = make_uchar4(bg, bg, bg, 255);
+    } else {
+      const uint32_t tri = (uint32_t)key;
+      HTri t;
+      int d0, d1, d2, d3;
+      setup_htri<false>(P, verts, idx, tri, t, d0, d1, d2, d3);
+      const float px = (float)i + 0.5f, py = (float)j + 0.5f;
+      float b[3];
+      hbary<false>(t, px, py, b);
+      // vertex shader outputs (VoxelConeTracing.vs:27-34), then perspective-correct interpolation
+      V3 Pw = v3(0, 0, 0), Nw = v3(0, 0, 0), Tw = v3(0, 0, 0), Bw = v3(0, 0, 0);
+      float pdx = 0, pdy = 0, pdz = 0, pdw = 0;
+      {
+        F4 pw[3], pd[3], nw[3], tw[3], bw[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float* v = verts + (size_t)__ldg(&idx[tri * 3 + k]) * 14;
+          float p0 = __ldg(v), p1 = __ldg(v + 1), p2 = __ldg(v + 2);
+          pw[k] = mul_mat_vec(P.model, p0, p1, p2, 1.0f);
+          pd[k] = mul_mat_vec(P.depth_mvp, p0, p1, p2, 1.0f);
+          pd[k].x = pd[k].x * 0.5f + 0.5f; pd[k].y = pd[k].y * 0.5f + 0.5f; pd[k].z = pd[k].z * 0.5f + 0.5f;
+          nw[k] = mul_mat_vec(P.model, __ldg(v + 3), __ldg(v + 4), __ldg(v + 5), 0.0f);
+          tw[k] = mul_mat_vec(P.model, __ldg(v + 8), __ldg(v + 9), __ldg(v + 10), 0.0f);
+          bw[k] = mul_mat_vec(P.model, __ldg(v + 11), __ldg(v + 12), __ldg(v + 13), 0.0f);
+        }
+        Pw = v3(bary3(b, pw[0].x, pw[1].x, pw[2].x), bary3(b, pw[0].y, pw[1].y, pw[2].y), bary3(b, pw[0].z, pw[1].z, pw[2].z));
+        Nw = v3(bary3(b, nw[0].x, nw[1].x, nw[2].x), bary3(b, nw[0].y, nw[1].y, nw[2].y), bary3(b, nw[0].z, nw[1].z, nw[2].z));
+        Tw = v3(bary3(b, tw[0].x, tw[1].x, tw[2].x), bary3(b, tw[0].y, tw[1].y, tw[2].y), bary3(b, tw[0].z, tw[1].z, tw[2].z));
+        Bw = v3(bary3(b, bw[0].x, bw[1].x, bw[2].x), bary3(b, bw[0].y, bw[1].y, bw[2].y), bary3(b, bw[0].z, bw[1].z, bw[2].z));
+        pdx = bary3(b, pd[0].x, pd[1].x, pd[2].x); pdy = bary3(b, pd[0].y, pd[1].y, pd[2].y);
+        pdz = bary3(b, pd[0].z, pd[1].z, pd[2].z); pdw = bary3(b, pd[0].w, pd[1].w, pd[2].w);
+      }
+      const V3 Cd = vsub(v3(P.cam[0], P.cam[1], P.cam[2]), Pw);       // VoxelConeTracing.vs:34
+
+      const MaterialDev m = mats[trimat ? trimat[tri] : 0];
+      const PixelUV q = pixel_uv(verts, idx, tri, t, px, py, b);
+      const float4 mat = sample_mat(m.diffuse, m.dw, m.dh, q, 0.0f, 0.0f);    // :167
+
+      // TBN = inverse(transpose(mat3(T,B,N))), :175 -- rows of the matrix being inverted are T, B, N
+      const float c00 = Bw.y * Nw.z - Bw.z * Nw.y;
+      const float c01 = Bw.z * Nw.x - Bw.x * Nw.z;
+      const float c02 = Bw.x * Nw.y - Bw.y * Nw.x;
+      const float det = (Tw.x * c00 + Tw.y * c01) + Tw.z * c02;
+      const float id = 1.0f / det;
+      float inv[3][3];
+      inv[0][0] = c00 * id; inv[1][0] = c01 * id; inv[2][0] = c02 * id;
+      inv[0][1] = (Tw.z * Nw.y - Tw.y * Nw.z) * id;
+      inv[1][1] = (Tw.x * Nw.z - Tw.z * Nw.x) * id;
+      inv[2][1] = (Tw.y * Nw.x - Tw.x * Nw.y) * id;
+      inv[0][2] = (Tw.y * Bw.z - Tw.z * Bw.y) * id;
+      inv[1][2] = (Tw.z * Bw.x - Tw.x * Bw.z) * id;
+      inv[2][2] = (Tw.x * Bw.y - Tw.y * Bw.x) * id;
+      auto tbn_mul = [&](V3 a) {
+        return v3((inv[0][0] * a.x + inv[0][1] * a.y) + inv[0][2] * a.z,
+                  (inv[1][0] * a.x + inv[1][1] * a.y) + inv[1][2] * a.z,
+                  (inv[2][0] * a.x + inv[2][1] * a.y) + inv[2][2] * a.z);
+      };
+
+      // CalcBumpNormal, :110-128
+      const float offx = 1.0f / (float)m.hw, offy = 1.0f / (float)m.hh;
+      const float h0 = sample_mat(m.height, m.hw, m.hh, q, 0.0f, 0.0f).x;
+      const float hx = sample_mat(m.height, m.hw, m.hh, q, offx, 0.0f).x;
+      const float hy = sample_mat(m.height, m.hw, m.hh, q, 0.0f, offy).x;
+      const V3 t1 = vnormalize(v3(1.0f, 0.0f, hx - h0));
+      const V3 t2 = vnormalize(v3(0.0f, 1.0f, hy - h0));
+      const V3 bump = vnormalize(vcross(t1, t2));
+      const V3 N = vnormalize(tbn_mul(bump));
+      const V3 L = vnormalize(v3(P.light[0], P.light[1], P.light[2]));   // :179
+      const V3 E = vnormalize(Cd);                                         // :181
+
+      // :186 with the *0.111 normalisation of :158
+      const float shadow = pcf_lit_taps(depth, P.S, P.pcf_radius, P.shadow_bias, pdx, pdy, pdz, pdw) * 0.111f;
+      const float directDiffuse = shadow * fmaxf(vdot(N, L), 0.0f);
+
+      ConeConsts kc;
+      kc.vws = P.grid_world / (float)P.V;
+      kc.inv_half = P.grid_world * 0.5f;
+      kc.max_lod = (float)(P.levels - 1);
+      const V3 start = vadd(Pw, vscale(Nw, kc.vws));                       // :92
+      float ir = 0.0f, ig = 0.0f, ib = 0.0f, ia = 0.0f;
+      for (int cidx = 0; cidx < P.n_cones; ++cidx) {                      // :196-199
+        V3 dir = vnormalize(tbn_mul(v3(P.cone_dir[cidx * 3], P.cone_dir[cidx * 3 + 1], P.cone_dir[cidx * 3 + 2])));
+        float4 r = cone_march(grid, P, kc, start, dir, P.diffuse_tan, samples);
+        const float wgt = P.cone_w[cidx];
+        ir += wgt * r.x; ig += wgt * r.y; ib += wgt * r.z; ia += wgt * r.w;
+      }
+      const float occlusion = 1.0f - ia;                                   // :201
+
+      float4 sc = sample_mat(m.specular, m.sw, m.sh, q, 0.0f, 0.0f);      // :209
+      if (!(sqrtf(sc.y * sc.y + sc.z * sc.z) > 0.0f)) { sc.y = sc.x; sc.z = sc.x; }   // .rrra, :210
+      const V3 negL = v3(-L.x, -L.y, -L.z);
+      const V3 R = vnormalize(vsub(negL, vscale(N, 2.0f * vdot(N, negL))));           // :212
+      const float spec = powf(fmaxf(vdot(E, R), 0.0f), m.shininess);                  // :213
+      const float directSpec = spec * shadow;                                         // :214
+      const V3 negE = v3(-E.x, -E.y, -E.z);
+      const V3 refl = vnormalize(vsub(negE, vscale(N, 2.0f * vdot(N, negE))));        // :217
+      const float4 isp = cone_march(grid, P, kc, start, refl, P.spec_tan, samples);   // :218
+      const float specOcc = 1.0f - isp.w;                                             // :221
+
+      const float mr[3] = {mat.x, mat.y, mat.z}, ind[3] = {ir, ig, ib}, is3[3] = {isp.x, isp.y, isp.z};
+      const float sc3[3] = {sc.x, sc.y, sc.z};
+      unsigned char o8[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float diff = (directDiffuse + occlusion * ind[k]) * mr[k];          // :205
+        float specR = (is3[k] + specOcc * directSpec) * sc3[k];             // :223
+        float amb = (P.ambient * mr[k]) * occlusion;                        // :225
+        o8[k] = to_unorm8((amb + diff) + specR);                            // :227
+      }
+      out = make_uchar4(o8[0], o8[1], o8[2], to_unorm8(mat.w));
+    }
+    frame[(size_t)j * P.W + i] = out;
+  }
+  // executed textureLod calls (Gcone-samples/s numerator): one atomic per warp
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) samples += __shfl_xor_sync(0xffffffffu, samples, d);
+  if (lane == 0 && samples) atomicAdd(&ctr->cone_samples, (unsigned long long)samples);
+}
+
+int launch_cone(vct_context* c) {
+  int rc = ensure_frame(c); if (rc) return rc;
+  rc = ensure_grid(c); if (rc) return rc;
+  if (!c->depth_valid) return set_error(c, VCT_ERR_STATE, "vct_render: call vct_draw_depth first (shadow map missing)");
+  PassTimer timer(c, VCT_PASS_CONE);
+  VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->cone_samples, 0, sizeof(unsigned long long), c->stream));
+  dim3 b(256), g((c->P.W + 31) / 32, (c->P.H + 7) / 8);
+  cone_trace<<<g, b, 0, c->stream>>>(c->P, c->d_verts, c->d_idx, c->d_trimat, c->d_materials, c->d_depth, c->d_vis,
+                                     c->grid_tex, c->d_frame, c->d_counters, 0, c->P.H);
+  c->launches += 1;
+  VCT_CUDA(c, cudaGetLastError());
+  return VCT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Bounces >= 3 (extension; the reference has no re-injection pass, README.md:14 only claims one).
+// For every occupied voxel: one diffuse-aperture cone along each of +-X, +-Y, +-Z starting one voxel
+// out from the voxel centre, averaged; new = min(old + gathered * old, 1).  Reads the pyramid of the
+// previous bounce through the texture, writes a staging buffer, then level 0 (no read/write hazard).
+__global__ void __launch_bounds__(256) reinject_gather(Params P, cudaTextureObject_t grid, cudaSurfaceObject_t level0,
+                                                       uint32_t* __restrict__ staged) {
+  const int V = P.V;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), z = blockIdx.z;
+  if (x >= V || y >= V) return;
+  const size_t i = ((size_t)z * V + y) * V + x;
+  const uchar4 old = surf3Dread<uchar4>(level0, x * 4, y, z);
+  if (old.w == 0) { staged[i] = 0u; return; }
+  ConeConsts kc;
+  kc.vws = P.grid_world / (float)V;
+  kc.inv_half = P.grid_world * 0.5f;
+  kc.max_lod = (float)(P.levels - 1);
+  const V3 c = v3(((float)x + 0.5f) * kc.vws - 0.5f * P.grid_world, ((float)y + 0.5f) * kc.vws - 0.5f * P.grid_world,
+                  ((float)z + 0.5f) * kc.vws - 0.5f * P.grid_world);
+  float acc[3] = {0.0f, 0.0f, 0.0f};
+  unsigned dummy = 0;
+#pragma unroll 1
+  for (int a = 0; a < 6; ++a) {
+    const float sgn = (a & 1) ? -1.0f : 1.0f;
+    const V3 d = v3((a >> 1) == 0 ? sgn : 0.0f, (a >> 1) == 1 ? sgn : 0.0f, (a >> 1) == 2 ? sgn : 0.0f);
+    const float4 r = cone_march(grid, P, kc, vadd(c, vscale(d, kc.vws)), d, P.diffuse_tan, dummy);
+    acc[0] += r.x * (1.0f / 6.0f); acc[1] += r.y * (1.0f / 6.0f); acc[2] += r.z * (1.0f / 6.0f);
+  }
+  const float b0 = old.x * (1.0f / 255.0f), b1 = old.y * (1.0f / 255.0f), b2 = old.z * (1.0f / 255.0f);
+  uchar4 o;
+  o.x = (unsigned char)__float2int_rn(fminf(b0 + acc[0] * b0, 1.0f) * 255.0f);
+  o.y = (unsigned char)__float2int_rn(fminf(b1 + acc[1] * b1, 1.0f) * 255.0f);
+  o.z = (unsigned char)__float2int_rn(fminf(b2 + acc[2] * b2, 1.0f) * 255.0f);
+  o.w = old.w;
+  staged[i] = *reinterpret_cast<uint32_t*>(&o);
+}
+
+__global__ void reinject_commit(const uint32_t* __restrict__ staged, cudaSurfaceObject_t level0, int V) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), z = blockIdx.z;
+  if (x >= V || y >= V) return;
+  const uint32_t v = staged[((size_t)z * V + y) * V + x];
+  if (v) surf3Dwrite(v, level0, x * 4, y, z);
+}
+
+int launch_reinject(vct_context* c) {
+  int rc = ensure_grid(c); if (rc) return rc;
+  PassTimer timer(c, VCT_PASS_REINJECT);
+  const int V = c->P.V;
+  uint32_t* staged = nullptr;
+  VCT_CUDA(c, cudaMallocAsync(&staged, (size_t)V * V * V * 4, c->stream));
+  dim3 b(256), g((V + 31) / 32, (V + 7) / 8, V);
+  reinject_gather<<<g, b, 0, c->stream>>>(c->P, c->grid_tex, c->grid_surf[0], staged);
+  reinject_commit<<<g, b, 0, c->stream>>>(staged, c->grid_surf[0], V);
+  c->launches += 2;
+  VCT_CUDA(c, cudaFreeAsync(staged, c->stream));
+  c->accum_dense_dirty = c->accum_dense_dirty;   // level 0 still matches the touched list (same voxels occupied)
+  VCT_CUDA(c, cudaGetLastError());
+  return VCT_OK;
+}
+
+}  // namespace vct

@@ -1,0 +1,328 @@
+// vct_internal.h -- context, parameter block and device helpers shared by the kernels of libvct_b200.
+// Compiled with --fmad=false: every float expression below is a sequence of single IEEE binary32
+// operations in source order, which is what makes coverage / depth-slice / shadow-compare decisions
+// reproducible bit for bit against the CPU oracle (DESIGN.md "Defined semantics").
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/vct_c_api.h"
+
+#define VCT_MAX_CONES 16
+
+namespace vct {
+
+// Uniform block handed to every kernel by value (fits in constant bank param space).
+struct Params {
+  int V;                 // VoxelDimensions
+  int levels;            // log2(V)+1
+  float grid_world;      // VoxelGridWorldSize
+  int S;                 // ShadowMapSize
+  int W, H;              // screen_width, screen_height
+  float model[16], model_view[16], proj[16], depth_mvp[16], projx[16], projy[16], projz[16];
+  float cam[3], light[3];
+  float ambient;
+  int n_cones;
+  float cone_dir[VCT_MAX_CONES * 3];
+  float cone_w[VCT_MAX_CONES];
+  float diffuse_tan, spec_tan, step_mult, max_dist, max_alpha;
+  int pcf_radius;
+  float shadow_bias;
+  int coverage;          // 0 CENTER, 1 MSAA4_ANY, 2 CONSERVATIVE
+  int bounces;
+};
+
+struct MaterialDev {
+  cudaTextureObject_t diffuse, specular, height;
+  int dw, dh, sw, sh, hw, hh;   // level-0 sizes (for the implicit LOD and HeightTextureSize)
+  float shininess;
+  int alpha_test;               // diffuse texture has texels with alpha < 255
+};
+
+struct TextureEntry {
+  cudaMipmappedArray_t array = nullptr;
+  cudaTextureObject_t tex = 0;
+  int w = 0, h = 0;
+  bool has_alpha = false;
+};
+
+struct MaterialHost { int d = -1, s = -1, h = -1; float shininess = 20.0f; };
+
+// Device counters, one cache line each to keep unrelated atomics apart.
+struct Counters {
+  unsigned int n_fragments;   unsigned int pad0[31];
+  unsigned int n_items;       unsigned int pad1[31];
+  unsigned int n_touched;     unsigned int pad2[31];
+  unsigned int overflow;      unsigned int pad3[31];
+  unsigned long long cone_samples; unsigned int pad4[30];
+  unsigned int n_prev_touched; unsigned int pad5[31];
+};
+
+struct TileItem { uint32_t tri; uint32_t origin; };   // origin = tile_x | tile_y << 16 (in tiles)
+
+}  // namespace vct
+
+struct vct_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  vct::Params P{};
+  bool profile = true;
+  int dense_resolve = 0;
+  int grid_format = 0;
+  size_t max_fragments = 16u << 20;
+  size_t max_items = 4u << 20;
+
+  // scene
+  float* d_verts = nullptr; uint32_t* d_idx = nullptr; uint16_t* d_trimat = nullptr;
+  size_t nv = 0, nt = 0;
+  std::vector<vct::TextureEntry> textures;
+  std::vector<vct::MaterialHost> materials;
+  vct::MaterialDev* d_materials = nullptr; size_t n_materials_dev = 0; bool materials_dirty = true;
+  cudaTextureObject_t white_tex = 0; cudaMipmappedArray_t white_arr = nullptr;
+
+  // shadow map (u32 d24, linear)
+  uint32_t* d_depth = nullptr; int depth_S = 0; bool depth_valid = false;
+
+  // voxel grid
+  int grid_V = 0;
+  unsigned long long* d_accum = nullptr;       // 2 x u64 per voxel: (r<<32|g), (b<<32|count)
+  uint32_t* d_touched = nullptr; uint32_t* d_prev_touched = nullptr; size_t touched_cap = 0;
+  cudaMipmappedArray_t grid_array = nullptr;
+  std::vector<cudaSurfaceObject_t> grid_surf;
+  cudaTextureObject_t grid_tex = 0;
+  bool accum_dense_dirty = false;              // accumulator holds data not described by the touched list
+
+  // work queues
+  uint2* d_frags = nullptr; size_t frags_cap = 0;
+  vct::TileItem* d_items = nullptr; size_t items_cap = 0;
+  vct::Counters* d_counters = nullptr;
+  vct::Counters* h_counters = nullptr;          // pinned mirror
+
+  // frame
+  unsigned long long* d_vis = nullptr; uchar4* d_frame = nullptr; int frame_W = 0, frame_H = 0;
+  uint8_t* h_frame_pinned = nullptr; size_t h_frame_bytes = 0;
+
+  // timing
+  cudaEvent_t ev_begin[VCT_PASS_COUNT]{}, ev_end[VCT_PASS_COUNT]{};
+  bool ev_recorded[VCT_PASS_COUNT]{};
+  uint64_t launches = 0;
+
+  std::string err;
+};
+
+namespace vct {
+
+int set_error(vct_context* c, int code, const std::string& msg);
+int check_cuda(vct_context* c, cudaError_t e, const char* what);
+#define VCT_CUDA(c, call)                                              \
+  do {                                                                 \
+    int _rc = vct::check_cuda((c), (call), #call);                     \
+    if (_rc) return _rc;                                               \
+  } while (0)
+
+struct PassTimer {
+  vct_context* c; int pass;
+  PassTimer(vct_context* c_, int p) : c(c_), pass(p) {
+    if (c->profile) { cudaEventRecord(c->ev_begin[p], c->stream); }
+  }
+  ~PassTimer() {
+    if (c->profile) { cudaEventRecord(c->ev_end[pass], c->stream); c->ev_recorded[pass] = true; }
+  }
+};
+
+// pass entry points implemented in the kernel files
+int ensure_grid(vct_context* c);
+int ensure_shadow(vct_context* c);
+int ensure_frame(vct_context* c);
+int ensure_queues(vct_context* c);
+int sync_materials(vct_context* c);
+int launch_shadow(vct_context* c);
+int launch_voxel_clear(vct_context* c);
+int launch_voxelize(vct_context* c, size_t tb, size_t te);
+int launch_resolve(vct_context* c, bool dense);
+int launch_mip(vct_context* c);
+int launch_visibility(vct_context* c);
+int launch_cone(vct_context* c);
+int launch_reinject(vct_context* c);
+int check_overflow(vct_context* c);
+
+// ------------------------------------------------------------------------------------ device helpers
+#ifdef __CUDACC__
+
+struct F4 { float x, y, z, w; };
+
+// ((m0*x + m1*y) + m2*z) + m3*w -- same order as the oracle (no FMA: the TU is built with --fmad=false)
+__device__ __forceinline__ F4 mul_mat_vec(const float* __restrict__ m, float x, float y, float z, float w) {
+  F4 r;
+  r.x = ((m[0] * x + m[4] * y) + m[8] * z) + m[12] * w;
+  r.y = ((m[1] * x + m[5] * y) + m[9] * z) + m[13] * w;
+  r.z = ((m[2] * x + m[6] * y) + m[10] * z) + m[14] * w;
+  r.w = ((m[3] * x + m[7] * y) + m[11] * z) + m[15] * w;
+  return r;
+}
+
+constexpr int SUBPIX = 256;
+constexpr float SNAP_LIMIT = 8388608.0f;
+
+__device__ __forceinline__ bool snap(float v, long long* out) {
+  float s = v * (float)SUBPIX;
+  if (!(s == s)) return false;
+  s = fminf(fmaxf(s, -SNAP_LIMIT), SNAP_LIMIT);
+  *out = (long long)__float2int_rn(s);
+  return true;
+}
+
+// Exact integer triangle in 24.8 window coordinates, counter-clockwise after set-up.
+struct RasterTri {
+  int X0, Y0, X1, Y1, X2, Y2;   // |coords| <= 2^23
+  long long area;
+  int flipped;
+
+  // edge a->b evaluated at p: dx*(py-ay) - dy*(px-ax)
+  __device__ __forceinline__ static long long ev(int ax, int ay, int bx, int by, int px, int py) {
+    return (long long)(bx - ax) * (long long)(py - ay) - (long long)(by - ay) * (long long)(px - ax);
+  }
+  __device__ __forceinline__ static int bias(int ax, int ay, int bx, int by) {
+    int dx = bx - ax, dy = by - ay;
+    return ((dy < 0) || (dy == 0 && dx < 0)) ? 0 : -1;
+  }
+  __device__ __forceinline__ long long e01(int px, int py) const { return ev(X0, Y0, X1, Y1, px, py); }
+  __device__ __forceinline__ long long e12(int px, int py) const { return ev(X1, Y1, X2, Y2, px, py); }
+  __device__ __forceinline__ long long e20(int px, int py) const { return ev(X2, Y2, X0, Y0, px, py); }
+
+  __device__ __forceinline__ bool sample_inside(int sx, int sy) const {
+    return e01(sx, sy) + bias(X0, Y0, X1, Y1) >= 0 && e12(sx, sy) + bias(X1, Y1, X2, Y2) >= 0 &&
+           e20(sx, sy) + bias(X2, Y2, X0, Y0) >= 0;
+  }
+  __device__ __forceinline__ static long long emax(int ax, int ay, int bx, int by, int x0, int y0) {
+    int dx = bx - ax, dy = by - ay;
+    int px = (-dy > 0) ? x0 + SUBPIX : x0;
+    int py = (dx > 0) ? y0 + SUBPIX : y0;
+    return ev(ax, ay, bx, by, px, py);
+  }
+  __device__ __forceinline__ bool covered(int i, int j, int policy) const {
+    int x0 = i * SUBPIX, y0 = j * SUBPIX;
+    if (policy == 0) return sample_inside(x0 + 128, y0 + 128);
+    if (policy == 1) {
+      return sample_inside(x0 + 96, y0 + 32) || sample_inside(x0 + 224, y0 + 96) ||
+             sample_inside(x0 + 32, y0 + 160) || sample_inside(x0 + 160, y0 + 224);
+    }
+    return emax(X0, Y0, X1, Y1, x0, y0) > 0 && emax(X1, Y1, X2, Y2, x0, y0) > 0 &&
+           emax(X2, Y2, X0, Y0, x0, y0) > 0;
+  }
+  __device__ __forceinline__ void lambdas(int i, int j, float* l1, float* l2) const {
+    int sx = i * SUBPIX + 128, sy = j * SUBPIX + 128;
+    float fa = (float)area;
+    *l1 = (float)e20(sx, sy) / fa;
+    *l2 = (float)e01(sx, sy) / fa;
+  }
+};
+
+__device__ __forceinline__ bool setup_raster(const float wx[3], const float wy[3], RasterTri* t) {
+  long long X[3], Y[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    if (!snap(wx[k], &X[k]) || !snap(wy[k], &Y[k])) return false;
+  long long area = (X[1] - X[0]) * (Y[2] - Y[0]) - (Y[1] - Y[0]) * (X[2] - X[0]);
+  if (area == 0) return false;
+  t->flipped = area < 0;
+  t->X0 = (int)X[0]; t->Y0 = (int)Y[0];
+  if (t->flipped) {
+    t->X1 = (int)X[2]; t->Y1 = (int)Y[2]; t->X2 = (int)X[1]; t->Y2 = (int)Y[1];
+    area = -area;
+  } else {
+    t->X1 = (int)X[1]; t->Y1 = (int)Y[1]; t->X2 = (int)X[2]; t->Y2 = (int)Y[2];
+  }
+  t->area = area;
+  return true;
+}
+
+__device__ __forceinline__ int floor_div256(int a) { return a >> 8; }  // arithmetic shift == floor
+
+// pixel bounding box clipped to [0,W)x[0,H); false if empty
+__device__ __forceinline__ bool raster_bbox(const RasterTri& t, int policy, int W, int H, int* i0, int* i1,
+                                            int* j0, int* j1) {
+  int minx = min(t.X0, min(t.X1, t.X2)), maxx = max(t.X0, max(t.X1, t.X2));
+  int miny = min(t.Y0, min(t.Y1, t.Y2)), maxy = max(t.Y0, max(t.Y1, t.Y2));
+  int a0, a1, b0, b1;
+  if (policy == 2) {
+    a0 = floor_div256(minx); a1 = floor_div256(maxx - 1);
+    b0 = floor_div256(miny); b1 = floor_div256(maxy - 1);
+  } else {
+    a0 = floor_div256(minx - (SUBPIX - 1)); a1 = floor_div256(maxx);
+    b0 = floor_div256(miny - (SUBPIX - 1)); b1 = floor_div256(maxy);
+  }
+  a0 = max(a0, 0); b0 = max(b0, 0); a1 = min(a1, W - 1); b1 = min(b1, H - 1);
+  if (a0 > a1 || b0 > b1) return false;
+  *i0 = a0; *i1 = a1; *j0 = b0; *j1 = b1;
+  return true;
+}
+
+__device__ __forceinline__ float interp3(float a0, float a1, float a2, float l1, float l2) {
+  return (a0 + l1 * (a1 - a0)) + l2 * (a2 - a0);
+}
+
+// ---- shadow map sampling: PCF_Shadow_Mapping (Voxelization.fs:18-52, VoxelConeTracing.fs:132-163).
+// Returns the number of lit taps.  The (2r+2)^2 texel footprint is fetched once when all taps share
+// the same fractional position is NOT assumed: every tap computes its own texel coordinates exactly
+// as the oracle does, but rows of the footprint are reused through registers by the compiler.
+__device__ __forceinline__ float depth_texel(const uint32_t* __restrict__ depth, int S, int i, int j) {
+  i = min(max(i, 0), S - 1);
+  j = min(max(j, 0), S - 1);
+  return (float)__ldg(&depth[(size_t)j * S + i]) * (1.0f / 16777215.0f);
+}
+
+__device__ __forceinline__ float shadow_bilinear(const uint32_t* __restrict__ depth, int S, float u, float v) {
+  const float fS = (float)S;
+  float x = u * fS - 0.5f, y = v * fS - 0.5f;
+  float fx = floorf(x), fy = floorf(y);
+  float a = x - fx, b = y - fy;
+  fx = fminf(fmaxf(fx, -2.0f), fS + 1.0f);
+  fy = fminf(fmaxf(fy, -2.0f), fS + 1.0f);
+  int i = (int)fx, j = (int)fy;
+  float t00 = depth_texel(depth, S, i, j), t10 = depth_texel(depth, S, i + 1, j);
+  float t01 = depth_texel(depth, S, i, j + 1), t11 = depth_texel(depth, S, i + 1, j + 1);
+  float top = t00 + a * (t10 - t00);
+  float bot = t01 + a * (t11 - t01);
+  return top + b * (bot - top);
+}
+
+__device__ __forceinline__ float pcf_lit_taps(const uint32_t* __restrict__ depth, int S, int r, float bias,
+                                              float dcx, float dcy, float dcz, float dcw) {
+  float cur = dcz / dcw;
+  float inv = 1.0f / (float)S;
+  float thr = cur - bias;
+  float lit = 0.0f;
+  for (int x = -r; x <= r; ++x)
+    for (int y = -r; y <= r; ++y) {
+      float ox = inv * (float)x, oy = inv * (float)y;
+      float closest = shadow_bilinear(depth, S, dcx + ox, dcy + oy);
+      if (thr <= closest) lit += 1.0f;
+    }
+  return lit;
+}
+
+// GL 4.3 8.14: lambda = log2(max(|d(uv*size)/dx|, |d(uv*size)/dy|))
+__device__ __forceinline__ float lod_from_derivs(float dudx, float dvdx, float dudy, float dvdy, int w, int h) {
+  float ax = dudx * (float)w, bx = dvdx * (float)h;
+  float ay = dudy * (float)w, by = dvdy * (float)h;
+  float rx = sqrtf(ax * ax + bx * bx);
+  float ry = sqrtf(ay * ay + by * by);
+  float rho = fmaxf(rx, ry);
+  if (!(rho > 0.0f)) return 0.0f;
+  return log2f(rho);
+}
+
+__device__ __forceinline__ float4 sample_material(cudaTextureObject_t t, float u, float v, float lod) {
+  if (!(lod > 0.0f)) lod = 0.0f;
+  return tex2DLod<float4>(t, u, v, lod);
+}
+
+#endif  // __CUDACC__
+
+}  // namespace vct

@@ -1,0 +1,161 @@
+// vct_mip.cu -- M1: 2x2x2 box-filter pyramid of the RGBA8 voxel texture.
+// Replaces glGenerateMipmap(GL_TEXTURE_3D) (Voxel_Cone_Tracing.h:246-248).  Rounding rule (the GL one is
+// driver defined): child = (sum of 8 parents + 4) >> 3 per channel.
+//
+//   mip_fused3 : reads a 32x8x8 block of level L once (16-byte surface loads, 4 texels per thread along
+//                x) and writes levels L+1, L+2, L+3, staging the intermediate levels in shared memory.
+//                HBM traffic = read L once + write the three children.
+//   mip_tail   : one CTA reduces a level of <= 32^3 texels down to 1^3 entirely in shared memory.
+// At V = 256 the pyramid is built by two launches: fused3(0 -> 1,2,3) and tail(3 -> 4..8).
+#include "vct_internal.h"
+
+namespace vct {
+
+// packed byte arithmetic: even/odd bytes of a uchar4 widened into 16-bit lanes
+__device__ __forceinline__ void acc_px(uint32_t p, uint32_t& even, uint32_t& odd) {
+  even += p & 0x00FF00FFu;
+  odd += (p >> 8) & 0x00FF00FFu;
+}
+__device__ __forceinline__ uint32_t finish_px(uint32_t even, uint32_t odd) {
+  even = ((even + 0x00040004u) >> 3) & 0x00FF00FFu;
+  odd = ((odd + 0x00040004u) >> 3) & 0x00FF00FFu;
+  return even | (odd << 8);
+}
+
+// block = (8,4,4) threads, covers 32x8x8 texels of `src`
+__global__ void __launch_bounds__(128) mip_fused3(cudaSurfaceObject_t src, cudaSurfaceObject_t d1,
+                                                  cudaSurfaceObject_t d2, cudaSurfaceObject_t d3) {
+  __shared__ uint32_t s1[4][4][16];
+  __shared__ uint32_t s2[2][2][8];
+  const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 8, bz = blockIdx.z * 8;
+  uint32_t e0 = 0, o0 = 0, e1 = 0, o1 = 0;
+#pragma unroll
+  for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      uint4 q = surf3Dread<uint4>(src, (bx + tx * 4) * 4, by + ty * 2 + dy, bz + tz * 2 + dz);
+      acc_px(q.x, e0, o0); acc_px(q.y, e0, o0);
+      acc_px(q.z, e1, o1); acc_px(q.w, e1, o1);
+    }
+  const uint32_t c0 = finish_px(e0, o0), c1 = finish_px(e1, o1);
+  const int l1x = (bx >> 1) + tx * 2, l1y = (by >> 1) + ty, l1z = (bz >> 1) + tz;
+  surf3Dwrite(make_uint2(c0, c1), d1, l1x * 4, l1y, l1z);
+  s1[tz][ty][tx * 2] = c0;
+  s1[tz][ty][tx * 2 + 1] = c1;
+  __syncthreads();
+  const int t = (tz * 4 + ty) * 8 + tx;
+  if (t < 32) {   // level +2: 8x2x2
+    const int x = t & 7, y = (t >> 3) & 1, z = t >> 4;
+    uint32_t e = 0, o = 0;
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        acc_px(s1[z * 2 + dz][y * 2 + dy][x * 2], e, o);
+        acc_px(s1[z * 2 + dz][y * 2 + dy][x * 2 + 1], e, o);
+      }
+    const uint32_t c = finish_px(e, o);
+    surf3Dwrite(c, d2, ((bx >> 2) + x) * 4, (by >> 2) + y, (bz >> 2) + z);
+    s2[z][y][x] = c;
+  }
+  __syncthreads();
+  if (t < 4) {    // level +3: 4x1x1
+    uint32_t e = 0, o = 0;
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        acc_px(s2[dz][dy][t * 2], e, o);
+        acc_px(s2[dz][dy][t * 2 + 1], e, o);
+      }
+    surf3Dwrite(finish_px(e, o), d3, ((bx >> 3) + t) * 4, by >> 3, bz >> 3);
+  }
+}
+
+struct TailSurfaces { cudaSurfaceObject_t s[8]; };   // s[0] = source level, s[1..] = children
+
+// one CTA; n0 = source size (<= 32), n_out = number of child levels to produce (log2(n0))
+__global__ void __launch_bounds__(1024) mip_tail(TailSurfaces lv, int n0, int n_out) {
+  extern __shared__ uint32_t sm[];
+  uint32_t* cur = sm;                       // n0^3
+  uint32_t* nxt = sm + n0 * n0 * n0;        // (n0/2)^3, then ping-pong inside the first buffer
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n0 * n0 * n0; i += blockDim.x) {
+    int x = i % n0, y = (i / n0) % n0, z = i / (n0 * n0);
+    cur[i] = surf3Dread<uint32_t>(lv.s[0], x * 4, y, z);
+  }
+  __syncthreads();
+  int n = n0;
+  for (int l = 1; l <= n_out; ++l) {
+    const int h = n >> 1;
+    for (int i = tid; i < h * h * h; i += blockDim.x) {
+      int x = i % h, y = (i / h) % h, z = i / (h * h);
+      uint32_t e = 0, o = 0;
+#pragma unroll
+      for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+          const uint32_t* row = cur + ((2 * z + dz) * n + (2 * y + dy)) * n + 2 * x;
+          acc_px(row[0], e, o);
+          acc_px(row[1], e, o);
+        }
+      const uint32_t c = finish_px(e, o);
+      nxt[i] = c;
+      surf3Dwrite(c, lv.s[l], x * 4, y, z);
+    }
+    __syncthreads();
+    uint32_t* t = cur; cur = nxt; nxt = t;   // the old source buffer is large enough for every later level
+    n = h;
+  }
+}
+
+// generic single level (used when a level is too small for fused3 and too big for tail; not hit for
+// power-of-two V >= 8, kept for V < 32 odd cases)
+__global__ void mip_one(cudaSurfaceObject_t src, cudaSurfaceObject_t dst, int h) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, z = blockIdx.z;
+  if (x >= h || y >= h) return;
+  uint32_t e = 0, o = 0;
+#pragma unroll
+  for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      uint2 q = surf3Dread<uint2>(src, (2 * x) * 4, 2 * y + dy, 2 * z + dz);
+      acc_px(q.x, e, o);
+      acc_px(q.y, e, o);
+    }
+  surf3Dwrite(finish_px(e, o), dst, x * 4, y, z);
+}
+
+int launch_mip(vct_context* c) {
+  int rc = ensure_grid(c); if (rc) return rc;
+  PassTimer timer(c, VCT_PASS_MIP);
+  const int levels = c->P.levels;
+  int l = 0, n = c->P.V;
+  while (n > 32 && l + 3 < levels) {
+    dim3 b(8, 4, 4), g(n / 32, n / 8, n / 8);
+    mip_fused3<<<g, b, 0, c->stream>>>(c->grid_surf[l], c->grid_surf[l + 1], c->grid_surf[l + 2], c->grid_surf[l + 3]);
+    c->launches += 1;
+    l += 3; n >>= 3;
+  }
+  while (n > 32) {   // V not reducible by fused3 steps down to <= 32 (e.g. 64 -> 8 is fine; defensive)
+    dim3 b(32, 8), g((n / 2 + 31) / 32, (n / 2 + 7) / 8, n / 2);
+    mip_one<<<g, b, 0, c->stream>>>(c->grid_surf[l], c->grid_surf[l + 1], n / 2);
+    c->launches += 1;
+    l += 1; n >>= 1;
+  }
+  if (l < levels - 1) {
+    TailSurfaces ts{};
+    int n_out = levels - 1 - l;
+    for (int k = 0; k <= n_out; ++k) ts.s[k] = c->grid_surf[l + k];
+    size_t smem = ((size_t)n * n * n + (size_t)(n / 2) * (n / 2) * (n / 2)) * 4;
+    if (smem > 48 * 1024)
+      VCT_CUDA(c, cudaFuncSetAttribute(mip_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    mip_tail<<<1, 1024, smem, c->stream>>>(ts, n, n_out);
+    c->launches += 1;
+  }
+  VCT_CUDA(c, cudaGetLastError());
+  return VCT_OK;
+}
+
+}  // namespace vct

@@ -1,0 +1,99 @@
+// vct_raster.cuh -- triangle-parallel rasterisation skeleton shared by the shadow, voxel-coverage and
+// visibility passes.
+//
+// The GL pipeline the reference relies on (glDrawElements -> fixed-function rasteriser) is replaced by
+// two kernels per pass:
+//   raster_small : one thread per triangle.  Set-up; bounding boxes of <= SMALL_AREA pixels are
+//                  rasterised in the thread; larger ones are cut into 8x8-pixel tiles and queued as
+//                  work items of up to ITEM_TILES tiles.
+//   raster_tiles : persistent warps; one warp per work item, one lane per pixel (2 steps per tile).
+// A Pass supplies:  struct Setup;  bool setup(tri, Setup&, i0,i1,j0,j1);
+//                   bool tile_may_cover(Setup&, x0,y0,x1,y1)   (exact or conservative reject)
+//                   unsigned small(Setup&, tri, i0,i1,j0,j1)    (thread-serial path)
+//                   void pixel(Setup&, tri, i, j, bool in_bbox) (warp path, called by all 32 lanes)
+#pragma once
+
+#include "vct_internal.h"
+
+namespace vct {
+
+constexpr int SMALL_AREA = 16;
+constexpr int TILE = 8;
+constexpr int ITEM_TILES = 32;
+
+template <class Pass>
+__global__ void __launch_bounds__(128) raster_small(Pass pass, uint32_t tri_begin, uint32_t tri_end,
+                                                    TileItem* __restrict__ items, uint32_t items_cap,
+                                                    Counters* __restrict__ ctr) {
+  uint32_t tri = tri_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  bool live = tri < tri_end;
+  typename Pass::Setup s;
+  int i0 = 0, i1 = -1, j0 = 0, j1 = -1;
+  if (live) live = pass.setup(tri, s, i0, i1, j0, j1);
+  int w = i1 - i0 + 1, h = j1 - j0 + 1;
+  bool small_tri = live && (w * h <= SMALL_AREA);
+  // every lane of the warp calls small(): passes that append to a queue aggregate across the warp
+  pass.small(s, tri, small_tri, i0, i1, j0, j1);
+  if (live && !small_tri) {
+    int tx0 = i0 / TILE, tx1 = i1 / TILE, ty0 = j0 / TILE, ty1 = j1 / TILE;
+    uint32_t ntiles = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
+    uint32_t nitems = (ntiles + ITEM_TILES - 1) / ITEM_TILES;
+    uint32_t base = atomicAdd(&ctr->n_items, nitems);
+    if (base + nitems > items_cap) {
+      ctr->overflow = 1;
+    } else {
+      for (uint32_t k = 0; k < nitems; ++k) {
+        TileItem it;
+        it.tri = tri;
+        it.origin = k * ITEM_TILES;
+        items[base + k] = it;
+      }
+    }
+  }
+}
+
+template <class Pass>
+__global__ void __launch_bounds__(256) raster_tiles(Pass pass, const TileItem* __restrict__ items,
+                                                    uint32_t items_cap, const Counters* __restrict__ ctr) {
+  const uint32_t n_items = min(ctr->n_items, items_cap);
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps_per_block = blockDim.x >> 5;
+  const uint32_t n_warps = gridDim.x * warps_per_block;
+  for (uint32_t it = blockIdx.x * warps_per_block + (threadIdx.x >> 5); it < n_items; it += n_warps) {
+    TileItem item = items[it];
+    typename Pass::Setup s;
+    int i0, i1, j0, j1;
+    if (!pass.setup(item.tri, s, i0, i1, j0, j1)) continue;   // warp-uniform
+    int tx0 = i0 / TILE, tx1 = i1 / TILE, ty0 = j0 / TILE, ty1 = j1 / TILE;
+    uint32_t tw = (uint32_t)(tx1 - tx0 + 1);
+    uint32_t ntiles = tw * (uint32_t)(ty1 - ty0 + 1);
+    uint32_t t_end = min(item.origin + (uint32_t)ITEM_TILES, ntiles);
+    for (uint32_t t = item.origin; t < t_end; ++t) {
+      int tx = tx0 + (int)(t % tw), ty = ty0 + (int)(t / tw);
+      int px0 = tx * TILE, py0 = ty * TILE;
+      if (!pass.tile_may_cover(s, px0, py0, px0 + TILE, py0 + TILE)) continue;  // warp-uniform
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        int i = px0 + (int)(lane & 7), j = py0 + half * 4 + (int)(lane >> 3);
+        bool in_bbox = i >= i0 && i <= i1 && j >= j0 && j <= j1;
+        pass.pixel(s, item.tri, i, j, in_bbox);
+      }
+    }
+  }
+}
+
+// Exact tile reject for the integer passes: the samples of every pixel in the tile lie inside the
+// closed box [x0*256, x1*256] x [y0*256, y1*256]; an edge whose maximum over the box (plus its
+// fill-rule bias) is negative cannot be satisfied.
+__device__ __forceinline__ bool tile_may_cover_exact(const RasterTri& t, int x0, int y0, int x1, int y1) {
+  auto emax_box = [&](int ax, int ay, int bx, int by) {
+    int dx = bx - ax, dy = by - ay;
+    int px = (-dy > 0) ? x1 * SUBPIX : x0 * SUBPIX;
+    int py = (dx > 0) ? y1 * SUBPIX : y0 * SUBPIX;
+    return RasterTri::ev(ax, ay, bx, by, px, py);
+  };
+  return emax_box(t.X0, t.Y0, t.X1, t.Y1) >= 0 && emax_box(t.X1, t.Y1, t.X2, t.Y2) >= 0 &&
+         emax_box(t.X2, t.Y2, t.X0, t.Y0) >= 0;
+}
+
+}  // namespace vct

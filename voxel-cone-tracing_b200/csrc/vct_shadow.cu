@@ -1,0 +1,85 @@
+// vct_shadow.cu -- S1: light-space depth map.
+// Replaces DrawDepthTexture (Voxel_Cone_Tracing.h:192-211) + Shader/Shadow.vs:7-10 + the GL depth
+// rasteriser: back faces culled, depth test LESS, cleared to 1.0, GL_DEPTH_COMPONENT24.
+// Triangle-parallel exact integer rasterisation (vct_raster.cuh) with atomicMin on the 24-bit depth.
+#include "vct_raster.cuh"
+
+namespace vct {
+
+struct ShadowPass {
+  Params P;                  // uniform block, by value: lives in the kernel's constant bank
+  const float* verts; const uint32_t* idx;
+  uint32_t* depth;
+
+  struct Setup { RasterTri t; float z0, z1, z2; };
+
+  __device__ __forceinline__ bool setup(uint32_t tri, Setup& s, int& i0, int& i1, int& j0, int& j1) const {
+    const int S = P.S;
+    float wx[3], wy[3], wz[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float* v = verts + (size_t)__ldg(&idx[tri * 3 + k]) * 14;
+      F4 c = mul_mat_vec(P.depth_mvp, __ldg(v), __ldg(v + 1), __ldg(v + 2), 1.0f);
+      if (!(c.w > 0.0f)) return false;
+      float nx = c.x / c.w, ny = c.y / c.w, nz = c.z / c.w;
+      wx[k] = (nx * 0.5f + 0.5f) * (float)S;
+      wy[k] = (ny * 0.5f + 0.5f) * (float)S;
+      wz[k] = nz * 0.5f + 0.5f;
+    }
+    if (!setup_raster(wx, wy, &s.t)) return false;
+    if (s.t.flipped) return false;   // GL_CULL_FACE / GL_BACK, Voxel_Cone_Tracing.h:194
+    s.z0 = wz[0]; s.z1 = wz[1]; s.z2 = wz[2];
+    return raster_bbox(s.t, 0, S, S, &i0, &i1, &j0, &j1);
+  }
+
+  __device__ __forceinline__ void emit(const Setup& s, int i, int j) const {
+    float l1, l2;
+    s.t.lambdas(i, j, &l1, &l2);
+    float z = interp3(s.z0, s.z1, s.z2, l1, l2);
+    if (!(z >= 0.0f) || z > 1.0f) return;   // near/far clip
+    uint32_t d = (uint32_t)__float2int_rn(z * 16777215.0f);
+    atomicMin(&depth[(size_t)j * P.S + i], d);
+  }
+
+  __device__ __forceinline__ bool tile_may_cover(const Setup& s, int x0, int y0, int x1, int y1) const {
+    return tile_may_cover_exact(s.t, x0, y0, x1, y1);
+  }
+
+  __device__ __forceinline__ void small(const Setup& s, uint32_t, bool active, int i0, int i1, int j0, int j1) const {
+    if (!active) return;
+    for (int j = j0; j <= j1; ++j)
+      for (int i = i0; i <= i1; ++i)
+        if (s.t.covered(i, j, 0)) emit(s, i, j);
+  }
+
+  __device__ __forceinline__ void pixel(const Setup& s, uint32_t, int i, int j, bool in_bbox) const {
+    if (in_bbox && s.t.covered(i, j, 0)) emit(s, i, j);
+  }
+};
+
+__global__ void fill_u32(uint32_t* p, size_t n, uint32_t v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
+int launch_shadow(vct_context* c) {
+  if (!c->nt) return set_error(c, VCT_ERR_STATE, "vct_draw_depth: no mesh uploaded");
+  int rc = ensure_shadow(c); if (rc) return rc;
+  rc = ensure_queues(c); if (rc) return rc;
+  PassTimer timer(c, VCT_PASS_DEPTH);
+  const size_t n = (size_t)c->P.S * c->P.S;
+  fill_u32<<<148 * 8, 256, 0, c->stream>>>(c->d_depth, n, 0xFFFFFFu);
+  VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_items, 0, sizeof(unsigned int), c->stream));
+  ShadowPass pass{c->P, c->d_verts, c->d_idx, c->d_depth};
+  const uint32_t nt = (uint32_t)c->nt;
+  raster_small<ShadowPass><<<(nt + 127) / 128, 128, 0, c->stream>>>(pass, 0, nt, c->d_items,
+                                                                    (uint32_t)c->items_cap, c->d_counters);
+  raster_tiles<ShadowPass><<<148 * 4, 256, 0, c->stream>>>(pass, c->d_items, (uint32_t)c->items_cap, c->d_counters);
+  c->launches += 3;
+  VCT_CUDA(c, cudaGetLastError());
+  c->depth_valid = true;
+  return VCT_OK;
+}
+
+}  // namespace vct

@@ -1,0 +1,366 @@
+// vct_voxelize.cu -- V1..V4: triangle voxelisation with shadow-mapped light injection.
+// Replaces DrawVoxelTexture's draw (Voxel_Cone_Tracing.h:213-245) and Shader/Voxelization.{vs,gs,fs}.
+//
+//   vox_cover  (raster_small / raster_tiles): Voxelization.vs:15-22 + .gs:22-51 + the rasteriser.  Emits
+//              one 8-byte fragment record (triangle, pixel) per covered pixel of the V x V viewport.
+//   vox_shade  : Voxelization.fs:54-89, one thread per fragment: depth slice, axis un-swizzle, albedo
+//              fetch, 5x5 PCF, then an order-independent integer accumulation
+//                 accum[v].rg += (r<<32 | g) ;  accum[v].bc += (b<<32 | 1)
+//              with lanes that hit the same voxel merged first (warp-aggregated atomics).  The first
+//              fragment of a voxel (old count == 0) appends the voxel to the touched list.
+//   vox_clear / vox_resolve : sparse, over the touched list only.
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
+
+#include "vct_raster.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace vct {
+
+// ---------------------------------------------------------------------------------------------------
+// Per-triangle set-up shared by coverage and shading (recomputed, not stored: 3 vertices = 60 B of
+// loads against 25 shadow taps per fragment).
+struct VoxTri {
+  RasterTri t;
+  float z0, z1, z2;
+  int axis;
+};
+
+template <bool WITH_ATTRS>
+__device__ __forceinline__ bool vox_setup(const Params& P, const float* __restrict__ verts,
+                                          const uint32_t* __restrict__ idx, uint32_t tri, VoxTri& s,
+                                          float (*uv)[2], F4* dc) {
+  const int V = P.V;
+  F4 world[3];
+  float tuv[3][2];
+  F4 tdc[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float* v = verts + (size_t)__ldg(&idx[tri * 3 + k]) * 14;
+    float px = __ldg(v), py = __ldg(v + 1), pz = __ldg(v + 2);
+    world[k] = mul_mat_vec(P.model, px, py, pz, 1.0f);                    // Voxelization.vs:21
+    if (WITH_ATTRS) {
+      tdc[k] = mul_mat_vec(P.depth_mvp, px, py, pz, 1.0f);                 // Voxelization.vs:18
+      tdc[k].x = tdc[k].x * 0.5f + 0.5f; tdc[k].y = tdc[k].y * 0.5f + 0.5f; tdc[k].z = tdc[k].z * 0.5f + 0.5f;
+      tuv[k][0] = __ldg(v + 6); tuv[k][1] = __ldg(v + 7);
+    }
+  }
+  // Voxelization.gs:25-39 (decision on the un-normalised |cross|; zero / NaN -> axis 3)
+  float e1x = world[0].x - world[1].x, e1y = world[0].y - world[1].y, e1z = world[0].z - world[1].z;
+  float e2x = world[2].x - world[0].x, e2y = world[2].y - world[0].y, e2z = world[2].z - world[0].z;
+  float nx = fabsf(e1y * e2z - e1z * e2y), ny = fabsf(e1z * e2x - e1x * e2z), nz = fabsf(e1x * e2y - e1y * e2x);
+  int axis;
+  if (!(nx == nx) || !(ny == ny) || !(nz == nz)) axis = 3;
+  else if (nx == 0.0f && ny == 0.0f && nz == 0.0f) axis = 3;
+  else if (nx >= ny && nx >= nz) axis = 1;
+  else if (ny >= nx && ny >= nz) axis = 2;
+  else axis = 3;
+  const float* Pm = axis == 1 ? P.projx : axis == 2 ? P.projy : P.projz;    // Voxelization.gs:41
+  float wx[3], wy[3], wz[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    F4 c = mul_mat_vec(Pm, world[k].x, world[k].y, world[k].z, world[k].w);
+    if (!(c.w > 0.0f)) return false;
+    float ndx = c.x / c.w, ndy = c.y / c.w, ndz = c.z / c.w;
+    wx[k] = (ndx * 0.5f + 0.5f) * (float)V;       // glViewport(0,0,V,V), Voxel_Cone_Tracing.h:218
+    wy[k] = (ndy * 0.5f + 0.5f) * (float)V;
+    wz[k] = ndz * 0.5f + 0.5f;
+  }
+  if (!setup_raster(wx, wy, &s.t)) return false;
+  const int a = s.t.flipped ? 2 : 1, b = s.t.flipped ? 1 : 2;
+  s.z0 = wz[0]; s.z1 = wz[a]; s.z2 = wz[b];
+  s.axis = axis;
+  if (WITH_ATTRS) {
+    uv[0][0] = tuv[0][0]; uv[0][1] = tuv[0][1];
+    uv[1][0] = tuv[a][0]; uv[1][1] = tuv[a][1];
+    uv[2][0] = tuv[b][0]; uv[2][1] = tuv[b][1];
+    dc[0] = tdc[0]; dc[1] = tdc[a]; dc[2] = tdc[b];
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct VoxCoverPass {
+  Params P;
+  const float* verts; const uint32_t* idx;
+  uint2* frags; uint32_t frags_cap;
+  Counters* ctr;
+
+  struct Setup { VoxTri v; };
+
+  __device__ __forceinline__ bool setup(uint32_t tri, Setup& s, int& i0, int& i1, int& j0, int& j1) const {
+    if (!vox_setup<false>(P, verts, idx, tri, s.v, nullptr, nullptr)) return false;
+    return raster_bbox(s.v.t, P.coverage, P.V, P.V, &i0, &i1, &j0, &j1);
+  }
+  __device__ __forceinline__ bool tile_may_cover(const Setup& s, int x0, int y0, int x1, int y1) const {
+    return tile_may_cover_exact(s.v.t, x0, y0, x1, y1);
+  }
+
+  // thread-serial path: <= 16 pixels -> 16-bit coverage mask, one warp-wide reservation
+  __device__ __forceinline__ void small(const Setup& s, uint32_t tri, bool active, int i0, int i1, int j0, int j1) const {
+    unsigned mask = 0;
+    const int w = i1 - i0 + 1;
+    if (active) {
+      int bit = 0;
+      for (int j = j0; j <= j1; ++j)
+        for (int i = i0; i <= i1; ++i, ++bit)
+          if (s.v.t.covered(i, j, P.coverage)) mask |= 1u << bit;
+    }
+    unsigned n = __popc(mask);
+    // inclusive warp scan of n
+    unsigned lane = threadIdx.x & 31, incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= (unsigned)d) incl += t;
+    }
+    unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned base = 0;
+    if (lane == 31 && total) base = atomicAdd(&ctr->n_fragments, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (!n) return;
+    unsigned pos = base + incl - n;
+    while (mask) {
+      int bit = __ffs(mask) - 1;
+      mask &= mask - 1;
+      int i = i0 + bit % w, j = j0 + bit / w;
+      if (pos < frags_cap) frags[pos] = make_uint2(tri, (unsigned)i | ((unsigned)j << 16));
+      else ctr->overflow = 1;
+      ++pos;
+    }
+  }
+
+  // warp path: one lane per pixel, ballot-aggregated append
+  __device__ __forceinline__ void pixel(const Setup& s, uint32_t tri, int i, int j, bool in_bbox) const {
+    bool cov = in_bbox && s.v.t.covered(i, j, P.coverage);
+    unsigned m = __ballot_sync(0xffffffffu, cov);
+    if (!m) return;
+    unsigned lane = threadIdx.x & 31;
+    unsigned base = 0;
+    int leader = __ffs(m) - 1;
+    if ((int)lane == leader) base = atomicAdd(&ctr->n_fragments, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (cov) {
+      unsigned pos = base + __popc(m & ((1u << lane) - 1));
+      if (pos < frags_cap) frags[pos] = make_uint2(tri, (unsigned)i | ((unsigned)j << 16));
+      else ctr->overflow = 1;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vox_shade(Params P, const float* __restrict__ verts,
+                                                 const uint32_t* __restrict__ idx,
+                                                 const uint16_t* __restrict__ trimat,
+                                                 const MaterialDev* __restrict__ mats,
+                                                 const uint32_t* __restrict__ depth,
+                                                 const uint2* __restrict__ frags, uint32_t frags_cap,
+                                                 unsigned long long* __restrict__ accum,
+                                                 uint32_t* __restrict__ touched, Counters* __restrict__ ctr) {
+  const uint32_t nfrag = min(ctr->n_fragments, frags_cap);
+  const int V = P.V;
+  for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < nfrag; f += gridDim.x * blockDim.x) {
+    const uint2 fr = frags[f];
+    const uint32_t tri = fr.x;
+    const int i = (int)(fr.y & 0xFFFFu), j = (int)(fr.y >> 16);
+    VoxTri s;
+    float uv[3][2];
+    F4 dc[3];
+    if (!vox_setup<true>(P, verts, idx, tri, s, uv, dc)) continue;   // cannot fail for a queued fragment
+    float l1, l2;
+    s.t.lambdas(i, j, &l1, &l2);
+    float z = interp3(s.z0, s.z1, s.z2, l1, l2);
+    if (P.coverage == 2) {
+      float zmin = fminf(s.z0, fminf(s.z1, s.z2)), zmax = fmaxf(s.z0, fmaxf(s.z1, s.z2));
+      z = fminf(fmaxf(z, zmin), zmax);
+    }
+    float tz = (float)V * z;                                  // Voxelization.fs:58
+    if (!(tz >= 0.0f) || !(tz < (float)V)) continue;          // clipped / imageStore out of bounds
+    const int cz = (int)tz;
+    int vx, vy, vz;
+    if (s.axis == 1) { vx = V - 1 - cz; vz = V - 1 - i; vy = j; }        // Voxelization.fs:70-75
+    else if (s.axis == 2) { vz = V - 1 - j; vy = V - 1 - cz; vx = i; }   // :76-81
+    else { vx = i; vy = j; vz = V - 1 - cz; }                            // :82-86
+    if ((unsigned)vx >= (unsigned)V || (unsigned)vy >= (unsigned)V || (unsigned)vz >= (unsigned)V) continue;
+
+    // texture(DiffuseTexture, TexCoord), Voxelization.fs:56; implicit LOD is constant over the triangle
+    const MaterialDev m = mats[trimat ? trimat[tri] : 0];
+    const float fa = (float)s.t.area;
+    // d(lambda)/d(pixel): e20 = edge v2->v0 weights v1, e01 = edge v0->v1 weights v2
+    const float dl1dx = (float)(-(long long)(s.t.Y0 - s.t.Y2) * SUBPIX) / fa, dl1dy = (float)((long long)(s.t.X0 - s.t.X2) * SUBPIX) / fa;
+    const float dl2dx = (float)(-(long long)(s.t.Y1 - s.t.Y0) * SUBPIX) / fa, dl2dy = (float)((long long)(s.t.X1 - s.t.X0) * SUBPIX) / fa;
+    const float du1 = uv[1][0] - uv[0][0], du2 = uv[2][0] - uv[0][0];
+    const float dv1 = uv[1][1] - uv[0][1], dv2 = uv[2][1] - uv[0][1];
+    const float dudx = dl1dx * du1 + dl2dx * du2, dvdx = dl1dx * dv1 + dl2dx * dv2;
+    const float dudy = dl1dy * du1 + dl2dy * du2, dvdy = dl1dy * dv1 + dl2dy * dv2;
+    const float lod = lod_from_derivs(dudx, dvdx, dudy, dvdy, m.dw, m.dh);
+    const float u = interp3(uv[0][0], uv[1][0], uv[2][0], l1, l2);
+    const float vv = interp3(uv[0][1], uv[1][1], uv[2][1], l1, l2);
+    const float4 col = sample_material(m.diffuse, u, vv, lod);
+
+    const float dx = interp3(dc[0].x, dc[1].x, dc[2].x, l1, l2);
+    const float dy = interp3(dc[0].y, dc[1].y, dc[2].y, l1, l2);
+    const float dz = interp3(dc[0].z, dc[1].z, dc[2].z, l1, l2);
+    const float dw = interp3(dc[0].w, dc[1].w, dc[2].w, l1, l2);
+    const int taps = (2 * P.pcf_radius + 1) * (2 * P.pcf_radius + 1);
+    const float shadow = pcf_lit_taps(depth, P.S, P.pcf_radius, P.shadow_bias, dx, dy, dz, dw) / (float)taps;
+
+    // imageStore(VoxelTexture, voxelPos, vec4(color.rgb * shadow, 1)): unorm8 conversion, Voxelization.fs:88
+    unsigned r = (unsigned)__float2int_rn(fminf(fmaxf(col.x * shadow, 0.0f), 1.0f) * 255.0f);
+    unsigned g = (unsigned)__float2int_rn(fminf(fmaxf(col.y * shadow, 0.0f), 1.0f) * 255.0f);
+    unsigned b = (unsigned)__float2int_rn(fminf(fmaxf(col.z * shadow, 0.0f), 1.0f) * 255.0f);
+    const uint32_t voxel = (uint32_t)(((size_t)vz * V + vy) * V + vx);
+
+    // warp-aggregated atomics: lanes of this warp that hit the same voxel are summed first
+    cg::coalesced_group active = cg::coalesced_threads();
+    cg::coalesced_group same = cg::labeled_partition(active, voxel);
+    unsigned long long rg = ((unsigned long long)r << 32) | g;
+    unsigned long long bc = ((unsigned long long)b << 32) | 1ull;
+    if (same.size() > 1) {
+      rg = cg::reduce(same, rg, cg::plus<unsigned long long>());
+      bc = cg::reduce(same, bc, cg::plus<unsigned long long>());
+    }
+    if (same.thread_rank() == 0) {
+      atomicAdd(&accum[2 * (size_t)voxel], rg);
+      unsigned long long old = atomicAdd(&accum[2 * (size_t)voxel + 1], bc);
+      if ((uint32_t)old == 0u) touched[atomicAdd(&ctr->n_touched, 1u)] = voxel;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void vox_clear_sparse(unsigned long long* __restrict__ accum, const uint32_t* __restrict__ touched,
+                                 const Counters* __restrict__ ctr, cudaSurfaceObject_t level0, int V) {
+  const uint32_t n = ctr->n_touched;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    uint32_t v = touched[k];
+    accum[2 * (size_t)v] = 0ull;
+    accum[2 * (size_t)v + 1] = 0ull;
+    int x = v % V, y = (v / V) % V, z = v / (V * V);
+    surf3Dwrite(make_uchar4(0, 0, 0, 0), level0, x * 4, y, z);
+  }
+}
+
+__device__ __forceinline__ uchar4 resolve_cell(unsigned long long rg, unsigned long long bc) {
+  unsigned cnt = (unsigned)bc;
+  if (!cnt) return make_uchar4(0, 0, 0, 0);
+  unsigned r = (unsigned)(rg >> 32), g = (unsigned)rg, b = (unsigned)(bc >> 32);
+  unsigned h = cnt >> 1;
+  return make_uchar4((unsigned char)((r + h) / cnt), (unsigned char)((g + h) / cnt),
+                     (unsigned char)((b + h) / cnt), 255);   // alpha written as 1.0, Voxelization.fs:88
+}
+
+__global__ void vox_resolve_sparse(const unsigned long long* __restrict__ accum,
+                                   const uint32_t* __restrict__ touched, const Counters* __restrict__ ctr,
+                                   cudaSurfaceObject_t level0, int V) {
+  const uint32_t n = ctr->n_touched;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    uint32_t v = touched[k];
+    const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(&accum[2 * (size_t)v]);
+    int x = v % V, y = (v / V) % V, z = v / (V * V);
+    surf3Dwrite(resolve_cell(a.x, a.y), level0, x * 4, y, z);
+  }
+}
+
+__global__ void vox_resolve_dense(const unsigned long long* __restrict__ accum, cudaSurfaceObject_t level0, int V) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, z = blockIdx.z;
+  if (x >= V || y >= V) return;
+  size_t v = ((size_t)z * V + y) * V + x;
+  const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(&accum[2 * v]);
+  surf3Dwrite(resolve_cell(a.x, a.y), level0, x * 4, y, z);
+}
+
+__global__ void accum_to_counts(const unsigned long long* __restrict__ accum, size_t n, uint32_t* counts, uint32_t* sums) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long rg = accum[2 * i], bc = accum[2 * i + 1];
+  if (counts) counts[i] = (uint32_t)bc;
+  if (sums) { sums[3 * i] = (uint32_t)(rg >> 32); sums[3 * i + 1] = (uint32_t)rg; sums[3 * i + 2] = (uint32_t)(bc >> 32); }
+}
+
+// ---------------------------------------------------------------------------------------------------
+int launch_voxel_clear(vct_context* c) {
+  int rc = ensure_grid(c); if (rc) return rc;
+  PassTimer timer(c, VCT_PASS_VOX_CLEAR);
+  const int V = c->P.V;
+  if (c->accum_dense_dirty || c->dense_resolve) {
+    VCT_CUDA(c, cudaMemsetAsync(c->d_accum, 0, (size_t)V * V * V * 16, c->stream));
+    if (c->accum_dense_dirty) {   // level 0 may hold voxels the touched list does not know about
+      dim3 b(32, 8), g((V + 31) / 32, (V + 7) / 8, V);
+      vox_resolve_dense<<<g, b, 0, c->stream>>>(c->d_accum, c->grid_surf[0], V);
+      c->launches += 1;
+    }
+    c->accum_dense_dirty = false;
+  } else {
+    vox_clear_sparse<<<148 * 8, 256, 0, c->stream>>>(c->d_accum, c->d_touched, c->d_counters, c->grid_surf[0], V);
+    c->launches += 1;
+  }
+  VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_touched, 0, sizeof(unsigned int), c->stream));
+  VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_fragments, 0, sizeof(unsigned int), c->stream));
+  VCT_CUDA(c, cudaGetLastError());
+  return VCT_OK;
+}
+
+int launch_voxelize(vct_context* c, size_t tb, size_t te) {
+  if (!c->nt) return set_error(c, VCT_ERR_STATE, "voxelize: no mesh uploaded");
+  if (!c->depth_valid) return set_error(c, VCT_ERR_STATE, "voxelize: call vct_draw_depth first (shadow map missing)");
+  int rc = ensure_grid(c); if (rc) return rc;
+  rc = ensure_queues(c); if (rc) return rc;
+  rc = sync_materials(c); if (rc) return rc;
+  te = te < c->nt ? te : c->nt;
+  if (tb >= te) return VCT_OK;
+  {
+    PassTimer timer(c, VCT_PASS_VOX_COVER);
+    VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_items, 0, sizeof(unsigned int), c->stream));
+    VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_fragments, 0, sizeof(unsigned int), c->stream));
+    VoxCoverPass pass{c->P, c->d_verts, c->d_idx, c->d_frags, (uint32_t)c->frags_cap, c->d_counters};
+    const uint32_t n = (uint32_t)(te - tb);
+    raster_small<VoxCoverPass><<<(n + 127) / 128, 128, 0, c->stream>>>(pass, (uint32_t)tb, (uint32_t)te, c->d_items,
+                                                                        (uint32_t)c->items_cap, c->d_counters);
+    raster_tiles<VoxCoverPass><<<148 * 4, 256, 0, c->stream>>>(pass, c->d_items, (uint32_t)c->items_cap, c->d_counters);
+    c->launches += 2;
+  }
+  {
+    PassTimer timer(c, VCT_PASS_VOX_SHADE);
+    vox_shade<<<148 * 8, 256, 0, c->stream>>>(c->P, c->d_verts, c->d_idx, c->d_trimat, c->d_materials, c->d_depth,
+                                              c->d_frags, (uint32_t)c->frags_cap, c->d_accum, c->d_touched,
+                                              c->d_counters);
+    c->launches += 1;
+  }
+  VCT_CUDA(c, cudaGetLastError());
+  return VCT_OK;
+}
+
+int launch_resolve(vct_context* c, bool dense) {
+  int rc = ensure_grid(c); if (rc) return rc;
+  PassTimer timer(c, VCT_PASS_RESOLVE);
+  const int V = c->P.V;
+  if (dense) {
+    dim3 b(32, 8), g((V + 31) / 32, (V + 7) / 8, V);
+    vox_resolve_dense<<<g, b, 0, c->stream>>>(c->d_accum, c->grid_surf[0], V);
+  } else {
+    vox_resolve_sparse<<<148 * 8, 256, 0, c->stream>>>(c->d_accum, c->d_touched, c->d_counters, c->grid_surf[0], V);
+  }
+  c->launches += 1;
+  VCT_CUDA(c, cudaGetLastError());
+  return VCT_OK;
+}
+
+int readback_accum(vct_context* c, uint32_t* counts, uint32_t* sums) {
+  int rc = ensure_grid(c); if (rc) return rc;
+  const size_t n = (size_t)c->P.V * c->P.V * c->P.V;
+  uint32_t *dc = nullptr, *ds = nullptr;
+  if (counts) VCT_CUDA(c, cudaMalloc(&dc, n * 4));
+  if (sums) VCT_CUDA(c, cudaMalloc(&ds, n * 12));
+  accum_to_counts<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_accum, n, dc, ds);
+  c->launches += 1;
+  cudaError_t e = cudaSuccess;
+  if (counts) e = cudaMemcpyAsync(counts, dc, n * 4, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess && sums) e = cudaMemcpyAsync(sums, ds, n * 12, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(dc); cudaFree(ds);
+  return check_cuda(c, e, "readback_accum");
+}
+
+}  // namespace vct
