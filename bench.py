@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- full frames/s (voxelize + mip + cone-trace) of the B200 path on BASELINE.json config 2.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode views|tiles|trishard]
+
+One process per GPU (torchrun for N > 1).  A step is one full frame: sparse clear -> voxelise (coverage +
+PCF-lit shading) -> resolve -> mip pyramid -> primary visibility -> cone trace, on the synthetic 260 K-triangle
+atrium at 256^3 / 1920x1080 (`config.workload`).  The shadow map is static (as in the reference, which draws it
+once at init) and is not part of the step.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "full frames/s (voxelize+mip+cone-trace), 256^3 grid, 1920x1080"
+UNIT = "frames/s"
+WORKLOAD = ("config2: synthetic Sponza-scale atrium 259608 tris (seed 1234), 256^3 RGBA8 grid, 1920x1080, "
+            "6 diffuse + 1 specular cone (reference table), 2 bounces (reference semantics), conservative coverage, "
+            "4096^2 shadow map")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="views", choices=["views", "tiles", "trishard"])
+    ap.add_argument("--detail", type=float, default=1.0, help="scene tessellation scale (1.0 = config 2)")
+    ap.add_argument("--grid", type=int, default=256)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--coverage", default="conservative")
+    ap.add_argument("--cones", default="6+1")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    return ap.parse_args()
+
+
+def make_scene_and_uniforms(args):
+    import vct_b200  # noqa: F401
+    from vct_b200 import scenes, uniforms
+    sc = scenes.atrium(detail=args.detail)
+    u = uniforms.scene_uniforms(sc, V=args.grid, width=args.width, height=args.height, shadow_map_size=4096,
+                                coverage=args.coverage, cones=args.cones)
+    return sc, u
+
+
+def camera_for(step, rank):
+    """Per-step input: a slow camera pan (every step has a new view matrix, as the reference's loop does)."""
+    yaw = -90.0 + 0.05 * step + 37.0 * rank
+    pos = (0.0 + 3.0 * rank, 4.0, 0.0)
+    return pos, yaw
+
+
+def set_camera(ctx, args, step, rank):
+    import vct_b200.glmath as gm
+    pos, yaw = camera_for(step, rank)
+    view = gm.view_matrix(pos, yaw, 0.0)
+    ctx.set_mat4("ModelViewMatrix", gm.colmajor((view @ gm.scale(0.05)).astype(np.float32)))
+    ctx.set_3f("CameraPosition", pos)
+    return 64 + 12          # bytes of per-step input handed to the device (as kernel parameters)
+
+
+class ClockSampler:
+    """Samples nvidia-smi during the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------ ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import vct_b200
+    from vct_b200 import parallel
+
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream()
+
+    vct_b200.load_library()                         # mandatory extension: raises if missing
+    sc, u = make_scene_and_uniforms(args)
+    ctx = vct_b200.Context(local)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_uniforms(u)
+    ctx.load_scene(sc)
+    H = args.height
+    if args.mode == "tiles" and world > 1:
+        b0, b1 = parallel.row_band(H, rank, world)
+        ctx.set_i("RowBegin", b0); ctx.set_i("RowEnd", b1)
+    ctx.draw_depth()                                # static light: once, like the reference's init
+    ctx.sync()
+    tri_rng = parallel.triangle_range(sc.n_tris, rank, world) if args.mode == "trishard" else None
+    acc = parallel.accumulator_tensor(ctx, dev) if args.mode == "trishard" else None
+    gather_buf = None
+    if args.mode == "tiles" and world > 1:
+        fptr, fbytes = ctx.frame_buffer()
+        frame_t = torch.as_tensor(parallel._DevicePointer(fptr, fbytes, "|u1"), device=dev)
+        gather_buf = frame_t
+
+    def step(i, host_out=None):
+        cam_rank = rank if args.mode == "views" else 0
+        set_camera(ctx, args, i, cam_rank)
+        if args.mode == "trishard":
+            ctx.voxelize_range(tri_rng[0], tri_rng[1], clear_first=True)
+            parallel.allreduce_accumulator(acc)
+            ctx.resolve_and_mip()
+            ctx.render(host_out)
+        else:
+            ctx.frame(host_out)
+            if gather_buf is not None:              # row bands -> every rank holds the full frame
+                b0, b1 = parallel.row_band(H, rank, world)
+                rows = [gather_buf[parallel.row_band(H, r, world)[0] * args.width * 4:
+                                   parallel.row_band(H, r, world)[1] * args.width * 4] for r in range(world)]
+                if len({r.numel() for r in rows}) == 1:
+                    dist.all_gather(rows, rows[rank].clone())
+                else:
+                    for r in range(world):
+                        dist.broadcast(rows[r], src=r)
+
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    launches0 = ctx.kernel_launches()
+    sampler = ClockSampler(local); sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    pass_names = ["vox_clear", "vox_cover", "vox_shade", "resolve", "mip", "visibility", "cone"]
+    pass_sum = {p: 0.0 for p in pass_names}
+    samples_sum = 0
+    barrier()
+    for i in range(args.steps):
+        if flush is not None:
+            flush.fill_(i & 0xFF)                   # untimed: evicts the previous frame's lines from L2
+        ev[i][0].record(stream)
+        step(args.warmup + i)
+        ev[i][1].record(stream)
+        ev[i][1].synchronize()
+        for p in pass_names:
+            try:
+                pass_sum[p] += ctx.pass_time_us(p)
+            except Exception:
+                pass
+        samples_sum += ctx.cone_samples()
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.kernel_launches() - launches0
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    frames = args.steps * (world if args.mode == "views" else 1)
+    value = frames / (total_ms * 1e-3)
+
+    # ---- end to end through the public API with a HOST frame buffer (pinned), D2H inside the timed region
+    host = torch.empty((args.height, args.width, 4), dtype=torch.uint8).pin_memory()
+    for i in range(3):
+        step(i, host)
+    barrier()
+    t0 = time.perf_counter()
+    h2d = 0
+    for i in range(args.steps):
+        h2d = set_camera(ctx, args, args.warmup + i, rank if args.mode == "views" else 0)
+        step(args.warmup + i, host)                 # returns after the frame is in host memory
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = frames / float(te.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peaks_kind = measured_peaks()
+    K = args.steps
+    cone_us = pass_sum["cone"] / K
+    samples_per_launch = samples_sum / K
+    tex_peak_frac_lod = ctx.bench_tex3d(V=args.grid, n_samples=1 << 28, pattern=0, lod=0.5, iters=3)
+    tex_peak_int_lod = ctx.bench_tex3d(V=args.grid, n_samples=1 << 28, pattern=0, lod=0.0, iters=3)
+    achieved_gs = samples_per_launch / (cone_us * 1e-6) * 1e-9 if cone_us > 0 else 0.0
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "cone_trace_traffic.json")
+    if os.path.exists(prof):
+        traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+    mip_us = pass_sum["mip"] / K
+    mip_bytes = sum((args.grid >> l) ** 3 * 4 for l in range(args.grid.bit_length()))     # read L0 once + write L1..: 73.14 MiB @256
+    out = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+        "ms_per_step": round(total_ms / K, 4), "higher_is_better": True,
+        "scaling": "weak" if args.mode == "views" else "strong", "vs_baseline": None, "dtype": "u8/u32 grid, f32 shading",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD if args.detail == 1.0 and args.grid == 256 else f"atrium detail={args.detail} V={args.grid} {args.width}x{args.height}",
+                   "mode": args.mode, "l2": "not flushed" if args.no_flush else "flushed between steps by an untimed 256 MiB write",
+                   "timing": "CUDA events per step on the launching stream, summed; max over ranks",
+                   "step": "clear+voxelize+resolve+mip+visibility+cone-trace (shadow map static, drawn once)"},
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": args.width * args.height * 4,
+                "note": "vct_frame(host_rgba) with a pinned host frame buffer; per-step input = view matrix + camera position"},
+        "gpu_launches": int(launches),
+        "passes_us": {p: round(pass_sum[p] / K, 2) for p in pass_names},
+        "cone_samples_per_frame": int(samples_per_launch),
+        "gcone_samples_per_s": round(achieved_gs, 2),
+        "roofline": {"kernel": "cone_trace", "bound": "texture", "achieved": round(achieved_gs, 2),
+                     "peak": round(tex_peak_frac_lod, 2), "unit": "Gsamples/s",
+                     "frac": round(achieved_gs / tex_peak_frac_lod, 4) if tex_peak_frac_lod else None,
+                     "traffic": traffic,
+                     "peak_source": "vct_bench_tex3d measured in this run: trilinear + mip-linear tex3DLod, RGBA8 256^3 pyramid, coherent walks (L2-resident)",
+                     "peak_single_level": round(tex_peak_int_lod, 2),
+                     "algorithmic_bytes_per_sample": 64},
+        "roofline_mip": {"kernel": "mip_fused3+mip_tail", "bound": "hbm",
+                         "achieved": round(mip_bytes / (mip_us * 1e-6) * 1e-9, 1) if mip_us > 0 else None,
+                         "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                         "frac": round(mip_bytes / (mip_us * 1e-6) * 1e-9 / peaks.get("hbm_gbs"), 4) if mip_us > 0 else None,
+                         "peak_source": f"MEASURED_PEAKS.json ({peaks_kind})", "algorithmic_bytes": mip_bytes},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, sc, u, budget_s=15.0)
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs
+def cpu_baseline(args, sc, u, budget_s):
+    """The oracle ("port": the reference's GLSL cannot run here) timed on the host cores, on a
+    bounded sample of the same workload: as many full config frames as fit in ~budget_s (at least one)."""
+    from oracle.oracle_py import Oracle
+    o = Oracle(); o.set_uniforms(u); o.load_scene(sc)
+    o.draw_depth()
+    t0 = time.perf_counter(); n = 0
+    while True:
+        o.draw_voxels(); o.render(); n += 1
+        if time.perf_counter() - t0 > budget_s or n >= 50:
+            break
+    dt = time.perf_counter() - t0
+    o.close()
+    return {"value": round(n / dt, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{n} full frame(s) of the same workload (voxelize+mip+cone-trace) in {dt:.1f} s, OpenMP over all host cores"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from oracle.oracle_py import Oracle
+    sc, u = make_scene_and_uniforms(args)
+    o = Oracle(); o.set_uniforms(u); o.load_scene(sc)
+    o.draw_depth()
+    H = args.height
+    # size each step so that the whole run fits in ~150 s: full voxelisation + a band of rows, scaled
+    t0 = time.perf_counter(); o.draw_voxels(); t_vox = time.perf_counter() - t0
+    t0 = time.perf_counter(); o.render_rows(H // 2 - 8, H // 2 + 8); t_rows16 = time.perf_counter() - t0
+    n_steps = args.steps + args.warmup
+    per_step = max(150.0 / max(n_steps, 1), 0.05)
+    rows = int(np.clip((per_step - t_vox) / max(t_rows16 / 16.0, 1e-6), 8, H)) // 8 * 8
+    rows = max(8, min(rows, H))
+    y0 = (H - rows) // 2
+    for i in range(args.warmup):
+        o.draw_voxels(); o.render_rows(y0, y0 + rows)
+    tv = tr = 0.0
+    for i in range(args.steps):
+        t0 = time.perf_counter(); o.draw_voxels(); t1 = time.perf_counter(); o.render_rows(y0, y0 + rows); t2 = time.perf_counter()
+        tv += t1 - t0; tr += t2 - t1
+    K = max(args.steps, 1)
+    frame_s = tv / K + (tr / K) * (H / rows)        # time of a full frame extrapolated from the row band
+    value = 1.0 / frame_s
+    sample = (f"each step = full voxelize+mip ({tv / K * 1e3:.0f} ms) + cone trace of {rows} of {H} rows "
+              f"({tr / K * 1e3:.0f} ms), extrapolated linearly to the full frame; CPU oracle (port), OpenMP, {os.cpu_count()} cores")
+    out = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(frame_s * 1e3, 2), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 grid, f32 shading", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "mode": "cpu"},
+           "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+           "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -57,6 +57,7 @@ const char* vct_version(void);
  * string keys the reference passes (Voxel_Cone_Tracing.h:167-187,224-243):
  *   int   : VoxelDimensions ShadowMapSize screen_width screen_height PcfRadius CoveragePolicy
  *           Bounces NumDiffuseCones GridFormat MaxFragments MaxTileItems DenseResolve Profile
+ *           RowBegin RowEnd (rows [RowBegin, RowEnd) of the frame are rendered; RowEnd 0 = all: row-band sharding)
  *           ShadowMap VoxelTexture (texture-unit numbers: accepted and ignored)
  *   float : VoxelGridWorldSize ambientFactor DiffuseTanHalfAngle SpecularTanHalfAngle StepMultiplier
  *           MaxDistance MaxAlpha ShadowBias
@@ -115,6 +116,13 @@ int vct_frame_buffer(vct_handle h, void** device_ptr, size_t* n_bytes);
 int vct_cone_samples(vct_handle h, uint64_t* n);       /* textureLod calls of the last vct_render */
 int vct_fragment_count(vct_handle h, uint64_t* n);     /* fragments of the last voxelisation */
 int vct_occupied_voxels(vct_handle h, uint64_t* n);
+
+/* ---- cone queries: Voxel_Cone_Tracing(direction, tanHalfAngle) (VoxelConeTracing.fs:82-107) for arbitrary
+ * start points (already offset along the normal, :92).  Host arrays: starts/dirs n*3, tan_half n,
+ * out_rgb_occ n*4 (rgb, occlusion), out_steps n (may be NULL).  Used by probes and by the parity tests to
+ * exercise the hardware-filtered tex3DLod path sample by sample. */
+int vct_trace_cones(vct_handle h, size_t n, const float* starts, const float* dirs, const float* tan_half,
+                    float* out_rgb_occ, uint32_t* out_steps);
 
 /* ---- execution control */
 int vct_set_stream(vct_handle h, void* cuda_stream);   /* run on the caller's stream (e.g. torch's) */

@@ -144,6 +144,9 @@ class Oracle:
     def render(self):
         assert self.L.orc_render(self.h) == 0
 
+    def render_rows(self, y0, y1):
+        assert self.L.orc_render_rows(self.h, int(y0), int(y1)) == 0
+
     # ---- read-back ------------------------------------------------------------------------------
     @property
     def V(self):

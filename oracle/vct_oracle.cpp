@@ -773,7 +773,7 @@ inline uint32_t float_bits(float f) { uint32_t u; std::memcpy(&u, &f, 4); return
 
 }  // namespace
 
-static void orc_visibility(orc_ctx* o) {
+static void orc_visibility(orc_ctx* o, int y0, int y1) {
   const int W = o->p.screen_width, H = o->p.screen_height;
   o->vis.assign((size_t)W * H, ~0ull);
   const size_t nt = o->idx.size() / 3;
@@ -784,7 +784,7 @@ static void orc_visibility(orc_ctx* o) {
     const Material& m = o->materials[o->tri_mat.empty() ? 0 : o->tri_mat[ti]];
     const Texture* dt = get_tex(o, m.diffuse);
     const bool alpha_test = dt && dt->has_alpha;
-    for (int j = t.j0; j <= t.j1; ++j)
+    for (int j = std::max(t.j0, y0); j <= std::min(t.j1, y1 - 1); ++j)
       for (int i = t.i0; i <= t.i1; ++i) {
         float px = (float)i + 0.5f, py = (float)j + 0.5f;
         float b[3];
@@ -930,17 +930,22 @@ static void shade_pixel(const orc_ctx* o, size_t ti, int i, int j, uint8_t out[4
   out[3] = (uint8_t)std::lrintf(a * 255.0f);
 }
 
-extern "C" int orc_render(orc_ctx* o) {
+extern "C" int orc_render_rows(orc_ctx* o, int y0, int y1);
+extern "C" int orc_render(orc_ctx* o) { return orc_render_rows(o, 0, o->p.screen_height); }
+
+/* rows [y0, y1) only: what one rank does when the frame is sharded by row bands */
+extern "C" int orc_render_rows(orc_ctx* o, int y0, int y1) {
   const int W = o->p.screen_width, H = o->p.screen_height;
+  y0 = std::max(y0, 0); y1 = std::min(y1, H);
   ensure_grid(o);
-  orc_visibility(o);
+  orc_visibility(o, y0, y1);
   o->frame.assign((size_t)W * H * 4, 0);
   /* glClearColor, Voxel_Cone_Tracing.h:156-159 */
   float cc = o->p.ambientFactor < 0.5f ? 0.5f : 1.0f;
   uint8_t bg = (uint8_t)std::lrintf(cc * 255.0f);
   uint64_t total = 0;
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : total)
-  for (int j = 0; j < H; ++j)
+  for (int j = y0; j < y1; ++j)
     for (int i = 0; i < W; ++i) {
       uint64_t key = o->vis[(size_t)j * W + i];
       uint8_t* px = &o->frame[((size_t)j * W + i) * 4];

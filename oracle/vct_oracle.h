@@ -73,6 +73,7 @@ int orc_draw_voxels(orc_ctx*);         /* clear + V1..V4 + resolve + M1 (+ re-in
 int orc_draw_voxels_range(orc_ctx*, size_t tri_begin, size_t tri_end, int clear_first); /* accumulate only */
 int orc_resolve_and_mip(orc_ctx*);
 int orc_render(orc_ctx*);              /* S2 + C1..C6 */
+int orc_render_rows(orc_ctx*, int y_begin, int y_end);   /* same, rows [y_begin, y_end) only */
 
 int orc_get_depth(orc_ctx*, uint32_t* d24);                 /* S*S */
 int orc_get_counts(orc_ctx*, uint32_t* counts);             /* V^3, index (z*V+y)*V+x */

@@ -1,0 +1,385 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against the CPU
+oracle on the same seeded inputs, against the committed golden fixtures, and -- at BASELINE config-2 size --
+through size-independent properties.
+
+Bars (BASELINE.json north_star): shadow map, voxel occupancy and fragment counts bit-exact; radiance and
+frames PSNR >= 40 dB and |diff| <= 2/255 on >= 99.9 % of voxels/pixels.
+"""
+import importlib.util
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import frac_within, psnr
+from vct_b200 import capi, scenes, uniforms
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+make_golden = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(make_golden)
+
+PSNR_MIN = 40.0       # dB, north_star
+LSB_TOL = 2           # /255
+FRAC_MIN = 0.999
+
+
+def run_gpu(c, sc, u):
+    c.set_uniforms(u)
+    c.load_scene(sc)
+    c.draw_depth()
+    c.draw_voxels()
+    c.render()
+    c.sync()
+
+
+def run_oracle(o, sc, u):
+    o.set_uniforms(u)
+    o.load_scene(sc)
+    o.draw_depth()
+    o.draw_voxels()
+    o.render()
+
+
+def assert_radiance_close(a, b, what):
+    assert a.shape == b.shape
+    occ = (a[..., 3] > 0) | (b[..., 3] > 0) if a.shape[-1] == 4 else np.ones(a.shape[:-1], bool)
+    if occ.any():
+        d = np.abs(a.astype(int) - b.astype(int)).max(-1)[occ]
+        assert (d <= LSB_TOL).mean() >= FRAC_MIN, f"{what}: {(d <= LSB_TOL).mean():.5f} within {LSB_TOL}"
+    assert psnr(a, b) >= PSNR_MIN, f"{what}: psnr {psnr(a, b):.2f}"
+
+
+def assert_frame_close(fg, fo, what):
+    assert psnr(fg[..., :3], fo[..., :3]) >= PSNR_MIN, f"{what}: psnr {psnr(fg[..., :3], fo[..., :3]):.2f}"
+    assert frac_within(fg, fo, LSB_TOL) >= FRAC_MIN, f"{what}: {frac_within(fg, fo, LSB_TOL):.5f}"
+
+
+# ------------------------------------------------------------------------------------------ golden fixtures
+@pytest.mark.parametrize("name", sorted(make_golden.CASES))
+def test_gpu_matches_golden_fixture(gpu_ctx, name):
+    gold = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    factory, kw = make_golden.CASES[name]
+    sc = factory()
+    run_gpu(gpu_ctx, sc, uniforms.scene_uniforms(sc, **kw))
+    d = gpu_ctx.depth()
+    assert np.uint32(zlib.crc32(d.tobytes())) == gold["depth_crc"]
+    assert np.array_equal(gpu_ctx.counts().astype(np.uint16), gold["counts"])          # bit-exact
+    assert np.array_equal(gpu_ctx.grid(0)[..., 3], gold["grid0"][..., 3])               # occupancy bit-exact
+    for lvl, key in ((0, "grid0"), (1, "grid1"), (2, "grid2"), (4, "grid4")):
+        assert_radiance_close(gpu_ctx.grid(lvl), gold[key], f"{name} grid L{lvl}")
+    vis = gpu_ctx.visibility()
+    assert (vis != gold["visibility"]).mean() <= 1e-3
+    assert_frame_close(gpu_ctx.read_frame(), gold["frame"], name)
+    if "cornell" in name:      # 1x1 textures: no hardware texture filtering involved => exact integers
+        assert np.array_equal(gpu_ctx.sums(), gold["sums"])
+        assert np.array_equal(gpu_ctx.grid(0), gold["grid0"]) and np.array_equal(gpu_ctx.grid(2), gold["grid2"])
+        assert np.array_equal(vis, gold["visibility"])
+
+
+# ------------------------------------------------------------------------------------------ config 1
+@pytest.mark.parametrize("coverage", ["center", "msaa4", "conservative"])
+def test_cornell_config1_vs_oracle(gpu_ctx, oracle, coverage):
+    sc = scenes.cornell()
+    u = uniforms.scene_uniforms(sc, V=64, width=256, height=256, shadow_map_size=1024, coverage=coverage)
+    run_gpu(gpu_ctx, sc, u)
+    run_oracle(oracle, sc, u)
+    assert np.array_equal(gpu_ctx.depth(), oracle.depth())
+    assert np.array_equal(gpu_ctx.counts(), oracle.counts())
+    assert np.array_equal(gpu_ctx.sums(), oracle.sums())
+    for l in range(7):
+        assert np.array_equal(gpu_ctx.grid(l), oracle.grid(l)), f"level {l}"
+    assert np.array_equal(gpu_ctx.visibility(), oracle.visibility())
+    assert_frame_close(gpu_ctx.read_frame(), oracle.frame(), f"cornell {coverage}")
+    assert abs(gpu_ctx.cone_samples() - oracle.cone_samples()) <= 1e-4 * oracle.cone_samples()
+    assert gpu_ctx.occupied_voxels() == int((oracle.counts() > 0).sum())
+
+
+def test_reference_default_cone_sets(gpu_ctx, oracle):
+    sc = scenes.cornell()
+    for cones in ("5+1", "9+1"):
+        u = uniforms.scene_uniforms(sc, V=32, width=128, height=128, shadow_map_size=512, cones=cones)
+        run_gpu(gpu_ctx, sc, u)
+        run_oracle(oracle, sc, u)
+        assert_frame_close(gpu_ctx.read_frame(), oracle.frame(), cones)
+
+
+# ------------------------------------------------------------------------------------------ textured scene
+def test_atrium_reduced_vs_oracle(gpu_ctx, oracle):
+    sc = scenes.atrium(detail=0.3, tex_size=128)
+    u = uniforms.scene_uniforms(sc, V=128, width=640, height=360, shadow_map_size=2048, coverage="conservative")
+    run_gpu(gpu_ctx, sc, u)
+    run_oracle(oracle, sc, u)
+    assert np.array_equal(gpu_ctx.depth(), oracle.depth())
+    cg, co = gpu_ctx.counts(), oracle.counts()
+    assert np.array_equal(cg, co)                                     # occupancy and counts: bit-exact
+    assert cg.sum() > 100_000
+    # sums differ only through the hardware-filtered albedo fetch: <= 1 LSB per fragment
+    ds = np.abs(gpu_ctx.sums().astype(np.int64) - oracle.sums().astype(np.int64)).max(-1)
+    assert np.all(ds <= cg)
+    for l in range(8):
+        g, o = gpu_ctx.grid(l), oracle.grid(l)
+        assert np.array_equal(g[..., 3] > 0, o[..., 3] > 0)
+        assert np.abs(g.astype(int) - o.astype(int)).max() <= LSB_TOL
+    assert (gpu_ctx.visibility() != oracle.visibility()).mean() <= 1e-3
+    assert_frame_close(gpu_ctx.read_frame(), oracle.frame(), "atrium reduced")
+
+
+# ------------------------------------------------------------------------------------------ mip kernel
+@pytest.mark.parametrize("V", [2, 8, 16, 32, 64, 128, 256])
+def test_mip_pyramid_bit_exact(gpu_ctx, oracle, V):
+    rng = np.random.default_rng(V)
+    g = rng.integers(0, 256, (V, V, V, 4), dtype=np.uint8)
+    g[rng.random((V, V, V)) < 0.7] = 0                                # sparse like a voxelised scene
+    for x in (gpu_ctx, oracle):
+        x.set_uniforms({"VoxelDimensions": V}) if x is gpu_ctx else x.set_uniforms(uniforms.reference_uniforms(V=V))
+    gpu_ctx.upload_grid_level0(g)
+    oracle.set_grid_level0(g)
+    gpu_ctx.sync()
+    for l in range(V.bit_length()):
+        assert np.array_equal(gpu_ctx.grid(l), oracle.grid(l)), f"V={V} level {l}"
+
+
+def test_mip_rounding_kat_on_gpu(gpu_ctx):
+    V = 16
+    gpu_ctx.set_i("VoxelDimensions", V)
+    g = np.zeros((V, V, V, 4), dtype=np.uint8)
+    g[5, 9, 3] = 255
+    gpu_ctx.upload_grid_level0(g)
+    assert gpu_ctx.grid(1)[2, 4, 1, 0] == 32 and gpu_ctx.grid(2)[1, 2, 0, 0] == 4
+    assert gpu_ctx.grid(3)[0, 1, 0, 0] == 1 and gpu_ctx.grid(4)[0, 0, 0, 0] == 0
+
+
+# ------------------------------------------------------------------------------------------ cone marching
+def test_trace_cones_vs_oracle(gpu_ctx, oracle):
+    V = 64
+    rng = np.random.default_rng(3)
+    # smooth-ish random field so that the 8-bit hardware filter weights stay inside the tolerance
+    g = np.zeros((V, V, V, 4), dtype=np.uint8)
+    blob = rng.random((V // 4, V // 4, V // 4)) < 0.25
+    blob = np.kron(blob, np.ones((4, 4, 4), dtype=bool))
+    g[blob] = rng.integers(30, 255, (int(blob.sum()), 4), dtype=np.uint8)
+    g[..., 3][blob] = 255
+    u = uniforms.reference_uniforms(V=V)
+    gpu_ctx.set_uniforms(u); oracle.set_uniforms(u)
+    gpu_ctx.upload_grid_level0(g); oracle.set_grid_level0(g)
+    n = 4000
+    starts = rng.uniform(-70, 70, (n, 3)).astype(np.float32)
+    dirs = rng.normal(size=(n, 3)); dirs = (dirs / np.linalg.norm(dirs, axis=1, keepdims=True)).astype(np.float32)
+    tans = np.where(np.arange(n) % 2 == 0, 0.577, 0.07).astype(np.float32)
+    out, steps = gpu_ctx.trace_cones(starts, dirs, tans)
+    ref = np.zeros_like(out); rsteps = np.zeros(n, dtype=np.int64)
+    for i in range(n):
+        ref[i], rsteps[i] = oracle.cone(starts[i], dirs[i], float(tans[i]))
+    # the alpha >= 0.95 early-out may fire one step apart when alpha sits on the threshold
+    assert (np.abs(steps.astype(np.int64) - rsteps) <= 1).mean() > 0.995
+    same = steps == rsteps
+    err = np.abs(out - ref)[same]
+    assert np.percentile(err, 99.9) <= 2.5 / 255 and err.mean() < 0.5 / 255, (np.percentile(err, 99.9), err.mean())
+
+
+def test_uniform_grid_cone_kat_on_gpu(gpu_ctx):
+    V = 128
+    gpu_ctx.set_uniforms(uniforms.reference_uniforms(V=V))
+    g = np.empty((V, V, V, 4), dtype=np.uint8); g[..., :3] = 153; g[..., 3] = 255
+    gpu_ctx.upload_grid_level0(g)
+    out, steps = gpu_ctx.trace_cones([[1.0, 2.0, 3.0]] * 2, [[0, 1, 0]] * 2, [0.07, 0.577])
+    assert list(steps) == [1, 1]
+    np.testing.assert_allclose(out[0, :3], 153 / 255.0, atol=1e-3)
+    np.testing.assert_allclose(out[0, 3], 0.966038, atol=1e-4)         # 1/(1+0.03*vws), SURVEY A.7
+    g[:] = 0
+    gpu_ctx.upload_grid_level0(g)
+    out, steps = gpu_ctx.trace_cones([[0, 0, 0]] * 2, [[0, 0, 1]] * 2, [0.577, 0.07])
+    assert list(steps) == [6, 23] and np.all(out == 0)                 # A.5 step table at V=128
+
+
+# ------------------------------------------------------------------------------------------ edge cases
+def _tri_mesh(tris_world):
+    t = np.asarray(tris_world, dtype=np.float64).reshape(-1, 3, 3) * 20.0
+    v = np.zeros((t.shape[0] * 3, 14), dtype=np.float32)
+    v[:, :3] = t.reshape(-1, 3)
+    v[:, 3:6] = (0, 0, 1); v[:, 8:11] = (1, 0, 0); v[:, 11:14] = (0, 1, 0)
+    v[:, 6:8] = np.tile([[0, 0], [1, 0], [0, 1]], (t.shape[0], 1))
+    return v, np.arange(t.shape[0] * 3, dtype=np.uint32).reshape(-1, 3)
+
+
+def test_degenerate_offgrid_and_huge_triangles(gpu_ctx, oracle):
+    nan = float("nan")
+    tris = [
+        [(0, 0, 0), (0, 0, 0), (0, 0, 0)],                      # point
+        [(0, 0, 0), (10, 10, 10), (20, 20, 20)],                # zero area (collinear)
+        [(200, 200, 200), (210, 200, 200), (200, 210, 200)],    # entirely outside the grid
+        [(-9000, -3.3, -9000), (9000, -3.3, -9000), (0, -3.3, 18000)],   # far larger than the grid (guard band)
+        [(-80, 20, 5), (80, 20.5, 5), (0, 21, -70)],            # straddles the grid boundary
+        [(nan, 0, 0), (1, 0, 0), (0, 1, 0)],                    # NaN vertex
+        [(1e30, 0, 0), (0, 1e30, 0), (0, 0, 1e30)],             # overflowing coordinates
+        [(10, 10, 74.9), (20, 10, 75.2), (10, 20, 75.0)],       # touches the far clip plane of ProjZ
+    ]
+    v, i = _tri_mesh(tris)
+    for cov in ("center", "msaa4", "conservative"):
+        u = uniforms.reference_uniforms(V=64, width=64, height=64, shadow_map_size=256, coverage=cov)
+        for x in (gpu_ctx, oracle):
+            x.set_uniforms(u)
+            x.upload_texture(0, scenes.solid_texture((200, 100, 50)))
+            x.upload_mesh(v, i)
+            x.draw_depth(); x.draw_voxels(); x.render()
+        gpu_ctx.sync()
+        assert np.array_equal(gpu_ctx.depth(), oracle.depth()), cov
+        assert np.array_equal(gpu_ctx.counts(), oracle.counts()), cov
+        assert oracle.counts().sum() > 64 * 64                   # the huge triangle fills a slab
+        assert np.array_equal(gpu_ctx.visibility(), oracle.visibility()), cov
+
+
+def test_errors_are_reported_not_swallowed(gpu_ctx):
+    c = gpu_ctx
+    with pytest.raises(capi.VctError) as e:
+        c.set_i("NoSuchUniform", 1)
+    assert e.value.code == -1 and "NoSuchUniform" in str(e.value)
+    with pytest.raises(capi.VctError):
+        c.set_i("VoxelDimensions", 100)                          # not a power of two
+    with pytest.raises(capi.VctError):
+        c.set_mat4("NoSuchMatrix", np.eye(4))
+    with pytest.raises(capi.VctError) as e:
+        c.draw_depth()                                           # no mesh yet
+    assert e.value.code == -3
+    v, i = _tri_mesh([[(0, 0, 0), (10, 0, 0), (0, 10, 0)]])
+    with pytest.raises(capi.VctError):
+        c.upload_mesh(v, np.array([[0, 1, 7]], dtype=np.uint32))  # index out of range
+    c.upload_mesh(v, i)
+    with pytest.raises(capi.VctError) as e:
+        c.draw_voxels()                                          # shadow map missing
+    assert e.value.code == -3
+
+
+def test_queue_overflow_is_detected(gpu_ctx):
+    sc = scenes.cornell()
+    u = uniforms.scene_uniforms(sc, V=64, width=64, height=64, shadow_map_size=256)
+    gpu_ctx.set_uniforms(u)
+    gpu_ctx.set_i("MaxFragments", 2048)
+    gpu_ctx.load_scene(sc)
+    gpu_ctx.draw_depth()
+    gpu_ctx.draw_voxels()
+    with pytest.raises(capi.VctError) as e:
+        gpu_ctx.sync()
+    assert e.value.code == -4
+    gpu_ctx.set_i("MaxFragments", 1 << 20)
+    gpu_ctx.draw_voxels()
+    gpu_ctx.sync()
+
+
+def test_maximum_grid_size_512(gpu_ctx):
+    sc = scenes.cornell()
+    u = uniforms.scene_uniforms(sc, V=512, width=128, height=128, shadow_map_size=1024, coverage="center")
+    run_gpu(gpu_ctx, sc, u)
+    c = gpu_ctx.counts()
+    assert c.sum() > 500_000 and gpu_ctx.occupied_voxels() == int((c > 0).sum())
+    g0 = gpu_ctx.grid(0)
+    assert np.array_equal(g0[..., 3] == 255, c > 0)
+    s = g0.astype(np.int64).reshape(256, 2, 256, 2, 256, 2, 4).sum((1, 3, 5))
+    assert np.array_equal(((s + 4) >> 3).astype(np.uint8), gpu_ctx.grid(1))
+    assert gpu_ctx.grid(9).shape == (1, 1, 1, 4)
+
+
+# ------------------------------------------------------------------------------------------ config-2 size
+@pytest.fixture(scope="module")
+def atrium_full():
+    return scenes.atrium()
+
+
+def _cfg2(sc, **kw):
+    kw.setdefault("coverage", "conservative")
+    return uniforms.scene_uniforms(sc, V=256, width=1920, height=1080, shadow_map_size=4096, **kw)
+
+
+def test_config2_properties(gpu_ctx, atrium_full):
+    sc, c = atrium_full, gpu_ctx
+    run_gpu(c, sc, _cfg2(sc))
+    counts, sums, g0, frame = c.counts(), c.sums(), c.grid(0), c.read_frame()
+    occ = counts > 0
+    assert 200_000 < occ.sum() < 2_000_000 and c.occupied_voxels() == int(occ.sum())
+    assert np.array_equal(g0[..., 3] == 255, occ)
+    avg = (sums.astype(np.int64) + (counts // 2)[..., None]) // np.maximum(counts, 1)[..., None]
+    assert np.array_equal(g0[..., :3][occ], avg[occ].astype(np.uint8))            # resolve rule, every voxel
+    for l in range(1, 9):                                                         # mip rule, every level
+        p = c.grid(l - 1).astype(np.int64)
+        n = p.shape[0] // 2
+        s = p.reshape(n, 2, n, 2, n, 2, 4).sum((1, 3, 5))
+        assert np.array_equal(((s + 4) >> 3).astype(np.uint8), c.grid(l)), f"level {l}"
+    # idempotence: a second full frame (sparse clear + re-voxelise) reproduces everything bit for bit
+    c.frame(); c.sync()
+    assert np.array_equal(c.counts(), counts) and np.array_equal(c.sums(), sums)
+    assert np.array_equal(c.grid(0), g0) and np.array_equal(c.read_frame(), frame)
+    # order independence: shuffled triangle order gives identical integer accumulators
+    perm = np.random.default_rng(0).permutation(sc.n_tris)
+    c.upload_mesh(sc.verts, sc.idx[perm], sc.tri_material[perm])
+    c.draw_depth(); c.draw_voxels(); c.sync()
+    assert np.array_equal(c.counts(), counts) and np.array_equal(c.sums(), sums)
+    # triangle-range split (what each GPU does when voxelisation is sharded) == single pass
+    k = sc.n_tris // 3
+    c.voxelize_range(0, k, clear_first=True)
+    c.voxelize_range(k, sc.n_tris, clear_first=False)
+    c.resolve_and_mip(); c.sync()
+    assert np.array_equal(c.counts(), counts) and np.array_equal(c.sums(), sums) and np.array_equal(c.grid(0), g0)
+    # and back to the sparse path after a dense one
+    c.draw_voxels(); c.sync()
+    assert np.array_equal(c.counts(), counts) and np.array_equal(c.grid(0), g0) and np.array_equal(c.grid(3), c.grid(3))
+    # host-buffer path returns the same frame
+    c.upload_mesh(sc.verts, sc.idx, sc.tri_material)
+    c.draw_depth()
+    out = np.zeros_like(frame)
+    c.frame(out)
+    assert np.array_equal(out, frame)
+
+
+def test_dynamic_positions_round_trip(gpu_ctx):
+    sc = scenes.dynamic_knot(nu=256, nv=128)
+    u = uniforms.scene_uniforms(sc, V=128, width=320, height=180, shadow_map_size=1024, coverage="conservative")
+    c = gpu_ctx
+    run_gpu(c, sc, u)
+    c0, g0 = c.counts(), c.grid(0)
+    P1 = scenes.torus_knot_positions(256, 128, t=0.7).reshape(-1, 3) * 20.0
+    c.update_positions(P1.astype(np.float32))
+    c.draw_depth(); c.draw_voxels(); c.sync()
+    c1 = c.counts()
+    assert not np.array_equal(c1 > 0, c0 > 0)                       # the mesh really moved
+    assert np.array_equal(c.grid(0)[..., 3] == 255, c1 > 0)         # stale voxels were cleared
+    c.update_positions(sc.verts[:, :3])
+    c.draw_depth(); c.draw_voxels(); c.sync()
+    assert np.array_equal(c.counts(), c0) and np.array_equal(c.grid(0), g0)
+
+
+def test_bounce_extension_vs_oracle(gpu_ctx, oracle):
+    sc = scenes.cornell()
+    u = uniforms.scene_uniforms(sc, V=32, width=96, height=96, shadow_map_size=512, bounces=3)
+    run_gpu(gpu_ctx, sc, u)
+    run_oracle(oracle, sc, u)
+    g, o = gpu_ctx.grid(0), oracle.grid(0)
+    assert np.array_equal(g[..., 3], o[..., 3])
+    assert np.abs(g.astype(int) - o.astype(int)).max() <= LSB_TOL
+    u2 = dict(u); u2["Bounces"] = 2
+    oracle.set_uniforms(u2); oracle.draw_voxels()
+    assert oracle.grid(0)[..., :3].astype(int).sum() < o[..., :3].astype(int).sum()   # the extra bounce adds light
+    assert_frame_close(gpu_ctx.read_frame(), oracle_frame_with(oracle, u), "bounces=3")
+
+
+def oracle_frame_with(oracle, u):
+    oracle.set_uniforms(u)
+    oracle.draw_voxels()
+    oracle.render()
+    return oracle.frame()
+
+
+def test_runs_on_a_caller_stream_and_reports_pass_times(gpu_ctx):
+    import torch
+    s = torch.cuda.Stream()
+    gpu_ctx.set_stream(s.cuda_stream)
+    sc = scenes.cornell()
+    run_gpu(gpu_ctx, sc, uniforms.scene_uniforms(sc, V=64, width=128, height=128, shadow_map_size=512))
+    s.synchronize()
+    for p in ("depth", "vox_cover", "vox_shade", "resolve", "mip", "visibility", "cone"):
+        assert gpu_ctx.pass_time_us(p) > 0
+    assert gpu_ctx.kernel_launches() > 10
+    gpu_ctx.set_stream(0)

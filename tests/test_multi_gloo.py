@@ -1,0 +1,68 @@
+"""world_size-2 gloo test of the triangle-sharded voxelisation exchange (BASELINE config 4):
+each rank accumulates its triangle range, the uint32 accumulators are summed with all_reduce, and the
+result must be bit-identical to the unsharded one.  The oracle stands in for the device here (CPU box)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import vct_b200  # noqa: F401
+    from vct_b200 import parallel, scenes, uniforms
+    from oracle.oracle_py import Oracle
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    sc = scenes.atrium(detail=0.12, tex_size=32)
+    u = uniforms.scene_uniforms(sc, V=32, width=64, height=64, shadow_map_size=256, coverage="conservative")
+    o = Oracle(); o.set_uniforms(u); o.load_scene(sc)
+    o.draw_depth()
+    tb, te = parallel.triangle_range(sc.n_tris, rank, world)
+    o.draw_voxels_range(tb, te, clear_first=True)
+    acc = parallel.pack_accumulator(o.counts(), o.sums())
+    t = torch.from_numpy(acc.view(np.int32).reshape(-1))
+    parallel.allreduce_accumulator(t)
+    counts, sums = parallel.unpack_accumulator(t.numpy().view(np.uint32))
+    o.set_accum(counts, sums)
+    o.resolve_and_mip()
+    # rows of the frame: every rank renders its band, bands are gathered on rank 0
+    o.render()
+    b0, b1 = parallel.row_band(64, rank, world)
+    band = torch.from_numpy(o.frame()[b0:b1].copy())
+    bands = [torch.empty_like(band) for _ in range(world)] if rank == 0 else None
+    dist.gather(band, bands, dst=0)
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "sharded.npz"), counts=counts, sums=sums, grid0=o.grid(0), grid3=o.grid(3),
+                 frame=np.concatenate([b.numpy() for b in bands], 0))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_triangle_sharded_voxelisation_allreduce_is_bit_exact(tmp_path, oracle_mod):
+    import torch.multiprocessing as mp
+    from vct_b200 import scenes, uniforms
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(tmp_path / "sharded.npz")
+    sc = scenes.atrium(detail=0.12, tex_size=32)
+    u = uniforms.scene_uniforms(sc, V=32, width=64, height=64, shadow_map_size=256, coverage="conservative")
+    o = oracle_mod.Oracle(); o.set_uniforms(u); o.load_scene(sc)
+    o.draw_depth(); o.draw_voxels(); o.render()
+    assert np.array_equal(got["counts"], o.counts().reshape(-1))
+    assert np.array_equal(got["sums"], o.sums().reshape(-1, 3))
+    assert np.array_equal(got["grid0"], o.grid(0)) and np.array_equal(got["grid3"], o.grid(3))
+    assert np.array_equal(got["frame"], o.frame())
+    assert got["counts"].sum() > 1000

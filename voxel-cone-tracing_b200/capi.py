@@ -21,7 +21,7 @@ SYMBOLS = [
     "vct_voxelize_range", "vct_accum_buffer", "vct_resolve_and_mip", "vct_readback_depth", "vct_readback_counts",
     "vct_readback_sums", "vct_readback_grid", "vct_upload_grid_level0", "vct_build_mips", "vct_readback_visibility",
     "vct_readback_frame", "vct_frame_buffer", "vct_cone_samples", "vct_fragment_count", "vct_occupied_voxels",
-    "vct_set_stream", "vct_sync", "vct_pass_time_us", "vct_kernel_launches", "vct_bench_tex3d",
+    "vct_trace_cones", "vct_set_stream", "vct_sync", "vct_pass_time_us", "vct_kernel_launches", "vct_bench_tex3d",
 ]
 
 
@@ -62,7 +62,7 @@ def load_library(path=None):
         "vct_readback_visibility": [vp, vp], "vct_readback_frame": [vp, vp],
         "vct_frame_buffer": [vp, C.POINTER(vp), C.POINTER(sz)], "vct_cone_samples": [vp, C.POINTER(C.c_uint64)],
         "vct_fragment_count": [vp, C.POINTER(C.c_uint64)], "vct_occupied_voxels": [vp, C.POINTER(C.c_uint64)],
-        "vct_set_stream": [vp, vp], "vct_sync": [vp], "vct_pass_time_us": [vp, i, C.POINTER(f)],
+        "vct_trace_cones": [vp, sz, vp, vp, vp, vp, vp], "vct_set_stream": [vp, vp], "vct_sync": [vp], "vct_pass_time_us": [vp, i, C.POINTER(f)],
         "vct_kernel_launches": [vp, C.POINTER(C.c_uint64)],
         "vct_bench_tex3d": [vp, i, C.c_uint64, i, f, i, C.POINTER(f)],
     }
@@ -137,7 +137,7 @@ class Context:
         self._ck(self.L.vct_set_cones(self.h, d.shape[0], _ptr(d), _ptr(w)))
 
     _INT = {"VoxelDimensions", "ShadowMapSize", "screen_width", "screen_height", "PcfRadius", "CoveragePolicy",
-            "Bounces", "GridFormat", "MaxFragments", "MaxTileItems", "DenseResolve", "Profile"}
+            "Bounces", "GridFormat", "MaxFragments", "MaxTileItems", "DenseResolve", "Profile", "RowBegin", "RowEnd"}
     _VEC3 = {"CameraPosition", "LightDirection"}
     _MAT4 = {"ModelMatrix", "ModelViewMatrix", "ProjectionMatrix", "DepthModelViewProjectionMatrix", "ProjX",
              "ProjY", "ProjZ"}
@@ -280,6 +280,15 @@ class Context:
 
     def kernel_launches(self):
         return self._u64(self.L.vct_kernel_launches)
+
+    def trace_cones(self, starts, dirs, tan_half):
+        s = np.ascontiguousarray(starts, dtype=np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dirs, dtype=np.float32).reshape(-1, 3)
+        t = np.ascontiguousarray(np.broadcast_to(np.asarray(tan_half, dtype=np.float32), (s.shape[0],)))
+        out = np.empty((s.shape[0], 4), dtype=np.float32)
+        steps = np.empty(s.shape[0], dtype=np.uint32)
+        self._ck(self.L.vct_trace_cones(self.h, s.shape[0], _ptr(s), _ptr(d), _ptr(t), _ptr(out), _ptr(steps)))
+        return out, steps
 
     # ---- execution control
     def set_stream(self, cuda_stream_ptr):

@@ -19,6 +19,8 @@ int check_cuda(vct_context* c, cudaError_t e, const char* what) {
 }
 
 int readback_accum(vct_context* c, uint32_t* counts, uint32_t* sums);
+int trace_cones(vct_context* c, size_t n, const float* starts, const float* dirs, const float* tans, float* out,
+                uint32_t* steps);
 
 // ------------------------------------------------------------------------------------------ helpers
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
@@ -381,6 +383,8 @@ int vct_set_i(vct_handle c, const char* name, int v) {
   else if (k == "GridFormat") { if (v != 0) return set_error(c, VCT_ERR_INVALID, "GridFormat: only 0 (RGBA8) is implemented"); c->grid_format = v; }
   else if (k == "MaxFragments") { if (v < 1024) return set_error(c, VCT_ERR_INVALID, "MaxFragments too small"); c->max_fragments = (size_t)v; }
   else if (k == "MaxTileItems") { if (v < 1024) return set_error(c, VCT_ERR_INVALID, "MaxTileItems too small"); c->max_items = (size_t)v; }
+  else if (k == "RowBegin") { if (v < 0) return set_error(c, VCT_ERR_INVALID, "RowBegin < 0"); P.row_begin = v; }
+  else if (k == "RowEnd") { if (v < 0) return set_error(c, VCT_ERR_INVALID, "RowEnd < 0"); P.row_end = v; }
   else if (k == "DenseResolve") c->dense_resolve = v != 0;
   else if (k == "Profile") c->profile = v != 0;
   else if (k == "ShadowMap" || k == "VoxelTexture") { /* texture unit numbers: meaningless here */ }
@@ -399,6 +403,7 @@ int vct_get_i(vct_handle c, const char* name, int* v) {
   else if (k == "Bounces") *v = P.bounces; else if (k == "NumDiffuseCones") *v = P.n_cones;
   else if (k == "GridFormat") *v = c->grid_format; else if (k == "MipLevels") *v = P.levels;
   else if (k == "MaxFragments") *v = (int)c->max_fragments; else if (k == "MaxTileItems") *v = (int)c->max_items;
+  else if (k == "RowBegin") *v = P.row_begin; else if (k == "RowEnd") *v = P.row_end;
   else if (k == "DenseResolve") *v = c->dense_resolve; else if (k == "Profile") *v = c->profile;
   else return set_error(c, VCT_ERR_INVALID, "unknown int uniform '" + k + "'");
   return VCT_OK;
@@ -710,6 +715,13 @@ int vct_occupied_voxels(vct_handle c, uint64_t* n) {
   int rc = read_counter(c, &c->d_counters->n_touched, &v, 4);
   if (n) *n = v;
   return rc;
+}
+
+int vct_trace_cones(vct_handle c, size_t n, const float* starts, const float* dirs, const float* tans, float* out,
+                    uint32_t* steps) {
+  NEED(c);
+  if (n && (!starts || !dirs || !tans || !out)) return set_error(c, VCT_ERR_INVALID, "vct_trace_cones: null argument");
+  return trace_cones(c, n, starts, dirs, tans, out, steps);
 }
 
 // ---- execution control

@@ -87,7 +87,8 @@ __device__ __forceinline__ bool setup_htri(const Params& P, const float* __restr
   }
   if (!(minx <= maxx)) return false;
   float fx0 = fmaxf(floorf(minx) - 1.0f, 0.0f), fx1 = fminf(ceilf(maxx) + 1.0f, W - 1.0f);
-  float fy0 = fmaxf(floorf(miny) - 1.0f, 0.0f), fy1 = fminf(ceilf(maxy) + 1.0f, H - 1.0f);
+  const float rb = (float)P.row_begin, re = (float)((P.row_end > 0 && P.row_end < P.H) ? P.row_end : P.H);
+  float fy0 = fmaxf(floorf(miny) - 1.0f, rb), fy1 = fminf(ceilf(maxy) + 1.0f, re - 1.0f);
   if (!(fx0 <= fx1) || !(fy0 <= fy1)) return false;
   i0 = (int)fx0; i1 = (int)fx1; j0 = (int)fy0; j1 = (int)fy1;
   return true;
@@ -390,9 +391,11 @@ int launch_cone(vct_context* c) {
   if (!c->depth_valid) return set_error(c, VCT_ERR_STATE, "vct_render: call vct_draw_depth first (shadow map missing)");
   PassTimer timer(c, VCT_PASS_CONE);
   VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->cone_samples, 0, sizeof(unsigned long long), c->stream));
-  dim3 b(256), g((c->P.W + 31) / 32, (c->P.H + 7) / 8);
+  const int y0 = c->P.row_begin, y1 = (c->P.row_end > 0 && c->P.row_end < c->P.H) ? c->P.row_end : c->P.H;
+  if (y0 >= y1) return VCT_OK;
+  dim3 b(256), g((c->P.W + 31) / 32, (y1 - y0 + 7) / 8);
   cone_trace<<<g, b, 0, c->stream>>>(c->P, c->d_verts, c->d_idx, c->d_trimat, c->d_materials, c->d_depth, c->d_vis,
-                                     c->grid_tex, c->d_frame, c->d_counters, 0, c->P.H);
+                                     c->grid_tex, c->d_frame, c->d_counters, y0, y1);
   c->launches += 1;
   VCT_CUDA(c, cudaGetLastError());
   return VCT_OK;
@@ -456,6 +459,41 @@ int launch_reinject(vct_context* c) {
   c->accum_dense_dirty = c->accum_dense_dirty;   // level 0 still matches the touched list (same voxels occupied)
   VCT_CUDA(c, cudaGetLastError());
   return VCT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void trace_cones_kernel(Params P, cudaTextureObject_t grid, size_t n, const float* __restrict__ starts,
+                                   const float* __restrict__ dirs, const float* __restrict__ tans,
+                                   float4* __restrict__ out, uint32_t* __restrict__ steps) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ConeConsts kc;
+  kc.vws = P.grid_world / (float)P.V;
+  kc.inv_half = P.grid_world * 0.5f;
+  kc.max_lod = (float)(P.levels - 1);
+  unsigned cnt = 0;
+  out[i] = cone_march(grid, P, kc, v3(starts[3 * i], starts[3 * i + 1], starts[3 * i + 2]),
+                      v3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), tans[i], cnt);
+  if (steps) steps[i] = cnt;
+}
+
+int trace_cones(vct_context* c, size_t n, const float* starts, const float* dirs, const float* tans, float* out,
+                uint32_t* steps) {
+  int rc = ensure_grid(c); if (rc) return rc;
+  if (!n) return VCT_OK;
+  float *d_s = nullptr, *d_d = nullptr, *d_t = nullptr; float4* d_o = nullptr; uint32_t* d_n = nullptr;
+  VCT_CUDA(c, cudaMalloc(&d_s, n * 12)); VCT_CUDA(c, cudaMalloc(&d_d, n * 12)); VCT_CUDA(c, cudaMalloc(&d_t, n * 4));
+  VCT_CUDA(c, cudaMalloc(&d_o, n * 16)); VCT_CUDA(c, cudaMalloc(&d_n, n * 4));
+  cudaMemcpyAsync(d_s, starts, n * 12, cudaMemcpyHostToDevice, c->stream);
+  cudaMemcpyAsync(d_d, dirs, n * 12, cudaMemcpyHostToDevice, c->stream);
+  cudaMemcpyAsync(d_t, tans, n * 4, cudaMemcpyHostToDevice, c->stream);
+  trace_cones_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->P, c->grid_tex, n, d_s, d_d, d_t, d_o, d_n);
+  c->launches += 1;
+  cudaMemcpyAsync(out, d_o, n * 16, cudaMemcpyDeviceToHost, c->stream);
+  if (steps) cudaMemcpyAsync(steps, d_n, n * 4, cudaMemcpyDeviceToHost, c->stream);
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  cudaFree(d_s); cudaFree(d_d); cudaFree(d_t); cudaFree(d_o); cudaFree(d_n);
+  return check_cuda(c, e, "vct_trace_cones");
 }
 
 }  // namespace vct

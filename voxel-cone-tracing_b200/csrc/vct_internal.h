@@ -34,6 +34,7 @@ struct Params {
   float shadow_bias;
   int coverage;          // 0 CENTER, 1 MSAA4_ANY, 2 CONSERVATIVE
   int bounces;
+  int row_begin, row_end;   // rows of the frame this context renders (row-band sharding); row_end 0 = H
 };
 
 struct MaterialDev {

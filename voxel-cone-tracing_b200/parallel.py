@@ -1,0 +1,73 @@
+"""Host-side sharding for multi-GPU runs (one process per GPU, torch.distributed for the plumbing).
+
+The reference is single-GPU (one GL context, main.cpp:44); SURVEY.md 8e lists where the path shards:
+  * cone tracing: image rows / whole views are independent given the grid (grid replicated, no collective);
+  * voxelisation of large dynamic meshes: contiguous triangle ranges per rank into a private integer
+    accumulator, then ONE exchange step: all-reduce(sum) of the uint32 accumulator.  Integer sums are
+    order independent, so the sharded result is bit-identical to the single-GPU one.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def triangle_range(n_tris: int, rank: int, world: int):
+    """Contiguous, balanced [begin, end) triangle range of `rank`."""
+    base, rem = divmod(int(n_tris), int(world))
+    b = rank * base + min(rank, rem)
+    return b, b + base + (1 if rank < rem else 0)
+
+
+def row_band(height: int, rank: int, world: int, align: int = 8):
+    """[begin, end) rows of the frame for `rank`; bands are multiples of `align` rows (cone_trace's warp
+    tile height) except possibly the last."""
+    blocks = (height + align - 1) // align
+    b0, b1 = triangle_range(blocks, rank, world)
+    return min(b0 * align, height), min(b1 * align, height)
+
+
+def views_for_rank(n_views: int, rank: int, world: int):
+    """Round-robin view assignment (light-probe bake, BASELINE config 5)."""
+    return list(range(rank, n_views, world))
+
+
+class _DevicePointer:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can wrap it without a copy."""
+
+    def __init__(self, ptr, n, typestr="<i4"):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def accumulator_tensor(ctx, device):
+    """The context's integer accumulator (4 x uint32 per voxel) as an int32 torch tensor sharing memory.
+    int32 two's-complement addition is bit-identical to uint32 addition, and NCCL has no uint32 sum in torch."""
+    import torch
+    ptr, n = ctx.accum_buffer()
+    return torch.as_tensor(_DevicePointer(ptr, n), device=device)
+
+
+def allreduce_accumulator(acc, group=None):
+    """The one exchange step of triangle-sharded voxelisation: sum of the per-rank accumulators."""
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+    return acc
+
+
+def pack_accumulator(counts: np.ndarray, sums: np.ndarray) -> np.ndarray:
+    """(V,V,V) counts + (V,V,V,3) sums -> the device layout: per voxel two little-endian u64 words
+    (r<<32 | g), (b<<32 | count), i.e. uint32 order [g, r, count, b]."""
+    out = np.empty(counts.shape + (4,), dtype=np.uint32)
+    out[..., 0] = sums[..., 1]
+    out[..., 1] = sums[..., 0]
+    out[..., 2] = counts
+    out[..., 3] = sums[..., 2]
+    return out
+
+
+def unpack_accumulator(acc: np.ndarray):
+    acc = acc.reshape(-1, 4)
+    counts = acc[:, 2].copy()
+    sums = np.stack([acc[:, 1], acc[:, 0], acc[:, 3]], -1)
+    return counts, sums

@@ -261,8 +261,9 @@ def atrium(seed=1234, detail=1.0, tex_size=512, name="atrium"):
         b.quad((cx - 4, top - 16, zc), (cx + 4, top - 16, zc), (cx + 4, top, zc), (cx - 4, top, zc), mat, d(10), d(20), (1, 2))
         b.quad((cx + 4, top - 16, zc), (cx - 4, top - 16, zc), (cx - 4, top, zc), (cx + 4, top, zc), mat, d(10), d(20), (1, 2))
     nfol = d(3300)
-    pos = np.stack([rng.uniform(x0 + 8, x1 - 8, nfol), rng.uniform(y0 + 2.3, y0 + 9.0, nfol),
-                    rng.uniform(-16.0, 16.0, nfol)], -1)
+    fx = rng.uniform(x0 + 8, x1 - 8 - 30.0, nfol)
+    fx = np.where(fx > -15.0, fx + 30.0, fx)          # keep |x| < 15 around the default camera clear
+    pos = np.stack([fx, rng.uniform(y0 + 2.3, y0 + 9.0, nfol), rng.uniform(-16.0, 16.0, nfol)], -1)
     ang = rng.uniform(0, np.pi, nfol)
     sz = rng.uniform(0.8, 2.2, nfol)
     for k in range(nfol):
