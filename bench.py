@@ -139,7 +139,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)          # one explicit stream for our kernels, torch's events and NCCL
+    torch.cuda.set_stream(stream)
 
     vct_b200.load_library()                         # mandatory extension: raises if missing
     sc, u = make_scene_and_uniforms(args)

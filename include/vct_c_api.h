@@ -124,8 +124,14 @@ int vct_occupied_voxels(vct_handle h, uint64_t* n);
 int vct_trace_cones(vct_handle h, size_t n, const float* starts, const float* dirs, const float* tan_half,
                     float* out_rgb_occ, uint32_t* out_steps);
 
+/* SampleVoxels(World_Position, lod) (VoxelConeTracing.fs:59-66) for n points: pos n*3, lod n, out n*4 */
+int vct_sample_voxels(vct_handle h, size_t n, const float* world_pos, const float* lod, float* out_rgba);
+
 /* ---- execution control */
-int vct_set_stream(vct_handle h, void* cuda_stream);   /* run on the caller's stream (e.g. torch's) */
+/* run on the caller's stream (e.g. torch's current stream); NULL selects the CUDA default stream, exactly as
+ * in the CUDA API.  vct_use_own_stream returns to the context's private non-blocking stream. */
+int vct_set_stream(vct_handle h, void* cuda_stream);
+int vct_use_own_stream(vct_handle h);
 int vct_sync(vct_handle h);
 int vct_pass_time_us(vct_handle h, int pass, float* us);   /* CUDA-event time of the last run of a pass */
 int vct_kernel_launches(vct_handle h, uint64_t* n);        /* kernels launched by this context so far */

@@ -204,6 +204,13 @@ class Oracle:
     def fragment_count(self):
         return int(self.L.orc_fragment_count(self.h))
 
+    def debug_pixel(self, i, j):
+        out = (C.c_float * 110)()
+        rgba = (C.c_uint8 * 4)()
+        rc = self.L.orc_debug_pixel(self.h, int(i), int(j), out, rgba)
+        a = np.array(out[:], dtype=np.float32)
+        return rc, a[:88].reshape(8, 11), a[88:], np.array(rgba[:])
+
     # ---- probes ---------------------------------------------------------------------------------
     def sample_voxels(self, pos, lod):
         p = (C.c_float * 3)(*map(float, pos))

@@ -609,7 +609,7 @@ void sample_voxels(const orc_ctx* o, V3 pos, float lod, float out[4]) {
   if (lod > (float)maxl) lod = (float)maxl;
   int l0 = (int)std::floor(lod);
   float f = lod - (float)l0;
-  if (o->p.FilterMode == 1) f = std::floor(f * 256.0f + 0.5f) * (1.0f / 256.0f);
+  if (o->p.FilterMode == 1) f = std::floor(f * 256.0f) * (1.0f / 256.0f);   /* hardware truncates the LOD fraction */
   float a[4];
   sample_grid_level(o, l0, u, v, w, a);
   if (f > 0.0f && l0 < maxl) {
@@ -805,6 +805,9 @@ static void orc_visibility(orc_ctx* o, int y0, int y1) {
   }
 }
 
+/* optional per-pixel trace for diagnostics: 8 cones x (start3, dir3, tan1, result4) + shadow, N3 */
+static float* g_debug = nullptr;
+
 /* VoxelConeTracing.fs:165-229 for one visible pixel */
 static void shade_pixel(const orc_ctx* o, size_t ti, int i, int j, uint8_t out[4], uint64_t* samples) {
   const orc_params& p = o->p;
@@ -893,6 +896,11 @@ static void shade_pixel(const orc_ctx* o, size_t ti, int i, int j, uint8_t out[4
     V3 dir = normalize3(tbn_mul(d));
     float r[4];
     cone_trace(o, start, dir, p.DiffuseTanHalfAngle, r, samples);
+    if (g_debug && c < 7) {
+      float* d = g_debug + c * 11;
+      d[0] = start.x; d[1] = start.y; d[2] = start.z; d[3] = dir.x; d[4] = dir.y; d[5] = dir.z; d[6] = p.DiffuseTanHalfAngle;
+      for (int k = 0; k < 4; ++k) d[7 + k] = r[k];
+    }
     for (int k = 0; k < 4; ++k) ind[k] += p.ConeWeights[c] * r[k];
   }
   float occlusion = 1.0f - ind[3];                                     /* :201 */
@@ -914,6 +922,13 @@ static void shade_pixel(const orc_ctx* o, size_t ti, int i, int j, uint8_t out[4
   V3 refl = normalize3(sub3(negE, scale3(N, 2.0f * dne)));             /* :217 */
   float isp[4];
   cone_trace(o, start, refl, p.SpecularTanHalfAngle, isp, samples);    /* :218 */
+  if (g_debug) {
+    float* d = g_debug + 7 * 11;
+    d[0] = start.x; d[1] = start.y; d[2] = start.z; d[3] = refl.x; d[4] = refl.y; d[5] = refl.z; d[6] = p.SpecularTanHalfAngle;
+    for (int k = 0; k < 4; ++k) d[7 + k] = isp[k];
+    d[11] = shadow; d[12] = N.x; d[13] = N.y; d[14] = N.z; d[15] = mat[0]; d[16] = mat[1]; d[17] = mat[2];
+    d[18] = sc[0]; d[19] = sc[1]; d[20] = sc[2]; d[21] = spec;
+  }
   float specOcc = 1.0f - isp[3];                                       /* :221 */
   float col[3];
   for (int k = 0; k < 3; ++k) {
@@ -1057,7 +1072,7 @@ extern "C" void orc_default_params(orc_params* p) {
   p->CoveragePolicy = 1;
   p->VoxelStoreMode = 0;
   p->Bounces = 2;
-  p->FilterMode = 0;
+  p->FilterMode = 1;   /* 8-bit fixed-point filter weights: what texture hardware and llvmpipe's RGBA8 path use */
 }
 
 extern "C" orc_ctx* orc_create(void) {
@@ -1163,6 +1178,20 @@ extern "C" int orc_get_frame(orc_ctx* o, uint8_t* rgba) {
   std::memcpy(rgba, o->frame.data(), o->frame.size());
   return 0;
 }
+/* diagnostics: re-shade pixel (i,j) of the last render and return 8 x 11 cone records + 11 scalars */
+extern "C" int orc_debug_pixel(orc_ctx* o, int i, int j, float* out110, uint8_t* rgba) {
+  const int W = o->p.screen_width;
+  if (o->vis.empty()) return -1;
+  uint64_t key = o->vis[(size_t)j * W + i];
+  if (key == ~0ull) return 1;
+  for (int k = 0; k < 110; ++k) out110[k] = 0;
+  g_debug = out110;
+  uint64_t n = 0;
+  shade_pixel(o, (size_t)(uint32_t)key, i, j, rgba, &n);
+  g_debug = nullptr;
+  return 0;
+}
+
 extern "C" uint64_t orc_cone_samples(orc_ctx* o) { return o->cone_samples; }
 extern "C" uint64_t orc_fragment_count(orc_ctx* o) { return o->fragments; }
 

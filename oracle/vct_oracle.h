@@ -51,7 +51,9 @@ typedef struct orc_params {
   int32_t CoveragePolicy;            /* 0 CENTER, 1 MSAA4_ANY, 2 CONSERVATIVE */
   int32_t VoxelStoreMode;            /* 0 sum+count average, 1 last writer in primitive order */
   int32_t Bounces;                   /* 2 = reference; >=3 = voxel-space re-injection extension */
-  int32_t FilterMode;                /* 0 fp32 weights (GL spec), 1 emulate 8-bit fixed-point weights */
+  int32_t FilterMode;                /* voxel-texture filter weights: 1 (default) = 8 fractional bits, rounded (LOD
+                                        fraction truncated), as measured on B200 texture hardware and as llvmpipe's
+                                        RGBA8 path does; 0 = fp32 weights */
 } orc_params;
 
 typedef struct orc_ctx orc_ctx;

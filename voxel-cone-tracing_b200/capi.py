@@ -21,7 +21,7 @@ SYMBOLS = [
     "vct_voxelize_range", "vct_accum_buffer", "vct_resolve_and_mip", "vct_readback_depth", "vct_readback_counts",
     "vct_readback_sums", "vct_readback_grid", "vct_upload_grid_level0", "vct_build_mips", "vct_readback_visibility",
     "vct_readback_frame", "vct_frame_buffer", "vct_cone_samples", "vct_fragment_count", "vct_occupied_voxels",
-    "vct_trace_cones", "vct_set_stream", "vct_sync", "vct_pass_time_us", "vct_kernel_launches", "vct_bench_tex3d",
+    "vct_trace_cones", "vct_sample_voxels", "vct_set_stream", "vct_use_own_stream", "vct_sync", "vct_pass_time_us", "vct_kernel_launches", "vct_bench_tex3d",
 ]
 
 
@@ -62,7 +62,7 @@ def load_library(path=None):
         "vct_readback_visibility": [vp, vp], "vct_readback_frame": [vp, vp],
         "vct_frame_buffer": [vp, C.POINTER(vp), C.POINTER(sz)], "vct_cone_samples": [vp, C.POINTER(C.c_uint64)],
         "vct_fragment_count": [vp, C.POINTER(C.c_uint64)], "vct_occupied_voxels": [vp, C.POINTER(C.c_uint64)],
-        "vct_trace_cones": [vp, sz, vp, vp, vp, vp, vp], "vct_set_stream": [vp, vp], "vct_sync": [vp], "vct_pass_time_us": [vp, i, C.POINTER(f)],
+        "vct_trace_cones": [vp, sz, vp, vp, vp, vp, vp], "vct_sample_voxels": [vp, sz, vp, vp, vp], "vct_set_stream": [vp, vp], "vct_use_own_stream": [vp], "vct_sync": [vp], "vct_pass_time_us": [vp, i, C.POINTER(f)],
         "vct_kernel_launches": [vp, C.POINTER(C.c_uint64)],
         "vct_bench_tex3d": [vp, i, C.c_uint64, i, f, i, C.POINTER(f)],
     }
@@ -292,7 +292,18 @@ class Context:
 
     # ---- execution control
     def set_stream(self, cuda_stream_ptr):
+        """Run on the given CUDA stream handle (0 / None = the CUDA default stream)."""
         self._ck(self.L.vct_set_stream(self.h, C.c_void_p(int(cuda_stream_ptr)) if cuda_stream_ptr else None))
+
+    def use_own_stream(self):
+        self._ck(self.L.vct_use_own_stream(self.h))
+
+    def sample_voxels(self, pos, lod):
+        p = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+        l = np.ascontiguousarray(np.broadcast_to(np.asarray(lod, dtype=np.float32), (p.shape[0],)))
+        out = np.empty((p.shape[0], 4), dtype=np.float32)
+        self._ck(self.L.vct_sample_voxels(self.h, p.shape[0], _ptr(p), _ptr(l), _ptr(out)))
+        return out
 
     def sync(self):
         self._ck(self.L.vct_sync(self.h))

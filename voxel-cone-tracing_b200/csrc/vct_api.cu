@@ -19,6 +19,7 @@ int check_cuda(vct_context* c, cudaError_t e, const char* what) {
 }
 
 int readback_accum(vct_context* c, uint32_t* counts, uint32_t* sums);
+int sample_voxels(vct_context* c, size_t n, const float* pos, const float* lod, float* out);
 int trace_cones(vct_context* c, size_t n, const float* starts, const float* dirs, const float* tans, float* out,
                 uint32_t* steps);
 
@@ -725,12 +726,27 @@ int vct_trace_cones(vct_handle c, size_t n, const float* starts, const float* di
 }
 
 // ---- execution control
+int vct_sample_voxels(vct_handle c, size_t n, const float* pos, const float* lod, float* out) {
+  NEED(c);
+  if (n && (!pos || !lod || !out)) return set_error(c, VCT_ERR_INVALID, "vct_sample_voxels: null argument");
+  return sample_voxels(c, n, pos, lod, out);
+}
+
 int vct_set_stream(vct_handle c, void* s) {
   NEED(c);
   cudaStreamSynchronize(c->stream);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
-  if (s) { c->stream = (cudaStream_t)s; c->own_stream = false; }
-  else { VCT_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  c->stream = (cudaStream_t)s;     // NULL = the CUDA default stream
+  c->own_stream = false;
+  return VCT_OK;
+}
+
+int vct_use_own_stream(vct_handle c) {
+  NEED(c);
+  cudaStreamSynchronize(c->stream);
+  if (c->own_stream) return VCT_OK;
+  VCT_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->own_stream = true;
   return VCT_OK;
 }
 

@@ -496,4 +496,28 @@ int trace_cones(vct_context* c, size_t n, const float* starts, const float* dirs
   return check_cuda(c, e, "vct_trace_cones");
 }
 
+__global__ void sample_voxels_kernel(Params P, cudaTextureObject_t grid, size_t n, const float* __restrict__ pos,
+                                     const float* __restrict__ lod, float4* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float half = P.grid_world * 0.5f;
+  float u = (pos[3 * i] / half) * 0.5f + 0.5f, v = (pos[3 * i + 1] / half) * 0.5f + 0.5f, w = (pos[3 * i + 2] / half) * 0.5f + 0.5f;
+  out[i] = tex3DLod<float4>(grid, u, v, w, lod[i]);
+}
+
+int sample_voxels(vct_context* c, size_t n, const float* pos, const float* lod, float* out) {
+  int rc = ensure_grid(c); if (rc) return rc;
+  if (!n) return VCT_OK;
+  float *d_p = nullptr, *d_l = nullptr; float4* d_o = nullptr;
+  VCT_CUDA(c, cudaMalloc(&d_p, n * 12)); VCT_CUDA(c, cudaMalloc(&d_l, n * 4)); VCT_CUDA(c, cudaMalloc(&d_o, n * 16));
+  cudaMemcpyAsync(d_p, pos, n * 12, cudaMemcpyHostToDevice, c->stream);
+  cudaMemcpyAsync(d_l, lod, n * 4, cudaMemcpyHostToDevice, c->stream);
+  sample_voxels_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->P, c->grid_tex, n, d_p, d_l, d_o);
+  c->launches += 1;
+  cudaMemcpyAsync(out, d_o, n * 16, cudaMemcpyDeviceToHost, c->stream);
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  cudaFree(d_p); cudaFree(d_l); cudaFree(d_o);
+  return check_cuda(c, e, "vct_sample_voxels");
+}
+
 }  // namespace vct
