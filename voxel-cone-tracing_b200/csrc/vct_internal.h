@@ -269,9 +269,10 @@ __device__ __forceinline__ float interp3(float a0, float a1, float a2, float l1,
 }
 
 // ---- shadow map sampling: PCF_Shadow_Mapping (Voxelization.fs:18-52, VoxelConeTracing.fs:132-163).
-// Returns the number of lit taps.  The (2r+2)^2 texel footprint is fetched once when all taps share
-// the same fractional position is NOT assumed: every tap computes its own texel coordinates exactly
-// as the oracle does, but rows of the footprint are reused through registers by the compiler.
+// Returns the number of lit taps; the caller applies /25 (voxelisation) or *0.111 (cone trace).
+// Every tap is `texture(ShadowMap, DepthCoord.xy + offset).r` = one GL_LINEAR, CLAMP_TO_EDGE fetch of the
+// D24 map (no compare mode, Voxel_Cone_Tracing.h:93-96), i.e. a 2x2 footprint and three lerps in the order
+// top = t00 + a*(t10-t00); bot = t01 + a*(t11-t01); d = top + b*(bot-top).
 __device__ __forceinline__ float depth_texel(const uint32_t* __restrict__ depth, int S, int i, int j) {
   i = min(max(i, 0), S - 1);
   j = min(max(j, 0), S - 1);
@@ -293,8 +294,9 @@ __device__ __forceinline__ float shadow_bilinear(const uint32_t* __restrict__ de
   return top + b * (bot - top);
 }
 
-__device__ __forceinline__ float pcf_lit_taps(const uint32_t* __restrict__ depth, int S, int r, float bias,
-                                              float dcx, float dcy, float dcz, float dcw) {
+// reference form: every tap on its own (any radius)
+static __device__ __noinline__ float pcf_lit_taps_generic(const uint32_t* __restrict__ depth, int S, int r, float bias,
+                                                    float dcx, float dcy, float dcz, float dcw) {
   float cur = dcz / dcw;
   float inv = 1.0f / (float)S;
   float thr = cur - bias;
@@ -306,6 +308,67 @@ __device__ __forceinline__ float pcf_lit_taps(const uint32_t* __restrict__ depth
       if (thr <= closest) lit += 1.0f;
     }
   return lit;
+}
+
+// Footprint-sharing form for the reference's radius 2 (5x5 taps): the 25 taps read a 6x6 texel block, the
+// horizontal lerp of a (texel row, tap column) pair is the `bot` of one tap and the `top` of the next, so 30
+// horizontal + 25 vertical lerps replace 75.  Per-column fractions a[k] and per-row fractions b[k] are
+// computed exactly as the per-tap form does, and every lerp has the same operands in the same order, so the
+// result is bit-identical to pcf_lit_taps_generic; if the tap columns/rows are not consecutive texels
+// (float rounding of `coord + k/S`, or far outside the map) the generic form is used.
+template <int R>
+__device__ __forceinline__ float pcf_lit_taps_block(const uint32_t* __restrict__ depth, int S, float bias, float dcx,
+                                                    float dcy, float dcz, float dcw) {
+  constexpr int T = 2 * R + 1;
+  const float fS = (float)S;
+  const float cur = dcz / dcw;
+  const float inv = 1.0f / fS;
+  const float thr = cur - bias;
+  float ax[T], by[T];
+  int ix0 = 0, iy0 = 0;
+  bool regular = true;
+#pragma unroll
+  for (int k = 0; k < T; ++k) {
+    float ox = inv * (float)(k - R);
+    float x = (dcx + ox) * fS - 0.5f, y = (dcy + ox) * fS - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    ax[k] = x - fx; by[k] = y - fy;
+    int i = (int)fminf(fmaxf(fx, -2.0f), fS + 1.0f), j = (int)fminf(fmaxf(fy, -2.0f), fS + 1.0f);
+    if (k == 0) { ix0 = i; iy0 = j; }
+    else regular = regular && (i == ix0 + k) && (j == iy0 + k);
+  }
+  if (!regular) return pcf_lit_taps_generic(depth, S, R, bias, dcx, dcy, dcz, dcw);
+  int cx[T + 1];
+#pragma unroll
+  for (int c = 0; c <= T; ++c) cx[c] = min(max(ix0 + c, 0), S - 1);
+  float hprev[T];
+  float lit = 0.0f;
+#pragma unroll
+  for (int r = 0; r <= T; ++r) {
+    const uint32_t* row = depth + (size_t)min(max(iy0 + r, 0), S - 1) * S;
+    float t[T + 1];
+#pragma unroll
+    for (int c = 0; c <= T; ++c) t[c] = (float)__ldg(row + cx[c]) * (1.0f / 16777215.0f);
+    float h[T];
+#pragma unroll
+    for (int k = 0; k < T; ++k) h[k] = t[k] + ax[k] * (t[k + 1] - t[k]);
+    if (r >= 1) {
+#pragma unroll
+      for (int k = 0; k < T; ++k) {
+        float d = hprev[k] + by[r - 1] * (h[k] - hprev[k]);
+        if (thr <= d) lit += 1.0f;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < T; ++k) hprev[k] = h[k];
+  }
+  return lit;
+}
+
+__device__ __forceinline__ float pcf_lit_taps(const uint32_t* __restrict__ depth, int S, int r, float bias,
+                                              float dcx, float dcy, float dcz, float dcw) {
+  if (r == 2) return pcf_lit_taps_block<2>(depth, S, bias, dcx, dcy, dcz, dcw);
+  return pcf_lit_taps_generic(depth, S, r, bias, dcx, dcy, dcz, dcw);
 }
 
 // GL 4.3 8.14: lambda = log2(max(|d(uv*size)/dx|, |d(uv*size)/dy|))
