@@ -254,6 +254,91 @@ __device__ __forceinline__ float4 cone_march(cudaTextureObject_t grid, const Par
   return make_float4(cr, cg, cb, occ);
 }
 
+// All diffuse cones of a pixel share tanHalfAngle and the start distance, hence the whole (dist, diameter,
+// lod) sequence: they are marched in lockstep so that every step issues up to NC independent tex3DLod
+// fetches (memory-level parallelism) instead of NC dependent chains, and the specular cone -- the longest
+// chain, up to 29 steps at 256^3 -- advances in the same loop.  The per-cone weights (Cone_Weights,
+// VoxelConeTracing.fs:48) are folded into the accumulation: sum_c w_c * sum_i (1-alpha_c,i) * s_c,i.
+template <int NC>
+struct ConeBundle {
+  float du[NC], dv[NC], dw[NC];   // direction / grid size
+  float alpha[NC];
+};
+
+template <int NC>
+__device__ __forceinline__ void march_pixel(cudaTextureObject_t grid, const Params& P, const ConeConsts& k, V3 start,
+                                            const ConeBundle<NC>& cb_in, V3 spec_dir, float4& diffuse, float4& specular,
+                                            unsigned& samples) {
+  ConeBundle<NC> cb = cb_in;
+  const int n = min(P.n_cones, NC);
+  const float u0 = __fmaf_rn(start.x, k.inv_grid, 0.5f), v0 = __fmaf_rn(start.y, k.inv_grid, 0.5f),
+              w0 = __fmaf_rn(start.z, k.inv_grid, 0.5f);
+  const float max_dist = P.max_dist, max_alpha = P.max_alpha, step_mult = P.step_mult;
+  // diffuse state (shared distance sequence)
+  float dr = 0.0f, dg = 0.0f, db = 0.0f, docc = 0.0f;
+  float ddist = k.vws;
+  const float d2t = 2.0f * P.diffuse_tan;
+  bool d_any = n > 0;
+  // specular state
+  float sr = 0.0f, sg = 0.0f, sb = 0.0f, socc = 0.0f, salpha = 0.0f;
+  float sdist = k.vws;
+  const float s2t = 2.0f * P.spec_tan;
+  const float su = spec_dir.x * k.inv_grid, sv = spec_dir.y * k.inv_grid, sw = spec_dir.z * k.inv_grid;
+  bool s_on = true;
+  while (true) {
+    d_any = d_any && (ddist < max_dist);
+    s_on = s_on && (sdist < max_dist) && (salpha < max_alpha);
+    if (!d_any && !s_on) break;
+    float4 ss = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float sdiam = 0.0f;
+    if (s_on) {                                  // issue the specular fetch first: it heads the longest chain
+      sdiam = fmaxf(k.vws, s2t * sdist);
+      ss = tex3DLod<float4>(grid, __fmaf_rn(sdist, su, u0), __fmaf_rn(sdist, sv, v0), __fmaf_rn(sdist, sw, w0),
+                            __log2f(sdiam * k.inv_vws));
+      ++samples;
+    }
+    if (d_any) {
+      const float diam = fmaxf(k.vws, d2t * ddist);
+      const float lod = __log2f(diam * k.inv_vws);
+      const float rocc = __frcp_rn(__fmaf_rn(0.03f, diam, 1.0f));
+      float4 s[NC];
+      bool on[NC];
+      bool any = false;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        on[c] = (c < n) && (cb.alpha[c] < max_alpha);
+        if (on[c]) {
+          s[c] = tex3DLod<float4>(grid, __fmaf_rn(ddist, cb.du[c], u0), __fmaf_rn(ddist, cb.dv[c], v0),
+                                  __fmaf_rn(ddist, cb.dw[c], w0), lod);
+          ++samples;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        if (on[c]) {
+          const float t = P.cone_w[c] * (1.0f - cb.alpha[c]);
+          dr = __fmaf_rn(t, s[c].x, dr); dg = __fmaf_rn(t, s[c].y, dg); db = __fmaf_rn(t, s[c].z, db);
+          docc = __fmaf_rn(t * s[c].w, rocc, docc);
+          cb.alpha[c] = __fmaf_rn(1.0f - cb.alpha[c], s[c].w, cb.alpha[c]);
+          any = any || (cb.alpha[c] < max_alpha);
+        }
+      }
+      d_any = any;
+      ddist = __fmaf_rn(diam, step_mult, ddist);
+    }
+    if (s_on) {
+      const float t = 1.0f - salpha;
+      sr = __fmaf_rn(t, ss.x, sr); sg = __fmaf_rn(t, ss.y, sg); sb = __fmaf_rn(t, ss.z, sb);
+      const float ta = t * ss.w;
+      socc = __fmaf_rn(ta, __frcp_rn(__fmaf_rn(0.03f, sdiam, 1.0f)), socc);
+      salpha += ta;
+      sdist = __fmaf_rn(sdiam, step_mult, sdist);
+    }
+  }
+  diffuse = make_float4(dr, dg, db, docc);
+  specular = make_float4(sr, sg, sb, socc);
+}
+
 __device__ __forceinline__ unsigned char to_unorm8(float x) {
   x = fminf(fmaxf(x, 0.0f), 1.0f);
   if (!(x == x)) x = 0.0f;
@@ -261,7 +346,8 @@ __device__ __forceinline__ unsigned char to_unorm8(float x) {
 }
 
 // one warp = 8x4 pixels; block = 8 warps = 32x8 pixels
-__global__ void __launch_bounds__(256) cone_trace(Params P, const float* __restrict__ verts,
+template <int NC>
+__global__ void __launch_bounds__(256, 3) cone_trace(Params P, const float* __restrict__ verts,
                                                   const uint32_t* __restrict__ idx,
                                                   const uint16_t* __restrict__ trimat,
                                                   const MaterialDev* __restrict__ mats,
@@ -355,15 +441,15 @@ __global__ void __launch_bounds__(256) cone_trace(Params P, const float* __restr
 
       const ConeConsts kc = cone_consts(P);
       const V3 start = vadd(Pw, vscale(Nw, kc.vws));                       // :92
-      float ir = 0.0f, ig = 0.0f, ib = 0.0f, ia = 0.0f;
-      for (int cidx = 0; cidx < P.n_cones; ++cidx) {                      // :196-199
-        V3 dir = vnormalize(tbn_mul(v3(P.cone_dir[cidx * 3], P.cone_dir[cidx * 3 + 1], P.cone_dir[cidx * 3 + 2])));
-        float4 r = cone_march(grid, P, kc, start, dir, P.diffuse_tan, samples);
-        const float wgt = P.cone_w[cidx];
-        ir += wgt * r.x; ig += wgt * r.y; ib += wgt * r.z; ia += wgt * r.w;
+      ConeBundle<NC> cb;
+#pragma unroll
+      for (int cidx = 0; cidx < NC; ++cidx) {                              // :196-199
+        V3 dir = v3(0.0f, 0.0f, 1.0f);
+        if (cidx < P.n_cones)
+          dir = vnormalize(tbn_mul(v3(P.cone_dir[cidx * 3], P.cone_dir[cidx * 3 + 1], P.cone_dir[cidx * 3 + 2])));
+        cb.du[cidx] = dir.x * kc.inv_grid; cb.dv[cidx] = dir.y * kc.inv_grid; cb.dw[cidx] = dir.z * kc.inv_grid;
+        cb.alpha[cidx] = 0.0f;
       }
-      const float occlusion = 1.0f - ia;                                   // :201
-
       float4 sc = sample_mat(m.specular, m.sw, m.sh, q, 0.0f, 0.0f);      // :209
       if (!(sqrtf(sc.y * sc.y + sc.z * sc.z) > 0.0f)) { sc.y = sc.x; sc.z = sc.x; }   // .rrra, :210
       const V3 negL = v3(-L.x, -L.y, -L.z);
@@ -372,7 +458,10 @@ __global__ void __launch_bounds__(256) cone_trace(Params P, const float* __restr
       const float directSpec = spec * shadow;                                         // :214
       const V3 negE = v3(-E.x, -E.y, -E.z);
       const V3 refl = vnormalize(vsub(negE, vscale(N, 2.0f * vdot(N, negE))));        // :217
-      const float4 isp = cone_march(grid, P, kc, start, refl, P.spec_tan, samples);   // :218
+      float4 idf, isp;
+      march_pixel<NC>(grid, P, kc, start, cb, refl, idf, isp, samples);               // :196-199 and :218
+      const float ir = idf.x, ig = idf.y, ib = idf.z, ia = idf.w;
+      const float occlusion = 1.0f - ia;                                   // :201
       const float specOcc = 1.0f - isp.w;                                             // :221
 
       const float mr[3] = {mat.x, mat.y, mat.z}, ind[3] = {ir, ig, ib}, is3[3] = {isp.x, isp.y, isp.z};
@@ -404,8 +493,12 @@ int launch_cone(vct_context* c) {
   const int y0 = c->P.row_begin, y1 = (c->P.row_end > 0 && c->P.row_end < c->P.H) ? c->P.row_end : c->P.H;
   if (y0 >= y1) return VCT_OK;
   dim3 b(256), g((c->P.W + 31) / 32, (y1 - y0 + 7) / 8);
-  cone_trace<<<g, b, 0, c->stream>>>(c->P, c->d_verts, c->d_idx, c->d_trimat, c->d_materials, c->d_depth, c->d_vis,
-                                     c->grid_tex, c->d_frame, c->d_counters, y0, y1);
+  if (c->P.n_cones <= 6)
+    cone_trace<6><<<g, b, 0, c->stream>>>(c->P, c->d_verts, c->d_idx, c->d_trimat, c->d_materials, c->d_depth, c->d_vis,
+                                          c->grid_tex, c->d_frame, c->d_counters, y0, y1);
+  else
+    cone_trace<16><<<g, b, 0, c->stream>>>(c->P, c->d_verts, c->d_idx, c->d_trimat, c->d_materials, c->d_depth, c->d_vis,
+                                           c->grid_tex, c->d_frame, c->d_counters, y0, y1);
   c->launches += 1;
   VCT_CUDA(c, cudaGetLastError());
   return VCT_OK;
