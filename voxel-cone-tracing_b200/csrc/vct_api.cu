@@ -386,6 +386,8 @@ int vct_set_i(vct_handle c, const char* name, int v) {
   else if (k == "MaxTileItems") { if (v < 1024) return set_error(c, VCT_ERR_INVALID, "MaxTileItems too small"); c->max_items = (size_t)v; }
   else if (k == "RowBegin") { if (v < 0) return set_error(c, VCT_ERR_INVALID, "RowBegin < 0"); P.row_begin = v; }
   else if (k == "RowEnd") { if (v < 0) return set_error(c, VCT_ERR_INVALID, "RowEnd < 0"); P.row_end = v; }
+  else if (k == "DebugLaneMap") c->debug_lane_map = v;
+  else if (k == "DebugSpecAhead") c->debug_spec_ahead = v;
   else if (k == "DenseResolve") c->dense_resolve = v != 0;
   else if (k == "Profile") c->profile = v != 0;
   else if (k == "ShadowMap" || k == "VoxelTexture") { /* texture unit numbers: meaningless here */ }

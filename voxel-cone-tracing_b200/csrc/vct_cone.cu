@@ -215,6 +215,13 @@ __device__ __forceinline__ V3 vnormalize(V3 a) {
   return v3(a.x / l, a.y / l, a.z / l);
 }
 
+// tolerance-level normalisation (MUFU.RSQ, ~2 ulp) for shading vectors; anything that feeds a coverage or
+// shadow-compare decision keeps IEEE division / sqrt.
+__device__ __forceinline__ V3 vnormalize_fast(V3 a) {
+  float r = rsqrtf(vdot(a, a));
+  return v3(a.x * r, a.y * r, a.z * r);
+}
+
 struct ConeConsts { float vws, inv_vws, inv_grid; };
 
 __device__ __forceinline__ ConeConsts cone_consts(const Params& P) {
@@ -259,21 +266,20 @@ __device__ __forceinline__ float4 cone_march(cudaTextureObject_t grid, const Par
 // fetches (memory-level parallelism) instead of NC dependent chains, and the specular cone -- the longest
 // chain, up to 29 steps at 256^3 -- advances in the same loop.  The per-cone weights (Cone_Weights,
 // VoxelConeTracing.fs:48) are folded into the accumulation: sum_c w_c * sum_i (1-alpha_c,i) * s_c,i.
-template <int NC>
-struct ConeBundle {
-  float du[NC], dv[NC], dw[NC];   // direction / grid size
-  float alpha[NC];
-};
-
-template <int NC>
+// Cone directions live in shared memory ([component][cone][thread], conflict free) so that the march loop
+// keeps its register budget for the accumulators: 18 LDS per lockstep step on an otherwise idle LSU pipe.
+template <int NC, int SU>
 __device__ __forceinline__ void march_pixel(cudaTextureObject_t grid, const Params& P, const ConeConsts& k, V3 start,
-                                            const ConeBundle<NC>& cb_in, V3 spec_dir, float4& diffuse, float4& specular,
-                                            unsigned& samples) {
-  ConeBundle<NC> cb = cb_in;
+                                            const float* __restrict__ sdir /* smem, stride blockDim.x */,
+                                            V3 spec_dir, float4& diffuse, float4& specular, unsigned& samples) {
   const int n = min(P.n_cones, NC);
+  const int stride = blockDim.x;
   const float u0 = __fmaf_rn(start.x, k.inv_grid, 0.5f), v0 = __fmaf_rn(start.y, k.inv_grid, 0.5f),
               w0 = __fmaf_rn(start.z, k.inv_grid, 0.5f);
   const float max_dist = P.max_dist, max_alpha = P.max_alpha, step_mult = P.step_mult;
+  float alpha[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) alpha[c] = 0.0f;
   // diffuse state (shared distance sequence)
   float dr = 0.0f, dg = 0.0f, db = 0.0f, docc = 0.0f;
   float ddist = k.vws;
@@ -285,17 +291,25 @@ __device__ __forceinline__ void march_pixel(cudaTextureObject_t grid, const Para
   const float s2t = 2.0f * P.spec_tan;
   const float su = spec_dir.x * k.inv_grid, sv = spec_dir.y * k.inv_grid, sw = spec_dir.z * k.inv_grid;
   bool s_on = true;
+  // The sample positions of a cone depend only on the step index, never on the fetched values (only the
+  // early exit does), so SU specular steps are fetched ahead per iteration and composited in order; fetches
+  // past the exit are discarded (<= SU-1 per pixel) and not counted as samples.
   while (true) {
     d_any = d_any && (ddist < max_dist);
     s_on = s_on && (sdist < max_dist) && (salpha < max_alpha);
     if (!d_any && !s_on) break;
-    float4 ss = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    float sdiam = 0.0f;
-    if (s_on) {                                  // issue the specular fetch first: it heads the longest chain
-      sdiam = fmaxf(k.vws, s2t * sdist);
-      ss = tex3DLod<float4>(grid, __fmaf_rn(sdist, su, u0), __fmaf_rn(sdist, sv, v0), __fmaf_rn(sdist, sw, w0),
-                            __log2f(sdiam * k.inv_vws));
-      ++samples;
+    float4 ss[SU];
+    float sdiam[SU];
+    if (s_on) {                                  // issue the specular fetches first: they head the longest chain
+      float dk = sdist;
+#pragma unroll
+      for (int q = 0; q < SU; ++q) {
+        sdiam[q] = fmaxf(k.vws, s2t * dk);
+        if (dk < max_dist)
+          ss[q] = tex3DLod<float4>(grid, __fmaf_rn(dk, su, u0), __fmaf_rn(dk, sv, v0), __fmaf_rn(dk, sw, w0),
+                                   __log2f(sdiam[q] * k.inv_vws));
+        dk = __fmaf_rn(sdiam[q], step_mult, dk);
+      }
     }
     if (d_any) {
       const float diam = fmaxf(k.vws, d2t * ddist);
@@ -306,33 +320,39 @@ __device__ __forceinline__ void march_pixel(cudaTextureObject_t grid, const Para
       bool any = false;
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        on[c] = (c < n) && (cb.alpha[c] < max_alpha);
+        on[c] = (c < n) && (alpha[c] < max_alpha);
         if (on[c]) {
-          s[c] = tex3DLod<float4>(grid, __fmaf_rn(ddist, cb.du[c], u0), __fmaf_rn(ddist, cb.dv[c], v0),
-                                  __fmaf_rn(ddist, cb.dw[c], w0), lod);
+          const float du = sdir[(0 * NC + c) * stride], dv = sdir[(1 * NC + c) * stride], dw = sdir[(2 * NC + c) * stride];
+          s[c] = tex3DLod<float4>(grid, __fmaf_rn(ddist, du, u0), __fmaf_rn(ddist, dv, v0), __fmaf_rn(ddist, dw, w0), lod);
           ++samples;
         }
       }
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         if (on[c]) {
-          const float t = P.cone_w[c] * (1.0f - cb.alpha[c]);
+          const float t = P.cone_w[c] * (1.0f - alpha[c]);
           dr = __fmaf_rn(t, s[c].x, dr); dg = __fmaf_rn(t, s[c].y, dg); db = __fmaf_rn(t, s[c].z, db);
           docc = __fmaf_rn(t * s[c].w, rocc, docc);
-          cb.alpha[c] = __fmaf_rn(1.0f - cb.alpha[c], s[c].w, cb.alpha[c]);
-          any = any || (cb.alpha[c] < max_alpha);
+          alpha[c] = __fmaf_rn(1.0f - alpha[c], s[c].w, alpha[c]);
+          any = any || (alpha[c] < max_alpha);
         }
       }
       d_any = any;
       ddist = __fmaf_rn(diam, step_mult, ddist);
     }
     if (s_on) {
-      const float t = 1.0f - salpha;
-      sr = __fmaf_rn(t, ss.x, sr); sg = __fmaf_rn(t, ss.y, sg); sb = __fmaf_rn(t, ss.z, sb);
-      const float ta = t * ss.w;
-      socc = __fmaf_rn(ta, __frcp_rn(__fmaf_rn(0.03f, sdiam, 1.0f)), socc);
-      salpha += ta;
-      sdist = __fmaf_rn(sdiam, step_mult, sdist);
+#pragma unroll
+      for (int q = 0; q < SU; ++q) {
+        if (sdist < max_dist && salpha < max_alpha) {   // VoxelConeTracing.fs:94 loop condition, evaluated per step
+          const float t = 1.0f - salpha;
+          sr = __fmaf_rn(t, ss[q].x, sr); sg = __fmaf_rn(t, ss[q].y, sg); sb = __fmaf_rn(t, ss[q].z, sb);
+          const float ta = t * ss[q].w;
+          socc = __fmaf_rn(ta, __frcp_rn(__fmaf_rn(0.03f, sdiam[q], 1.0f)), socc);
+          salpha += ta;
+          sdist = __fmaf_rn(sdiam[q], step_mult, sdist);
+          ++samples;
+        }
+      }
     }
   }
   diffuse = make_float4(dr, dg, db, docc);
@@ -346,18 +366,22 @@ __device__ __forceinline__ unsigned char to_unorm8(float x) {
 }
 
 // one warp = 8x4 pixels; block = 8 warps = 32x8 pixels
-template <int NC>
-__global__ void __launch_bounds__(256, 3) cone_trace(Params P, const float* __restrict__ verts,
+template <int NC, int SU>
+__global__ void __launch_bounds__(256, 2) cone_trace(Params P, const float* __restrict__ verts,
                                                   const uint32_t* __restrict__ idx,
                                                   const uint16_t* __restrict__ trimat,
                                                   const MaterialDev* __restrict__ mats,
                                                   const uint32_t* __restrict__ depth,
                                                   const unsigned long long* __restrict__ vis,
                                                   cudaTextureObject_t grid, uchar4* __restrict__ frame,
-                                                  Counters* __restrict__ ctr, int y_begin, int y_end) {
+                                                  Counters* __restrict__ ctr, int y_begin, int y_end, int lane_map) {
+  extern __shared__ float s_dirs[];   // [3][NC][blockDim.x]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
-  const int j = y_begin + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+  int lx, ly;
+  if (lane_map == 1) { lx = (lane & 1) | ((lane >> 1) & 6); ly = ((lane >> 1) & 1) | ((lane >> 3) & 2); }   // 2x2 quads in 8x4
+  else { lx = lane & 7; ly = lane >> 3; }                                                                     // rows of 8
+  const int i = blockIdx.x * 32 + (warp & 3) * 8 + lx;
+  const int j = y_begin + blockIdx.y * 8 + (warp >> 2) * 4 + ly;
   unsigned samples = 0;
   if (i < P.W && j < y_end) {
     const unsigned long long key = vis[(size_t)j * P.W + i];
@@ -408,7 +432,7 @@ __global__ void __launch_bounds__(256, 3) cone_trace(Params P, const float* __re
       const float c01 = Bw.z * Nw.x - Bw.x * Nw.z;
       const float c02 = Bw.x * Nw.y - Bw.y * Nw.x;
       const float det = (Tw.x * c00 + Tw.y * c01) + Tw.z * c02;
-      const float id = 1.0f / det;
+      const float id = __frcp_rn(det);
       float inv[3][3];
       inv[0][0] = c00 * id; inv[1][0] = c01 * id; inv[2][0] = c02 * id;
       inv[0][1] = (Tw.z * Nw.y - Tw.y * Nw.z) * id;
@@ -428,12 +452,12 @@ __global__ void __launch_bounds__(256, 3) cone_trace(Params P, const float* __re
       const float h0 = sample_mat(m.height, m.hw, m.hh, q, 0.0f, 0.0f).x;
       const float hx = sample_mat(m.height, m.hw, m.hh, q, offx, 0.0f).x;
       const float hy = sample_mat(m.height, m.hw, m.hh, q, 0.0f, offy).x;
-      const V3 t1 = vnormalize(v3(1.0f, 0.0f, hx - h0));
-      const V3 t2 = vnormalize(v3(0.0f, 1.0f, hy - h0));
-      const V3 bump = vnormalize(vcross(t1, t2));
-      const V3 N = vnormalize(tbn_mul(bump));
-      const V3 L = vnormalize(v3(P.light[0], P.light[1], P.light[2]));   // :179
-      const V3 E = vnormalize(Cd);                                         // :181
+      const V3 t1 = vnormalize_fast(v3(1.0f, 0.0f, hx - h0));
+      const V3 t2 = vnormalize_fast(v3(0.0f, 1.0f, hy - h0));
+      const V3 bump = vnormalize_fast(vcross(t1, t2));
+      const V3 N = vnormalize_fast(tbn_mul(bump));
+      const V3 L = vnormalize_fast(v3(P.light[0], P.light[1], P.light[2]));   // :179
+      const V3 E = vnormalize_fast(Cd);                                         // :181
 
       // :186 with the *0.111 normalisation of :158
       const float shadow = pcf_lit_taps(depth, P.S, P.pcf_radius, P.shadow_bias, pdx, pdy, pdz, pdw) * 0.111f;
@@ -441,25 +465,26 @@ __global__ void __launch_bounds__(256, 3) cone_trace(Params P, const float* __re
 
       const ConeConsts kc = cone_consts(P);
       const V3 start = vadd(Pw, vscale(Nw, kc.vws));                       // :92
-      ConeBundle<NC> cb;
+      float* sdir = s_dirs + threadIdx.x;
 #pragma unroll
       for (int cidx = 0; cidx < NC; ++cidx) {                              // :196-199
-        V3 dir = v3(0.0f, 0.0f, 1.0f);
-        if (cidx < P.n_cones)
-          dir = vnormalize(tbn_mul(v3(P.cone_dir[cidx * 3], P.cone_dir[cidx * 3 + 1], P.cone_dir[cidx * 3 + 2])));
-        cb.du[cidx] = dir.x * kc.inv_grid; cb.dv[cidx] = dir.y * kc.inv_grid; cb.dw[cidx] = dir.z * kc.inv_grid;
-        cb.alpha[cidx] = 0.0f;
+        if (cidx < P.n_cones) {
+          const V3 dir = vnormalize_fast(tbn_mul(v3(P.cone_dir[cidx * 3], P.cone_dir[cidx * 3 + 1], P.cone_dir[cidx * 3 + 2])));
+          sdir[(0 * NC + cidx) * blockDim.x] = dir.x * kc.inv_grid;
+          sdir[(1 * NC + cidx) * blockDim.x] = dir.y * kc.inv_grid;
+          sdir[(2 * NC + cidx) * blockDim.x] = dir.z * kc.inv_grid;
+        }
       }
       float4 sc = sample_mat(m.specular, m.sw, m.sh, q, 0.0f, 0.0f);      // :209
       if (!(sqrtf(sc.y * sc.y + sc.z * sc.z) > 0.0f)) { sc.y = sc.x; sc.z = sc.x; }   // .rrra, :210
       const V3 negL = v3(-L.x, -L.y, -L.z);
-      const V3 R = vnormalize(vsub(negL, vscale(N, 2.0f * vdot(N, negL))));           // :212
-      const float spec = powf(fmaxf(vdot(E, R), 0.0f), m.shininess);                  // :213
+      const V3 R = vnormalize_fast(vsub(negL, vscale(N, 2.0f * vdot(N, negL))));      // :212
+      const float spec = __powf(fmaxf(vdot(E, R), 0.0f), m.shininess);                // :213
       const float directSpec = spec * shadow;                                         // :214
       const V3 negE = v3(-E.x, -E.y, -E.z);
-      const V3 refl = vnormalize(vsub(negE, vscale(N, 2.0f * vdot(N, negE))));        // :217
+      const V3 refl = vnormalize_fast(vsub(negE, vscale(N, 2.0f * vdot(N, negE))));   // :217
       float4 idf, isp;
-      march_pixel<NC>(grid, P, kc, start, cb, refl, idf, isp, samples);               // :196-199 and :218
+      march_pixel<NC, SU>(grid, P, kc, start, sdir, refl, idf, isp, samples);               // :196-199 and :218
       const float ir = idf.x, ig = idf.y, ib = idf.z, ia = idf.w;
       const float occlusion = 1.0f - ia;                                   // :201
       const float specOcc = 1.0f - isp.w;                                             // :221
@@ -493,12 +518,16 @@ int launch_cone(vct_context* c) {
   const int y0 = c->P.row_begin, y1 = (c->P.row_end > 0 && c->P.row_end < c->P.H) ? c->P.row_end : c->P.H;
   if (y0 >= y1) return VCT_OK;
   dim3 b(256), g((c->P.W + 31) / 32, (y1 - y0 + 7) / 8);
-  if (c->P.n_cones <= 6)
-    cone_trace<6><<<g, b, 0, c->stream>>>(c->P, c->d_verts, c->d_idx, c->d_trimat, c->d_materials, c->d_depth, c->d_vis,
-                                          c->grid_tex, c->d_frame, c->d_counters, y0, y1);
-  else
-    cone_trace<16><<<g, b, 0, c->stream>>>(c->P, c->d_verts, c->d_idx, c->d_trimat, c->d_materials, c->d_depth, c->d_vis,
-                                           c->grid_tex, c->d_frame, c->d_counters, y0, y1);
+#define VCT_LAUNCH_CONE(NC, SU)                                                                                   \
+  cone_trace<NC, SU><<<g, b, 3 * NC * 256 * sizeof(float), c->stream>>>(c->P, c->d_verts, c->d_idx, c->d_trimat,    \
+      c->d_materials, c->d_depth, c->d_vis, c->grid_tex, c->d_frame, c->d_counters, y0, y1, c->debug_lane_map)
+  const int su = c->debug_spec_ahead;
+  if (c->P.n_cones <= 6) {
+    if (su == 1) VCT_LAUNCH_CONE(6, 1); else if (su == 2) VCT_LAUNCH_CONE(6, 2); else VCT_LAUNCH_CONE(6, 4);
+  } else {
+    if (su == 1) VCT_LAUNCH_CONE(16, 1); else VCT_LAUNCH_CONE(16, 2);
+  }
+#undef VCT_LAUNCH_CONE
   c->launches += 1;
   VCT_CUDA(c, cudaGetLastError());
   return VCT_OK;

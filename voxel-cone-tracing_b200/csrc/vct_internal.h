@@ -75,6 +75,8 @@ struct vct_context {
   bool profile = true;
   int dense_resolve = 0;
   int grid_format = 0;
+  int debug_lane_map = 1;
+  int debug_spec_ahead = 4;   // specular steps fetched ahead per iteration (1, 2, 4)
   size_t max_fragments = 16u << 20;
   size_t max_items = 4u << 20;
 
@@ -375,11 +377,10 @@ __device__ __forceinline__ float pcf_lit_taps(const uint32_t* __restrict__ depth
 __device__ __forceinline__ float lod_from_derivs(float dudx, float dvdx, float dudy, float dvdy, int w, int h) {
   float ax = dudx * (float)w, bx = dvdx * (float)h;
   float ay = dudy * (float)w, by = dvdy * (float)h;
-  float rx = sqrtf(ax * ax + bx * bx);
-  float ry = sqrtf(ay * ay + by * by);
-  float rho = fmaxf(rx, ry);
-  if (!(rho > 0.0f)) return 0.0f;
-  return log2f(rho);
+  // log2(max(sqrt(p), sqrt(q))) = 0.5 * log2(max(p, q)); MUFU.LG2 -- the hardware quantises lambda to 1/256 anyway
+  float rho2 = fmaxf(ax * ax + bx * bx, ay * ay + by * by);
+  if (!(rho2 > 0.0f)) return 0.0f;
+  return 0.5f * __log2f(rho2);
 }
 
 __device__ __forceinline__ float4 sample_material(cudaTextureObject_t t, float u, float v, float lod) {
