@@ -277,6 +277,55 @@ int sync_materials(vct_context* c) {
   return VCT_OK;
 }
 
+// ---- vertex pass
+__global__ void vertex_pass(Params P, const float* __restrict__ verts, size_t nv, VertexCache vc) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nv) return;
+  const float* v = verts + i * 14;
+  const float px = v[0], py = v[1], pz = v[2];
+  F4 w = mul_mat_vec(P.model, px, py, pz, 1.0f);                         // Voxelization.vs:21, VoxelConeTracing.vs:27
+  vc.world[i] = make_float4(w.x, w.y, w.z, w.w);
+  F4 d = mul_mat_vec(P.depth_mvp, px, py, pz, 1.0f);                     // Voxelization.vs:18-19, VoxelConeTracing.vs:28-29
+  vc.dc[i] = make_float4(d.x * 0.5f + 0.5f, d.y * 0.5f + 0.5f, d.z * 0.5f + 0.5f, d.w);
+  F4 e = mul_mat_vec(P.model_view, px, py, pz, 1.0f);                    // VoxelConeTracing.vs:25
+  F4 c = mul_mat_vec(P.proj, e.x, e.y, e.z, e.w);
+  const bool finite = isfinite(c.x) && isfinite(c.y) && isfinite(c.z) && isfinite(c.w);
+  vc.clip[i] = make_float4((c.x + c.w) * (0.5f * (float)P.W), (c.y + c.w) * (0.5f * (float)P.H),
+                           finite ? c.w : __int_as_float(0x7fc00000), c.z);
+  F4 n = mul_mat_vec(P.model, v[3], v[4], v[5], 0.0f);                   // VoxelConeTracing.vs:31-33
+  F4 t = mul_mat_vec(P.model, v[8], v[9], v[10], 0.0f);
+  F4 b = mul_mat_vec(P.model, v[11], v[12], v[13], 0.0f);
+  vc.nrm_u[i] = make_float4(n.x, n.y, n.z, v[6]);
+  vc.tan_v[i] = make_float4(t.x, t.y, t.z, v[7]);
+  vc.bit[i] = make_float4(b.x, b.y, b.z, 0.0f);
+}
+
+static void free_vertex_cache(vct_context* c) {
+  cudaFree(c->vcache.world); cudaFree(c->vcache.dc); cudaFree(c->vcache.clip);
+  cudaFree(c->vcache.nrm_u); cudaFree(c->vcache.tan_v); cudaFree(c->vcache.bit);
+  c->vcache = VertexCache{}; c->vcache_nv = 0; c->vcache_valid = false;
+}
+
+int ensure_vertex_cache(vct_context* c) {
+  if (!c->nv) return set_error(c, VCT_ERR_STATE, "no mesh uploaded");
+  if (c->vcache_nv != c->nv) {
+    free_vertex_cache(c);
+    float4** arr[] = {&c->vcache.world, &c->vcache.dc, &c->vcache.clip, &c->vcache.nrm_u, &c->vcache.tan_v, &c->vcache.bit};
+    for (float4** a : arr) VCT_CUDA(c, cudaMalloc(a, c->nv * sizeof(float4)));
+    c->vcache_nv = c->nv;
+  }
+  const Params& P = c->P; const Params& Q = c->vcache_params;
+  const bool same = c->vcache_valid && P.W == Q.W && P.H == Q.H && !std::memcmp(P.model, Q.model, sizeof(P.model)) &&
+                    !std::memcmp(P.model_view, Q.model_view, sizeof(P.model_view)) && !std::memcmp(P.proj, Q.proj, sizeof(P.proj)) &&
+                    !std::memcmp(P.depth_mvp, Q.depth_mvp, sizeof(P.depth_mvp));
+  if (same) return VCT_OK;
+  vertex_pass<<<(unsigned)((c->nv + 127) / 128), 128, 0, c->stream>>>(c->P, c->d_verts, c->nv, c->vcache);
+  c->launches += 1;
+  c->vcache_params = c->P;
+  c->vcache_valid = true;
+  return check_cuda(c, cudaGetLastError(), "vertex_pass");
+}
+
 // ------------------------------------------------------------------------------------------ tex bench
 __global__ void fill_level_random(cudaSurfaceObject_t s, int n, unsigned seed) {
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, z = blockIdx.z;
@@ -347,6 +396,7 @@ int vct_destroy(vct_handle c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   free_grid(c);
+  free_vertex_cache(c);
   for (auto& t : c->textures) free_texture(t);
   if (c->white_tex) cudaDestroyTextureObject(c->white_tex);
   if (c->white_arr) cudaFreeMipmappedArray(c->white_arr);
@@ -517,6 +567,7 @@ int vct_upload_mesh(vct_handle c, const float* verts, size_t nv, const uint32_t*
   VCT_CUDA(c, cudaStreamSynchronize(c->stream));
   c->nv = nv; c->nt = nt;
   c->depth_valid = false;
+  c->vcache_valid = false;
   return VCT_OK;
 }
 
@@ -542,6 +593,7 @@ int vct_update_positions(vct_handle c, const float* xyz, size_t nv, int on_devic
   c->launches += 1;
   if (tmp) { cudaStreamSynchronize(c->stream); cudaFree(tmp); }
   c->depth_valid = false;
+  c->vcache_valid = false;
   return check_cuda(c, cudaGetLastError(), "scatter_positions");
 }
 

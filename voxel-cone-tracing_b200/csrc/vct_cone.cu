@@ -36,7 +36,7 @@ struct HTri {
 
 // VoxelConeTracing.vs:25 + viewport transform + GL_CULL_FACE(GL_BACK) as homogeneous set-up
 template <bool WITH_BBOX>
-__device__ __forceinline__ bool setup_htri(const Params& P, const float* __restrict__ verts,
+__device__ __forceinline__ bool setup_htri(const Params& P, const VertexCache& vc,
                                            const uint32_t* __restrict__ idx, uint32_t tri, HTri& t, int& i0,
                                            int& i1, int& j0, int& j1) {
   const float W = (float)P.W, H = (float)P.H;
@@ -44,15 +44,10 @@ __device__ __forceinline__ bool setup_htri(const Params& P, const float* __restr
   bool any_near = false;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    const float* v = verts + (size_t)__ldg(&idx[tri * 3 + k]) * 14;
-    F4 e = mul_mat_vec(P.model_view, __ldg(v), __ldg(v + 1), __ldg(v + 2), 1.0f);
-    F4 c = mul_mat_vec(P.proj, e.x, e.y, e.z, e.w);
-    if (!isfinite(c.x) || !isfinite(c.y) || !isfinite(c.z) || !isfinite(c.w)) return false;
-    t.c[k].X = (c.x + c.w) * (0.5f * W);
-    t.c[k].Y = (c.y + c.w) * (0.5f * H);
-    t.c[k].w = c.w;
-    t.c[k].zc = c.z;
-    in_near[k] = (c.z >= -c.w) && (c.w > 0.0f);
+    const float4 c = __ldg(&vc.clip[__ldg(&idx[tri * 3 + k])]);       // VoxelConeTracing.vs:25 + viewport (vertex_pass)
+    if (!(c.z == c.z)) return false;                                   // a clip coordinate was not finite
+    t.c[k].X = c.x; t.c[k].Y = c.y; t.c[k].w = c.z; t.c[k].zc = c.w;
+    in_near[k] = (c.w >= -c.z) && (c.z > 0.0f);
     any_near |= in_near[k];
   }
   if (!any_near) return false;
@@ -110,13 +105,11 @@ __device__ __forceinline__ float bary3(const float b[3], float a0, float a1, flo
 
 struct PixelUV { float u, v, dudx, dvdx, dudy, dvdy; };
 
-__device__ __forceinline__ PixelUV pixel_uv(const float* __restrict__ verts, const uint32_t* __restrict__ idx,
+__device__ __forceinline__ PixelUV pixel_uv(const VertexCache& vc, const uint32_t* __restrict__ idx,
                                             uint32_t tri, const HTri& t, float px, float py, const float b[3]) {
-  const float* v0 = verts + (size_t)__ldg(&idx[tri * 3 + 0]) * 14;
-  const float* v1 = verts + (size_t)__ldg(&idx[tri * 3 + 1]) * 14;
-  const float* v2 = verts + (size_t)__ldg(&idx[tri * 3 + 2]) * 14;
-  const float u0 = __ldg(v0 + 6), u1 = __ldg(v1 + 6), u2 = __ldg(v2 + 6);
-  const float w0 = __ldg(v0 + 7), w1 = __ldg(v1 + 7), w2 = __ldg(v2 + 7);
+  const uint32_t i0 = __ldg(&idx[tri * 3 + 0]), i1 = __ldg(&idx[tri * 3 + 1]), i2 = __ldg(&idx[tri * 3 + 2]);
+  const float u0 = __ldg(&vc.nrm_u[i0].w), u1 = __ldg(&vc.nrm_u[i1].w), u2 = __ldg(&vc.nrm_u[i2].w);
+  const float w0 = __ldg(&vc.tan_v[i0].w), w1 = __ldg(&vc.tan_v[i1].w), w2 = __ldg(&vc.tan_v[i2].w);
   PixelUV r;
   r.u = bary3(b, u0, u1, u2);
   r.v = bary3(b, w0, w1, w2);
@@ -138,13 +131,13 @@ __device__ __forceinline__ float4 sample_mat(cudaTextureObject_t tex, int w, int
 // ---------------------------------------------------------------------------------------------------
 struct VisibilityPass {
   Params P;
-  const float* verts; const uint32_t* idx; const uint16_t* trimat; const MaterialDev* mats;
+  VertexCache vc; const uint32_t* idx; const uint16_t* trimat; const MaterialDev* mats;
   unsigned long long* vis;
 
   struct Setup { HTri t; };
 
   __device__ __forceinline__ bool setup(uint32_t tri, Setup& s, int& i0, int& i1, int& j0, int& j1) const {
-    return setup_htri<true>(P, verts, idx, tri, s.t, i0, i1, j0, j1);
+    return setup_htri<true>(P, vc, idx, tri, s.t, i0, i1, j0, j1);
   }
   __device__ __forceinline__ bool tile_may_cover(const Setup&, int, int, int, int) const { return true; }
 
@@ -158,7 +151,7 @@ struct VisibilityPass {
     if (!(zw >= 0.0f) || zw > 1.0f) return;                 // near / far clip
     const MaterialDev& m = mats[trimat ? trimat[tri] : 0];
     if (m.alpha_test) {                                     // discard, VoxelConeTracing.fs:167-172
-      PixelUV q = pixel_uv(verts, idx, tri, s.t, px, py, b);
+      PixelUV q = pixel_uv(vc, idx, tri, s.t, px, py, b);
       float4 c = sample_mat(m.diffuse, m.dw, m.dh, q, 0.0f, 0.0f);
       if (c.w < 0.5f) return;
     }
@@ -186,11 +179,12 @@ int launch_visibility(vct_context* c) {
   int rc = ensure_frame(c); if (rc) return rc;
   rc = ensure_queues(c); if (rc) return rc;
   rc = sync_materials(c); if (rc) return rc;
+  rc = ensure_vertex_cache(c); if (rc) return rc;
   PassTimer timer(c, VCT_PASS_VISIBILITY);
   const size_t n = (size_t)c->P.W * c->P.H;
   fill_u64<<<148 * 4, 256, 0, c->stream>>>(c->d_vis, n, ~0ull);
   VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_items, 0, sizeof(unsigned int), c->stream));
-  VisibilityPass pass{c->P, c->d_verts, c->d_idx, c->d_trimat, c->d_materials, c->d_vis};
+  VisibilityPass pass{c->P, c->vcache, c->d_idx, c->d_trimat, c->d_materials, c->d_vis};
   const uint32_t nt = (uint32_t)c->nt;
   raster_small<VisibilityPass><<<(nt + 127) / 128, 128, 0, c->stream>>>(pass, 0, nt, c->d_items,
                                                                         (uint32_t)c->items_cap, c->d_counters);
@@ -367,7 +361,7 @@ __device__ __forceinline__ unsigned char to_unorm8(float x) {
 
 // one warp = 8x4 pixels; block = 8 warps = 32x8 pixels
 template <int NC, int SU>
-__global__ void __launch_bounds__(256, 2) cone_trace(Params P, const float* __restrict__ verts,
+__global__ void __launch_bounds__(256, 2) cone_trace(Params P, VertexCache vc,
                                                   const uint32_t* __restrict__ idx,
                                                   const uint16_t* __restrict__ trimat,
                                                   const MaterialDev* __restrict__ mats,
@@ -394,7 +388,7 @@ __global__ void __launch_bounds__(256, 2) cone_trace(Params P, const float* __re
       const uint32_t tri = (uint32_t)key;
       HTri t;
       int d0, d1, d2, d3;
-      setup_htri<false>(P, verts, idx, tri, t, d0, d1, d2, d3);
+      setup_htri<false>(P, vc, idx, tri, t, d0, d1, d2, d3);
       const float px = (float)i + 0.5f, py = (float)j + 0.5f;
       float b[3];
       hbary<false>(t, px, py, b);
@@ -402,17 +396,12 @@ __global__ void __launch_bounds__(256, 2) cone_trace(Params P, const float* __re
       V3 Pw = v3(0, 0, 0), Nw = v3(0, 0, 0), Tw = v3(0, 0, 0), Bw = v3(0, 0, 0);
       float pdx = 0, pdy = 0, pdz = 0, pdw = 0;
       {
-        F4 pw[3], pd[3], nw[3], tw[3], bw[3];
+        float4 pw[3], pd[3], nw[3], tw[3], bw[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          const float* v = verts + (size_t)__ldg(&idx[tri * 3 + k]) * 14;
-          float p0 = __ldg(v), p1 = __ldg(v + 1), p2 = __ldg(v + 2);
-          pw[k] = mul_mat_vec(P.model, p0, p1, p2, 1.0f);
-          pd[k] = mul_mat_vec(P.depth_mvp, p0, p1, p2, 1.0f);
-          pd[k].x = pd[k].x * 0.5f + 0.5f; pd[k].y = pd[k].y * 0.5f + 0.5f; pd[k].z = pd[k].z * 0.5f + 0.5f;
-          nw[k] = mul_mat_vec(P.model, __ldg(v + 3), __ldg(v + 4), __ldg(v + 5), 0.0f);
-          tw[k] = mul_mat_vec(P.model, __ldg(v + 8), __ldg(v + 9), __ldg(v + 10), 0.0f);
-          bw[k] = mul_mat_vec(P.model, __ldg(v + 11), __ldg(v + 12), __ldg(v + 13), 0.0f);
+          const uint32_t vi = __ldg(&idx[tri * 3 + k]);
+          pw[k] = __ldg(&vc.world[vi]); pd[k] = __ldg(&vc.dc[vi]);
+          nw[k] = __ldg(&vc.nrm_u[vi]); tw[k] = __ldg(&vc.tan_v[vi]); bw[k] = __ldg(&vc.bit[vi]);
         }
         Pw = v3(bary3(b, pw[0].x, pw[1].x, pw[2].x), bary3(b, pw[0].y, pw[1].y, pw[2].y), bary3(b, pw[0].z, pw[1].z, pw[2].z));
         Nw = v3(bary3(b, nw[0].x, nw[1].x, nw[2].x), bary3(b, nw[0].y, nw[1].y, nw[2].y), bary3(b, nw[0].z, nw[1].z, nw[2].z));
@@ -424,7 +413,7 @@ __global__ void __launch_bounds__(256, 2) cone_trace(Params P, const float* __re
       const V3 Cd = vsub(v3(P.cam[0], P.cam[1], P.cam[2]), Pw);       // VoxelConeTracing.vs:34
 
       const MaterialDev m = mats[trimat ? trimat[tri] : 0];
-      const PixelUV q = pixel_uv(verts, idx, tri, t, px, py, b);
+      const PixelUV q = pixel_uv(vc, idx, tri, t, px, py, b);
       const float4 mat = sample_mat(m.diffuse, m.dw, m.dh, q, 0.0f, 0.0f);    // :167
 
       // TBN = inverse(transpose(mat3(T,B,N))), :175 -- rows of the matrix being inverted are T, B, N
@@ -513,13 +502,14 @@ int launch_cone(vct_context* c) {
   int rc = ensure_frame(c); if (rc) return rc;
   rc = ensure_grid(c); if (rc) return rc;
   if (!c->depth_valid) return set_error(c, VCT_ERR_STATE, "vct_render: call vct_draw_depth first (shadow map missing)");
+  rc = ensure_vertex_cache(c); if (rc) return rc;
   PassTimer timer(c, VCT_PASS_CONE);
   VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->cone_samples, 0, sizeof(unsigned long long), c->stream));
   const int y0 = c->P.row_begin, y1 = (c->P.row_end > 0 && c->P.row_end < c->P.H) ? c->P.row_end : c->P.H;
   if (y0 >= y1) return VCT_OK;
   dim3 b(256), g((c->P.W + 31) / 32, (y1 - y0 + 7) / 8);
 #define VCT_LAUNCH_CONE(NC, SU)                                                                                   \
-  cone_trace<NC, SU><<<g, b, 3 * NC * 256 * sizeof(float), c->stream>>>(c->P, c->d_verts, c->d_idx, c->d_trimat,    \
+  cone_trace<NC, SU><<<g, b, 3 * NC * 256 * sizeof(float), c->stream>>>(c->P, c->vcache, c->d_idx, c->d_trimat,    \
       c->d_materials, c->d_depth, c->d_vis, c->grid_tex, c->d_frame, c->d_counters, y0, y1, c->debug_lane_map)
   const int su = c->debug_spec_ahead;
   if (c->P.n_cones <= 6) {

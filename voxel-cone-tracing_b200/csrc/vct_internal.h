@@ -63,6 +63,19 @@ struct Counters {
   unsigned int n_prev_touched; unsigned int pad5[31];
 };
 
+// Per-vertex transform cache written once per frame by vertex_pass -- the vertex-shader stage of the three
+// reference programs (Voxelization.vs:15-22, VoxelConeTracing.vs:23-37) evaluated once per vertex, as GL does,
+// instead of once per triangle / tile / pixel.  Same arithmetic as the per-use form, so every consumer sees
+// bit-identical values.
+struct VertexCache {
+  float4* world;   // ModelMatrix * (Position,1)
+  float4* dc;      // DepthMVP * (Position,1), xyz*0.5+0.5
+  float4* clip;    // window-homogeneous (X, Y, w, z_clip); w = NaN if any clip coordinate is not finite
+  float4* nrm_u;   // (ModelMatrix*(Normal,0)).xyz, TexCoords.x
+  float4* tan_v;   // (ModelMatrix*(Tangent,0)).xyz, TexCoords.y
+  float4* bit;     // (ModelMatrix*(BiTangent,0)).xyz, 0
+};
+
 struct TileItem { uint32_t tri; uint32_t origin; };   // origin = tile_x | tile_y << 16 (in tiles)
 
 }  // namespace vct
@@ -87,6 +100,8 @@ struct vct_context {
   std::vector<vct::MaterialHost> materials;
   vct::MaterialDev* d_materials = nullptr; size_t n_materials_dev = 0; bool materials_dirty = true;
   cudaTextureObject_t white_tex = 0; cudaMipmappedArray_t white_arr = nullptr;
+
+  vct::VertexCache vcache{}; size_t vcache_nv = 0; bool vcache_valid = false; vct::Params vcache_params{};
 
   // shadow map (u32 d24, linear)
   uint32_t* d_depth = nullptr; int depth_S = 0; bool depth_valid = false;
@@ -144,6 +159,7 @@ int ensure_shadow(vct_context* c);
 int ensure_frame(vct_context* c);
 int ensure_queues(vct_context* c);
 int sync_materials(vct_context* c);
+int ensure_vertex_cache(vct_context* c);
 int launch_shadow(vct_context* c);
 int launch_voxel_clear(vct_context* c);
 int launch_voxelize(vct_context* c, size_t tb, size_t te);

@@ -6,7 +6,7 @@
 //                x) and writes levels L+1, L+2, L+3, staging the intermediate levels in shared memory.
 //                HBM traffic = read L once + write the three children.
 //   mip_tail   : one CTA reduces a level of <= 32^3 texels down to 1^3 entirely in shared memory.
-// At V = 256 the pyramid is built by two launches: fused3(0 -> 1,2,3) and tail(3 -> 4..8).
+// At V = 256 the pyramid is built by three launches: fused3(0 -> 1,2,3), fused3(3 -> 4,5,6), tail(6 -> 7,8).
 #include "vct_internal.h"
 
 namespace vct {
@@ -132,7 +132,7 @@ int launch_mip(vct_context* c) {
   PassTimer timer(c, VCT_PASS_MIP);
   const int levels = c->P.levels;
   int l = 0, n = c->P.V;
-  while (n > 32 && l + 3 < levels) {
+  while (n >= 32 && l + 3 < levels) {
     dim3 b(8, 4, 4), g(n / 32, n / 8, n / 8);
     mip_fused3<<<g, b, 0, c->stream>>>(c->grid_surf[l], c->grid_surf[l + 1], c->grid_surf[l + 2], c->grid_surf[l + 3]);
     c->launches += 1;

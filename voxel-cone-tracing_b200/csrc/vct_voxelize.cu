@@ -28,7 +28,7 @@ struct VoxTri {
 };
 
 template <bool WITH_ATTRS>
-__device__ __forceinline__ bool vox_setup(const Params& P, const float* __restrict__ verts,
+__device__ __forceinline__ bool vox_setup(const Params& P, const VertexCache& vc,
                                           const uint32_t* __restrict__ idx, uint32_t tri, VoxTri& s,
                                           float (*uv)[2], F4* dc) {
   const int V = P.V;
@@ -37,13 +37,13 @@ __device__ __forceinline__ bool vox_setup(const Params& P, const float* __restri
   F4 tdc[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    const float* v = verts + (size_t)__ldg(&idx[tri * 3 + k]) * 14;
-    float px = __ldg(v), py = __ldg(v + 1), pz = __ldg(v + 2);
-    world[k] = mul_mat_vec(P.model, px, py, pz, 1.0f);                    // Voxelization.vs:21
+    const uint32_t vi = __ldg(&idx[tri * 3 + k]);
+    const float4 w = __ldg(&vc.world[vi]);                                // Voxelization.vs:21 (vertex_pass)
+    world[k].x = w.x; world[k].y = w.y; world[k].z = w.z; world[k].w = w.w;
     if (WITH_ATTRS) {
-      tdc[k] = mul_mat_vec(P.depth_mvp, px, py, pz, 1.0f);                 // Voxelization.vs:18
-      tdc[k].x = tdc[k].x * 0.5f + 0.5f; tdc[k].y = tdc[k].y * 0.5f + 0.5f; tdc[k].z = tdc[k].z * 0.5f + 0.5f;
-      tuv[k][0] = __ldg(v + 6); tuv[k][1] = __ldg(v + 7);
+      const float4 d = __ldg(&vc.dc[vi]);                                  // Voxelization.vs:18-19
+      tdc[k].x = d.x; tdc[k].y = d.y; tdc[k].z = d.z; tdc[k].w = d.w;
+      tuv[k][0] = __ldg(&vc.nrm_u[vi].w); tuv[k][1] = __ldg(&vc.tan_v[vi].w);
     }
   }
   // Voxelization.gs:25-39 (decision on the un-normalised |cross|; zero / NaN -> axis 3)
@@ -83,14 +83,14 @@ __device__ __forceinline__ bool vox_setup(const Params& P, const float* __restri
 // ---------------------------------------------------------------------------------------------------
 struct VoxCoverPass {
   Params P;
-  const float* verts; const uint32_t* idx;
+  VertexCache vc; const uint32_t* idx;
   uint2* frags; uint32_t frags_cap;
   Counters* ctr;
 
   struct Setup { VoxTri v; };
 
   __device__ __forceinline__ bool setup(uint32_t tri, Setup& s, int& i0, int& i1, int& j0, int& j1) const {
-    if (!vox_setup<false>(P, verts, idx, tri, s.v, nullptr, nullptr)) return false;
+    if (!vox_setup<false>(P, vc, idx, tri, s.v, nullptr, nullptr)) return false;
     return raster_bbox(s.v.t, P.coverage, P.V, P.V, &i0, &i1, &j0, &j1);
   }
   __device__ __forceinline__ bool tile_may_cover(const Setup& s, int x0, int y0, int x1, int y1) const {
@@ -150,7 +150,7 @@ struct VoxCoverPass {
 };
 
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) vox_shade(Params P, const float* __restrict__ verts,
+__global__ void __launch_bounds__(256) vox_shade(Params P, VertexCache vc,
                                                  const uint32_t* __restrict__ idx,
                                                  const uint16_t* __restrict__ trimat,
                                                  const MaterialDev* __restrict__ mats,
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256) vox_shade(Params P, const float* __restri
     VoxTri s;
     float uv[3][2];
     F4 dc[3];
-    if (!vox_setup<true>(P, verts, idx, tri, s, uv, dc)) continue;   // cannot fail for a queued fragment
+    if (!vox_setup<true>(P, vc, idx, tri, s, uv, dc)) continue;   // cannot fail for a queued fragment
     float l1, l2;
     s.t.lambdas(i, j, &l1, &l2);
     float z = interp3(s.z0, s.z1, s.z2, l1, l2);
@@ -308,13 +308,14 @@ int launch_voxelize(vct_context* c, size_t tb, size_t te) {
   int rc = ensure_grid(c); if (rc) return rc;
   rc = ensure_queues(c); if (rc) return rc;
   rc = sync_materials(c); if (rc) return rc;
+  rc = ensure_vertex_cache(c); if (rc) return rc;
   te = te < c->nt ? te : c->nt;
   if (tb >= te) return VCT_OK;
   {
     PassTimer timer(c, VCT_PASS_VOX_COVER);
     VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_items, 0, sizeof(unsigned int), c->stream));
     VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_fragments, 0, sizeof(unsigned int), c->stream));
-    VoxCoverPass pass{c->P, c->d_verts, c->d_idx, c->d_frags, (uint32_t)c->frags_cap, c->d_counters};
+    VoxCoverPass pass{c->P, c->vcache, c->d_idx, c->d_frags, (uint32_t)c->frags_cap, c->d_counters};
     const uint32_t n = (uint32_t)(te - tb);
     raster_small<VoxCoverPass><<<(n + 127) / 128, 128, 0, c->stream>>>(pass, (uint32_t)tb, (uint32_t)te, c->d_items,
                                                                         (uint32_t)c->items_cap, c->d_counters);
@@ -323,7 +324,7 @@ int launch_voxelize(vct_context* c, size_t tb, size_t te) {
   }
   {
     PassTimer timer(c, VCT_PASS_VOX_SHADE);
-    vox_shade<<<148 * 8, 256, 0, c->stream>>>(c->P, c->d_verts, c->d_idx, c->d_trimat, c->d_materials, c->d_depth,
+    vox_shade<<<148 * 8, 256, 0, c->stream>>>(c->P, c->vcache, c->d_idx, c->d_trimat, c->d_materials, c->d_depth,
                                               c->d_frags, (uint32_t)c->frags_cap, c->d_accum, c->d_touched,
                                               c->d_counters);
     c->launches += 1;
