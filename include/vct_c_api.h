@@ -116,6 +116,7 @@ int vct_frame_buffer(vct_handle h, void** device_ptr, size_t* n_bytes);
 int vct_cone_samples(vct_handle h, uint64_t* n);       /* textureLod calls of the last vct_render */
 int vct_fragment_count(vct_handle h, uint64_t* n);     /* fragments of the last voxelisation */
 int vct_occupied_voxels(vct_handle h, uint64_t* n);
+int vct_debug_counter(vct_handle h, int which, uint64_t* n);   /* diagnostics: 0 = tile work items of the last raster pass */
 
 /* ---- cone queries: Voxel_Cone_Tracing(direction, tanHalfAngle) (VoxelConeTracing.fs:82-107) for arbitrary
  * start points (already offset along the normal, :92).  Host arrays: starts/dirs n*3, tan_half n,

@@ -787,13 +787,18 @@ static void orc_visibility(orc_ctx* o, int y0, int y1) {
     for (int j = std::max(t.j0, y0); j <= std::min(t.j1, y1 - 1); ++j)
       for (int i = t.i0; i <= t.i1; ++i) {
         float px = (float)i + 0.5f, py = (float)j + 0.5f;
-        float b[3];
-        if (!hbary(t, px, py, b, true)) continue;
-        float zc = bary3(b, t.c[0].zc, t.c[1].zc, t.c[2].zc);
-        float w = bary3(b, t.c[0].w, t.c[1].w, t.c[2].w);
+        /* window depth = z_clip / w_clip at the pixel; both are linear in the (unnormalised) homogeneous edge
+         * functions, so the common 1/sum cancels: one division per fragment */
+        float e0 = heval(t.e[0], px, py), e1 = heval(t.e[1], px, py), e2 = heval(t.e[2], px, py);
+        if (!(hinside(t.e[0], e0) && hinside(t.e[1], e1) && hinside(t.e[2], e2))) continue;
+        if (!((e0 + e1) + e2 > 0.0f)) continue;
+        float zc = (e0 * t.c[0].zc + e1 * t.c[1].zc) + e2 * t.c[2].zc;
+        float w = (e0 * t.c[0].w + e1 * t.c[1].w) + e2 * t.c[2].w;
         float zw = (zc / w) * 0.5f + 0.5f;
         if (!(zw >= 0.0f) || zw > 1.0f) continue;           /* near / far clip */
+        float b[3];
         if (alpha_test) {                                   /* discard, VoxelConeTracing.fs:167-172 */
+          hbary(t, px, py, b, false);
           PixelUV q = pixel_uv(o, (size_t)ti, t, px, py, b);
           float c[4];
           sample_material(o, m.diffuse, q, 0, 0, c);

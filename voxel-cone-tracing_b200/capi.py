@@ -20,7 +20,7 @@ SYMBOLS = [
     "vct_upload_mesh", "vct_update_positions", "vct_draw_depth", "vct_draw_voxels", "vct_render", "vct_frame",
     "vct_voxelize_range", "vct_accum_buffer", "vct_resolve_and_mip", "vct_readback_depth", "vct_readback_counts",
     "vct_readback_sums", "vct_readback_grid", "vct_upload_grid_level0", "vct_build_mips", "vct_readback_visibility",
-    "vct_readback_frame", "vct_frame_buffer", "vct_cone_samples", "vct_fragment_count", "vct_occupied_voxels",
+    "vct_readback_frame", "vct_frame_buffer", "vct_cone_samples", "vct_fragment_count", "vct_occupied_voxels", "vct_debug_counter",
     "vct_trace_cones", "vct_sample_voxels", "vct_set_stream", "vct_use_own_stream", "vct_sync", "vct_pass_time_us", "vct_kernel_launches", "vct_bench_tex3d",
 ]
 
@@ -61,7 +61,7 @@ def load_library(path=None):
         "vct_readback_grid": [vp, i, vp], "vct_upload_grid_level0": [vp, vp], "vct_build_mips": [vp],
         "vct_readback_visibility": [vp, vp], "vct_readback_frame": [vp, vp],
         "vct_frame_buffer": [vp, C.POINTER(vp), C.POINTER(sz)], "vct_cone_samples": [vp, C.POINTER(C.c_uint64)],
-        "vct_fragment_count": [vp, C.POINTER(C.c_uint64)], "vct_occupied_voxels": [vp, C.POINTER(C.c_uint64)],
+        "vct_fragment_count": [vp, C.POINTER(C.c_uint64)], "vct_occupied_voxels": [vp, C.POINTER(C.c_uint64)], "vct_debug_counter": [vp, i, C.POINTER(C.c_uint64)],
         "vct_trace_cones": [vp, sz, vp, vp, vp, vp, vp], "vct_sample_voxels": [vp, sz, vp, vp, vp], "vct_set_stream": [vp, vp], "vct_use_own_stream": [vp], "vct_sync": [vp], "vct_pass_time_us": [vp, i, C.POINTER(f)],
         "vct_kernel_launches": [vp, C.POINTER(C.c_uint64)],
         "vct_bench_tex3d": [vp, i, C.c_uint64, i, f, i, C.POINTER(f)],
@@ -277,6 +277,11 @@ class Context:
 
     def occupied_voxels(self):
         return self._u64(self.L.vct_occupied_voxels)
+
+    def debug_counter(self, which=0):
+        v = C.c_uint64()
+        self._ck(self.L.vct_debug_counter(self.h, int(which), C.byref(v)))
+        return v.value
 
     def kernel_launches(self):
         return self._u64(self.L.vct_kernel_launches)

@@ -764,6 +764,13 @@ int vct_fragment_count(vct_handle c, uint64_t* n) {
   if (n) *n = v;
   return rc;
 }
+int vct_debug_counter(vct_handle c, int which, uint64_t* n) {   /* 0 = work items of the last raster pass */
+  NEED(c);
+  unsigned int v = 0;
+  int rc = read_counter(c, which == 0 ? (const void*)&c->d_counters->n_items : (const void*)&c->d_counters->overflow, &v, 4);
+  if (n) *n = v;
+  return rc;
+}
 int vct_occupied_voxels(vct_handle c, uint64_t* n) {
   NEED(c);
   unsigned int v = 0;

@@ -134,29 +134,47 @@ struct VisibilityPass {
   VertexCache vc; const uint32_t* idx; const uint16_t* trimat; const MaterialDev* mats;
   unsigned long long* vis;
 
+  static constexpr bool kAppends = false;
   struct Setup { HTri t; };
 
   __device__ __forceinline__ bool setup(uint32_t tri, Setup& s, int& i0, int& i1, int& j0, int& j1) const {
     return setup_htri<true>(P, vc, idx, tri, s.t, i0, i1, j0, j1);
   }
-  __device__ __forceinline__ bool tile_may_cover(const Setup&, int, int, int, int) const { return true; }
+  // Exact tile reject.  IEEE rounding is monotonic, so the COMPUTED value (A*px + B*py) + C is monotonic in px
+  // and in py separately; its maximum over the pixel centres of a tile is the computed value at the corner
+  // chosen by the signs of A and B.  If that maximum fails the inside test no pixel of the tile can pass.
+  __device__ __forceinline__ bool tile_may_cover(const Setup& s, int x0, int y0, int x1, int y1) const {
+    const float xa = (float)x0 + 0.5f, xb = (float)(x1 - 1) + 0.5f, ya = (float)y0 + 0.5f, yb = (float)(y1 - 1) + 0.5f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const HEdge& e = s.t.e[k];
+      const float v = heval(e, e.A >= 0.0f ? xb : xa, e.B >= 0.0f ? yb : ya);
+      if (!hinside(e, v)) return false;
+    }
+    return true;
+  }
 
   __device__ __forceinline__ void shade(const Setup& s, uint32_t tri, int i, int j) const {
     const float px = (float)i + 0.5f, py = (float)j + 0.5f;
-    float b[3];
-    if (!hbary<true>(s.t, px, py, b)) return;
-    float zc = bary3(b, s.t.c[0].zc, s.t.c[1].zc, s.t.c[2].zc);
-    float w = bary3(b, s.t.c[0].w, s.t.c[1].w, s.t.c[2].w);
-    float zw = (zc / w) * 0.5f + 0.5f;
+    const float e0 = heval(s.t.e[0], px, py), e1 = heval(s.t.e[1], px, py), e2 = heval(s.t.e[2], px, py);
+    if (!(hinside(s.t.e[0], e0) && hinside(s.t.e[1], e1) && hinside(s.t.e[2], e2))) return;
+    if (!((e0 + e1) + e2 > 0.0f)) return;
+    // z_clip / w_clip: the common 1/(e0+e1+e2) cancels -> one division per fragment
+    const float zc = (e0 * s.t.c[0].zc + e1 * s.t.c[1].zc) + e2 * s.t.c[2].zc;
+    const float w = (e0 * s.t.c[0].w + e1 * s.t.c[1].w) + e2 * s.t.c[2].w;
+    const float zw = (zc / w) * 0.5f + 0.5f;
     if (!(zw >= 0.0f) || zw > 1.0f) return;                 // near / far clip
+    const unsigned long long key = ((unsigned long long)__float_as_uint(zw) << 32) | tri;
+    unsigned long long* cell = &vis[(size_t)j * P.W + i];   // no early-z read: RED.MIN is fire-and-forget, a load is not
     const MaterialDev& m = mats[trimat ? trimat[tri] : 0];
     if (m.alpha_test) {                                     // discard, VoxelConeTracing.fs:167-172
+      float b[3];
+      hbary<false>(s.t, px, py, b);
       PixelUV q = pixel_uv(vc, idx, tri, s.t, px, py, b);
       float4 c = sample_mat(m.diffuse, m.dw, m.dh, q, 0.0f, 0.0f);
       if (c.w < 0.5f) return;
     }
-    unsigned long long key = ((unsigned long long)__float_as_uint(zw) << 32) | tri;
-    atomicMin(&vis[(size_t)j * P.W + i], key);
+    atomicMin(cell, key);
   }
   __device__ __forceinline__ void small(const Setup& s, uint32_t tri, bool active, int i0, int i1, int j0, int j1) const {
     if (!active) return;
@@ -184,6 +202,7 @@ int launch_visibility(vct_context* c) {
   const size_t n = (size_t)c->P.W * c->P.H;
   fill_u64<<<148 * 4, 256, 0, c->stream>>>(c->d_vis, n, ~0ull);
   VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_items, 0, sizeof(unsigned int), c->stream));
+    VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->next_item, 0, sizeof(unsigned int), c->stream));
   VisibilityPass pass{c->P, c->vcache, c->d_idx, c->d_trimat, c->d_materials, c->d_vis};
   const uint32_t nt = (uint32_t)c->nt;
   raster_small<VisibilityPass><<<(nt + 127) / 128, 128, 0, c->stream>>>(pass, 0, nt, c->d_items,

@@ -60,7 +60,7 @@ struct Counters {
   unsigned int n_touched;     unsigned int pad2[31];
   unsigned int overflow;      unsigned int pad3[31];
   unsigned long long cone_samples; unsigned int pad4[30];
-  unsigned int n_prev_touched; unsigned int pad5[31];
+  unsigned int next_item;     unsigned int pad5[31];
 };
 
 // Per-vertex transform cache written once per frame by vertex_pass -- the vertex-shader stage of the three

@@ -11,6 +11,7 @@
 //                   bool tile_may_cover(Setup&, x0,y0,x1,y1)   (exact or conservative reject)
 //                   unsigned small(Setup&, tri, i0,i1,j0,j1)    (thread-serial path)
 //                   void pixel(Setup&, tri, i, j, bool in_bbox) (warp path, called by all 32 lanes)
+//                   static constexpr bool kAppends; if true also covered(), reserve(n), emit(tri,i,j,pos)
 #pragma once
 
 #include "vct_internal.h"
@@ -19,7 +20,7 @@ namespace vct {
 
 constexpr int SMALL_AREA = 16;
 constexpr int TILE = 8;
-constexpr int ITEM_TILES = 32;
+constexpr int ITEM_TILES = 16;
 
 template <class Pass>
 __global__ void __launch_bounds__(128) raster_small(Pass pass, uint32_t tri_begin, uint32_t tri_end,
@@ -54,12 +55,16 @@ __global__ void __launch_bounds__(128) raster_small(Pass pass, uint32_t tri_begi
 
 template <class Pass>
 __global__ void __launch_bounds__(256) raster_tiles(Pass pass, const TileItem* __restrict__ items,
-                                                    uint32_t items_cap, const Counters* __restrict__ ctr) {
+                                                    uint32_t items_cap, Counters* __restrict__ ctr) {
   const uint32_t n_items = min(ctr->n_items, items_cap);
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t warps_per_block = blockDim.x >> 5;
-  const uint32_t n_warps = gridDim.x * warps_per_block;
-  for (uint32_t it = blockIdx.x * warps_per_block + (threadIdx.x >> 5); it < n_items; it += n_warps) {
+  // dynamic distribution: item costs vary by orders of magnitude (slivers vs. screen-filling triangles), so
+  // each warp takes the next item from a ticket counter instead of a static stride
+  while (true) {
+    uint32_t it = 0;
+    if (lane == 0) it = atomicAdd(&ctr->next_item, 1u);
+    it = __shfl_sync(0xffffffffu, it, 0);
+    if (it >= n_items) break;
     TileItem item = items[it];
     typename Pass::Setup s;
     int i0, i1, j0, j1;
@@ -68,15 +73,47 @@ __global__ void __launch_bounds__(256) raster_tiles(Pass pass, const TileItem* _
     uint32_t tw = (uint32_t)(tx1 - tx0 + 1);
     uint32_t ntiles = tw * (uint32_t)(ty1 - ty0 + 1);
     uint32_t t_end = min(item.origin + (uint32_t)ITEM_TILES, ntiles);
-    for (uint32_t t = item.origin; t < t_end; ++t) {
-      int tx = tx0 + (int)(t % tw), ty = ty0 + (int)(t / tw);
-      int px0 = tx * TILE, py0 = ty * TILE;
-      if (!pass.tile_may_cover(s, px0, py0, px0 + TILE, py0 + TILE)) continue;  // warp-uniform
+    if constexpr (Pass::kAppends) {
+      // Passes that append to a queue: count the item's fragments first (ballots only), reserve the whole
+      // range with ONE atomic per item, then write.  The fragment order inside the item stays tile by tile.
+      uint32_t total = 0;
+      for (uint32_t t = item.origin; t < t_end; ++t) {
+        int px0 = (tx0 + (int)(t % tw)) * TILE, py0 = (ty0 + (int)(t / tw)) * TILE;
+        if (!pass.tile_may_cover(s, px0, py0, px0 + TILE, py0 + TILE)) continue;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        int i = px0 + (int)(lane & 7), j = py0 + half * 4 + (int)(lane >> 3);
-        bool in_bbox = i >= i0 && i <= i1 && j >= j0 && j <= j1;
-        pass.pixel(s, item.tri, i, j, in_bbox);
+        for (int half = 0; half < 2; ++half) {
+          int i = px0 + (int)(lane & 7), j = py0 + half * 4 + (int)(lane >> 3);
+          bool cov = i >= i0 && i <= i1 && j >= j0 && j <= j1 && pass.covered(s, i, j);
+          total += __popc(__ballot_sync(0xffffffffu, cov));
+        }
+      }
+      if (!total) continue;
+      uint32_t base = 0;
+      if (lane == 0) base = pass.reserve(total);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      for (uint32_t t = item.origin; t < t_end; ++t) {
+        int px0 = (tx0 + (int)(t % tw)) * TILE, py0 = (ty0 + (int)(t / tw)) * TILE;
+        if (!pass.tile_may_cover(s, px0, py0, px0 + TILE, py0 + TILE)) continue;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          int i = px0 + (int)(lane & 7), j = py0 + half * 4 + (int)(lane >> 3);
+          bool cov = i >= i0 && i <= i1 && j >= j0 && j <= j1 && pass.covered(s, i, j);
+          unsigned m = __ballot_sync(0xffffffffu, cov);
+          if (cov) pass.emit(item.tri, i, j, base + __popc(m & ((1u << lane) - 1)));
+          base += __popc(m);
+        }
+      }
+    } else {
+      for (uint32_t t = item.origin; t < t_end; ++t) {
+        int tx = tx0 + (int)(t % tw), ty = ty0 + (int)(t / tw);
+        int px0 = tx * TILE, py0 = ty * TILE;
+        if (!pass.tile_may_cover(s, px0, py0, px0 + TILE, py0 + TILE)) continue;  // warp-uniform
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          int i = px0 + (int)(lane & 7), j = py0 + half * 4 + (int)(lane >> 3);
+          bool in_bbox = i >= i0 && i <= i1 && j >= j0 && j <= j1;
+          pass.pixel(s, item.tri, i, j, in_bbox);
+        }
       }
     }
   }

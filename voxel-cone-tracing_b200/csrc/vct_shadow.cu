@@ -11,6 +11,7 @@ struct ShadowPass {
   const float* verts; const uint32_t* idx;
   uint32_t* depth;
 
+  static constexpr bool kAppends = false;
   struct Setup { RasterTri t; float z0, z1, z2; };
 
   __device__ __forceinline__ bool setup(uint32_t tri, Setup& s, int& i0, int& i1, int& j0, int& j1) const {
@@ -71,6 +72,7 @@ int launch_shadow(vct_context* c) {
   const size_t n = (size_t)c->P.S * c->P.S;
   fill_u32<<<148 * 8, 256, 0, c->stream>>>(c->d_depth, n, 0xFFFFFFu);
   VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_items, 0, sizeof(unsigned int), c->stream));
+    VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->next_item, 0, sizeof(unsigned int), c->stream));
   ShadowPass pass{c->P, c->d_verts, c->d_idx, c->d_depth};
   const uint32_t nt = (uint32_t)c->nt;
   raster_small<ShadowPass><<<(nt + 127) / 128, 128, 0, c->stream>>>(pass, 0, nt, c->d_items,

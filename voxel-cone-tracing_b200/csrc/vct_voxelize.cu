@@ -131,22 +131,15 @@ struct VoxCoverPass {
     }
   }
 
-  // warp path: one lane per pixel, ballot-aggregated append
-  __device__ __forceinline__ void pixel(const Setup& s, uint32_t tri, int i, int j, bool in_bbox) const {
-    bool cov = in_bbox && s.v.t.covered(i, j, P.coverage);
-    unsigned m = __ballot_sync(0xffffffffu, cov);
-    if (!m) return;
-    unsigned lane = threadIdx.x & 31;
-    unsigned base = 0;
-    int leader = __ffs(m) - 1;
-    if ((int)lane == leader) base = atomicAdd(&ctr->n_fragments, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (cov) {
-      unsigned pos = base + __popc(m & ((1u << lane) - 1));
-      if (pos < frags_cap) frags[pos] = make_uint2(tri, (unsigned)i | ((unsigned)j << 16));
-      else ctr->overflow = 1;
-    }
+  // warp path (raster_tiles, kAppends protocol)
+  static constexpr bool kAppends = true;
+  __device__ __forceinline__ bool covered(const Setup& s, int i, int j) const { return s.v.t.covered(i, j, P.coverage); }
+  __device__ __forceinline__ uint32_t reserve(uint32_t n) const { return atomicAdd(&ctr->n_fragments, n); }
+  __device__ __forceinline__ void emit(uint32_t tri, int i, int j, uint32_t pos) const {
+    if (pos < frags_cap) frags[pos] = make_uint2(tri, (unsigned)i | ((unsigned)j << 16));
+    else ctr->overflow = 1;
   }
+  __device__ __forceinline__ void pixel(const Setup&, uint32_t, int, int, bool) const {}
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -314,6 +307,7 @@ int launch_voxelize(vct_context* c, size_t tb, size_t te) {
   {
     PassTimer timer(c, VCT_PASS_VOX_COVER);
     VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_items, 0, sizeof(unsigned int), c->stream));
+    VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->next_item, 0, sizeof(unsigned int), c->stream));
     VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_fragments, 0, sizeof(unsigned int), c->stream));
     VoxCoverPass pass{c->P, c->vcache, c->d_idx, c->d_frags, (uint32_t)c->frags_cap, c->d_counters};
     const uint32_t n = (uint32_t)(te - tb);
