@@ -96,6 +96,15 @@ int vct_render(vct_handle h, uint8_t* host_rgba);
 /* vct_draw_voxels + vct_render as one call (what the metric "full frames/s" times) */
 int vct_frame(vct_handle h, uint8_t* host_rgba);
 
+/* Pipelined form of vct_frame for render loops (the reference's loop is glClear -> Render -> glfwSwapBuffers,
+ * main.cpp:77-94; swapping is what lets a GL driver overlap frames).  vct_frame_async renders into one of two
+ * device frame buffers and queues the device->host copy of that frame to host_rgba on a separate copy stream;
+ * it returns without waiting.  vct_frame_wait blocks until the OLDEST frame still in flight has fully arrived
+ * in its host buffer (at most two frames are in flight; a third vct_frame_async waits for the oldest itself).
+ * host_rgba should be pinned memory for the copy to overlap. */
+int vct_frame_async(vct_handle h, uint8_t* host_rgba);
+int vct_frame_wait(vct_handle h);
+
 /* split form of vct_draw_voxels for triangle-sharded voxelisation across GPUs: accumulate a triangle
  * range into the integer accumulator, exchange (all-reduce the buffer returned by vct_accum_buffer as
  * uint32 sum), then resolve + mip.  clear_first zeroes the accumulator. */

@@ -388,3 +388,36 @@ def test_runs_on_a_caller_stream_and_reports_pass_times(gpu_ctx):
         assert gpu_ctx.pass_time_us(p) > 0
     assert gpu_ctx.kernel_launches() > 10
     gpu_ctx.use_own_stream()
+
+
+def test_pipelined_frames_equal_synchronous_frames(gpu_ctx):
+    import torch
+    import vct_b200.glmath as gm
+    sc = scenes.cornell()
+    u = uniforms.scene_uniforms(sc, V=64, width=160, height=96, shadow_map_size=512)
+    c = gpu_ctx
+    c.set_uniforms(u); c.load_scene(sc); c.draw_depth()
+
+    def cam(i):
+        view = gm.view_matrix((2.0 * i, 0.0, 205.0), -90.0 + 1.5 * i, 0.0)
+        c.set_mat4("ModelViewMatrix", gm.colmajor((view @ gm.scale(0.05)).astype(np.float32)))
+        c.set_3f("CameraPosition", (2.0 * i, 0.0, 205.0))
+
+    ref = []
+    for i in range(5):
+        cam(i)
+        out = np.zeros((96, 160, 4), dtype=np.uint8)
+        c.frame(out)
+        ref.append(out)
+    assert not np.array_equal(ref[0], ref[4])
+    hosts = [torch.zeros((96, 160, 4), dtype=torch.uint8).pin_memory() for _ in range(5)]
+    for i in range(5):
+        cam(i)
+        c.frame_async(hosts[i])
+        if i >= 1:
+            c.frame_wait()
+            assert np.array_equal(hosts[i - 1].numpy(), ref[i - 1])      # frame i-1 is complete after the wait
+    c.frame_wait()
+    c.frame_wait()                                                       # idempotent when nothing is in flight
+    for i in range(5):
+        assert np.array_equal(hosts[i].numpy(), ref[i])

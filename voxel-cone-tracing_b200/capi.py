@@ -17,7 +17,7 @@ PASSES = {"depth": 0, "vox_clear": 1, "vox_cover": 2, "vox_shade": 3, "resolve":
 SYMBOLS = [
     "vct_create", "vct_destroy", "vct_last_error", "vct_version", "vct_set_i", "vct_set_f", "vct_set_3f",
     "vct_set_mat4", "vct_get_i", "vct_get_f", "vct_set_cones", "vct_upload_texture", "vct_set_material",
-    "vct_upload_mesh", "vct_update_positions", "vct_draw_depth", "vct_draw_voxels", "vct_render", "vct_frame",
+    "vct_upload_mesh", "vct_update_positions", "vct_draw_depth", "vct_draw_voxels", "vct_render", "vct_frame", "vct_frame_async", "vct_frame_wait",
     "vct_voxelize_range", "vct_accum_buffer", "vct_resolve_and_mip", "vct_readback_depth", "vct_readback_counts",
     "vct_readback_sums", "vct_readback_grid", "vct_upload_grid_level0", "vct_build_mips", "vct_readback_visibility",
     "vct_readback_frame", "vct_frame_buffer", "vct_cone_samples", "vct_fragment_count", "vct_occupied_voxels", "vct_debug_counter",
@@ -55,7 +55,7 @@ def load_library(path=None):
         "vct_set_cones": [vp, i, vp, vp], "vct_upload_texture": [vp, i, i, i, i, vp],
         "vct_set_material": [vp, i, i, i, i, f], "vct_upload_mesh": [vp, vp, sz, vp, sz, vp],
         "vct_update_positions": [vp, vp, sz, i], "vct_draw_depth": [vp], "vct_draw_voxels": [vp],
-        "vct_render": [vp, vp], "vct_frame": [vp, vp], "vct_voxelize_range": [vp, sz, sz, i],
+        "vct_render": [vp, vp], "vct_frame": [vp, vp], "vct_frame_async": [vp, vp], "vct_frame_wait": [vp], "vct_voxelize_range": [vp, sz, sz, i],
         "vct_accum_buffer": [vp, C.POINTER(vp), C.POINTER(sz)], "vct_resolve_and_mip": [vp],
         "vct_readback_depth": [vp, vp], "vct_readback_counts": [vp, vp], "vct_readback_sums": [vp, vp],
         "vct_readback_grid": [vp, i, vp], "vct_upload_grid_level0": [vp, vp], "vct_build_mips": [vp],
@@ -201,6 +201,13 @@ class Context:
 
     def frame(self, out=None):
         self._ck(self.L.vct_frame(self.h, None if out is None else _host_ptr(out)))
+
+    def frame_async(self, out):
+        """Pipelined frame: renders and queues the copy into `out` (pinned host buffer); see frame_wait()."""
+        self._ck(self.L.vct_frame_async(self.h, _host_ptr(out)))
+
+    def frame_wait(self):
+        self._ck(self.L.vct_frame_wait(self.h))
 
     def voxelize_range(self, tb, te, clear_first=True):
         self._ck(self.L.vct_voxelize_range(self.h, int(tb), int(te), int(bool(clear_first))))

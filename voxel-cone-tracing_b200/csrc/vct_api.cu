@@ -401,8 +401,10 @@ int vct_destroy(vct_handle c) {
   if (c->white_tex) cudaDestroyTextureObject(c->white_tex);
   if (c->white_arr) cudaFreeMipmappedArray(c->white_arr);
   cudaFree(c->d_verts); cudaFree(c->d_idx); cudaFree(c->d_trimat); cudaFree(c->d_materials);
-  cudaFree(c->d_depth); cudaFree(c->d_frags); cudaFree(c->d_items); cudaFree(c->d_counters);
+  cudaFree(c->d_voxrec); cudaFree(c->d_depth); cudaFree(c->d_frags); cudaFree(c->d_items); cudaFree(c->d_counters);
   cudaFree(c->d_vis); cudaFree(c->d_frame);
+  for (int k = 0; k < 2; ++k) { cudaFree(c->d_frame2[k]); if (c->ev_rendered[k]) cudaEventDestroy(c->ev_rendered[k]); if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]); }
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   for (int p = 0; p < VCT_PASS_COUNT; ++p) { cudaEventDestroy(c->ev_begin[p]); cudaEventDestroy(c->ev_end[p]); }
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -665,6 +667,61 @@ int vct_frame(vct_handle c, uint8_t* host_rgba) {
     VCT_CUDA(c, cudaMemcpyAsync(host_rgba, c->d_frame, (size_t)c->P.W * c->P.H * 4, cudaMemcpyDeviceToHost, c->stream));
     VCT_CUDA(c, cudaStreamSynchronize(c->stream));
   }
+  return VCT_OK;
+}
+
+static int ensure_async(vct_context* c) {
+  if (!c->copy_stream) {
+    VCT_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+      VCT_CUDA(c, cudaEventCreateWithFlags(&c->ev_rendered[k], cudaEventDisableTiming));
+      VCT_CUDA(c, cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
+    }
+  }
+  if (c->frame2_W != c->P.W || c->frame2_H != c->P.H || !c->d_frame2[0]) {
+    for (int k = 0; k < 2; ++k) {
+      if (c->in_flight[k]) { cudaEventSynchronize(c->ev_copied[k]); c->in_flight[k] = false; }
+      cudaFree(c->d_frame2[k]); c->d_frame2[k] = nullptr;
+      VCT_CUDA(c, cudaMalloc(&c->d_frame2[k], (size_t)c->P.W * c->P.H * 4));
+    }
+    c->frame2_W = c->P.W; c->frame2_H = c->P.H;
+  }
+  return VCT_OK;
+}
+
+int vct_frame_wait(vct_handle c) {
+  NEED(c);
+  // oldest in-flight slot: frames alternate slots, so it is the one the NEXT frame would use if both are busy,
+  // otherwise whichever is busy
+  const int next = c->frame_seq & 1;
+  int slot = c->in_flight[next] ? next : (c->in_flight[next ^ 1] ? (next ^ 1) : -1);
+  if (slot < 0) return VCT_OK;
+  VCT_CUDA(c, cudaEventSynchronize(c->ev_copied[slot]));
+  c->in_flight[slot] = false;
+  return VCT_OK;
+}
+
+int vct_frame_async(vct_handle c, uint8_t* host_rgba) {
+  NEED(c);
+  if (!host_rgba) return set_error(c, VCT_ERR_INVALID, "vct_frame_async: host buffer required");
+  int rc = ensure_frame(c); if (rc) return rc;
+  rc = ensure_async(c); if (rc) return rc;
+  const int slot = c->frame_seq & 1;
+  if (c->in_flight[slot]) {                       // this device buffer is still being copied out
+    VCT_CUDA(c, cudaEventSynchronize(c->ev_copied[slot]));
+    c->in_flight[slot] = false;
+  }
+  uchar4* saved = c->d_frame;
+  c->d_frame = c->d_frame2[slot];                 // render straight into the slot
+  rc = vct_frame(c, nullptr);
+  c->d_frame = saved;
+  if (rc) return rc;
+  VCT_CUDA(c, cudaEventRecord(c->ev_rendered[slot], c->stream));
+  VCT_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_rendered[slot], 0));
+  VCT_CUDA(c, cudaMemcpyAsync(host_rgba, c->d_frame2[slot], (size_t)c->P.W * c->P.H * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+  VCT_CUDA(c, cudaEventRecord(c->ev_copied[slot], c->copy_stream));
+  c->in_flight[slot] = true;
+  c->frame_seq++;
   return VCT_OK;
 }
 

@@ -143,6 +143,9 @@ struct VisibilityPass {
   // Exact tile reject.  IEEE rounding is monotonic, so the COMPUTED value (A*px + B*py) + C is monotonic in px
   // and in py separately; its maximum over the pixel centres of a tile is the computed value at the corner
   // chosen by the signs of A and B.  If that maximum fails the inside test no pixel of the tile can pass.
+  __device__ __forceinline__ bool setup_full(uint32_t tri, Setup& s, int& i0, int& i1, int& j0, int& j1) const {
+    return setup(tri, s, i0, i1, j0, j1);
+  }
   __device__ __forceinline__ bool tile_may_cover(const Setup& s, int x0, int y0, int x1, int y1) const {
     const float xa = (float)x0 + 0.5f, xb = (float)(x1 - 1) + 0.5f, ya = (float)y0 + 0.5f, yb = (float)(y1 - 1) + 0.5f;
 #pragma unroll

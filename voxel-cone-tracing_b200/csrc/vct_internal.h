@@ -115,6 +115,8 @@ struct vct_context {
   cudaTextureObject_t grid_tex = 0;
   bool accum_dense_dirty = false;              // accumulator holds data not described by the touched list
 
+  void* d_voxrec = nullptr; size_t voxrec_nt = 0;   // per-triangle voxelisation records (vct_voxelize.cu)
+
   // work queues
   uint2* d_frags = nullptr; size_t frags_cap = 0;
   vct::TileItem* d_items = nullptr; size_t items_cap = 0;
@@ -123,6 +125,10 @@ struct vct_context {
 
   // frame
   unsigned long long* d_vis = nullptr; uchar4* d_frame = nullptr; int frame_W = 0, frame_H = 0;
+  // double-buffered frames for vct_frame_async
+  uchar4* d_frame2[2] = {nullptr, nullptr}; int frame2_W = 0, frame2_H = 0;
+  cudaStream_t copy_stream = nullptr; cudaEvent_t ev_rendered[2]{}, ev_copied[2]{}; bool in_flight[2] = {false, false};
+  unsigned frame_seq = 0;
   uint8_t* h_frame_pinned = nullptr; size_t h_frame_bytes = 0;
 
   // timing

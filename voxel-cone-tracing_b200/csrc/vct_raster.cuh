@@ -7,7 +7,8 @@
 //                  rasterised in the thread; larger ones are cut into 8x8-pixel tiles and queued as
 //                  work items of up to ITEM_TILES tiles.
 //   raster_tiles : persistent warps; one warp per work item, one lane per pixel (2 steps per tile).
-// A Pass supplies:  struct Setup;  bool setup(tri, Setup&, i0,i1,j0,j1);
+// A Pass supplies:  struct Setup;  bool setup_full(tri, Setup&, i0,i1,j0,j1)  (raster_small: from the vertex cache)
+//                   bool setup(tri, Setup&, i0,i1,j0,j1)       (raster_tiles: may reload a stored record)
 //                   bool tile_may_cover(Setup&, x0,y0,x1,y1)   (exact or conservative reject)
 //                   unsigned small(Setup&, tri, i0,i1,j0,j1)    (thread-serial path)
 //                   void pixel(Setup&, tri, i, j, bool in_bbox) (warp path, called by all 32 lanes)
@@ -30,7 +31,7 @@ __global__ void __launch_bounds__(128) raster_small(Pass pass, uint32_t tri_begi
   bool live = tri < tri_end;
   typename Pass::Setup s;
   int i0 = 0, i1 = -1, j0 = 0, j1 = -1;
-  if (live) live = pass.setup(tri, s, i0, i1, j0, j1);
+  if (live) live = pass.setup_full(tri, s, i0, i1, j0, j1);   // may also write a per-triangle record for later stages
   int w = i1 - i0 + 1, h = j1 - j0 + 1;
   bool small_tri = live && (w * h <= SMALL_AREA);
   // every lane of the warp calls small(): passes that append to a queue aggregate across the warp

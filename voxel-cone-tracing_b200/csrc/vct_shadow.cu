@@ -42,6 +42,9 @@ struct ShadowPass {
     atomicMin(&depth[(size_t)j * P.S + i], d);
   }
 
+  __device__ __forceinline__ bool setup_full(uint32_t tri, Setup& s, int& i0, int& i1, int& j0, int& j1) const {
+    return setup(tri, s, i0, i1, j0, j1);
+  }
   __device__ __forceinline__ bool tile_may_cover(const Setup& s, int x0, int y0, int x1, int y1) const {
     return tile_may_cover_exact(s.t, x0, y0, x1, y1);
   }

@@ -19,8 +19,10 @@ namespace cg = cooperative_groups;
 namespace vct {
 
 // ---------------------------------------------------------------------------------------------------
-// Per-triangle set-up shared by coverage and shading (recomputed, not stored: 3 vertices = 60 B of
-// loads against 25 shadow taps per fragment).
+// Per-triangle set-up.  raster_small evaluates it once per triangle (Voxelization.vs + .gs) and stores a 128-byte
+// record -- snapped window coordinates, depth, axis, material, texture LOD, uv and light-space coordinates in
+// rasterisation order -- which the tile stage and the per-fragment shading stage reload instead of redoing the
+// geometry-shader work per tile / per fragment.
 struct VoxTri {
   RasterTri t;
   float z0, z1, z2;
@@ -80,17 +82,66 @@ __device__ __forceinline__ bool vox_setup(const Params& P, const VertexCache& vc
   return true;
 }
 
+// 8 x 16 B per triangle
+struct VoxRecord {
+  int4 a;      // X0 Y0 X1 Y1
+  int4 b;      // X2 Y2 axis material
+  float4 z;    // z0 z1 z2 lod
+  float4 uv01; // uv0.xy uv1.xy
+  float4 uv2;  // uv2.xy - -
+  float4 dc0, dc1, dc2;
+};
+
+__device__ __forceinline__ void load_raster_tri(const VoxRecord* __restrict__ rec, uint32_t tri, VoxTri& s) {
+  const int4 a = __ldg(&rec[tri].a), b = __ldg(&rec[tri].b);
+  s.t.X0 = a.x; s.t.Y0 = a.y; s.t.X1 = a.z; s.t.Y1 = a.w; s.t.X2 = b.x; s.t.Y2 = b.y;
+  s.t.area = (long long)(s.t.X1 - s.t.X0) * (long long)(s.t.Y2 - s.t.Y0) - (long long)(s.t.Y1 - s.t.Y0) * (long long)(s.t.X2 - s.t.X0);
+  s.t.flipped = 0;
+  s.axis = b.z;
+}
+
 // ---------------------------------------------------------------------------------------------------
 struct VoxCoverPass {
   Params P;
   VertexCache vc; const uint32_t* idx;
+  const uint16_t* trimat; const MaterialDev* mats;
+  VoxRecord* rec;
   uint2* frags; uint32_t frags_cap;
   Counters* ctr;
 
   struct Setup { VoxTri v; };
 
+  // raster_small: full set-up from the vertex cache + the per-triangle record
+  __device__ __forceinline__ bool setup_full(uint32_t tri, Setup& s, int& i0, int& i1, int& j0, int& j1) const {
+    float uv[3][2];
+    F4 dc[3];
+    if (!vox_setup<true>(P, vc, idx, tri, s.v, uv, dc)) return false;
+    if (!raster_bbox(s.v.t, P.coverage, P.V, P.V, &i0, &i1, &j0, &j1)) return false;
+    const int mat = trimat ? trimat[tri] : 0;
+    // implicit LOD of texture(DiffuseTexture, TexCoord) (Voxelization.fs:56): uv is affine over the triangle
+    const RasterTri& t = s.v.t;
+    const float fa = (float)t.area;
+    const float dl1dx = (float)(-(long long)(t.Y0 - t.Y2) * SUBPIX) / fa, dl1dy = (float)((long long)(t.X0 - t.X2) * SUBPIX) / fa;
+    const float dl2dx = (float)(-(long long)(t.Y1 - t.Y0) * SUBPIX) / fa, dl2dy = (float)((long long)(t.X1 - t.X0) * SUBPIX) / fa;
+    const float du1 = uv[1][0] - uv[0][0], du2 = uv[2][0] - uv[0][0];
+    const float dv1 = uv[1][1] - uv[0][1], dv2 = uv[2][1] - uv[0][1];
+    const float lod = lod_from_derivs(dl1dx * du1 + dl2dx * du2, dl1dx * dv1 + dl2dx * dv2,
+                                      dl1dy * du1 + dl2dy * du2, dl1dy * dv1 + dl2dy * dv2, mats[mat].dw, mats[mat].dh);
+    VoxRecord r;
+    r.a = make_int4(t.X0, t.Y0, t.X1, t.Y1);
+    r.b = make_int4(t.X2, t.Y2, s.v.axis, mat);
+    r.z = make_float4(s.v.z0, s.v.z1, s.v.z2, lod);
+    r.uv01 = make_float4(uv[0][0], uv[0][1], uv[1][0], uv[1][1]);
+    r.uv2 = make_float4(uv[2][0], uv[2][1], 0.0f, 0.0f);
+    r.dc0 = make_float4(dc[0].x, dc[0].y, dc[0].z, dc[0].w);
+    r.dc1 = make_float4(dc[1].x, dc[1].y, dc[1].z, dc[1].w);
+    r.dc2 = make_float4(dc[2].x, dc[2].y, dc[2].z, dc[2].w);
+    rec[tri] = r;
+    return true;
+  }
+  // raster_tiles: reload the snapped triangle
   __device__ __forceinline__ bool setup(uint32_t tri, Setup& s, int& i0, int& i1, int& j0, int& j1) const {
-    if (!vox_setup<false>(P, vc, idx, tri, s.v, nullptr, nullptr)) return false;
+    load_raster_tri(rec, tri, s.v);
     return raster_bbox(s.v.t, P.coverage, P.V, P.V, &i0, &i1, &j0, &j1);
   }
   __device__ __forceinline__ bool tile_may_cover(const Setup& s, int x0, int y0, int x1, int y1) const {
@@ -143,9 +194,7 @@ struct VoxCoverPass {
 };
 
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) vox_shade(Params P, VertexCache vc,
-                                                 const uint32_t* __restrict__ idx,
-                                                 const uint16_t* __restrict__ trimat,
+__global__ void __launch_bounds__(256) vox_shade(Params P, const VoxRecord* __restrict__ rec,
                                                  const MaterialDev* __restrict__ mats,
                                                  const uint32_t* __restrict__ depth,
                                                  const uint2* __restrict__ frags, uint32_t frags_cap,
@@ -158,14 +207,13 @@ __global__ void __launch_bounds__(256) vox_shade(Params P, VertexCache vc,
     const uint32_t tri = fr.x;
     const int i = (int)(fr.y & 0xFFFFu), j = (int)(fr.y >> 16);
     VoxTri s;
-    float uv[3][2];
-    F4 dc[3];
-    if (!vox_setup<true>(P, vc, idx, tri, s, uv, dc)) continue;   // cannot fail for a queued fragment
+    load_raster_tri(rec, tri, s);
+    const float4 zl = __ldg(&rec[tri].z);
     float l1, l2;
     s.t.lambdas(i, j, &l1, &l2);
-    float z = interp3(s.z0, s.z1, s.z2, l1, l2);
+    float z = interp3(zl.x, zl.y, zl.z, l1, l2);
     if (P.coverage == 2) {
-      float zmin = fminf(s.z0, fminf(s.z1, s.z2)), zmax = fmaxf(s.z0, fmaxf(s.z1, s.z2));
+      float zmin = fminf(zl.x, fminf(zl.y, zl.z)), zmax = fmaxf(zl.x, fmaxf(zl.y, zl.z));
       z = fminf(fmaxf(z, zmin), zmax);
     }
     float tz = (float)V * z;                                  // Voxelization.fs:58
@@ -177,25 +225,18 @@ __global__ void __launch_bounds__(256) vox_shade(Params P, VertexCache vc,
     else { vx = i; vy = j; vz = V - 1 - cz; }                            // :82-86
     if ((unsigned)vx >= (unsigned)V || (unsigned)vy >= (unsigned)V || (unsigned)vz >= (unsigned)V) continue;
 
-    // texture(DiffuseTexture, TexCoord), Voxelization.fs:56; implicit LOD is constant over the triangle
-    const MaterialDev m = mats[trimat ? trimat[tri] : 0];
-    const float fa = (float)s.t.area;
-    // d(lambda)/d(pixel): e20 = edge v2->v0 weights v1, e01 = edge v0->v1 weights v2
-    const float dl1dx = (float)(-(long long)(s.t.Y0 - s.t.Y2) * SUBPIX) / fa, dl1dy = (float)((long long)(s.t.X0 - s.t.X2) * SUBPIX) / fa;
-    const float dl2dx = (float)(-(long long)(s.t.Y1 - s.t.Y0) * SUBPIX) / fa, dl2dy = (float)((long long)(s.t.X1 - s.t.X0) * SUBPIX) / fa;
-    const float du1 = uv[1][0] - uv[0][0], du2 = uv[2][0] - uv[0][0];
-    const float dv1 = uv[1][1] - uv[0][1], dv2 = uv[2][1] - uv[0][1];
-    const float dudx = dl1dx * du1 + dl2dx * du2, dvdx = dl1dx * dv1 + dl2dx * dv2;
-    const float dudy = dl1dy * du1 + dl2dy * du2, dvdy = dl1dy * dv1 + dl2dy * dv2;
-    const float lod = lod_from_derivs(dudx, dvdx, dudy, dvdy, m.dw, m.dh);
-    const float u = interp3(uv[0][0], uv[1][0], uv[2][0], l1, l2);
-    const float vv = interp3(uv[0][1], uv[1][1], uv[2][1], l1, l2);
-    const float4 col = sample_material(m.diffuse, u, vv, lod);
+    // texture(DiffuseTexture, TexCoord), Voxelization.fs:56
+    const MaterialDev& m = mats[__ldg(&rec[tri].b.w)];
+    const float4 uv01 = __ldg(&rec[tri].uv01), uv2 = __ldg(&rec[tri].uv2);
+    const float u = interp3(uv01.x, uv01.z, uv2.x, l1, l2);
+    const float vv = interp3(uv01.y, uv01.w, uv2.y, l1, l2);
+    const float4 col = sample_material(m.diffuse, u, vv, zl.w);
 
-    const float dx = interp3(dc[0].x, dc[1].x, dc[2].x, l1, l2);
-    const float dy = interp3(dc[0].y, dc[1].y, dc[2].y, l1, l2);
-    const float dz = interp3(dc[0].z, dc[1].z, dc[2].z, l1, l2);
-    const float dw = interp3(dc[0].w, dc[1].w, dc[2].w, l1, l2);
+    const float4 d0 = __ldg(&rec[tri].dc0), d1 = __ldg(&rec[tri].dc1), d2 = __ldg(&rec[tri].dc2);
+    const float dx = interp3(d0.x, d1.x, d2.x, l1, l2);
+    const float dy = interp3(d0.y, d1.y, d2.y, l1, l2);
+    const float dz = interp3(d0.z, d1.z, d2.z, l1, l2);
+    const float dw = interp3(d0.w, d1.w, d2.w, l1, l2);
     const int taps = (2 * P.pcf_radius + 1) * (2 * P.pcf_radius + 1);
     const float shadow = pcf_lit_taps(depth, P.S, P.pcf_radius, P.shadow_bias, dx, dy, dz, dw) / (float)taps;
 
@@ -302,6 +343,11 @@ int launch_voxelize(vct_context* c, size_t tb, size_t te) {
   rc = ensure_queues(c); if (rc) return rc;
   rc = sync_materials(c); if (rc) return rc;
   rc = ensure_vertex_cache(c); if (rc) return rc;
+  if (c->voxrec_nt != c->nt) {
+    cudaFree(c->d_voxrec); c->d_voxrec = nullptr;
+    VCT_CUDA(c, cudaMalloc(&c->d_voxrec, c->nt * sizeof(VoxRecord)));
+    c->voxrec_nt = c->nt;
+  }
   te = te < c->nt ? te : c->nt;
   if (tb >= te) return VCT_OK;
   {
@@ -309,7 +355,7 @@ int launch_voxelize(vct_context* c, size_t tb, size_t te) {
     VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_items, 0, sizeof(unsigned int), c->stream));
     VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->next_item, 0, sizeof(unsigned int), c->stream));
     VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_fragments, 0, sizeof(unsigned int), c->stream));
-    VoxCoverPass pass{c->P, c->vcache, c->d_idx, c->d_frags, (uint32_t)c->frags_cap, c->d_counters};
+    VoxCoverPass pass{c->P, c->vcache, c->d_idx, c->d_trimat, c->d_materials, (VoxRecord*)c->d_voxrec, c->d_frags, (uint32_t)c->frags_cap, c->d_counters};
     const uint32_t n = (uint32_t)(te - tb);
     raster_small<VoxCoverPass><<<(n + 127) / 128, 128, 0, c->stream>>>(pass, (uint32_t)tb, (uint32_t)te, c->d_items,
                                                                         (uint32_t)c->items_cap, c->d_counters);
@@ -318,7 +364,7 @@ int launch_voxelize(vct_context* c, size_t tb, size_t te) {
   }
   {
     PassTimer timer(c, VCT_PASS_VOX_SHADE);
-    vox_shade<<<148 * 8, 256, 0, c->stream>>>(c->P, c->vcache, c->d_idx, c->d_trimat, c->d_materials, c->d_depth,
+    vox_shade<<<148 * 8, 256, 0, c->stream>>>(c->P, (const VoxRecord*)c->d_voxrec, c->d_materials, c->d_depth,
                                               c->d_frags, (uint32_t)c->frags_cap, c->d_accum, c->d_touched,
                                               c->d_counters);
     c->launches += 1;
