@@ -381,9 +381,10 @@ __device__ __forceinline__ unsigned char to_unorm8(float x) {
   return (unsigned char)__float2int_rn(x * 255.0f);
 }
 
-// one warp = 8x4 pixels; block = 8 warps = 32x8 pixels
+// one warp = 8x4 pixels; block = 2 warps = 8x8 pixels (small blocks: the specular chain length varies a lot
+// between warps and a block holds its registers until its slowest warp is done)
 template <int NC, int SU>
-__global__ void __launch_bounds__(256, 2) cone_trace(Params P, VertexCache vc,
+__global__ void __launch_bounds__(64, 8) cone_trace(Params P, VertexCache vc,
                                                   const uint32_t* __restrict__ idx,
                                                   const uint16_t* __restrict__ trimat,
                                                   const MaterialDev* __restrict__ mats,
@@ -396,8 +397,8 @@ __global__ void __launch_bounds__(256, 2) cone_trace(Params P, VertexCache vc,
   int lx, ly;
   if (lane_map == 1) { lx = (lane & 1) | ((lane >> 1) & 6); ly = ((lane >> 1) & 1) | ((lane >> 3) & 2); }   // 2x2 quads in 8x4
   else { lx = lane & 7; ly = lane >> 3; }                                                                     // rows of 8
-  const int i = blockIdx.x * 32 + (warp & 3) * 8 + lx;
-  const int j = y_begin + blockIdx.y * 8 + (warp >> 2) * 4 + ly;
+  const int i = blockIdx.x * 8 + lx;
+  const int j = y_begin + blockIdx.y * 8 + warp * 4 + ly;
   unsigned samples = 0;
   if (i < P.W && j < y_end) {
     const unsigned long long key = vis[(size_t)j * P.W + i];
@@ -529,9 +530,9 @@ int launch_cone(vct_context* c) {
   VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->cone_samples, 0, sizeof(unsigned long long), c->stream));
   const int y0 = c->P.row_begin, y1 = (c->P.row_end > 0 && c->P.row_end < c->P.H) ? c->P.row_end : c->P.H;
   if (y0 >= y1) return VCT_OK;
-  dim3 b(256), g((c->P.W + 31) / 32, (y1 - y0 + 7) / 8);
+  dim3 b(64), g((c->P.W + 7) / 8, (y1 - y0 + 7) / 8);
 #define VCT_LAUNCH_CONE(NC, SU)                                                                                   \
-  cone_trace<NC, SU><<<g, b, 3 * NC * 256 * sizeof(float), c->stream>>>(c->P, c->vcache, c->d_idx, c->d_trimat,    \
+  cone_trace<NC, SU><<<g, b, 3 * NC * 64 * sizeof(float), c->stream>>>(c->P, c->vcache, c->d_idx, c->d_trimat,    \
       c->d_materials, c->d_depth, c->d_vis, c->grid_tex, c->d_frame, c->d_counters, y0, y1, c->debug_lane_map)
   const int su = c->debug_spec_ahead;
   if (c->P.n_cones <= 6) {
