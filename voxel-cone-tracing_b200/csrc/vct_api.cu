@@ -117,7 +117,20 @@ int ensure_grid(vct_context* c) {
 int ensure_shadow(vct_context* c) {
   if (c->depth_S == c->P.S && c->d_depth) return VCT_OK;
   cudaFree(c->d_depth); c->d_depth = nullptr; c->depth_valid = false;
+  if (c->depth_tex) { cudaDestroyTextureObject(c->depth_tex); c->depth_tex = 0; }
+  if (c->depth_array) { cudaFreeArray(c->depth_array); c->depth_array = nullptr; }
   VCT_CUDA(c, cudaMalloc(&c->d_depth, (size_t)c->P.S * c->P.S * 4));
+  cudaChannelFormatDesc dd = cudaCreateChannelDesc<unsigned int>();
+  VCT_CUDA(c, cudaMallocArray(&c->depth_array, &dd, c->P.S, c->P.S, cudaArrayTextureGather));
+  cudaResourceDesc rd{};
+  rd.resType = cudaResourceTypeArray;
+  rd.res.array.array = c->depth_array;
+  cudaTextureDesc td{};
+  td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;    // GL_CLAMP_TO_EDGE, Voxel_Cone_Tracing.h:95-96
+  td.filterMode = cudaFilterModePoint;
+  td.readMode = cudaReadModeElementType;
+  td.normalizedCoords = 0;
+  VCT_CUDA(c, cudaCreateTextureObject(&c->depth_tex, &rd, &td, nullptr));
   c->depth_S = c->P.S;
   return VCT_OK;
 }
@@ -401,6 +414,8 @@ int vct_destroy(vct_handle c) {
   if (c->white_tex) cudaDestroyTextureObject(c->white_tex);
   if (c->white_arr) cudaFreeMipmappedArray(c->white_arr);
   cudaFree(c->d_verts); cudaFree(c->d_idx); cudaFree(c->d_trimat); cudaFree(c->d_materials);
+  if (c->depth_tex) cudaDestroyTextureObject(c->depth_tex);
+  if (c->depth_array) cudaFreeArray(c->depth_array);
   cudaFree(c->d_voxrec); cudaFree(c->d_depth); cudaFree(c->d_frags); cudaFree(c->d_items); cudaFree(c->d_counters);
   cudaFree(c->d_vis); cudaFree(c->d_frame);
   for (int k = 0; k < 2; ++k) { cudaFree(c->d_frame2[k]); if (c->ev_rendered[k]) cudaEventDestroy(c->ev_rendered[k]); if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]); }

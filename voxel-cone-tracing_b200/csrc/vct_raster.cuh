@@ -24,7 +24,7 @@ constexpr int TILE = 8;
 constexpr int ITEM_TILES = 16;
 
 template <class Pass>
-__global__ void __launch_bounds__(128) raster_small(Pass pass, uint32_t tri_begin, uint32_t tri_end,
+__global__ void __launch_bounds__(128, 5) raster_small(Pass pass, uint32_t tri_begin, uint32_t tri_end,
                                                     TileItem* __restrict__ items, uint32_t items_cap,
                                                     Counters* __restrict__ ctr) {
   uint32_t tri = tri_begin + blockIdx.x * blockDim.x + threadIdx.x;

@@ -83,6 +83,9 @@ int launch_shadow(vct_context* c) {
   raster_tiles<ShadowPass><<<148 * 4, 256, 0, c->stream>>>(pass, c->d_items, (uint32_t)c->items_cap, c->d_counters);
   c->launches += 3;
   VCT_CUDA(c, cudaGetLastError());
+  // array copy for tex2Dgather (voxel shading)
+  VCT_CUDA(c, cudaMemcpy2DToArrayAsync(c->depth_array, 0, 0, c->d_depth, (size_t)c->P.S * 4, (size_t)c->P.S * 4, c->P.S,
+                                       cudaMemcpyDeviceToDevice, c->stream));
   c->depth_valid = true;
   return VCT_OK;
 }

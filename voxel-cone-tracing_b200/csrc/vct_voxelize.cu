@@ -193,17 +193,34 @@ struct VoxCoverPass {
   __device__ __forceinline__ void pixel(const Setup&, uint32_t, int, int, bool) const {}
 };
 
+// first fragment of a voxel (old count == 0): append the voxel to the touched list, one counter atomic per warp-step
+__device__ __forceinline__ void append_first_touch(bool& pending, unsigned long long old, uint32_t voxel,
+                                                   uint32_t* __restrict__ touched, Counters* __restrict__ ctr) {
+  if (pending && (uint32_t)old == 0u) {
+    cg::coalesced_group firsts = cg::coalesced_threads();
+    uint32_t base = 0;
+    if (firsts.thread_rank() == 0) base = atomicAdd(&ctr->n_touched, (uint32_t)firsts.size());
+    base = firsts.shfl(base, 0);
+    touched[base + firsts.thread_rank()] = voxel;
+  }
+  pending = false;
+}
+
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) vox_shade(Params P, const VoxRecord* __restrict__ rec,
                                                  const MaterialDev* __restrict__ mats,
-                                                 const uint32_t* __restrict__ depth,
+                                                 const uint32_t* __restrict__ depth, cudaTextureObject_t depth_tex,
                                                  const uint2* __restrict__ frags, uint32_t frags_cap,
                                                  unsigned long long* __restrict__ accum,
                                                  uint32_t* __restrict__ touched, Counters* __restrict__ ctr) {
   const uint32_t nfrag = min(ctr->n_fragments, frags_cap);
   const int V = P.V;
+  bool pending = false;
+  unsigned long long pend_old = 0ull;
+  uint32_t pend_voxel = 0u;
   for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < nfrag; f += gridDim.x * blockDim.x) {
     const uint2 fr = frags[f];
+    append_first_touch(pending, pend_old, pend_voxel, touched, ctr);
     const uint32_t tri = fr.x;
     const int i = (int)(fr.y & 0xFFFFu), j = (int)(fr.y >> 16);
     VoxTri s;
@@ -238,7 +255,9 @@ __global__ void __launch_bounds__(256) vox_shade(Params P, const VoxRecord* __re
     const float dz = interp3(d0.z, d1.z, d2.z, l1, l2);
     const float dw = interp3(d0.w, d1.w, d2.w, l1, l2);
     const int taps = (2 * P.pcf_radius + 1) * (2 * P.pcf_radius + 1);
-    const float shadow = pcf_lit_taps(depth, P.S, P.pcf_radius, P.shadow_bias, dx, dy, dz, dw) / (float)taps;
+    const float lit = P.pcf_radius == 2 ? pcf_lit_taps_gather(depth_tex, depth, P.S, P.shadow_bias, dx, dy, dz, dw)
+                                        : pcf_lit_taps_generic(depth, P.S, P.pcf_radius, P.shadow_bias, dx, dy, dz, dw);
+    const float shadow = lit / (float)taps;
 
     // imageStore(VoxelTexture, voxelPos, vec4(color.rgb * shadow, 1)): unorm8 conversion, Voxelization.fs:88
     unsigned r = (unsigned)__float2int_rn(fminf(fmaxf(col.x * shadow, 0.0f), 1.0f) * 255.0f);
@@ -257,10 +276,14 @@ __global__ void __launch_bounds__(256) vox_shade(Params P, const VoxRecord* __re
     }
     if (same.thread_rank() == 0) {
       atomicAdd(&accum[2 * (size_t)voxel], rg);
-      unsigned long long old = atomicAdd(&accum[2 * (size_t)voxel + 1], bc);
-      if ((uint32_t)old == 0u) touched[atomicAdd(&ctr->n_touched, 1u)] = voxel;
+      // The returned old count is consumed one iteration later (append_first_touch at the loop top), so the
+      // warp does not sit on the L2 round trip of this atomic.
+      pend_old = atomicAdd(&accum[2 * (size_t)voxel + 1], bc);
+      pend_voxel = voxel;
+      pending = true;
     }
   }
+  append_first_touch(pending, pend_old, pend_voxel, touched, ctr);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -365,7 +388,7 @@ int launch_voxelize(vct_context* c, size_t tb, size_t te) {
   {
     PassTimer timer(c, VCT_PASS_VOX_SHADE);
     vox_shade<<<148 * 8, 256, 0, c->stream>>>(c->P, (const VoxRecord*)c->d_voxrec, c->d_materials, c->d_depth,
-                                              c->d_frags, (uint32_t)c->frags_cap, c->d_accum, c->d_touched,
+                                              c->depth_tex, c->d_frags, (uint32_t)c->frags_cap, c->d_accum, c->d_touched,
                                               c->d_counters);
     c->launches += 1;
   }
