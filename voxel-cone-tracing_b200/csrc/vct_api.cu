@@ -161,11 +161,16 @@ int ensure_queues(vct_context* c) {
 }
 
 int check_overflow(vct_context* c) {
-  unsigned int ov = 0;
+  unsigned int ov = 0, ov2 = 0;
   VCT_CUDA(c, cudaMemcpyAsync(&ov, &c->d_counters->overflow, 4, cudaMemcpyDeviceToHost, c->stream));
   VCT_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (ov) {
+  if (c->d_counters_vis) {
+    VCT_CUDA(c, cudaStreamSynchronize(c->stream2));
+    VCT_CUDA(c, cudaMemcpy(&ov2, &c->d_counters_vis->overflow, 4, cudaMemcpyDeviceToHost));
+  }
+  if (ov || ov2) {
     cudaMemsetAsync(&c->d_counters->overflow, 0, 4, c->stream);
+    if (c->d_counters_vis) cudaMemset(&c->d_counters_vis->overflow, 0, 4);
     return set_error(c, VCT_ERR_OVERFLOW, "device work queue overflow: raise MaxFragments / MaxTileItems");
   }
   return VCT_OK;
@@ -420,6 +425,8 @@ int vct_destroy(vct_handle c) {
   cudaFree(c->d_vis); cudaFree(c->d_frame);
   for (int k = 0; k < 2; ++k) { cudaFree(c->d_frame2[k]); if (c->ev_rendered[k]) cudaEventDestroy(c->ev_rendered[k]); if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]); }
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->stream2) { cudaStreamDestroy(c->stream2); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
+  cudaFree(c->d_items_vis); cudaFree(c->d_counters_vis);
   for (int p = 0; p < VCT_PASS_COUNT; ++p) { cudaEventDestroy(c->ev_begin[p]); cudaEventDestroy(c->ev_end[p]); }
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -454,6 +461,8 @@ int vct_set_i(vct_handle c, const char* name, int v) {
   else if (k == "RowBegin") { if (v < 0) return set_error(c, VCT_ERR_INVALID, "RowBegin < 0"); P.row_begin = v; }
   else if (k == "RowEnd") { if (v < 0) return set_error(c, VCT_ERR_INVALID, "RowEnd < 0"); P.row_end = v; }
   else if (k == "DebugLaneMap") c->debug_lane_map = v;
+  else if (k == "OverlapVisibility") c->overlap_visibility = v != 0;
+  else if (k == "DebugFlags") P.debug_flags = v;
   else if (k == "DebugSpecAhead") c->debug_spec_ahead = v;
   else if (k == "DenseResolve") c->dense_resolve = v != 0;
   else if (k == "Profile") c->profile = v != 0;
@@ -671,11 +680,48 @@ int vct_render(vct_handle c, uint8_t* host_rgba) {
   return VCT_OK;
 }
 
+static int ensure_overlap(vct_context* c) {
+  if (!c->stream2) {
+    VCT_CUDA(c, cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    VCT_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    VCT_CUDA(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    VCT_CUDA(c, cudaMalloc(&c->d_counters_vis, sizeof(Counters)));
+    VCT_CUDA(c, cudaMemset(c->d_counters_vis, 0, sizeof(Counters)));
+  }
+  if (c->items_vis_cap != c->max_items || !c->d_items_vis) {
+    cudaFree(c->d_items_vis); c->d_items_vis = nullptr;
+    VCT_CUDA(c, cudaMalloc(&c->d_items_vis, c->max_items * sizeof(TileItem)));
+    c->items_vis_cap = c->max_items;
+  }
+  return VCT_OK;
+}
+
 int vct_frame(vct_handle c, uint8_t* host_rgba) {
   NEED(c);
   if (c->profile) cudaEventRecord(c->ev_begin[VCT_PASS_FRAME], c->stream);
-  int rc = vct_draw_voxels(c); if (rc) return rc;
-  rc = launch_visibility(c); if (rc) return rc;
+  int rc;
+  if (c->overlap_visibility) {
+    // primary visibility needs only the vertex cache and the materials: it runs on a second stream beside
+    // clear -> voxelise -> resolve -> mip (all of them latency-bound at partial occupancy) and joins before cone_trace
+    rc = ensure_frame(c); if (rc) return rc;
+    rc = ensure_queues(c); if (rc) return rc;
+    rc = sync_materials(c); if (rc) return rc;
+    rc = ensure_vertex_cache(c); if (rc) return rc;
+    rc = ensure_overlap(c); if (rc) return rc;
+    VCT_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+    VCT_CUDA(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    cudaStream_t main_stream = c->stream; TileItem* main_items = c->d_items; Counters* main_ctr = c->d_counters;
+    c->stream = c->stream2; c->d_items = c->d_items_vis; c->d_counters = c->d_counters_vis;
+    rc = launch_visibility(c);
+    c->stream = main_stream; c->d_items = main_items; c->d_counters = main_ctr;
+    if (rc) return rc;
+    VCT_CUDA(c, cudaEventRecord(c->ev_join, c->stream2));
+    rc = vct_draw_voxels(c); if (rc) return rc;
+    VCT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  } else {
+    rc = vct_draw_voxels(c); if (rc) return rc;
+    rc = launch_visibility(c); if (rc) return rc;
+  }
   rc = launch_cone(c); if (rc) return rc;
   if (c->profile) { cudaEventRecord(c->ev_end[VCT_PASS_FRAME], c->stream); c->ev_recorded[VCT_PASS_FRAME] = true; }
   if (host_rgba) {

@@ -35,6 +35,7 @@ struct Params {
   int coverage;          // 0 CENTER, 1 MSAA4_ANY, 2 CONSERVATIVE
   int bounces;
   int row_begin, row_end;   // rows of the frame this context renders (row-band sharding); row_end 0 = H
+  int debug_flags;          // diagnostics only (tools/): bit0 skip voxel atomics, bit1 skip voxel PCF, bit2 skip albedo fetch
 };
 
 struct MaterialDev {
@@ -123,6 +124,11 @@ struct vct_context {
   vct::TileItem* d_items = nullptr; size_t items_cap = 0;
   vct::Counters* d_counters = nullptr;
   vct::Counters* h_counters = nullptr;          // pinned mirror
+
+  // second stream: the visibility pass is independent of voxelisation + mip and runs beside them in vct_frame
+  cudaStream_t stream2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  vct::TileItem* d_items_vis = nullptr; size_t items_vis_cap = 0; vct::Counters* d_counters_vis = nullptr;
+  int overlap_visibility = 1;
 
   // frame
   unsigned long long* d_vis = nullptr; uchar4* d_frame = nullptr; int frame_W = 0, frame_H = 0;

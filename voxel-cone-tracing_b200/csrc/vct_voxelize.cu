@@ -218,8 +218,17 @@ __global__ void __launch_bounds__(256) vox_shade(Params P, const VoxRecord* __re
   bool pending = false;
   unsigned long long pend_old = 0ull;
   uint32_t pend_voxel = 0u;
-  for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < nfrag; f += gridDim.x * blockDim.x) {
-    const uint2 fr = frags[f];
+  // software pipeline: the next fragment's queue entry is loaded one iteration ahead and its triangle record
+  // (one 128-byte line) is prefetched, so the dependent chain queue -> record -> shadow texels starts warm
+  const uint32_t stride = gridDim.x * blockDim.x;
+  uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  uint2 fr_next = f < nfrag ? frags[f] : make_uint2(0u, 0u);
+  for (; f < nfrag; f += stride) {
+    const uint2 fr = fr_next;
+    if (f + stride < nfrag) {
+      fr_next = frags[f + stride];
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(&rec[fr_next.x]));
+    }
     append_first_touch(pending, pend_old, pend_voxel, touched, ctr);
     const uint32_t tri = fr.x;
     const int i = (int)(fr.y & 0xFFFFu), j = (int)(fr.y >> 16);
