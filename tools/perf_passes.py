@@ -19,6 +19,21 @@ print("depth %.1f us" % c.pass_time_us("depth"))
 print("  ".join(f"{k} {np.median(v):.1f}" for k, v in acc.items()))
 tot = np.median(acc["frame"])
 print(f"frame {tot:.1f} us -> {1e6 / tot:.1f} fps ; cone samples {c.cone_samples()} -> {c.cone_samples() / np.median(acc['cone']) * 1e-3:.1f} Gs/s; frags {c.fragment_count()} occupied {c.occupied_voxels()}")
+c.set_i("Profile", 0)
+for i in range(5): c.frame()
+c.sync(); t0 = time.perf_counter()
+N = 200
+for i in range(N): c.frame()
+c.sync(); dt = (time.perf_counter() - t0) / N
+print(f"back-to-back throughput (pipelined, Profile=0): {dt * 1e6:.1f} us/frame -> {1 / dt:.1f} fps")
+c.set_i("PipelineFrames", 0)
+for i in range(5): c.frame()
+c.sync(); t0 = time.perf_counter()
+for i in range(N): c.frame()
+c.sync(); dt = (time.perf_counter() - t0) / N
+print(f"back-to-back throughput (PipelineFrames=0): {dt * 1e6:.1f} us/frame -> {1 / dt:.1f} fps")
+c.set_i("PipelineFrames", 1); c.set_i("Profile", 1)
+c.frame(); c.sync()
 f = c.read_frame()
 import zlib
 print("frame crc", zlib.crc32(f.tobytes()), "grid0 crc", zlib.crc32(c.grid(0).tobytes()), "counts crc", zlib.crc32(c.counts().tobytes()))

@@ -60,57 +60,71 @@ __global__ void zero_u64(unsigned long long* p, size_t n) {
 }
 
 static void free_grid(vct_context* c) {
-  if (c->grid_tex) cudaDestroyTextureObject(c->grid_tex);
-  for (auto s : c->grid_surf) cudaDestroySurfaceObject(s);
-  c->grid_surf.clear();
-  if (c->grid_array) cudaFreeMipmappedArray(c->grid_array);
-  cudaFree(c->d_accum); cudaFree(c->d_touched);
-  c->grid_tex = 0; c->grid_array = nullptr; c->d_accum = nullptr; c->d_touched = nullptr; c->grid_V = 0;
+  for (auto& g : c->grid) {
+    if (g.tex) cudaDestroyTextureObject(g.tex);
+    for (auto s : g.surf) cudaDestroySurfaceObject(s);
+    g.surf.clear();
+    if (g.array) cudaFreeMipmappedArray(g.array);
+    cudaFree(g.touched); cudaFree(g.n_touched);
+    g = vct_context::GridBuf();
+  }
+  cudaFree(c->d_accum);
+  c->d_accum = nullptr; c->grid_V = 0; c->accum_list_slot = -1;
 }
 
 int ensure_grid(vct_context* c) {
   const int V = c->P.V;
   if (c->grid_V == V) return VCT_OK;
+  cudaStreamSynchronize(c->stream);
+  if (c->stream_vox) cudaStreamSynchronize(c->stream_vox);
   free_grid(c);
   const size_t n = (size_t)V * V * V;
   VCT_CUDA(c, cudaMalloc(&c->d_accum, n * 16));
-  VCT_CUDA(c, cudaMalloc(&c->d_touched, n * 4));
   c->touched_cap = n;
   cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
-  VCT_CUDA(c, cudaMallocMipmappedArray(&c->grid_array, &desc, make_cudaExtent(V, V, V), c->P.levels,
-                                       cudaArraySurfaceLoadStore));
-  for (int l = 0; l < c->P.levels; ++l) {
-    cudaArray_t lvl;
-    VCT_CUDA(c, cudaGetMipmappedArrayLevel(&lvl, c->grid_array, l));
+  for (auto& g : c->grid) {
+    VCT_CUDA(c, cudaMalloc(&g.touched, n * 4));
+    VCT_CUDA(c, cudaMalloc(&g.n_touched, 128));
+    VCT_CUDA(c, cudaMemsetAsync(g.n_touched, 0, 128, c->stream));
+    VCT_CUDA(c, cudaMallocMipmappedArray(&g.array, &desc, make_cudaExtent(V, V, V), c->P.levels, cudaArraySurfaceLoadStore));
+    for (int l = 0; l < c->P.levels; ++l) {
+      cudaArray_t lvl;
+      VCT_CUDA(c, cudaGetMipmappedArrayLevel(&lvl, g.array, l));
+      cudaResourceDesc rd{};
+      rd.resType = cudaResourceTypeArray;
+      rd.res.array.array = lvl;
+      cudaSurfaceObject_t s;
+      VCT_CUDA(c, cudaCreateSurfaceObject(&s, &rd));
+      g.surf.push_back(s);
+    }
+    // sampler state of the reference's voxel texture: MIN = LINEAR_MIPMAP_LINEAR, MAG = LINEAR
+    // (Voxel_Cone_Tracing.h:112-113), wrap never set => GL_REPEAT on s,t,r.
     cudaResourceDesc rd{};
-    rd.resType = cudaResourceTypeArray;
-    rd.res.array.array = lvl;
-    cudaSurfaceObject_t s;
-    VCT_CUDA(c, cudaCreateSurfaceObject(&s, &rd));
-    c->grid_surf.push_back(s);
+    rd.resType = cudaResourceTypeMipmappedArray;
+    rd.res.mipmap.mipmap = g.array;
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeWrap;
+    td.filterMode = cudaFilterModeLinear;
+    td.mipmapFilterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeNormalizedFloat;
+    td.normalizedCoords = 1;
+    td.minMipmapLevelClamp = 0.0f;
+    td.maxMipmapLevelClamp = (float)(c->P.levels - 1);
+    VCT_CUDA(c, cudaCreateTextureObject(&g.tex, &rd, &td, nullptr));
+    g.list_valid = true;
   }
-  // sampler state of the reference's voxel texture: MIN = LINEAR_MIPMAP_LINEAR, MAG = LINEAR
-  // (Voxel_Cone_Tracing.h:112-113), wrap never set => GL_REPEAT on s,t,r.
-  cudaResourceDesc rd{};
-  rd.resType = cudaResourceTypeMipmappedArray;
-  rd.res.mipmap.mipmap = c->grid_array;
-  cudaTextureDesc td{};
-  td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeWrap;
-  td.filterMode = cudaFilterModeLinear;
-  td.mipmapFilterMode = cudaFilterModeLinear;
-  td.readMode = cudaReadModeNormalizedFloat;
-  td.normalizedCoords = 1;
-  td.minMipmapLevelClamp = 0.0f;
-  td.maxMipmapLevelClamp = (float)(c->P.levels - 1);
-  VCT_CUDA(c, cudaCreateTextureObject(&c->grid_tex, &rd, &td, nullptr));
   c->grid_V = V;
-  // zero everything: accumulator, touched list, and all mip levels (the reference uploads a zeroed
-  // texture and calls glGenerateMipmap, Voxel_Cone_Tracing.h:115-126)
+  // zero everything: accumulator and all mip levels of both slots (the reference uploads a zeroed texture and
+  // calls glGenerateMipmap, Voxel_Cone_Tracing.h:115-126)
   VCT_CUDA(c, cudaMemsetAsync(c->d_accum, 0, n * 16, c->stream));
-  VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_touched, 0, sizeof(unsigned int), c->stream));
-  c->accum_dense_dirty = false;
-  int rc = launch_resolve(c, true); if (rc) return rc;
-  rc = launch_mip(c); if (rc) return rc;
+  for (int k = 0; k < 2; ++k) {
+    c->cur = k;
+    int rc = launch_resolve(c, true); if (rc) return rc;
+    rc = launch_mip(c); if (rc) return rc;
+    c->grid[k].list_valid = true;     // all zero: the (empty) list is exact
+  }
+  c->cur = 0;
+  c->accum_list_slot = 0;             // accumulator all zero, slot 0's empty list describes it
   return VCT_OK;
 }
 
@@ -137,10 +151,12 @@ int ensure_shadow(vct_context* c) {
 
 int ensure_frame(vct_context* c) {
   if (c->frame_W == c->P.W && c->frame_H == c->P.H && c->d_frame) return VCT_OK;
-  cudaFree(c->d_vis); cudaFree(c->d_frame);
-  c->d_vis = nullptr; c->d_frame = nullptr;
+  cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_vis2[0]); cudaFree(c->d_vis2[1]); cudaFree(c->d_frame);
+  c->d_vis2[0] = c->d_vis2[1] = nullptr; c->d_frame = nullptr;
   const size_t n = (size_t)c->P.W * c->P.H;
-  VCT_CUDA(c, cudaMalloc(&c->d_vis, n * 8));
+  VCT_CUDA(c, cudaMalloc(&c->d_vis2[0], n * 8));
+  VCT_CUDA(c, cudaMalloc(&c->d_vis2[1], n * 8));
   VCT_CUDA(c, cudaMalloc(&c->d_frame, n * 4));
   c->frame_W = c->P.W; c->frame_H = c->P.H;
   return VCT_OK;
@@ -165,6 +181,7 @@ int check_overflow(vct_context* c) {
   VCT_CUDA(c, cudaMemcpyAsync(&ov, &c->d_counters->overflow, 4, cudaMemcpyDeviceToHost, c->stream));
   VCT_CUDA(c, cudaStreamSynchronize(c->stream));
   if (c->d_counters_vis) {
+    VCT_CUDA(c, cudaStreamSynchronize(c->stream_vox));
     VCT_CUDA(c, cudaStreamSynchronize(c->stream2));
     VCT_CUDA(c, cudaMemcpy(&ov2, &c->d_counters_vis->overflow, 4, cudaMemcpyDeviceToHost));
   }
@@ -319,29 +336,56 @@ __global__ void vertex_pass(Params P, const float* __restrict__ verts, size_t nv
 }
 
 static void free_vertex_cache(vct_context* c) {
-  cudaFree(c->vcache.world); cudaFree(c->vcache.dc); cudaFree(c->vcache.clip);
-  cudaFree(c->vcache.nrm_u); cudaFree(c->vcache.tan_v); cudaFree(c->vcache.bit);
-  c->vcache = VertexCache{}; c->vcache_nv = 0; c->vcache_valid = false;
+  for (int k = 0; k < 2; ++k) {
+    VertexCache& vc = c->vcache2[k];
+    cudaFree(vc.world); cudaFree(vc.dc); cudaFree(vc.clip); cudaFree(vc.nrm_u); cudaFree(vc.tan_v); cudaFree(vc.bit);
+    vc = VertexCache{}; c->vcache_nv[k] = 0; c->vcache_valid[k] = false;
+  }
 }
 
+// (re)computes the vertex cache of the CURRENT slot if the mesh or any matrix it depends on changed
 int ensure_vertex_cache(vct_context* c) {
   if (!c->nv) return set_error(c, VCT_ERR_STATE, "no mesh uploaded");
-  if (c->vcache_nv != c->nv) {
-    free_vertex_cache(c);
-    float4** arr[] = {&c->vcache.world, &c->vcache.dc, &c->vcache.clip, &c->vcache.nrm_u, &c->vcache.tan_v, &c->vcache.bit};
-    for (float4** a : arr) VCT_CUDA(c, cudaMalloc(a, c->nv * sizeof(float4)));
-    c->vcache_nv = c->nv;
+  const int k = c->cur;
+  VertexCache& vc = c->vcache2[k];
+  if (c->vcache_nv[k] != c->nv) {
+    cudaStreamSynchronize(c->stream);
+    float4** arr[] = {&vc.world, &vc.dc, &vc.clip, &vc.nrm_u, &vc.tan_v, &vc.bit};
+    for (float4** a : arr) { cudaFree(*a); *a = nullptr; VCT_CUDA(c, cudaMalloc(a, c->nv * sizeof(float4))); }
+    c->vcache_nv[k] = c->nv;
+    c->vcache_valid[k] = false;
   }
-  const Params& P = c->P; const Params& Q = c->vcache_params;
-  const bool same = c->vcache_valid && P.W == Q.W && P.H == Q.H && !std::memcmp(P.model, Q.model, sizeof(P.model)) &&
+  const Params& P = c->P; const Params& Q = c->vcache_params[k];
+  const bool same = c->vcache_valid[k] && P.W == Q.W && P.H == Q.H && !std::memcmp(P.model, Q.model, sizeof(P.model)) &&
                     !std::memcmp(P.model_view, Q.model_view, sizeof(P.model_view)) && !std::memcmp(P.proj, Q.proj, sizeof(P.proj)) &&
                     !std::memcmp(P.depth_mvp, Q.depth_mvp, sizeof(P.depth_mvp));
   if (same) return VCT_OK;
-  vertex_pass<<<(unsigned)((c->nv + 127) / 128), 128, 0, c->stream>>>(c->P, c->d_verts, c->nv, c->vcache);
+  vertex_pass<<<(unsigned)((c->nv + 127) / 128), 128, 0, c->stream>>>(c->P, c->d_verts, c->nv, vc);
   c->launches += 1;
-  c->vcache_params = c->P;
-  c->vcache_valid = true;
+  c->vcache_params[k] = c->P;
+  c->vcache_valid[k] = true;
   return check_cuda(c, cudaGetLastError(), "vertex_pass");
+}
+
+// ---- frame slots
+void mark_slot_read(vct_context* c) {
+  if (!c->slot_read_done[0]) {
+    cudaEventCreateWithFlags(&c->slot_read_done[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->slot_read_done[1], cudaEventDisableTiming);
+  }
+  cudaEventRecord(c->slot_read_done[c->cur], c->stream);
+  c->slot_read_pending[c->cur] = true;
+}
+
+// Switch to the other slot.  Whatever stream c->stream currently is (main, or the voxel stream inside a pipelined
+// vct_frame) first waits for the last reader of that slot.
+int begin_voxel_slot(vct_context* c) {
+  const int nxt = c->cur ^ 1;
+  if (c->slot_read_pending[nxt]) {
+    VCT_CUDA(c, cudaStreamWaitEvent(c->stream, c->slot_read_done[nxt], 0));
+  }
+  c->cur = nxt;
+  return VCT_OK;
 }
 
 // ------------------------------------------------------------------------------------------ tex bench
@@ -422,7 +466,9 @@ int vct_destroy(vct_handle c) {
   if (c->depth_tex) cudaDestroyTextureObject(c->depth_tex);
   if (c->depth_array) cudaFreeArray(c->depth_array);
   cudaFree(c->d_voxrec); cudaFree(c->d_depth); cudaFree(c->d_frags); cudaFree(c->d_items); cudaFree(c->d_counters);
-  cudaFree(c->d_vis); cudaFree(c->d_frame);
+  cudaFree(c->d_vis2[0]); cudaFree(c->d_vis2[1]); cudaFree(c->d_frame);
+  for (int k = 0; k < 2; ++k) if (c->slot_read_done[k]) cudaEventDestroy(c->slot_read_done[k]);
+  if (c->stream_vox) { cudaStreamDestroy(c->stream_vox); cudaEventDestroy(c->ev_vox_done); cudaEventDestroy(c->ev_vtx_done); }
   for (int k = 0; k < 2; ++k) { cudaFree(c->d_frame2[k]); if (c->ev_rendered[k]) cudaEventDestroy(c->ev_rendered[k]); if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]); }
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->stream2) { cudaStreamDestroy(c->stream2); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
@@ -461,7 +507,9 @@ int vct_set_i(vct_handle c, const char* name, int v) {
   else if (k == "RowBegin") { if (v < 0) return set_error(c, VCT_ERR_INVALID, "RowBegin < 0"); P.row_begin = v; }
   else if (k == "RowEnd") { if (v < 0) return set_error(c, VCT_ERR_INVALID, "RowEnd < 0"); P.row_end = v; }
   else if (k == "DebugLaneMap") c->debug_lane_map = v;
+  else if (k == "ConeSmemPad") { if (v < 0 || v > 90000) return set_error(c, VCT_ERR_INVALID, "ConeSmemPad out of range"); c->debug_cone_smem_pad = v; }
   else if (k == "OverlapVisibility") c->overlap_visibility = v != 0;
+  else if (k == "PipelineFrames") c->pipeline_frames = v != 0;
   else if (k == "DebugFlags") P.debug_flags = v;
   else if (k == "DebugSpecAhead") c->debug_spec_ahead = v;
   else if (k == "DenseResolve") c->dense_resolve = v != 0;
@@ -560,6 +608,7 @@ int vct_upload_texture(vct_handle c, int id, int w, int h, int ch, const uint8_t
   if ((int)c->textures.size() <= id) c->textures.resize(id + 1);
   free_texture(c->textures[id]);
   c->materials_dirty = true;
+  c->scene_epoch++;
   return make_texture(c, c->textures[id], w, h, ch, px);
 }
 
@@ -569,6 +618,7 @@ int vct_set_material(vct_handle c, int mat, int d, int s, int h, float shininess
   if ((int)c->materials.size() <= mat) c->materials.resize(mat + 1);
   c->materials[mat].d = d; c->materials[mat].s = s; c->materials[mat].h = h; c->materials[mat].shininess = shininess;
   c->materials_dirty = true;
+  c->scene_epoch++;
   return VCT_OK;
 }
 
@@ -593,7 +643,8 @@ int vct_upload_mesh(vct_handle c, const float* verts, size_t nv, const uint32_t*
   VCT_CUDA(c, cudaStreamSynchronize(c->stream));
   c->nv = nv; c->nt = nt;
   c->depth_valid = false;
-  c->vcache_valid = false;
+  c->vcache_valid[0] = c->vcache_valid[1] = false;
+  c->scene_epoch++;
   return VCT_OK;
 }
 
@@ -619,15 +670,16 @@ int vct_update_positions(vct_handle c, const float* xyz, size_t nv, int on_devic
   c->launches += 1;
   if (tmp) { cudaStreamSynchronize(c->stream); cudaFree(tmp); }
   c->depth_valid = false;
-  c->vcache_valid = false;
+  c->vcache_valid[0] = c->vcache_valid[1] = false;
+  c->scene_epoch++;
   return check_cuda(c, cudaGetLastError(), "scatter_positions");
 }
 
 // ---- passes
-int vct_draw_depth(vct_handle c) { NEED(c); return launch_shadow(c); }
+int vct_draw_depth(vct_handle c) { NEED(c); c->scene_epoch++; return launch_shadow(c); }
 
-int vct_draw_voxels(vct_handle c) {
-  NEED(c);
+// clear + voxelise + resolve + mip (+ re-injection) into the current slot, on c->stream
+static int draw_voxels_body(vct_context* c) {
   int rc = launch_voxel_clear(c); if (rc) return rc;
   rc = launch_voxelize(c, 0, c->nt); if (rc) return rc;
   rc = launch_resolve(c, c->dense_resolve != 0); if (rc) return rc;
@@ -639,15 +691,27 @@ int vct_draw_voxels(vct_handle c) {
   return VCT_OK;
 }
 
+int vct_draw_voxels(vct_handle c) {
+  NEED(c);
+  c->scene_epoch++;
+  int rc = ensure_grid(c); if (rc) return rc;
+  rc = begin_voxel_slot(c); if (rc) return rc;    // build into the slot no cone_trace is reading
+  return draw_voxels_body(c);
+}
+
 int vct_voxelize_range(vct_handle c, size_t tb, size_t te, int clear_first) {
   NEED(c);
   int rc = ensure_grid(c); if (rc) return rc;
+  c->scene_epoch++;
   if (clear_first) {
-    c->accum_dense_dirty = true;   // force the dense clear path: after an all-reduce the touched list is stale
+    // dense path: after an all-reduce the accumulator holds other ranks' voxels that no local list describes
+    rc = begin_voxel_slot(c); if (rc) return rc;
+    c->accum_list_slot = -1;
     rc = launch_voxel_clear(c); if (rc) return rc;
   }
-  c->accum_dense_dirty = true;
-  return launch_voxelize(c, tb, te);
+  rc = launch_voxelize(c, tb, te);
+  c->accum_list_slot = -1;
+  return rc;
 }
 
 int vct_accum_buffer(vct_handle c, void** p, size_t* n) {
@@ -660,6 +724,7 @@ int vct_accum_buffer(vct_handle c, void** p, size_t* n) {
 
 int vct_resolve_and_mip(vct_handle c) {
   NEED(c);
+  c->scene_epoch++;
   int rc = launch_resolve(c, true); if (rc) return rc;
   rc = launch_mip(c); if (rc) return rc;
   for (int b = 3; b <= c->P.bounces; ++b) {
@@ -671,6 +736,7 @@ int vct_resolve_and_mip(vct_handle c) {
 
 int vct_render(vct_handle c, uint8_t* host_rgba) {
   NEED(c);
+  c->scene_epoch++;
   int rc = launch_visibility(c); if (rc) return rc;
   rc = launch_cone(c); if (rc) return rc;
   if (host_rgba) {
@@ -682,11 +748,18 @@ int vct_render(vct_handle c, uint8_t* host_rgba) {
 
 static int ensure_overlap(vct_context* c) {
   if (!c->stream2) {
-    VCT_CUDA(c, cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    // higher priority than the main stream: cone_trace fills the machine with ~32 K small blocks, and the block
+    // scheduler only hands SM slots to another grid ahead of them if that grid's stream has priority
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    VCT_CUDA(c, cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_hi));
     VCT_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     VCT_CUDA(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     VCT_CUDA(c, cudaMalloc(&c->d_counters_vis, sizeof(Counters)));
     VCT_CUDA(c, cudaMemset(c->d_counters_vis, 0, sizeof(Counters)));
+    VCT_CUDA(c, cudaStreamCreateWithPriority(&c->stream_vox, cudaStreamNonBlocking, prio_hi));
+    VCT_CUDA(c, cudaEventCreateWithFlags(&c->ev_vox_done, cudaEventDisableTiming));
+    VCT_CUDA(c, cudaEventCreateWithFlags(&c->ev_vtx_done, cudaEventDisableTiming));
   }
   if (c->items_vis_cap != c->max_items || !c->d_items_vis) {
     cudaFree(c->d_items_vis); c->d_items_vis = nullptr;
@@ -699,27 +772,45 @@ static int ensure_overlap(vct_context* c) {
 int vct_frame(vct_handle c, uint8_t* host_rgba) {
   NEED(c);
   if (c->profile) cudaEventRecord(c->ev_begin[VCT_PASS_FRAME], c->stream);
-  int rc;
+  int rc = ensure_grid(c); if (rc) return rc;
   if (c->overlap_visibility) {
-    // primary visibility needs only the vertex cache and the materials: it runs on a second stream beside
-    // clear -> voxelise -> resolve -> mip (all of them latency-bound at partial occupancy) and joins before cone_trace
+    // Three streams.  voxel stream: vertex pass -> clear -> voxelise -> resolve -> mip into the slot that the
+    // previous frame's cone_trace is not reading; visibility stream: primary visibility (needs only the vertex
+    // cache); main stream: cone_trace after both.  With PipelineFrames the voxel and visibility stages of frame
+    // i+1 do not wait for cone_trace of frame i (they are latency-bound, cone_trace is texture-bound), unless
+    // device-side inputs changed in between (scene_epoch), in which case they are ordered after the main stream.
     rc = ensure_frame(c); if (rc) return rc;
     rc = ensure_queues(c); if (rc) return rc;
     rc = sync_materials(c); if (rc) return rc;
-    rc = ensure_vertex_cache(c); if (rc) return rc;
     rc = ensure_overlap(c); if (rc) return rc;
-    VCT_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
-    VCT_CUDA(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    const bool ordered = !c->pipeline_frames || c->scene_epoch != c->frame_epoch;
     cudaStream_t main_stream = c->stream; TileItem* main_items = c->d_items; Counters* main_ctr = c->d_counters;
-    c->stream = c->stream2; c->d_items = c->d_items_vis; c->d_counters = c->d_counters_vis;
-    rc = launch_visibility(c);
+    if (ordered) VCT_CUDA(c, cudaEventRecord(c->ev_fork, main_stream));
+    // --- voxel stream
+    c->stream = c->stream_vox;
+    rc = VCT_OK;
+    if (ordered) rc = check_cuda(c, cudaStreamWaitEvent(c->stream_vox, c->ev_fork, 0), "wait fork");
+    if (!rc) rc = begin_voxel_slot(c);
+    if (!rc) rc = ensure_vertex_cache(c);
+    if (!rc) rc = check_cuda(c, cudaEventRecord(c->ev_vtx_done, c->stream_vox), "record vtx");
+    if (!rc) rc = draw_voxels_body(c);
+    if (!rc) rc = check_cuda(c, cudaEventRecord(c->ev_vox_done, c->stream_vox), "record vox");
+    // --- visibility stream (ordered after the vertex pass, hence after the slot became free)
+    if (!rc) {
+      c->stream = c->stream2; c->d_items = c->d_items_vis; c->d_counters = c->d_counters_vis;
+      rc = check_cuda(c, cudaStreamWaitEvent(c->stream2, c->ev_vtx_done, 0), "wait vtx");
+      if (!rc) rc = launch_visibility(c);
+      if (!rc) rc = check_cuda(c, cudaEventRecord(c->ev_join, c->stream2), "record join");
+    }
     c->stream = main_stream; c->d_items = main_items; c->d_counters = main_ctr;
     if (rc) return rc;
-    VCT_CUDA(c, cudaEventRecord(c->ev_join, c->stream2));
-    rc = vct_draw_voxels(c); if (rc) return rc;
+    // --- main stream
+    VCT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_vox_done, 0));
     VCT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    c->frame_epoch = c->scene_epoch;
   } else {
-    rc = vct_draw_voxels(c); if (rc) return rc;
+    rc = begin_voxel_slot(c); if (rc) return rc;
+    rc = draw_voxels_body(c); if (rc) return rc;
     rc = launch_visibility(c); if (rc) return rc;
   }
   rc = launch_cone(c); if (rc) return rc;
@@ -802,7 +893,7 @@ int vct_readback_grid(vct_handle c, int level, uint8_t* rgba) {
   if (level < 0 || level >= c->P.levels || !rgba) return set_error(c, VCT_ERR_INVALID, "bad mip level");
   const int n = c->P.V >> level;
   cudaArray_t lvl;
-  VCT_CUDA(c, cudaGetMipmappedArrayLevel(&lvl, c->grid_array, level));
+  VCT_CUDA(c, cudaGetMipmappedArrayLevel(&lvl, c->grid[c->cur].array, level));
   cudaMemcpy3DParms p{};
   p.srcArray = lvl;
   p.dstPtr = make_cudaPitchedPtr(rgba, (size_t)n * 4, n, n);
@@ -817,14 +908,15 @@ int vct_upload_grid_level0(vct_handle c, const uint8_t* rgba) {
   int rc = ensure_grid(c); if (rc) return rc;
   const int n = c->P.V;
   cudaArray_t lvl;
-  VCT_CUDA(c, cudaGetMipmappedArrayLevel(&lvl, c->grid_array, 0));
+  VCT_CUDA(c, cudaGetMipmappedArrayLevel(&lvl, c->grid[c->cur].array, 0));
   cudaMemcpy3DParms p{};
   p.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(rgba), (size_t)n * 4, n, n);
   p.dstArray = lvl;
   p.extent = make_cudaExtent(n, n, n);
   p.kind = cudaMemcpyHostToDevice;
   VCT_CUDA(c, cudaMemcpy3DAsync(&p, c->stream));
-  c->accum_dense_dirty = true;   // level 0 no longer matches the touched list
+  c->grid[c->cur].list_valid = false;   // level 0 no longer matches the touched list
+  c->scene_epoch++;
   return check_cuda(c, cudaStreamSynchronize(c->stream), "sync");
 }
 
@@ -837,11 +929,11 @@ __global__ void vis_to_tri(const unsigned long long* __restrict__ vis, uint32_t*
 
 int vct_readback_visibility(vct_handle c, uint32_t* tri) {
   NEED(c);
-  if (!c->d_vis || !tri) return set_error(c, VCT_ERR_STATE, "no frame rendered");
+  if (!c->d_vis2[c->cur] || !tri) return set_error(c, VCT_ERR_STATE, "no frame rendered");
   const size_t n = (size_t)c->P.W * c->P.H;
   uint32_t* d = nullptr;
   VCT_CUDA(c, cudaMalloc(&d, n * 4));
-  vis_to_tri<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_vis, d, n);
+  vis_to_tri<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_vis2[c->cur], d, n);
   c->launches += 1;
   cudaError_t e = cudaMemcpyAsync(tri, d, n * 4, cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -892,7 +984,8 @@ int vct_debug_counter(vct_handle c, int which, uint64_t* n) {   /* 0 = work item
 int vct_occupied_voxels(vct_handle c, uint64_t* n) {
   NEED(c);
   unsigned int v = 0;
-  int rc = read_counter(c, &c->d_counters->n_touched, &v, 4);
+  int rc = ensure_grid(c); if (rc) return rc;
+  rc = read_counter(c, c->grid[c->cur].n_touched, &v, 4);
   if (n) *n = v;
   return rc;
 }

@@ -203,10 +203,10 @@ int launch_visibility(vct_context* c) {
   rc = ensure_vertex_cache(c); if (rc) return rc;
   PassTimer timer(c, VCT_PASS_VISIBILITY);
   const size_t n = (size_t)c->P.W * c->P.H;
-  fill_u64<<<148 * 4, 256, 0, c->stream>>>(c->d_vis, n, ~0ull);
+  fill_u64<<<148 * 4, 256, 0, c->stream>>>(c->d_vis2[c->cur], n, ~0ull);
   VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_items, 0, sizeof(unsigned int), c->stream));
     VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->next_item, 0, sizeof(unsigned int), c->stream));
-  VisibilityPass pass{c->P, c->vcache, c->d_idx, c->d_trimat, c->d_materials, c->d_vis};
+  VisibilityPass pass{c->P, c->vcache2[c->cur], c->d_idx, c->d_trimat, c->d_materials, c->d_vis2[c->cur]};
   const uint32_t nt = (uint32_t)c->nt;
   raster_small<VisibilityPass><<<(nt + 127) / 128, 128, 0, c->stream>>>(pass, 0, nt, c->d_items,
                                                                         (uint32_t)c->items_cap, c->d_counters);
@@ -531,9 +531,12 @@ int launch_cone(vct_context* c) {
   const int y0 = c->P.row_begin, y1 = (c->P.row_end > 0 && c->P.row_end < c->P.H) ? c->P.row_end : c->P.H;
   if (y0 >= y1) return VCT_OK;
   dim3 b(64), g((c->P.W + 7) / 8, (y1 - y0 + 7) / 8);
+  if (c->debug_cone_smem_pad > 40000) {
+    cudaFuncSetAttribute(cone_trace<6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  }
 #define VCT_LAUNCH_CONE(NC, SU)                                                                                   \
-  cone_trace<NC, SU><<<g, b, 3 * NC * 64 * sizeof(float), c->stream>>>(c->P, c->vcache, c->d_idx, c->d_trimat,    \
-      c->d_materials, c->d_depth, c->d_vis, c->grid_tex, c->d_frame, c->d_counters, y0, y1, c->debug_lane_map)
+  cone_trace<NC, SU><<<g, b, 3 * NC * 64 * sizeof(float) + (size_t)c->debug_cone_smem_pad, c->stream>>>(c->P, c->vcache2[c->cur], c->d_idx, c->d_trimat, \
+      c->d_materials, c->d_depth, c->d_vis2[c->cur], c->grid[c->cur].tex, c->d_frame, c->d_counters, y0, y1, c->debug_lane_map)
   const int su = c->debug_spec_ahead;
   if (c->P.n_cones <= 6) {
     if (su == 1) VCT_LAUNCH_CONE(6, 1); else if (su == 2) VCT_LAUNCH_CONE(6, 2); else VCT_LAUNCH_CONE(6, 4);
@@ -542,6 +545,7 @@ int launch_cone(vct_context* c) {
   }
 #undef VCT_LAUNCH_CONE
   c->launches += 1;
+  mark_slot_read(c);
   VCT_CUDA(c, cudaGetLastError());
   return VCT_OK;
 }
@@ -594,11 +598,10 @@ int launch_reinject(vct_context* c) {
   uint32_t* staged = nullptr;
   VCT_CUDA(c, cudaMallocAsync(&staged, (size_t)V * V * V * 4, c->stream));
   dim3 b(256), g((V + 31) / 32, (V + 7) / 8, V);
-  reinject_gather<<<g, b, 0, c->stream>>>(c->P, c->grid_tex, c->grid_surf[0], staged);
-  reinject_commit<<<g, b, 0, c->stream>>>(staged, c->grid_surf[0], V);
+  reinject_gather<<<g, b, 0, c->stream>>>(c->P, c->grid[c->cur].tex, c->grid[c->cur].surf[0], staged);
+  reinject_commit<<<g, b, 0, c->stream>>>(staged, c->grid[c->cur].surf[0], V);
   c->launches += 2;
   VCT_CUDA(c, cudaFreeAsync(staged, c->stream));
-  c->accum_dense_dirty = c->accum_dense_dirty;   // level 0 still matches the touched list (same voxels occupied)
   VCT_CUDA(c, cudaGetLastError());
   return VCT_OK;
 }
@@ -626,7 +629,7 @@ int trace_cones(vct_context* c, size_t n, const float* starts, const float* dirs
   cudaMemcpyAsync(d_s, starts, n * 12, cudaMemcpyHostToDevice, c->stream);
   cudaMemcpyAsync(d_d, dirs, n * 12, cudaMemcpyHostToDevice, c->stream);
   cudaMemcpyAsync(d_t, tans, n * 4, cudaMemcpyHostToDevice, c->stream);
-  trace_cones_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->P, c->grid_tex, n, d_s, d_d, d_t, d_o, d_n);
+  trace_cones_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->P, c->grid[c->cur].tex, n, d_s, d_d, d_t, d_o, d_n);
   c->launches += 1;
   cudaMemcpyAsync(out, d_o, n * 16, cudaMemcpyDeviceToHost, c->stream);
   if (steps) cudaMemcpyAsync(steps, d_n, n * 4, cudaMemcpyDeviceToHost, c->stream);
@@ -651,7 +654,7 @@ int sample_voxels(vct_context* c, size_t n, const float* pos, const float* lod, 
   VCT_CUDA(c, cudaMalloc(&d_p, n * 12)); VCT_CUDA(c, cudaMalloc(&d_l, n * 4)); VCT_CUDA(c, cudaMalloc(&d_o, n * 16));
   cudaMemcpyAsync(d_p, pos, n * 12, cudaMemcpyHostToDevice, c->stream);
   cudaMemcpyAsync(d_l, lod, n * 4, cudaMemcpyHostToDevice, c->stream);
-  sample_voxels_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->P, c->grid_tex, n, d_p, d_l, d_o);
+  sample_voxels_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->P, c->grid[c->cur].tex, n, d_p, d_l, d_o);
   c->launches += 1;
   cudaMemcpyAsync(out, d_o, n * 16, cudaMemcpyDeviceToHost, c->stream);
   cudaError_t e = cudaStreamSynchronize(c->stream);

@@ -90,6 +90,8 @@ struct vct_context {
   int dense_resolve = 0;
   int grid_format = 0;
   int debug_lane_map = 1;
+  int debug_cone_smem_pad = 0;   // extra dynamic smem per cone_trace block: limits its blocks/SM so that the
+                                 // voxel/visibility stages of the next frame can be co-resident (pipelined frames)
   int debug_spec_ahead = 4;   // specular steps fetched ahead per iteration (1, 2, 4)
   size_t max_fragments = 16u << 20;
   size_t max_items = 4u << 20;
@@ -102,7 +104,16 @@ struct vct_context {
   vct::MaterialDev* d_materials = nullptr; size_t n_materials_dev = 0; bool materials_dirty = true;
   cudaTextureObject_t white_tex = 0; cudaMipmappedArray_t white_arr = nullptr;
 
-  vct::VertexCache vcache{}; size_t vcache_nv = 0; bool vcache_valid = false; vct::Params vcache_params{};
+  // Two frame slots (grid pyramid + touched list, visibility buffer, vertex cache): vct_frame / vct_draw_voxels
+  // build into the slot that the previous frame's cone_trace is NOT reading, so consecutive frames pipeline.
+  int cur = 0;                                   // slot of the most recent voxelisation / the one vct_render reads
+  vct::VertexCache vcache2[2]{}; size_t vcache_nv[2] = {0, 0}; bool vcache_valid[2] = {false, false};
+  vct::Params vcache_params[2]{};
+  cudaEvent_t slot_read_done[2] = {nullptr, nullptr};   // recorded on the main stream after the last reader of a slot
+  bool slot_read_pending[2] = {false, false};
+  cudaStream_t stream_vox = nullptr; cudaEvent_t ev_vox_done = nullptr, ev_vtx_done = nullptr;
+  unsigned long long scene_epoch = 1, frame_epoch = 0;   // device-side inputs changed since the last vct_frame?
+  int pipeline_frames = 1;
 
   // shadow map (u32 d24, linear)
   uint32_t* d_depth = nullptr; int depth_S = 0; bool depth_valid = false;
@@ -111,11 +122,16 @@ struct vct_context {
   // voxel grid
   int grid_V = 0;
   unsigned long long* d_accum = nullptr;       // 2 x u64 per voxel: (r<<32|g), (b<<32|count)
-  uint32_t* d_touched = nullptr; uint32_t* d_prev_touched = nullptr; size_t touched_cap = 0;
-  cudaMipmappedArray_t grid_array = nullptr;
-  std::vector<cudaSurfaceObject_t> grid_surf;
-  cudaTextureObject_t grid_tex = 0;
-  bool accum_dense_dirty = false;              // accumulator holds data not described by the touched list
+  struct GridBuf {
+    cudaMipmappedArray_t array = nullptr;
+    std::vector<cudaSurfaceObject_t> surf;
+    cudaTextureObject_t tex = 0;
+    uint32_t* touched = nullptr;               // voxels whose level-0 texel may be non-zero (exact when list_valid)
+    unsigned int* n_touched = nullptr;         // device counter
+    bool list_valid = true;                    // false: level 0 was written densely, a dense clear is needed before reuse
+  } grid[2];
+  size_t touched_cap = 0;
+  int accum_list_slot = -1;                    // slot whose touched list describes the accumulator's non-zero cells; -1 = dense dirty
 
   void* d_voxrec = nullptr; size_t voxrec_nt = 0;   // per-triangle voxelisation records (vct_voxelize.cu)
 
@@ -131,7 +147,7 @@ struct vct_context {
   int overlap_visibility = 1;
 
   // frame
-  unsigned long long* d_vis = nullptr; uchar4* d_frame = nullptr; int frame_W = 0, frame_H = 0;
+  unsigned long long* d_vis2[2] = {nullptr, nullptr}; uchar4* d_frame = nullptr; int frame_W = 0, frame_H = 0;
   // double-buffered frames for vct_frame_async
   uchar4* d_frame2[2] = {nullptr, nullptr}; int frame2_W = 0, frame2_H = 0;
   cudaStream_t copy_stream = nullptr; cudaEvent_t ev_rendered[2]{}, ev_copied[2]{}; bool in_flight[2] = {false, false};
@@ -175,6 +191,8 @@ int sync_materials(vct_context* c);
 int ensure_vertex_cache(vct_context* c);
 int launch_shadow(vct_context* c);
 int launch_voxel_clear(vct_context* c);
+int begin_voxel_slot(vct_context* c);     // flips c->cur to the other slot (after making it safe to overwrite)
+void mark_slot_read(vct_context* c);       // records slot_read_done[c->cur] on the main stream
 int launch_voxelize(vct_context* c, size_t tb, size_t te);
 int launch_resolve(vct_context* c, bool dense);
 int launch_mip(vct_context* c);

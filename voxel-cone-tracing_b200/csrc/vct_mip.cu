@@ -134,20 +134,20 @@ int launch_mip(vct_context* c) {
   int l = 0, n = c->P.V;
   while (n >= 32 && l + 3 < levels) {
     dim3 b(8, 4, 4), g(n / 32, n / 8, n / 8);
-    mip_fused3<<<g, b, 0, c->stream>>>(c->grid_surf[l], c->grid_surf[l + 1], c->grid_surf[l + 2], c->grid_surf[l + 3]);
+    mip_fused3<<<g, b, 0, c->stream>>>(c->grid[c->cur].surf[l], c->grid[c->cur].surf[l + 1], c->grid[c->cur].surf[l + 2], c->grid[c->cur].surf[l + 3]);
     c->launches += 1;
     l += 3; n >>= 3;
   }
   while (n > 32) {   // V not reducible by fused3 steps down to <= 32 (e.g. 64 -> 8 is fine; defensive)
     dim3 b(32, 8), g((n / 2 + 31) / 32, (n / 2 + 7) / 8, n / 2);
-    mip_one<<<g, b, 0, c->stream>>>(c->grid_surf[l], c->grid_surf[l + 1], n / 2);
+    mip_one<<<g, b, 0, c->stream>>>(c->grid[c->cur].surf[l], c->grid[c->cur].surf[l + 1], n / 2);
     c->launches += 1;
     l += 1; n >>= 1;
   }
   if (l < levels - 1) {
     TailSurfaces ts{};
     int n_out = levels - 1 - l;
-    for (int k = 0; k <= n_out; ++k) ts.s[k] = c->grid_surf[l + k];
+    for (int k = 0; k <= n_out; ++k) ts.s[k] = c->grid[c->cur].surf[l + k];
     size_t smem = ((size_t)n * n * n + (size_t)(n / 2) * (n / 2) * (n / 2)) * 4;
     if (smem > 48 * 1024)
       VCT_CUDA(c, cudaFuncSetAttribute(mip_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));

@@ -195,11 +195,11 @@ struct VoxCoverPass {
 
 // first fragment of a voxel (old count == 0): append the voxel to the touched list, one counter atomic per warp-step
 __device__ __forceinline__ void append_first_touch(bool& pending, unsigned long long old, uint32_t voxel,
-                                                   uint32_t* __restrict__ touched, Counters* __restrict__ ctr) {
+                                                   uint32_t* __restrict__ touched, unsigned int* __restrict__ n_touched) {
   if (pending && (uint32_t)old == 0u) {
     cg::coalesced_group firsts = cg::coalesced_threads();
     uint32_t base = 0;
-    if (firsts.thread_rank() == 0) base = atomicAdd(&ctr->n_touched, (uint32_t)firsts.size());
+    if (firsts.thread_rank() == 0) base = atomicAdd(n_touched, (uint32_t)firsts.size());
     base = firsts.shfl(base, 0);
     touched[base + firsts.thread_rank()] = voxel;
   }
@@ -212,7 +212,8 @@ __global__ void __launch_bounds__(256) vox_shade(Params P, const VoxRecord* __re
                                                  const uint32_t* __restrict__ depth, cudaTextureObject_t depth_tex,
                                                  const uint2* __restrict__ frags, uint32_t frags_cap,
                                                  unsigned long long* __restrict__ accum,
-                                                 uint32_t* __restrict__ touched, Counters* __restrict__ ctr) {
+                                                 uint32_t* __restrict__ touched, unsigned int* __restrict__ n_touched,
+                                                 Counters* __restrict__ ctr) {
   const uint32_t nfrag = min(ctr->n_fragments, frags_cap);
   const int V = P.V;
   bool pending = false;
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(256) vox_shade(Params P, const VoxRecord* __re
       fr_next = frags[f + stride];
       asm volatile("prefetch.global.L1 [%0];" ::"l"(&rec[fr_next.x]));
     }
-    append_first_touch(pending, pend_old, pend_voxel, touched, ctr);
+    append_first_touch(pending, pend_old, pend_voxel, touched, n_touched);
     const uint32_t tri = fr.x;
     const int i = (int)(fr.y & 0xFFFFu), j = (int)(fr.y >> 16);
     VoxTri s;
@@ -292,20 +293,38 @@ __global__ void __launch_bounds__(256) vox_shade(Params P, const VoxRecord* __re
       pending = true;
     }
   }
-  append_first_touch(pending, pend_old, pend_voxel, touched, ctr);
+  append_first_touch(pending, pend_old, pend_voxel, touched, n_touched);
 }
 
 // ---------------------------------------------------------------------------------------------------
-__global__ void vox_clear_sparse(unsigned long long* __restrict__ accum, const uint32_t* __restrict__ touched,
-                                 const Counters* __restrict__ ctr, cudaSurfaceObject_t level0, int V) {
-  const uint32_t n = ctr->n_touched;
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    uint32_t v = touched[k];
-    accum[2 * (size_t)v] = 0ull;
-    accum[2 * (size_t)v + 1] = 0ull;
-    int x = v % V, y = (v / V) % V, z = v / (V * V);
-    surf3Dwrite(make_uchar4(0, 0, 0, 0), level0, x * 4, y, z);
+// Sparse clear before a voxelisation into slot B: (1) zero the accumulator cells named by the list of the previous
+// voxelisation (slot A), (2) zero the level-0 texels of slot B named by slot B's own old list (what the frame before
+// last left there).  Cost is proportional to the occupied voxels, not to V^3.
+__global__ void vox_clear_sparse(unsigned long long* __restrict__ accum, const uint32_t* __restrict__ listA,
+                                 const unsigned int* __restrict__ nA, cudaSurfaceObject_t level0B,
+                                 const uint32_t* __restrict__ listB, const unsigned int* __restrict__ nB, int V) {
+  const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (listA) {
+    const uint32_t n = *nA;
+    for (uint32_t k = t0; k < n; k += stride) {
+      uint32_t v = listA[k];
+      accum[2 * (size_t)v] = 0ull;
+      accum[2 * (size_t)v + 1] = 0ull;
+    }
   }
+  if (listB) {
+    const uint32_t n = *nB;
+    for (uint32_t k = t0; k < n; k += stride) {
+      uint32_t v = listB[k];
+      int x = v % V, y = (v / V) % V, z = v / (V * V);
+      surf3Dwrite(make_uchar4(0, 0, 0, 0), level0B, x * 4, y, z);
+    }
+  }
+}
+
+__global__ void zero_level0(cudaSurfaceObject_t level0, int V) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, z = blockIdx.z;
+  if (x < V && y < V) surf3Dwrite(make_uchar4(0, 0, 0, 0), level0, x * 4, y, z);
 }
 
 __device__ __forceinline__ uchar4 resolve_cell(unsigned long long rg, unsigned long long bc) {
@@ -318,9 +337,9 @@ __device__ __forceinline__ uchar4 resolve_cell(unsigned long long rg, unsigned l
 }
 
 __global__ void vox_resolve_sparse(const unsigned long long* __restrict__ accum,
-                                   const uint32_t* __restrict__ touched, const Counters* __restrict__ ctr,
+                                   const uint32_t* __restrict__ touched, const unsigned int* __restrict__ n_touched,
                                    cudaSurfaceObject_t level0, int V) {
-  const uint32_t n = ctr->n_touched;
+  const uint32_t n = *n_touched;
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     uint32_t v = touched[k];
     const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(&accum[2 * (size_t)v]);
@@ -346,24 +365,30 @@ __global__ void accum_to_counts(const unsigned long long* __restrict__ accum, si
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Prepares the CURRENT slot (c->cur, already switched by begin_voxel_slot) and the accumulator for a new
+// voxelisation.
 int launch_voxel_clear(vct_context* c) {
   int rc = ensure_grid(c); if (rc) return rc;
   PassTimer timer(c, VCT_PASS_VOX_CLEAR);
   const int V = c->P.V;
-  if (c->accum_dense_dirty || c->dense_resolve) {
-    VCT_CUDA(c, cudaMemsetAsync(c->d_accum, 0, (size_t)V * V * V * 16, c->stream));
-    if (c->accum_dense_dirty) {   // level 0 may hold voxels the touched list does not know about
-      dim3 b(32, 8), g((V + 31) / 32, (V + 7) / 8, V);
-      vox_resolve_dense<<<g, b, 0, c->stream>>>(c->d_accum, c->grid_surf[0], V);
-      c->launches += 1;
-    }
-    c->accum_dense_dirty = false;
-  } else {
-    vox_clear_sparse<<<148 * 8, 256, 0, c->stream>>>(c->d_accum, c->d_touched, c->d_counters, c->grid_surf[0], V);
+  vct_context::GridBuf& g = c->grid[c->cur];
+  const bool accum_sparse = c->accum_list_slot >= 0 && !c->dense_resolve;
+  if (!accum_sparse) VCT_CUDA(c, cudaMemsetAsync(c->d_accum, 0, (size_t)V * V * V * 16, c->stream));
+  if (!g.list_valid) {              // level 0 of this slot was written densely: zero all of it
+    dim3 b(32, 8), gr((V + 31) / 32, (V + 7) / 8, V);
+    zero_level0<<<gr, b, 0, c->stream>>>(g.surf[0], V);
     c->launches += 1;
   }
-  VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_touched, 0, sizeof(unsigned int), c->stream));
+  if (accum_sparse || g.list_valid) {
+    const vct_context::GridBuf* a = accum_sparse ? &c->grid[c->accum_list_slot] : nullptr;
+    vox_clear_sparse<<<148 * 8, 256, 0, c->stream>>>(c->d_accum, a ? a->touched : nullptr, a ? a->n_touched : nullptr,
+                                                     g.surf[0], g.list_valid ? g.touched : nullptr, g.n_touched, V);
+    c->launches += 1;
+  }
+  VCT_CUDA(c, cudaMemsetAsync(g.n_touched, 0, sizeof(unsigned int), c->stream));
   VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_fragments, 0, sizeof(unsigned int), c->stream));
+  g.list_valid = true;              // from here on the list (being rebuilt) describes this slot's level 0
+  c->accum_list_slot = c->cur;
   VCT_CUDA(c, cudaGetLastError());
   return VCT_OK;
 }
@@ -387,7 +412,7 @@ int launch_voxelize(vct_context* c, size_t tb, size_t te) {
     VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_items, 0, sizeof(unsigned int), c->stream));
     VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->next_item, 0, sizeof(unsigned int), c->stream));
     VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_fragments, 0, sizeof(unsigned int), c->stream));
-    VoxCoverPass pass{c->P, c->vcache, c->d_idx, c->d_trimat, c->d_materials, (VoxRecord*)c->d_voxrec, c->d_frags, (uint32_t)c->frags_cap, c->d_counters};
+    VoxCoverPass pass{c->P, c->vcache2[c->cur], c->d_idx, c->d_trimat, c->d_materials, (VoxRecord*)c->d_voxrec, c->d_frags, (uint32_t)c->frags_cap, c->d_counters};
     const uint32_t n = (uint32_t)(te - tb);
     raster_small<VoxCoverPass><<<(n + 127) / 128, 128, 0, c->stream>>>(pass, (uint32_t)tb, (uint32_t)te, c->d_items,
                                                                         (uint32_t)c->items_cap, c->d_counters);
@@ -397,7 +422,7 @@ int launch_voxelize(vct_context* c, size_t tb, size_t te) {
   {
     PassTimer timer(c, VCT_PASS_VOX_SHADE);
     vox_shade<<<148 * 8, 256, 0, c->stream>>>(c->P, (const VoxRecord*)c->d_voxrec, c->d_materials, c->d_depth,
-                                              c->depth_tex, c->d_frags, (uint32_t)c->frags_cap, c->d_accum, c->d_touched,
+                                              c->depth_tex, c->d_frags, (uint32_t)c->frags_cap, c->d_accum, c->grid[c->cur].touched, c->grid[c->cur].n_touched,
                                               c->d_counters);
     c->launches += 1;
   }
@@ -409,11 +434,14 @@ int launch_resolve(vct_context* c, bool dense) {
   int rc = ensure_grid(c); if (rc) return rc;
   PassTimer timer(c, VCT_PASS_RESOLVE);
   const int V = c->P.V;
+  vct_context::GridBuf& g = c->grid[c->cur];
   if (dense) {
-    dim3 b(32, 8), g((V + 31) / 32, (V + 7) / 8, V);
-    vox_resolve_dense<<<g, b, 0, c->stream>>>(c->d_accum, c->grid_surf[0], V);
+    dim3 b(32, 8), gr((V + 31) / 32, (V + 7) / 8, V);
+    vox_resolve_dense<<<gr, b, 0, c->stream>>>(c->d_accum, g.surf[0], V);
+    g.list_valid = false;           // every texel was rewritten from the accumulator, the list was not maintained
+    c->accum_list_slot = -1;
   } else {
-    vox_resolve_sparse<<<148 * 8, 256, 0, c->stream>>>(c->d_accum, c->d_touched, c->d_counters, c->grid_surf[0], V);
+    vox_resolve_sparse<<<148 * 8, 256, 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, g.surf[0], V);
   }
   c->launches += 1;
   VCT_CUDA(c, cudaGetLastError());
