@@ -116,7 +116,7 @@ int vct_resolve_and_mip(vct_handle h);   /* dense resolve of the whole accumulat
 int vct_readback_depth(vct_handle h, uint32_t* d24 /* S*S */);
 int vct_readback_counts(vct_handle h, uint32_t* counts /* V^3, (z*V+y)*V+x */);
 int vct_readback_sums(vct_handle h, uint32_t* rgb /* V^3*3 */);
-int vct_readback_grid(vct_handle h, int level, uint8_t* rgba /* (V>>level)^3*4 */);
+int vct_readback_grid(vct_handle h, int level, uint8_t* rgba /* (V>>level)^3 texels: 4 B (RGBA8) or 8 B (RGBA16F half bits) each */);
 int vct_upload_grid_level0(vct_handle h, const uint8_t* rgba);   /* then vct_build_mips */
 int vct_build_mips(vct_handle h);
 int vct_readback_visibility(vct_handle h, uint32_t* tri_id /* H*W, 0xFFFFFFFF = background */);

@@ -26,7 +26,7 @@ class OrcParams(C.Structure):
         ("DiffuseTanHalfAngle", C.c_float), ("SpecularTanHalfAngle", C.c_float), ("StepMultiplier", C.c_float),
         ("MaxDistance", C.c_float), ("MaxAlpha", C.c_float), ("PcfRadius", C.c_int32), ("ShadowBias", C.c_float),
         ("CoveragePolicy", C.c_int32), ("VoxelStoreMode", C.c_int32), ("Bounces", C.c_int32),
-        ("FilterMode", C.c_int32),
+        ("FilterMode", C.c_int32), ("GridFormat", C.c_int32),
     ]
 
 
@@ -176,15 +176,16 @@ class Oracle:
         self.L.orc_set_accum(self.h, _p(c, C.c_uint32), _p(s, C.c_uint32))
 
     def grid(self, level=0):
+        """(n,n,n,4) uint8 for RGBA8 grids, float16 for RGBA16F grids"""
         n = self.V >> level
-        a = np.empty((n, n, n, 4), dtype=np.uint8)
-        assert self.L.orc_get_grid(self.h, level, _p(a, C.c_uint8)) == 0
+        a = np.empty((n, n, n, 4), dtype=np.float16 if self.p.GridFormat == 1 else np.uint8)
+        assert self.L.orc_get_grid(self.h, level, a.ctypes.data_as(C.POINTER(C.c_uint8))) == 0
         return a
 
     def set_grid_level0(self, rgba, build_mips=True):
-        a = np.ascontiguousarray(rgba, dtype=np.uint8)
+        a = np.ascontiguousarray(rgba, dtype=np.float16 if self.p.GridFormat == 1 else np.uint8)
         assert a.size == self.V ** 3 * 4
-        self.L.orc_set_grid_level0(self.h, _p(a, C.c_uint8))
+        self.L.orc_set_grid_level0(self.h, a.ctypes.data_as(C.POINTER(C.c_uint8)))
         if build_mips:
             self.L.orc_build_mips(self.h)
 

@@ -69,6 +69,38 @@ inline void atomic_min(T* cell, T v) {
 inline void atomic_min_u32(uint32_t* c, uint32_t v) { atomic_min(c, v); }
 inline void atomic_min_u64(uint64_t* c, uint64_t v) { atomic_min(c, v); }
 
+/* IEEE binary16 <-> binary32, round to nearest even (what cvt.rn.f16.f32 / __float2half_rn do) */
+inline uint16_t float_to_half(float f) {
+  uint32_t x; std::memcpy(&x, &f, 4);
+  uint32_t sign = (x >> 16) & 0x8000u;
+  uint32_t mant = x & 0x007FFFFFu;
+  int32_t exp = (int32_t)((x >> 23) & 0xFF) - 127 + 15;
+  if (((x >> 23) & 0xFF) == 0xFF) return (uint16_t)(sign | 0x7C00u | (mant ? 0x200u : 0));
+  if (exp >= 31) return (uint16_t)(sign | 0x7C00u);
+  if (exp <= 0) {
+    if (exp < -10) return (uint16_t)sign;
+    mant |= 0x00800000u;
+    uint32_t shift = (uint32_t)(14 - exp);
+    uint32_t h = mant >> shift;
+    uint32_t rem = mant & ((1u << shift) - 1), half = 1u << (shift - 1);
+    if (rem > half || (rem == half && (h & 1))) ++h;
+    return (uint16_t)(sign | h);
+  }
+  uint32_t h = ((uint32_t)exp << 10) | (mant >> 13);
+  uint32_t rem = mant & 0x1FFFu;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1))) ++h;
+  return (uint16_t)(sign | h);
+}
+inline float half_to_float(uint16_t h) {
+  uint32_t sign = (uint32_t)(h & 0x8000u) << 16, exp = (h >> 10) & 0x1F, mant = h & 0x3FFu, x;
+  if (exp == 0) {
+    if (!mant) x = sign;
+    else { int e = -1; do { ++e; mant <<= 1; } while (!(mant & 0x400u)); x = sign | ((uint32_t)(127 - 15 - e) << 23) | ((mant & 0x3FFu) << 13); }
+  } else if (exp == 31) x = sign | 0x7F800000u | (mant << 13);
+  else x = sign | ((exp - 15 + 127) << 23) | (mant << 13);
+  float f; std::memcpy(&f, &x, 4); return f;
+}
+
 constexpr int SUBPIX = 256;                 /* 8 sub-pixel bits */
 constexpr float SNAP_LIMIT = 8388608.0f;    /* guard band: +-2^23 sub-pixel units */
 
@@ -91,6 +123,14 @@ struct orc_ctx {
   uint64_t cone_samples = 0;
   uint64_t fragments = 0;
   int gridV = 0;
+  int gridFmt = -1;
+  int bpt() const { return p.GridFormat == 1 ? 8 : 4; }   /* bytes per texel */
+  /* channel ch of texel i of level l as the float the sampler sees */
+  float texel(int l, size_t i, int ch) const {
+    if (p.GridFormat == 1) { uint16_t h; std::memcpy(&h, &grid[l][i * 8 + ch * 2], 2); return half_to_float(h); }
+    return grid[l][i * 4 + ch] * (1.0f / 255.0f);
+  }
+  void set_texel16(int l, size_t i, int ch, float v) { uint16_t h = float_to_half(v); std::memcpy(&grid[l][i * 8 + ch * 2], &h, 2); }
 };
 
 namespace {
@@ -490,10 +530,11 @@ void voxelize_triangle(const orc_ctx* o, size_t ti, Emit&& emit) {
 
 void ensure_grid(orc_ctx* o) {
   const int V = o->p.VoxelDimensions;
-  if (o->gridV == V && !o->grid.empty()) return;
+  if (o->gridV == V && o->gridFmt == o->p.GridFormat && !o->grid.empty()) return;
   o->gridV = V;
+  o->gridFmt = o->p.GridFormat;
   o->grid.clear();
-  for (int s = V; s >= 1; s >>= 1) o->grid.emplace_back((size_t)s * s * s * 4, 0);
+  for (int s = V; s >= 1; s >>= 1) o->grid.emplace_back((size_t)s * s * s * o->bpt(), 0);
   o->counts.assign((size_t)V * V * V, 0);
   o->sums.assign((size_t)V * V * V * 3, 0);
 }
@@ -541,6 +582,31 @@ extern "C" int orc_build_mips(orc_ctx* o) {
   /* glGenerateMipmap(GL_TEXTURE_3D), Voxel_Cone_Tracing.h:246-248: 2x2x2 box, round to nearest. */
   ensure_grid(o);
   int s = o->p.VoxelDimensions;
+  if (o->p.GridFormat == 1) {
+    /* RGBA16F: fp32 sum of the 8 parents in the fixed order ((a00 + a10) + a01) + a11, a_yz = the x pair, times
+     * 0.125, rounded to half (nearest even) */
+    for (size_t l = 1; l < o->grid.size(); ++l) {
+      int ps = s;
+      s >>= 1;
+#pragma omp parallel for schedule(static) if (s >= 16)
+      for (int z = 0; z < s; ++z)
+        for (int y = 0; y < s; ++y)
+          for (int x = 0; x < s; ++x)
+            for (int c = 0; c < 4; ++c) {
+              float acc = 0.0f;
+              bool first = true;
+              for (int dz = 0; dz < 2; ++dz)
+                for (int dy = 0; dy < 2; ++dy) {
+                  size_t i0 = (((size_t)(2 * z + dz)) * ps + (2 * y + dy)) * ps + 2 * x;
+                  float a = o->texel((int)l - 1, i0, c) + o->texel((int)l - 1, i0 + 1, c);
+                  acc = first ? a : acc + a;
+                  first = false;
+                }
+              o->set_texel16((int)l, ((size_t)z * s + y) * s + x, c, acc * 0.125f);
+            }
+    }
+    return 0;
+  }
   for (size_t l = 1; l < o->grid.size(); ++l) {
     int ps = s;
     s >>= 1;
@@ -580,10 +646,7 @@ void sample_grid_level(const orc_ctx* o, int l, float u, float v, float w, float
   int i0 = wrap_repeat((int)fx, N), i1 = wrap_repeat((int)fx + 1, N);
   int j0 = wrap_repeat((int)fy, N), j1 = wrap_repeat((int)fy + 1, N);
   int k0 = wrap_repeat((int)fz, N), k1 = wrap_repeat((int)fz + 1, N);
-  const uint8_t* g = o->grid[l].data();
-  auto at = [&](int i, int j, int k, int ch) {
-    return g[(((size_t)k * N + j) * N + i) * 4 + ch] * (1.0f / 255.0f);
-  };
+  auto at = [&](int i, int j, int k, int ch) { return o->texel(l, ((size_t)k * N + j) * N + i, ch); };
   for (int ch = 0; ch < 4; ++ch) {
     float c00 = at(i0, j0, k0, ch) + a * (at(i1, j0, k0, ch) - at(i0, j0, k0, ch));
     float c10 = at(i0, j1, k0, ch) + a * (at(i1, j1, k0, ch) - at(i0, j1, k0, ch));
@@ -983,6 +1046,17 @@ extern "C" int orc_render_rows(orc_ctx* o, int y0, int y1) {
 static void resolve_level0(orc_ctx* o) {
   const size_t n = o->counts.size();
   uint8_t* g = o->grid[0].data();
+  if (o->p.GridFormat == 1) {
+    /* RGBA16F: rgb = half(sum / (count * 255)), alpha = 1 */
+    for (size_t i = 0; i < n; ++i) {
+      uint32_t c = o->counts[i];
+      for (int k = 0; k < 4; ++k) o->set_texel16(0, i, k, 0.0f);
+      if (c == 0) continue;
+      for (int k = 0; k < 3; ++k) o->set_texel16(0, i, k, (float)o->sums[i * 3 + k] / ((float)c * 255.0f));
+      o->set_texel16(0, i, 3, 1.0f);
+    }
+    return;
+  }
   for (size_t i = 0; i < n; ++i) {
     uint32_t c = o->counts[i];
     if (c == 0) { g[i * 4 + 0] = g[i * 4 + 1] = g[i * 4 + 2] = g[i * 4 + 3] = 0; continue; }
@@ -1006,7 +1080,7 @@ static void reinject_bounce(orc_ctx* o) {
     for (int y = 0; y < V; ++y)
       for (int x = 0; x < V; ++x) {
         size_t i = ((size_t)z * V + y) * V + x;
-        if (o->grid[0][i * 4 + 3] == 0) continue;
+        if (o->texel(0, i, 3) == 0.0f) continue;
         V3 c = {((float)x + 0.5f) * vws - 0.5f * p.VoxelGridWorldSize,
                 ((float)y + 0.5f) * vws - 0.5f * p.VoxelGridWorldSize,
                 ((float)z + 0.5f) * vws - 0.5f * p.VoxelGridWorldSize};
@@ -1020,9 +1094,10 @@ static void reinject_bounce(orc_ctx* o) {
           for (int k = 0; k < 3; ++k) acc[k] += r[k] * (1.0f / 6.0f);
         }
         for (int k = 0; k < 3; ++k) {
-          float base = o->grid[0][i * 4 + k] * (1.0f / 255.0f);
+          float base = o->texel(0, i, k);
           float v = std::min(base + acc[k] * base, 1.0f);
-          next[i * 4 + k] = (uint8_t)std::lrintf(v * 255.0f);
+          if (o->p.GridFormat == 1) { uint16_t h = float_to_half(v); std::memcpy(&next[i * 8 + k * 2], &h, 2); }
+          else next[i * 4 + k] = (uint8_t)std::lrintf(v * 255.0f);
         }
       }
   o->grid[0].swap(next);
@@ -1077,6 +1152,7 @@ extern "C" void orc_default_params(orc_params* p) {
   p->CoveragePolicy = 1;
   p->VoxelStoreMode = 0;
   p->Bounces = 2;
+  p->GridFormat = 0;
   p->FilterMode = 1;   /* 8-bit fixed-point filter weights: what texture hardware and llvmpipe's RGBA8 path use */
 }
 
@@ -1091,7 +1167,7 @@ extern "C" void orc_destroy(orc_ctx* o) { delete o; }
 extern "C" int orc_set_params(orc_ctx* o, const orc_params* p) {
   if (p->VoxelDimensions < 1 || (p->VoxelDimensions & (p->VoxelDimensions - 1))) return -1;
   if (p->NumDiffuseCones < 0 || p->NumDiffuseCones > ORC_MAX_CONES) return -1;
-  bool regrid = p->VoxelDimensions != o->p.VoxelDimensions;
+  bool regrid = p->VoxelDimensions != o->p.VoxelDimensions || p->GridFormat != o->p.GridFormat;
   bool reshadow = p->ShadowMapSize != o->p.ShadowMapSize;
   o->p = *p;
   if (regrid) { o->grid.clear(); o->gridV = 0; }

@@ -54,6 +54,7 @@ typedef struct orc_params {
   int32_t FilterMode;                /* voxel-texture filter weights: 1 (default) = 8 fractional bits, rounded (LOD
                                         fraction truncated), as measured on B200 texture hardware and as llvmpipe's
                                         RGBA8 path does; 0 = fp32 weights */
+  int32_t GridFormat;                /* 0 = RGBA8 (the reference, Voxel_Cone_Tracing.h:119), 1 = RGBA16F (BASELINE config 3) */
 } orc_params;
 
 typedef struct orc_ctx orc_ctx;
@@ -81,7 +82,7 @@ int orc_get_depth(orc_ctx*, uint32_t* d24);                 /* S*S */
 int orc_get_counts(orc_ctx*, uint32_t* counts);             /* V^3, index (z*V+y)*V+x */
 int orc_get_sums(orc_ctx*, uint32_t* rgb_sums);             /* V^3*3 */
 int orc_set_accum(orc_ctx*, const uint32_t* counts, const uint32_t* rgb_sums);
-int orc_get_grid(orc_ctx*, int level, uint8_t* rgba);       /* (V>>level)^3*4 */
+int orc_get_grid(orc_ctx*, int level, uint8_t* rgba);       /* (V>>level)^3*4 bytes (RGBA8) or *8 (RGBA16F half bits) */
 int orc_set_grid_level0(orc_ctx*, const uint8_t* rgba);     /* then orc_build_mips */
 int orc_build_mips(orc_ctx*);
 int orc_get_visibility(orc_ctx*, uint32_t* tri_id);         /* H*W, 0xFFFFFFFF = background */

@@ -435,3 +435,74 @@ def test_cpp_facade_with_the_reference_class_surface_runs():
     assert out.returncode == 0, out.stdout + out.stderr
     sums = [int(l.split()[-1]) for l in out.stdout.splitlines() if l.startswith("frame")]
     assert len(sums) == 3 and all(s > 256 * 256 * 4 * 20 for s in sums) and len(set(sums)) == 3   # three different views
+
+
+# ------------------------------------------------------------------------------------------ RGBA16F grid (config 3)
+@pytest.mark.parametrize("V", [8, 32, 128])
+def test_fp16_mip_pyramid_bit_exact(gpu_ctx, oracle, V):
+    rng = np.random.default_rng(100 + V)
+    g = (rng.random((V, V, V, 4)) * 4.0).astype(np.float16)
+    g[rng.random((V, V, V)) < 0.7] = 0
+    gpu_ctx.set_i("GridFormat", 1)
+    gpu_ctx.set_i("VoxelDimensions", V)
+    oracle.set_uniforms(uniforms.reference_uniforms(V=V, grid_format=1))
+    gpu_ctx.upload_grid_level0(g)
+    oracle.set_grid_level0(g)
+    for l in range(V.bit_length()):
+        a, b = gpu_ctx.grid(l), oracle.grid(l)
+        assert a.dtype == np.float16 and np.array_equal(a.view(np.uint16), b.view(np.uint16)), f"V={V} level {l}"
+
+
+def test_fp16_grid_cornell_vs_oracle(gpu_ctx, oracle):
+    sc = scenes.cornell()
+    u = uniforms.scene_uniforms(sc, V=64, width=256, height=256, shadow_map_size=1024, coverage="conservative",
+                                cones="9+1", grid_format=1)
+    run_gpu(gpu_ctx, sc, u)
+    run_oracle(oracle, sc, u)
+    assert np.array_equal(gpu_ctx.counts(), oracle.counts())
+    for l in range(7):          # untextured scene: integer sums equal => half values and every mip level bit-exact
+        assert np.array_equal(gpu_ctx.grid(l).view(np.uint16), oracle.grid(l).view(np.uint16)), f"level {l}"
+    g0 = gpu_ctx.grid(0).astype(np.float32)
+    assert set(np.unique(g0[..., 3])) == {0.0, 1.0} and g0[..., :3].max() <= 1.0
+    assert_frame_close(gpu_ctx.read_frame(), oracle.frame(), "fp16 grid, 9+1 cones")
+    # the fp16 grid keeps what RGBA8 rounds away: same scene in RGBA8 differs slightly but stays close
+    u8 = dict(u); u8["GridFormat"] = 0
+    gpu_ctx.set_uniforms(u8); gpu_ctx.draw_voxels(); gpu_ctx.render(); gpu_ctx.sync()
+    assert gpu_ctx.grid(0).dtype == np.uint8
+    assert psnr(gpu_ctx.read_frame()[..., :3], oracle.frame()[..., :3]) > 40.0
+
+
+def test_config3_shape_fp16_512_tiles(gpu_ctx):
+    """BASELINE config 3 at reduced mesh detail: 512^3 RGBA16F grid, 3840x2160, 9 diffuse cones + specular, rendered
+    as two row bands (what two ranks would do) and as one frame: identical pixels."""
+    from vct_b200 import parallel
+    sc = scenes.atrium(detail=0.25, tex_size=64)
+    u = uniforms.scene_uniforms(sc, V=512, width=3840, height=2160, shadow_map_size=4096, coverage="conservative",
+                                cones="9+1", grid_format=1)
+    c = gpu_ctx
+    run_gpu(c, sc, u)
+    full = c.read_frame()
+    cnt = c.counts()
+    assert cnt.sum() > 1_000_000 and c.grid(0).dtype == np.float16
+    g1 = c.grid(1).astype(np.float32)
+    assert np.isfinite(g1).all() and g1[..., 3].max() <= 1.0
+    bands = []
+    for r in range(2):
+        b0, b1 = parallel.row_band(2160, r, 2)
+        c.set_i("RowBegin", b0); c.set_i("RowEnd", b1)
+        c.render(); c.sync()
+        bands.append(c.read_frame()[b0:b1])
+    c.set_i("RowBegin", 0); c.set_i("RowEnd", 0)
+    assert np.array_equal(np.concatenate(bands, 0), full)
+    assert c.cone_samples() > 0
+
+
+def test_fp16_bounce_extension_vs_oracle(gpu_ctx, oracle):
+    sc = scenes.cornell()
+    u = uniforms.scene_uniforms(sc, V=32, width=96, height=96, shadow_map_size=512, bounces=3, grid_format=1)
+    run_gpu(gpu_ctx, sc, u)
+    run_oracle(oracle, sc, u)
+    g, o = gpu_ctx.grid(0).astype(np.float32), oracle.grid(0).astype(np.float32)
+    assert np.array_equal(g[..., 3], o[..., 3])
+    assert np.abs(g - o).max() <= 2.0 / 255
+    assert_frame_close(gpu_ctx.read_frame(), oracle.frame(), "fp16 bounces=3", FRAC_MIN_SMALL)

@@ -241,12 +241,12 @@ class Context:
 
     def grid(self, level=0):
         n = self.get_i("VoxelDimensions") >> level
-        a = np.empty((n, n, n, 4), dtype=np.uint8)
+        a = np.empty((n, n, n, 4), dtype=np.float16 if self.get_i("GridFormat") == 1 else np.uint8)
         self._ck(self.L.vct_readback_grid(self.h, int(level), _ptr(a)))
         return a
 
     def upload_grid_level0(self, rgba, build_mips=True):
-        a = np.ascontiguousarray(rgba, dtype=np.uint8)
+        a = np.ascontiguousarray(rgba, dtype=np.float16 if self.get_i("GridFormat") == 1 else np.uint8)
         V = self.get_i("VoxelDimensions")
         assert a.size == V ** 3 * 4
         self._ck(self.L.vct_upload_grid_level0(self.h, _ptr(a)))

@@ -2,6 +2,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cuda_fp16.h>
+
 #include "vct_internal.h"
 
 namespace vct {
@@ -74,14 +76,16 @@ static void free_grid(vct_context* c) {
 
 int ensure_grid(vct_context* c) {
   const int V = c->P.V;
-  if (c->grid_V == V) return VCT_OK;
+  if (c->grid_V == V && c->grid_fmt_alloc == c->grid_format) return VCT_OK;
   cudaStreamSynchronize(c->stream);
   if (c->stream_vox) cudaStreamSynchronize(c->stream_vox);
   free_grid(c);
+  c->grid_fmt_alloc = c->grid_format;
   const size_t n = (size_t)V * V * V;
   VCT_CUDA(c, cudaMalloc(&c->d_accum, n * 16));
   c->touched_cap = n;
-  cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
+  // RGBA8 is the reference's format (GL_RGBA8, Voxel_Cone_Tracing.h:119); RGBA16F is BASELINE config 3
+  cudaChannelFormatDesc desc = c->grid_format == 1 ? cudaCreateChannelDescHalf4() : cudaCreateChannelDesc<uchar4>();
   for (auto& g : c->grid) {
     VCT_CUDA(c, cudaMalloc(&g.touched, n * 4));
     VCT_CUDA(c, cudaMalloc(&g.n_touched, 128));
@@ -106,7 +110,7 @@ int ensure_grid(vct_context* c) {
     td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeWrap;
     td.filterMode = cudaFilterModeLinear;
     td.mipmapFilterMode = cudaFilterModeLinear;
-    td.readMode = cudaReadModeNormalizedFloat;
+    td.readMode = c->grid_format == 1 ? cudaReadModeElementType : cudaReadModeNormalizedFloat;   // half texels read as float
     td.normalizedCoords = 1;
     td.minMipmapLevelClamp = 0.0f;
     td.maxMipmapLevelClamp = (float)(c->P.levels - 1);
@@ -501,7 +505,7 @@ int vct_set_i(vct_handle c, const char* name, int v) {
   else if (k == "CoveragePolicy") { if (v < 0 || v > 2) return set_error(c, VCT_ERR_INVALID, "CoveragePolicy must be 0,1,2"); P.coverage = v; }
   else if (k == "Bounces") { if (v < 1 || v > 8) return set_error(c, VCT_ERR_INVALID, "Bounces out of range"); P.bounces = v; }
   else if (k == "NumDiffuseCones") { if (v < 0 || v > VCT_MAX_CONES) return set_error(c, VCT_ERR_INVALID, "NumDiffuseCones out of range"); P.n_cones = v; }
-  else if (k == "GridFormat") { if (v != 0) return set_error(c, VCT_ERR_INVALID, "GridFormat: only 0 (RGBA8) is implemented"); c->grid_format = v; }
+  else if (k == "GridFormat") { if (v != 0 && v != 1) return set_error(c, VCT_ERR_INVALID, "GridFormat: 0 = RGBA8, 1 = RGBA16F"); if (v != c->grid_format) c->scene_epoch++; c->grid_format = v; }
   else if (k == "MaxFragments") { if (v < 1024) return set_error(c, VCT_ERR_INVALID, "MaxFragments too small"); c->max_fragments = (size_t)v; }
   else if (k == "MaxTileItems") { if (v < 1024) return set_error(c, VCT_ERR_INVALID, "MaxTileItems too small"); c->max_items = (size_t)v; }
   else if (k == "RowBegin") { if (v < 0) return set_error(c, VCT_ERR_INVALID, "RowBegin < 0"); P.row_begin = v; }
@@ -895,8 +899,9 @@ int vct_readback_grid(vct_handle c, int level, uint8_t* rgba) {
   cudaArray_t lvl;
   VCT_CUDA(c, cudaGetMipmappedArrayLevel(&lvl, c->grid[c->cur].array, level));
   cudaMemcpy3DParms p{};
+  const size_t bpt = c->grid_format == 1 ? 8 : 4;
   p.srcArray = lvl;
-  p.dstPtr = make_cudaPitchedPtr(rgba, (size_t)n * 4, n, n);
+  p.dstPtr = make_cudaPitchedPtr(rgba, (size_t)n * bpt, n, n);
   p.extent = make_cudaExtent(n, n, n);
   p.kind = cudaMemcpyDeviceToHost;
   VCT_CUDA(c, cudaMemcpy3DAsync(&p, c->stream));
@@ -910,7 +915,8 @@ int vct_upload_grid_level0(vct_handle c, const uint8_t* rgba) {
   cudaArray_t lvl;
   VCT_CUDA(c, cudaGetMipmappedArrayLevel(&lvl, c->grid[c->cur].array, 0));
   cudaMemcpy3DParms p{};
-  p.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(rgba), (size_t)n * 4, n, n);
+  const size_t bpt = c->grid_format == 1 ? 8 : 4;
+  p.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(rgba), (size_t)n * bpt, n, n);
   p.dstArray = lvl;
   p.extent = make_cudaExtent(n, n, n);
   p.kind = cudaMemcpyHostToDevice;

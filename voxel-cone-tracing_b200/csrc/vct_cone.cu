@@ -10,6 +10,8 @@
 //   cone_trace: one thread per pixel, one warp per 8x4 screen tile; rebuilds the interpolated varyings
 //        of the winning triangle and evaluates VoxelConeTracing.fs:165-229 exactly once per pixel.
 //        Voxel fetches are hardware trilinear tex3DLod on the mipmapped cudaArray (wrap = REPEAT).
+#include <cuda_fp16.h>
+
 #include "vct_raster.cuh"
 
 namespace vct {
@@ -556,13 +558,25 @@ int launch_cone(vct_context* c) {
 // out from the voxel centre, averaged; new = min(old + gathered * old, 1).  Reads the pyramid of the
 // previous bounce through the texture, writes a staging buffer, then level 0 (no read/write hazard).
 __global__ void __launch_bounds__(256) reinject_gather(Params P, cudaTextureObject_t grid, cudaSurfaceObject_t level0,
-                                                       uint32_t* __restrict__ staged) {
+                                                       uint2* __restrict__ staged, int f16) {
   const int V = P.V;
   const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), z = blockIdx.z;
   if (x >= V || y >= V) return;
   const size_t i = ((size_t)z * V + y) * V + x;
-  const uchar4 old = surf3Dread<uchar4>(level0, x * 4, y, z);
-  if (old.w == 0) { staged[i] = 0u; return; }
+  float b0, b1, b2;
+  uint2 raw;
+  if (f16) {
+    raw = surf3Dread<uint2>(level0, x * 8, y, z);
+    if ((raw.y >> 16) == 0u) { staged[i] = make_uint2(0u, 0u); return; }
+    b0 = __half2float(__ushort_as_half((unsigned short)(raw.x & 0xFFFFu)));
+    b1 = __half2float(__ushort_as_half((unsigned short)(raw.x >> 16)));
+    b2 = __half2float(__ushort_as_half((unsigned short)(raw.y & 0xFFFFu)));
+  } else {
+    const uchar4 old = surf3Dread<uchar4>(level0, x * 4, y, z);
+    if (old.w == 0) { staged[i] = make_uint2(0u, 0u); return; }
+    raw = make_uint2(0u, (unsigned)old.w);
+    b0 = old.x * (1.0f / 255.0f); b1 = old.y * (1.0f / 255.0f); b2 = old.z * (1.0f / 255.0f);
+  }
   const ConeConsts kc = cone_consts(P);
   const V3 c = v3(((float)x + 0.5f) * kc.vws - 0.5f * P.grid_world, ((float)y + 0.5f) * kc.vws - 0.5f * P.grid_world,
                   ((float)z + 0.5f) * kc.vws - 0.5f * P.grid_world);
@@ -575,31 +589,38 @@ __global__ void __launch_bounds__(256) reinject_gather(Params P, cudaTextureObje
     const float4 r = cone_march(grid, P, kc, vadd(c, vscale(d, kc.vws)), d, P.diffuse_tan, dummy);
     acc[0] += r.x * (1.0f / 6.0f); acc[1] += r.y * (1.0f / 6.0f); acc[2] += r.z * (1.0f / 6.0f);
   }
-  const float b0 = old.x * (1.0f / 255.0f), b1 = old.y * (1.0f / 255.0f), b2 = old.z * (1.0f / 255.0f);
-  uchar4 o;
-  o.x = (unsigned char)__float2int_rn(fminf(b0 + acc[0] * b0, 1.0f) * 255.0f);
-  o.y = (unsigned char)__float2int_rn(fminf(b1 + acc[1] * b1, 1.0f) * 255.0f);
-  o.z = (unsigned char)__float2int_rn(fminf(b2 + acc[2] * b2, 1.0f) * 255.0f);
-  o.w = old.w;
-  staged[i] = *reinterpret_cast<uint32_t*>(&o);
+  const float n0 = fminf(b0 + acc[0] * b0, 1.0f), n1 = fminf(b1 + acc[1] * b1, 1.0f), n2 = fminf(b2 + acc[2] * b2, 1.0f);
+  if (f16) {
+    staged[i] = make_uint2((unsigned)__half_as_ushort(__float2half_rn(n0)) | ((unsigned)__half_as_ushort(__float2half_rn(n1)) << 16),
+                           (unsigned)__half_as_ushort(__float2half_rn(n2)) | (raw.y & 0xFFFF0000u));
+  } else {
+    uchar4 o;
+    o.x = (unsigned char)__float2int_rn(n0 * 255.0f);
+    o.y = (unsigned char)__float2int_rn(n1 * 255.0f);
+    o.z = (unsigned char)__float2int_rn(n2 * 255.0f);
+    o.w = (unsigned char)raw.y;
+    staged[i] = make_uint2(*reinterpret_cast<uint32_t*>(&o), 1u);
+  }
 }
 
-__global__ void reinject_commit(const uint32_t* __restrict__ staged, cudaSurfaceObject_t level0, int V) {
+__global__ void reinject_commit(const uint2* __restrict__ staged, cudaSurfaceObject_t level0, int V, int f16) {
   const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), z = blockIdx.z;
   if (x >= V || y >= V) return;
-  const uint32_t v = staged[((size_t)z * V + y) * V + x];
-  if (v) surf3Dwrite(v, level0, x * 4, y, z);
+  const uint2 v = staged[((size_t)z * V + y) * V + x];
+  if (!(v.x | v.y)) return;
+  if (f16) surf3Dwrite(v, level0, x * 8, y, z);
+  else surf3Dwrite(v.x, level0, x * 4, y, z);
 }
 
 int launch_reinject(vct_context* c) {
   int rc = ensure_grid(c); if (rc) return rc;
   PassTimer timer(c, VCT_PASS_REINJECT);
   const int V = c->P.V;
-  uint32_t* staged = nullptr;
-  VCT_CUDA(c, cudaMallocAsync(&staged, (size_t)V * V * V * 4, c->stream));
+  uint2* staged = nullptr;
+  VCT_CUDA(c, cudaMallocAsync(&staged, (size_t)V * V * V * 8, c->stream));
   dim3 b(256), g((V + 31) / 32, (V + 7) / 8, V);
-  reinject_gather<<<g, b, 0, c->stream>>>(c->P, c->grid[c->cur].tex, c->grid[c->cur].surf[0], staged);
-  reinject_commit<<<g, b, 0, c->stream>>>(staged, c->grid[c->cur].surf[0], V);
+  reinject_gather<<<g, b, 0, c->stream>>>(c->P, c->grid[c->cur].tex, c->grid[c->cur].surf[0], staged, c->grid_format);
+  reinject_commit<<<g, b, 0, c->stream>>>(staged, c->grid[c->cur].surf[0], V, c->grid_format);
   c->launches += 2;
   VCT_CUDA(c, cudaFreeAsync(staged, c->stream));
   VCT_CUDA(c, cudaGetLastError());

@@ -120,7 +120,7 @@ struct vct_context {
   cudaArray_t depth_array = nullptr; cudaTextureObject_t depth_tex = 0;   // same texels as a 2D array for tex2Dgather
 
   // voxel grid
-  int grid_V = 0;
+  int grid_V = 0; int grid_fmt_alloc = -1;       // format the slots were allocated with (0 RGBA8, 1 RGBA16F)
   unsigned long long* d_accum = nullptr;       // 2 x u64 per voxel: (r<<32|g), (b<<32|count)
   struct GridBuf {
     cudaMipmappedArray_t array = nullptr;

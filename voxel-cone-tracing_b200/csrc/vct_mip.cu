@@ -7,6 +7,8 @@
 //                HBM traffic = read L once + write the three children.
 //   mip_tail   : one CTA reduces a level of <= 32^3 texels down to 1^3 entirely in shared memory.
 // At V = 256 the pyramid is built by three launches: fused3(0 -> 1,2,3), fused3(3 -> 4,5,6), tail(6 -> 7,8).
+#include <cuda_fp16.h>
+
 #include "vct_internal.h"
 
 namespace vct {
@@ -127,10 +129,46 @@ __global__ void mip_one(cudaSurfaceObject_t src, cudaSurfaceObject_t dst, int h)
   surf3Dwrite(finish_px(e, o), dst, x * 4, y, z);
 }
 
+// RGBA16F level: fp32 sum of the 8 parents in the fixed order ((a00 + a10) + a01) + a11 (a_yz = the x pair at
+// row 2y+dy, slice 2z+dz), times 0.125, rounded to half.  One thread per child texel; every level is read once and
+// written once (1.29 x level 0 in total), which is what bounds it: HBM.
+__global__ void mip_level_f16(cudaSurfaceObject_t src, cudaSurfaceObject_t dst, int h) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, z = blockIdx.z;
+  if (x >= h || y >= h) return;
+  float acc[4];
+#pragma unroll
+  for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const uint4 q = surf3Dread<uint4>(src, (2 * x) * 8, 2 * y + dy, 2 * z + dz);   // two texels
+      const unsigned w0[4] = {q.x & 0xFFFFu, q.x >> 16, q.y & 0xFFFFu, q.y >> 16};
+      const unsigned w1[4] = {q.z & 0xFFFFu, q.z >> 16, q.w & 0xFFFFu, q.w >> 16};
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        const float a = __half2float(__ushort_as_half((unsigned short)w0[ch])) + __half2float(__ushort_as_half((unsigned short)w1[ch]));
+        acc[ch] = (dz == 0 && dy == 0) ? a : acc[ch] + a;
+      }
+    }
+  unsigned short o[4];
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) o[ch] = __half_as_ushort(__float2half_rn(acc[ch] * 0.125f));
+  surf3Dwrite(make_uint2((unsigned)o[0] | ((unsigned)o[1] << 16), (unsigned)o[2] | ((unsigned)o[3] << 16)), dst, x * 8, y, z);
+}
+
 int launch_mip(vct_context* c) {
   int rc = ensure_grid(c); if (rc) return rc;
   PassTimer timer(c, VCT_PASS_MIP);
   const int levels = c->P.levels;
+  if (c->grid_format == 1) {
+    for (int l = 0, n = c->P.V; l + 1 < levels; ++l, n >>= 1) {
+      const int h = n >> 1;
+      dim3 b(32, 4), g((h + 31) / 32, (h + 3) / 4, h);
+      mip_level_f16<<<g, b, 0, c->stream>>>(c->grid[c->cur].surf[l], c->grid[c->cur].surf[l + 1], h);
+      c->launches += 1;
+    }
+    VCT_CUDA(c, cudaGetLastError());
+    return VCT_OK;
+  }
   int l = 0, n = c->P.V;
   while (n >= 32 && l + 3 < levels) {
     dim3 b(8, 4, 4), g(n / 32, n / 8, n / 8);

@@ -10,6 +10,7 @@
 //              fragment of a voxel (old count == 0) appends the voxel to the touched list.
 //   vox_clear / vox_resolve : sparse, over the touched list only.
 #include <cooperative_groups.h>
+#include <cuda_fp16.h>
 #include <cooperative_groups/reduce.h>
 
 #include "vct_raster.cuh"
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(256) vox_shade(Params P, const VoxRecord* __re
 // last left there).  Cost is proportional to the occupied voxels, not to V^3.
 __global__ void vox_clear_sparse(unsigned long long* __restrict__ accum, const uint32_t* __restrict__ listA,
                                  const unsigned int* __restrict__ nA, cudaSurfaceObject_t level0B,
-                                 const uint32_t* __restrict__ listB, const unsigned int* __restrict__ nB, int V) {
+                                 const uint32_t* __restrict__ listB, const unsigned int* __restrict__ nB, int V, int f16) {
   const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
   if (listA) {
     const uint32_t n = *nA;
@@ -317,14 +318,17 @@ __global__ void vox_clear_sparse(unsigned long long* __restrict__ accum, const u
     for (uint32_t k = t0; k < n; k += stride) {
       uint32_t v = listB[k];
       int x = v % V, y = (v / V) % V, z = v / (V * V);
-      surf3Dwrite(make_uchar4(0, 0, 0, 0), level0B, x * 4, y, z);
+      if (f16) surf3Dwrite(make_uint2(0u, 0u), level0B, x * 8, y, z);
+      else surf3Dwrite(make_uchar4(0, 0, 0, 0), level0B, x * 4, y, z);
     }
   }
 }
 
-__global__ void zero_level0(cudaSurfaceObject_t level0, int V) {
+__global__ void zero_level0(cudaSurfaceObject_t level0, int V, int f16) {
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, z = blockIdx.z;
-  if (x < V && y < V) surf3Dwrite(make_uchar4(0, 0, 0, 0), level0, x * 4, y, z);
+  if (x >= V || y >= V) return;
+  if (f16) surf3Dwrite(make_uint2(0u, 0u), level0, x * 8, y, z);
+  else surf3Dwrite(make_uchar4(0, 0, 0, 0), level0, x * 4, y, z);
 }
 
 __device__ __forceinline__ uchar4 resolve_cell(unsigned long long rg, unsigned long long bc) {
@@ -336,24 +340,37 @@ __device__ __forceinline__ uchar4 resolve_cell(unsigned long long rg, unsigned l
                      (unsigned char)((b + h) / cnt), 255);   // alpha written as 1.0, Voxelization.fs:88
 }
 
+// RGBA16F level 0: rgb = half(sum / (count * 255)), alpha = 1 (DESIGN.md "Defined semantics")
+__device__ __forceinline__ uint2 resolve_cell16(unsigned long long rg, unsigned long long bc) {
+  unsigned cnt = (unsigned)bc;
+  if (!cnt) return make_uint2(0u, 0u);
+  const float d = (float)cnt * 255.0f;
+  const __half r = __float2half_rn((float)(unsigned)(rg >> 32) / d), g = __float2half_rn((float)(unsigned)rg / d),
+               b = __float2half_rn((float)(unsigned)(bc >> 32) / d), a = __float2half_rn(1.0f);
+  return make_uint2((unsigned)__half_as_ushort(r) | ((unsigned)__half_as_ushort(g) << 16),
+                    (unsigned)__half_as_ushort(b) | ((unsigned)__half_as_ushort(a) << 16));
+}
+
 __global__ void vox_resolve_sparse(const unsigned long long* __restrict__ accum,
                                    const uint32_t* __restrict__ touched, const unsigned int* __restrict__ n_touched,
-                                   cudaSurfaceObject_t level0, int V) {
+                                   cudaSurfaceObject_t level0, int V, int f16) {
   const uint32_t n = *n_touched;
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     uint32_t v = touched[k];
     const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(&accum[2 * (size_t)v]);
     int x = v % V, y = (v / V) % V, z = v / (V * V);
-    surf3Dwrite(resolve_cell(a.x, a.y), level0, x * 4, y, z);
+    if (f16) surf3Dwrite(resolve_cell16(a.x, a.y), level0, x * 8, y, z);
+    else surf3Dwrite(resolve_cell(a.x, a.y), level0, x * 4, y, z);
   }
 }
 
-__global__ void vox_resolve_dense(const unsigned long long* __restrict__ accum, cudaSurfaceObject_t level0, int V) {
+__global__ void vox_resolve_dense(const unsigned long long* __restrict__ accum, cudaSurfaceObject_t level0, int V, int f16) {
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, z = blockIdx.z;
   if (x >= V || y >= V) return;
   size_t v = ((size_t)z * V + y) * V + x;
   const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(&accum[2 * v]);
-  surf3Dwrite(resolve_cell(a.x, a.y), level0, x * 4, y, z);
+  if (f16) surf3Dwrite(resolve_cell16(a.x, a.y), level0, x * 8, y, z);
+  else surf3Dwrite(resolve_cell(a.x, a.y), level0, x * 4, y, z);
 }
 
 __global__ void accum_to_counts(const unsigned long long* __restrict__ accum, size_t n, uint32_t* counts, uint32_t* sums) {
@@ -376,13 +393,13 @@ int launch_voxel_clear(vct_context* c) {
   if (!accum_sparse) VCT_CUDA(c, cudaMemsetAsync(c->d_accum, 0, (size_t)V * V * V * 16, c->stream));
   if (!g.list_valid) {              // level 0 of this slot was written densely: zero all of it
     dim3 b(32, 8), gr((V + 31) / 32, (V + 7) / 8, V);
-    zero_level0<<<gr, b, 0, c->stream>>>(g.surf[0], V);
+    zero_level0<<<gr, b, 0, c->stream>>>(g.surf[0], V, c->grid_format);
     c->launches += 1;
   }
   if (accum_sparse || g.list_valid) {
     const vct_context::GridBuf* a = accum_sparse ? &c->grid[c->accum_list_slot] : nullptr;
     vox_clear_sparse<<<148 * 8, 256, 0, c->stream>>>(c->d_accum, a ? a->touched : nullptr, a ? a->n_touched : nullptr,
-                                                     g.surf[0], g.list_valid ? g.touched : nullptr, g.n_touched, V);
+                                                     g.surf[0], g.list_valid ? g.touched : nullptr, g.n_touched, V, c->grid_format);
     c->launches += 1;
   }
   VCT_CUDA(c, cudaMemsetAsync(g.n_touched, 0, sizeof(unsigned int), c->stream));
@@ -437,11 +454,11 @@ int launch_resolve(vct_context* c, bool dense) {
   vct_context::GridBuf& g = c->grid[c->cur];
   if (dense) {
     dim3 b(32, 8), gr((V + 31) / 32, (V + 7) / 8, V);
-    vox_resolve_dense<<<gr, b, 0, c->stream>>>(c->d_accum, g.surf[0], V);
+    vox_resolve_dense<<<gr, b, 0, c->stream>>>(c->d_accum, g.surf[0], V, c->grid_format);
     g.list_valid = false;           // every texel was rewritten from the accumulator, the list was not maintained
     c->accum_list_slot = -1;
   } else {
-    vox_resolve_sparse<<<148 * 8, 256, 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, g.surf[0], V);
+    vox_resolve_sparse<<<148 * 8, 256, 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, g.surf[0], V, c->grid_format);
   }
   c->launches += 1;
   VCT_CUDA(c, cudaGetLastError());

@@ -41,7 +41,7 @@ def cone_set(kind="6+1"):
 def reference_uniforms(V=128, width=1280, height=720, shadow_map_size=4096, grid_world=150.0,
                        light_direction=(0.0, 1.0, 0.25), camera_pos=(0.0, 4.0, 0.0), yaw=-90.0, pitch=0.0,
                        fov_deg=45.0, model_scale=0.05, ambient=0.1, cones="6+1", coverage="msaa4",
-                       bounces=2):
+                       bounces=2, grid_format=0):
     G = np.float32(grid_world)
     model = gm.scale(model_scale)
     light = np.asarray(light_direction, dtype=np.float32)
@@ -66,7 +66,7 @@ def reference_uniforms(V=128, width=1280, height=720, shadow_map_size=4096, grid
         "DiffuseTanHalfAngle": 0.577, "SpecularTanHalfAngle": 0.07, "StepMultiplier": 1.0,
         "MaxDistance": 75.0, "MaxAlpha": 0.95, "PcfRadius": 2, "ShadowBias": 0.002,
         "CoveragePolicy": COVERAGE[coverage] if isinstance(coverage, str) else int(coverage),
-        "Bounces": int(bounces),
+        "Bounces": int(bounces), "GridFormat": int(grid_format),
     }
 
 
