@@ -36,25 +36,40 @@ def parse():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="views", choices=["views", "tiles", "trishard"])
+    ap.add_argument("--mode", default=None, choices=["views", "tiles", "trishard"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
+                    help="BASELINE.json config: 2 = headline (default); 3 = 512^3 fp16 grid, 4K, 9+1 cones, row bands; "
+                         "4 = dynamic 1M-triangle mesh re-voxelised every frame, triangle-sharded + all-reduce")
     ap.add_argument("--detail", type=float, default=1.0, help="scene tessellation scale (1.0 = config 2)")
     ap.add_argument("--grid", type=int, default=256)
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--coverage", default="conservative")
-    ap.add_argument("--cones", default="6+1")
+    ap.add_argument("--cones", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--flush", action="store_true", help="flush L2 between timed steps (per-step events, frames not pipelined); "
                     "default: no flush -- the per-frame working set (~220 MB, two alternating frame slots) exceeds the 126 MB L2")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.config == 3:
+        a.grid, a.width, a.height = 512, 3840, 2160
+        a.cones = a.cones or "9+1"
+        a.mode = a.mode or "tiles"
+    elif a.config == 4:
+        a.mode = a.mode or "trishard"
+    a.cones = a.cones or "6+1"
+    a.mode = a.mode or "views"
+    return a
 
 
 def make_scene_and_uniforms(args):
     import vct_b200  # noqa: F401
     from vct_b200 import scenes, uniforms
-    sc = scenes.atrium(detail=args.detail)
+    if args.config == 4:
+        sc = scenes.dynamic_knot()
+    else:
+        sc = scenes.atrium(detail=args.detail)
     u = uniforms.scene_uniforms(sc, V=args.grid, width=args.width, height=args.height, shadow_map_size=4096,
-                                coverage=args.coverage, cones=args.cones)
+                                coverage=args.coverage, cones=args.cones, grid_format=1 if args.config == 3 else 0)
     return sc, u
 
 
@@ -163,9 +178,23 @@ def run_ours(args):
         frame_t = torch.as_tensor(parallel._DevicePointer(fptr, fbytes, "|u1"), device=dev)
         gather_buf = frame_t
 
+    dyn = None
+    if args.config == 4:
+        # the mesh is re-generated on the device every frame (time-varying sine displacement along the normal)
+        base = torch.from_numpy(np.ascontiguousarray(sc.verts[:, :3])).to(dev)
+        nrm = torch.from_numpy(np.ascontiguousarray(sc.verts[:, 3:6])).to(dev)
+        phase = (base[:, 0] * 0.004 + base[:, 2] * 0.003)
+        dyn = (base, nrm, phase, torch.empty_like(base))
+
     def step(i, host_out=None):
         cam_rank = rank if args.mode == "views" else 0
-        set_camera(ctx, args, i, cam_rank)
+        if args.config != 4:
+            set_camera(ctx, args, i, cam_rank)
+        if dyn is not None:
+            base, nrm, phase, out = dyn
+            torch.add(base, nrm * (12.0 * torch.sin(phase + 0.21 * i)).unsqueeze(1), out=out)
+            ctx.update_positions(device_ptr=out.data_ptr(), n_verts=out.shape[0])
+            ctx.draw_depth()                        # the light-space depth map follows the mesh
         if args.mode == "trishard":
             ctx.voxelize_range(tri_rng[0], tri_rng[1], clear_first=True)
             parallel.allreduce_accumulator(acc)
@@ -300,7 +329,7 @@ def run_ours(args):
         "ms_per_step": round(total_ms / K, 4), "higher_is_better": True,
         "scaling": "weak" if args.mode == "views" else "strong", "vs_baseline": None, "dtype": "u8/u32 grid, f32 shading",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD if args.detail == 1.0 and args.grid == 256 else f"atrium detail={args.detail} V={args.grid} {args.width}x{args.height}",
+        "config": {"workload": WORKLOAD if (args.config == 2 and args.detail == 1.0 and args.grid == 256) else f"config{args.config}: {sc.name} {sc.n_tris} tris, V={args.grid} {'RGBA16F' if args.config == 3 else 'RGBA8'}, {args.width}x{args.height}, cones {args.cones}",
                    "mode": args.mode, "l2": ("flushed between steps by an untimed 256 MiB write; frames not pipelined" if args.flush else "no flush: per-frame working set ~220 MB (64 MiB level 0 + mips, shadow texels, accumulator lines, queues, vertex cache, visibility) in two alternating frame slots exceeds the 126 MB L2"),
                    "timing": "one CUDA-event pair around the K steps on the launching stream, barrier+synchronize both sides; max over ranks",
                    "step": "clear+voxelize+resolve+mip+visibility+cone-trace (shadow map static, drawn once)"},

@@ -112,6 +112,18 @@ int vct_voxelize_range(vct_handle h, size_t tri_begin, size_t tri_end, int clear
 int vct_accum_buffer(vct_handle h, void** device_ptr, size_t* n_uint32);
 int vct_resolve_and_mip(vct_handle h);   /* dense resolve of the whole accumulator, then mip */
 
+/* Fused form of the same exchange over NVLink / NVSwitch (one process per GPU): the accumulator lives in a
+ * symmetric allocation (same size on every rank, e.g. torch symmetric memory) that is also mapped through a
+ * MULTICAST address; the voxel-shading kernel reduces each fragment straight into EVERY rank's accumulator with
+ * multimem.red (one instruction, reduced in the switch), so there is no separate all-reduce: after a cross-rank
+ * barrier every rank resolves its own full copy.  Layout of the buffer: [16 B * V^3 accumulator][V^3 / 8 B occupancy
+ * bit mask].  With multicast_ptr == NULL (single GPU, or no multicast) plain local atomics are used.
+ *   per frame:  vct_voxelize_shared(range of this rank) -> barrier -> vct_resolve_shared() -> barrier */
+int vct_shared_accum_bytes(vct_handle h, size_t* bytes);
+int vct_set_shared_accum(vct_handle h, void* local_ptr, void* multicast_ptr);
+int vct_voxelize_shared(vct_handle h, size_t tri_begin, size_t tri_end);
+int vct_resolve_shared(vct_handle h);
+
 /* ---- read-back (the reference reads nothing back; these exist for parity checks and hosts) */
 int vct_readback_depth(vct_handle h, uint32_t* d24 /* S*S */);
 int vct_readback_counts(vct_handle h, uint32_t* counts /* V^3, (z*V+y)*V+x */);

@@ -506,3 +506,47 @@ def test_fp16_bounce_extension_vs_oracle(gpu_ctx, oracle):
     assert np.array_equal(g[..., 3], o[..., 3])
     assert np.abs(g - o).max() <= 2.0 / 255
     assert_frame_close(gpu_ctx.read_frame(), oracle.frame(), "fp16 bounces=3", FRAC_MIN_SMALL)
+
+
+# ------------------------------------------------------------------------------------------ fused sharded voxelisation
+def test_shared_accumulator_path_single_rank(gpu_ctx):
+    """vct_voxelize_shared / vct_resolve_shared with a one-rank accumulator (plain atomics + occupancy mask): identical
+    to vct_draw_voxels, also across frames, a moving mesh and a switch back to the private path."""
+    import torch
+    from vct_b200 import parallel
+    sc = scenes.dynamic_knot(nu=256, nv=128)
+    u = uniforms.scene_uniforms(sc, V=128, width=320, height=180, shadow_map_size=1024, coverage="conservative")
+    c = gpu_ctx
+    run_gpu(c, sc, u)
+    g_ref = [c.grid(l) for l in range(8)]
+    shared = parallel.SharedAccumulator(c, torch.device("cuda", 0))
+    n = sc.n_tris
+    for it in range(3):
+        c.voxelize_shared(0, n // 2)          # two ranges into the same accumulator = what two ranks would add
+        c.voxelize_shared(n // 2, n)
+        c.resolve_shared(); c.sync()
+        for l in range(8):
+            assert np.array_equal(c.grid(l), g_ref[l]), (it, l)
+    P1 = scenes.torus_knot_positions(256, 128, t=0.9).reshape(-1, 3) * 20.0
+    c.update_positions(P1.astype(np.float32)); c.draw_depth()
+    c.voxelize_shared(0, n); c.resolve_shared(); c.sync()
+    moved = c.grid(0)
+    c.draw_voxels(); c.sync()                  # private path on the same mesh
+    assert np.array_equal(c.grid(0), moved) and not np.array_equal(moved, g_ref[0])
+    c.update_positions(sc.verts[:, :3]); c.draw_depth()
+    c.voxelize_shared(0, n); c.resolve_shared(); c.sync()
+    assert np.array_equal(c.grid(0), g_ref[0]) and np.array_equal(c.grid(3), g_ref[3])     # stale voxels removed
+
+
+def test_fused_sharded_voxelisation_two_gpus():
+    """multimem.red path over NVSwitch multicast: needs two GPUs on the box (skipped otherwise)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(HERE)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(HERE, "mgpu_shared_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert "MGPU_SHARED_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]

@@ -18,7 +18,8 @@ SYMBOLS = [
     "vct_create", "vct_destroy", "vct_last_error", "vct_version", "vct_set_i", "vct_set_f", "vct_set_3f",
     "vct_set_mat4", "vct_get_i", "vct_get_f", "vct_set_cones", "vct_upload_texture", "vct_set_material",
     "vct_upload_mesh", "vct_update_positions", "vct_draw_depth", "vct_draw_voxels", "vct_render", "vct_frame", "vct_frame_async", "vct_frame_wait",
-    "vct_voxelize_range", "vct_accum_buffer", "vct_resolve_and_mip", "vct_readback_depth", "vct_readback_counts",
+    "vct_voxelize_range", "vct_accum_buffer", "vct_resolve_and_mip", "vct_shared_accum_bytes", "vct_set_shared_accum",
+    "vct_voxelize_shared", "vct_resolve_shared", "vct_readback_depth", "vct_readback_counts",
     "vct_readback_sums", "vct_readback_grid", "vct_upload_grid_level0", "vct_build_mips", "vct_readback_visibility",
     "vct_readback_frame", "vct_frame_buffer", "vct_cone_samples", "vct_fragment_count", "vct_occupied_voxels", "vct_debug_counter",
     "vct_trace_cones", "vct_sample_voxels", "vct_set_stream", "vct_use_own_stream", "vct_sync", "vct_pass_time_us", "vct_kernel_launches", "vct_bench_tex3d",
@@ -57,6 +58,8 @@ def load_library(path=None):
         "vct_update_positions": [vp, vp, sz, i], "vct_draw_depth": [vp], "vct_draw_voxels": [vp],
         "vct_render": [vp, vp], "vct_frame": [vp, vp], "vct_frame_async": [vp, vp], "vct_frame_wait": [vp], "vct_voxelize_range": [vp, sz, sz, i],
         "vct_accum_buffer": [vp, C.POINTER(vp), C.POINTER(sz)], "vct_resolve_and_mip": [vp],
+        "vct_shared_accum_bytes": [vp, C.POINTER(sz)], "vct_set_shared_accum": [vp, vp, vp],
+        "vct_voxelize_shared": [vp, sz, sz], "vct_resolve_shared": [vp],
         "vct_readback_depth": [vp, vp], "vct_readback_counts": [vp, vp], "vct_readback_sums": [vp, vp],
         "vct_readback_grid": [vp, i, vp], "vct_upload_grid_level0": [vp, vp], "vct_build_mips": [vp],
         "vct_readback_visibility": [vp, vp], "vct_readback_frame": [vp, vp],
@@ -219,6 +222,21 @@ class Context:
 
     def resolve_and_mip(self):
         self._ck(self.L.vct_resolve_and_mip(self.h))
+
+    # fused sharded voxelisation over a symmetric (optionally multicast-mapped) accumulator
+    def shared_accum_bytes(self):
+        n = C.c_size_t()
+        self._ck(self.L.vct_shared_accum_bytes(self.h, C.byref(n)))
+        return n.value
+
+    def set_shared_accum(self, local_ptr, multicast_ptr=0):
+        self._ck(self.L.vct_set_shared_accum(self.h, C.c_void_p(int(local_ptr)), C.c_void_p(int(multicast_ptr)) if multicast_ptr else None))
+
+    def voxelize_shared(self, tb, te):
+        self._ck(self.L.vct_voxelize_shared(self.h, int(tb), int(te)))
+
+    def resolve_shared(self):
+        self._ck(self.L.vct_resolve_shared(self.h))
 
     # ---- read-back
     def depth(self):

@@ -72,6 +72,7 @@ static void free_grid(vct_context* c) {
   }
   cudaFree(c->d_accum);
   c->d_accum = nullptr; c->grid_V = 0; c->accum_list_slot = -1;
+  c->mask_valid[0] = c->mask_valid[1] = false;
 }
 
 int ensure_grid(vct_context* c) {
@@ -469,6 +470,7 @@ int vct_destroy(vct_handle c) {
   cudaFree(c->d_verts); cudaFree(c->d_idx); cudaFree(c->d_trimat); cudaFree(c->d_materials);
   if (c->depth_tex) cudaDestroyTextureObject(c->depth_tex);
   if (c->depth_array) cudaFreeArray(c->depth_array);
+  cudaFree(c->mask_prev[0]); cudaFree(c->mask_prev[1]);
   cudaFree(c->d_voxrec); cudaFree(c->d_depth); cudaFree(c->d_frags); cudaFree(c->d_items); cudaFree(c->d_counters);
   cudaFree(c->d_vis2[0]); cudaFree(c->d_vis2[1]); cudaFree(c->d_frame);
   for (int k = 0; k < 2; ++k) if (c->slot_read_done[k]) cudaEventDestroy(c->slot_read_done[k]);
@@ -718,6 +720,40 @@ int vct_voxelize_range(vct_handle c, size_t tb, size_t te, int clear_first) {
   return rc;
 }
 
+int vct_shared_accum_bytes(vct_handle c, size_t* bytes) {
+  NEED(c);
+  const size_t n = (size_t)c->P.V * c->P.V * c->P.V;
+  if (bytes) *bytes = n * 16 + n / 8;
+  return VCT_OK;
+}
+
+int vct_set_shared_accum(vct_handle c, void* local_ptr, void* multicast_ptr) {
+  NEED(c);
+  c->shared_local = (unsigned long long*)local_ptr;
+  c->shared_mc = (unsigned long long*)multicast_ptr;
+  c->scene_epoch++;
+  return VCT_OK;
+}
+
+int vct_voxelize_shared(vct_handle c, size_t tb, size_t te) {
+  NEED(c);
+  c->scene_epoch++;
+  int rc = ensure_grid(c); if (rc) return rc;
+  return launch_voxelize_shared(c, tb, te);
+}
+
+int vct_resolve_shared(vct_handle c) {
+  NEED(c);
+  c->scene_epoch++;
+  int rc = launch_resolve_shared(c); if (rc) return rc;
+  rc = launch_mip(c); if (rc) return rc;
+  for (int b = 3; b <= c->P.bounces; ++b) {
+    rc = launch_reinject(c); if (rc) return rc;
+    rc = launch_mip(c); if (rc) return rc;
+  }
+  return VCT_OK;
+}
+
 int vct_accum_buffer(vct_handle c, void** p, size_t* n) {
   NEED(c);
   int rc = ensure_grid(c); if (rc) return rc;
@@ -922,6 +958,7 @@ int vct_upload_grid_level0(vct_handle c, const uint8_t* rgba) {
   p.kind = cudaMemcpyHostToDevice;
   VCT_CUDA(c, cudaMemcpy3DAsync(&p, c->stream));
   c->grid[c->cur].list_valid = false;   // level 0 no longer matches the touched list
+  c->mask_valid[c->cur] = false;
   c->scene_epoch++;
   return check_cuda(c, cudaStreamSynchronize(c->stream), "sync");
 }

@@ -131,6 +131,10 @@ struct vct_context {
     bool list_valid = true;                    // false: level 0 was written densely, a dense clear is needed before reuse
   } grid[2];
   size_t touched_cap = 0;
+  // fused sharded voxelisation: external symmetric accumulator + occupancy mask (local view and multicast view)
+  unsigned long long* shared_local = nullptr; unsigned long long* shared_mc = nullptr;
+  uint32_t* mask_prev[2] = {nullptr, nullptr}; int mask_prev_V = 0;   // occupancy mask of what each slot's level 0 holds
+  bool mask_valid[2] = {false, false};                                // ... and whether it is exact
   int accum_list_slot = -1;                    // slot whose touched list describes the accumulator's non-zero cells; -1 = dense dirty
 
   void* d_voxrec = nullptr; size_t voxrec_nt = 0;   // per-triangle voxelisation records (vct_voxelize.cu)
@@ -195,6 +199,8 @@ int begin_voxel_slot(vct_context* c);     // flips c->cur to the other slot (aft
 void mark_slot_read(vct_context* c);       // records slot_read_done[c->cur] on the main stream
 int launch_voxelize(vct_context* c, size_t tb, size_t te);
 int launch_resolve(vct_context* c, bool dense);
+int launch_voxelize_shared(vct_context* c, size_t tb, size_t te);
+int launch_resolve_shared(vct_context* c);
 int launch_mip(vct_context* c);
 int launch_visibility(vct_context* c);
 int launch_cone(vct_context* c);

@@ -207,7 +207,18 @@ __device__ __forceinline__ void append_first_touch(bool& pending, unsigned long 
   pending = false;
 }
 
+// multimem.red: one reduction instruction applied to the same offset of every rank's copy, performed in the NVSwitch
+__device__ __forceinline__ void multimem_add_u64(unsigned long long* mc_addr, unsigned long long v) {
+  asm volatile("multimem.red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(mc_addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_or_b32(uint32_t* mc_addr, uint32_t v) {
+  asm volatile("multimem.red.relaxed.sys.global.or.b32 [%0], %1;" ::"l"(mc_addr), "r"(v) : "memory");
+}
+
+// SHARED = 0: private accumulator + touched list.  SHARED = 1: symmetric accumulator + occupancy bit mask, plain
+// atomics on the local copy.  SHARED = 2: the same through the multicast mapping (all ranks' copies at once).
 // ---------------------------------------------------------------------------------------------------
+template <int SHARED>
 __global__ void __launch_bounds__(256) vox_shade(Params P, const VoxRecord* __restrict__ rec,
                                                  const MaterialDev* __restrict__ mats,
                                                  const uint32_t* __restrict__ depth, cudaTextureObject_t depth_tex,
@@ -231,7 +242,7 @@ __global__ void __launch_bounds__(256) vox_shade(Params P, const VoxRecord* __re
       fr_next = frags[f + stride];
       asm volatile("prefetch.global.L1 [%0];" ::"l"(&rec[fr_next.x]));
     }
-    append_first_touch(pending, pend_old, pend_voxel, touched, n_touched);
+    if (SHARED == 0) append_first_touch(pending, pend_old, pend_voxel, touched, n_touched);
     const uint32_t tri = fr.x;
     const int i = (int)(fr.y & 0xFFFFu), j = (int)(fr.y >> 16);
     VoxTri s;
@@ -286,15 +297,28 @@ __global__ void __launch_bounds__(256) vox_shade(Params P, const VoxRecord* __re
       bc = cg::reduce(same, bc, cg::plus<unsigned long long>());
     }
     if (same.thread_rank() == 0) {
-      atomicAdd(&accum[2 * (size_t)voxel], rg);
-      // The returned old count is consumed one iteration later (append_first_touch at the loop top), so the
-      // warp does not sit on the L2 round trip of this atomic.
-      pend_old = atomicAdd(&accum[2 * (size_t)voxel + 1], bc);
-      pend_voxel = voxel;
-      pending = true;
+      if (SHARED == 0) {
+        atomicAdd(&accum[2 * (size_t)voxel], rg);
+        // The returned old count is consumed one iteration later (append_first_touch at the loop top), so the
+        // warp does not sit on the L2 round trip of this atomic.
+        pend_old = atomicAdd(&accum[2 * (size_t)voxel + 1], bc);
+        pend_voxel = voxel;
+        pending = true;
+      } else {
+        uint32_t* mask = reinterpret_cast<uint32_t*>(accum + 2 * (size_t)V * V * V);
+        if (SHARED == 2) {
+          multimem_add_u64(&accum[2 * (size_t)voxel], rg);
+          multimem_add_u64(&accum[2 * (size_t)voxel + 1], bc);
+          multimem_or_b32(&mask[voxel >> 5], 1u << (voxel & 31));
+        } else {
+          atomicAdd(&accum[2 * (size_t)voxel], rg);
+          atomicAdd(&accum[2 * (size_t)voxel + 1], bc);
+          atomicOr(&mask[voxel >> 5], 1u << (voxel & 31));
+        }
+      }
     }
   }
-  append_first_touch(pending, pend_old, pend_voxel, touched, n_touched);
+  if (SHARED == 0) append_first_touch(pending, pend_old, pend_voxel, touched, n_touched);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -405,12 +429,13 @@ int launch_voxel_clear(vct_context* c) {
   VCT_CUDA(c, cudaMemsetAsync(g.n_touched, 0, sizeof(unsigned int), c->stream));
   VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_fragments, 0, sizeof(unsigned int), c->stream));
   g.list_valid = true;              // from here on the list (being rebuilt) describes this slot's level 0
+  c->mask_valid[c->cur] = false;
   c->accum_list_slot = c->cur;
   VCT_CUDA(c, cudaGetLastError());
   return VCT_OK;
 }
 
-int launch_voxelize(vct_context* c, size_t tb, size_t te) {
+static int voxelize_impl(vct_context* c, size_t tb, size_t te, int shared) {
   if (!c->nt) return set_error(c, VCT_ERR_STATE, "voxelize: no mesh uploaded");
   if (!c->depth_valid) return set_error(c, VCT_ERR_STATE, "voxelize: call vct_draw_depth first (shadow map missing)");
   int rc = ensure_grid(c); if (rc) return rc;
@@ -438,11 +463,91 @@ int launch_voxelize(vct_context* c, size_t tb, size_t te) {
   }
   {
     PassTimer timer(c, VCT_PASS_VOX_SHADE);
-    vox_shade<<<148 * 8, 256, 0, c->stream>>>(c->P, (const VoxRecord*)c->d_voxrec, c->d_materials, c->d_depth,
-                                              c->depth_tex, c->d_frags, (uint32_t)c->frags_cap, c->d_accum, c->grid[c->cur].touched, c->grid[c->cur].n_touched,
-                                              c->d_counters);
+    if (shared == 0)
+      vox_shade<0><<<148 * 8, 256, 0, c->stream>>>(c->P, (const VoxRecord*)c->d_voxrec, c->d_materials, c->d_depth,
+                                                   c->depth_tex, c->d_frags, (uint32_t)c->frags_cap, c->d_accum,
+                                                   c->grid[c->cur].touched, c->grid[c->cur].n_touched, c->d_counters);
+    else if (shared == 1)
+      vox_shade<1><<<148 * 8, 256, 0, c->stream>>>(c->P, (const VoxRecord*)c->d_voxrec, c->d_materials, c->d_depth,
+                                                   c->depth_tex, c->d_frags, (uint32_t)c->frags_cap, c->shared_local,
+                                                   nullptr, nullptr, c->d_counters);
+    else
+      vox_shade<2><<<148 * 8, 256, 0, c->stream>>>(c->P, (const VoxRecord*)c->d_voxrec, c->d_materials, c->d_depth,
+                                                   c->depth_tex, c->d_frags, (uint32_t)c->frags_cap, c->shared_mc,
+                                                   nullptr, nullptr, c->d_counters);
     c->launches += 1;
   }
+  VCT_CUDA(c, cudaGetLastError());
+  return VCT_OK;
+}
+
+int launch_voxelize(vct_context* c, size_t tb, size_t te) { return voxelize_impl(c, tb, te, 0); }
+
+int launch_voxelize_shared(vct_context* c, size_t tb, size_t te) {
+  if (!c->shared_local) return set_error(c, VCT_ERR_STATE, "vct_voxelize_shared: call vct_set_shared_accum first");
+  PassTimer* none = nullptr; (void)none;
+  return voxelize_impl(c, tb, te, c->shared_mc ? 2 : 1);
+}
+
+// Mask-driven resolve of the symmetric accumulator into the current slot: one thread per 32-voxel mask word.
+// Writes the resolved texel for every set bit, a zero texel for voxels that this slot held before and that are no
+// longer occupied, and leaves accumulator cells and mask word zeroed for the next frame.
+__global__ void vox_resolve_shared(unsigned long long* __restrict__ accum, uint32_t* __restrict__ mask,
+                                   uint32_t* __restrict__ mask_prev, cudaSurfaceObject_t level0, int V, int f16) {
+  const size_t n_words = ((size_t)V * V * V) >> 5;
+  for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t now = mask[w], before = mask_prev[w];
+    if (!(now | before)) continue;
+    uint32_t bits = now | before;
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const size_t v = (w << 5) + b;
+      const int x = (int)(v % V), y = (int)((v / V) % V), z = (int)(v / ((size_t)V * V));
+      if ((now >> b) & 1u) {
+        const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(&accum[2 * v]);
+        if (f16) surf3Dwrite(resolve_cell16(a.x, a.y), level0, x * 8, y, z);
+        else surf3Dwrite(resolve_cell(a.x, a.y), level0, x * 4, y, z);
+        accum[2 * v] = 0ull; accum[2 * v + 1] = 0ull;
+      } else {
+        if (f16) surf3Dwrite(make_uint2(0u, 0u), level0, x * 8, y, z);
+        else surf3Dwrite(make_uchar4(0, 0, 0, 0), level0, x * 4, y, z);
+      }
+    }
+    mask_prev[w] = now;
+    mask[w] = 0u;
+  }
+}
+
+int launch_resolve_shared(vct_context* c) {
+  if (!c->shared_local) return set_error(c, VCT_ERR_STATE, "vct_resolve_shared: call vct_set_shared_accum first");
+  int rc = ensure_grid(c); if (rc) return rc;
+  const int V = c->P.V;
+  const size_t n_words = ((size_t)V * V * V) >> 5;
+  if (c->mask_prev_V != V) {
+    for (int k = 0; k < 2; ++k) {
+      cudaFree(c->mask_prev[k]); c->mask_prev[k] = nullptr;
+      VCT_CUDA(c, cudaMalloc(&c->mask_prev[k], n_words * 4));
+    }
+    c->mask_prev_V = V;
+    c->mask_valid[0] = c->mask_valid[1] = false;
+  }
+  rc = begin_voxel_slot(c); if (rc) return rc;
+  vct_context::GridBuf& g = c->grid[c->cur];
+  PassTimer timer(c, VCT_PASS_RESOLVE);
+  if (!c->mask_valid[c->cur]) {    // this slot's level 0 is not described by mask_prev: zero it densely once
+    dim3 b(32, 8), gr((V + 31) / 32, (V + 7) / 8, V);
+    zero_level0<<<gr, b, 0, c->stream>>>(g.surf[0], V, c->grid_format);
+    VCT_CUDA(c, cudaMemsetAsync(c->mask_prev[c->cur], 0, n_words * 4, c->stream));
+    c->launches += 1;
+  }
+  uint32_t* mask = reinterpret_cast<uint32_t*>(c->shared_local + 2 * (size_t)V * V * V);
+  vox_resolve_shared<<<148 * 8, 256, 0, c->stream>>>(c->shared_local, mask, c->mask_prev[c->cur], g.surf[0], V, c->grid_format);
+  c->launches += 1;
+  // the slot is now described by mask_prev, not by a touched list: a later private-accumulator voxelisation into
+  // this slot must start from a dense zero, and mask_prev stays exact as long as only this path writes the slot
+  g.list_valid = false;
+  c->mask_valid[c->cur] = true;
   VCT_CUDA(c, cudaGetLastError());
   return VCT_OK;
 }
@@ -456,6 +561,7 @@ int launch_resolve(vct_context* c, bool dense) {
     dim3 b(32, 8), gr((V + 31) / 32, (V + 7) / 8, V);
     vox_resolve_dense<<<gr, b, 0, c->stream>>>(c->d_accum, g.surf[0], V, c->grid_format);
     g.list_valid = false;           // every texel was rewritten from the accumulator, the list was not maintained
+    c->mask_valid[c->cur] = false;
     c->accum_list_slot = -1;
   } else {
     vox_resolve_sparse<<<148 * 8, 256, 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, g.surf[0], V, c->grid_format);

@@ -71,3 +71,47 @@ def unpack_accumulator(acc: np.ndarray):
     counts = acc[:, 2].copy()
     sums = np.stack([acc[:, 1], acc[:, 0], acc[:, 3]], -1)
     return counts, sums
+
+
+class SharedAccumulator:
+    """Symmetric accumulator for the fused triangle-sharded voxelisation (vct_voxelize_shared / vct_resolve_shared).
+
+    Plumbing only: the memory comes from torch symmetric memory (same allocation size on every rank, mapped on the
+    peers and through an NVSwitch multicast address), the barrier is the symmetric-memory signal-pad barrier on the
+    current stream.  With world size 1 it is a plain zeroed device buffer and the barrier is a no-op."""
+
+    def __init__(self, ctx, device, group=None):
+        import torch
+        import torch.distributed as dist
+        self.ctx = ctx
+        nbytes = ctx.shared_accum_bytes()
+        n64 = (nbytes + 7) // 8
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.hdl = None
+        if self.world > 1:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.buf = symm_mem.empty(n64, dtype=torch.int64, device=device)
+            g = group or dist.group.WORLD
+            self.hdl = symm_mem.rendezvous(self.buf, group=g.group_name if hasattr(g, "group_name") else g)
+            self.buf.zero_()
+            torch.cuda.synchronize(device)
+            self.hdl.barrier()
+            mc = int(self.hdl.multicast_ptr or 0)
+            if not mc:
+                raise RuntimeError("no multicast mapping for symmetric memory on this system")
+            ctx.set_shared_accum(self.buf.data_ptr(), mc)
+        else:
+            self.buf = torch.zeros(n64, dtype=torch.int64, device=device)
+            ctx.set_shared_accum(self.buf.data_ptr(), 0)
+
+    def barrier(self):
+        if self.hdl is not None:
+            self.hdl.barrier()
+
+    def frame_voxels(self, tri_begin, tri_end):
+        """One sharded voxelisation: reduce this rank's triangle range into every rank's accumulator, barrier,
+        resolve + mip the local copy, barrier (so nobody adds into an accumulator that is still being resolved)."""
+        self.ctx.voxelize_shared(tri_begin, tri_end)
+        self.barrier()
+        self.ctx.resolve_shared()
+        self.barrier()
