@@ -36,7 +36,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default=None, choices=["views", "tiles", "trishard"])
+    ap.add_argument("--mode", default=None, choices=["views", "tiles", "trishard", "shard"],
+                    help="N>1: views = one camera per rank, grid replicated (weak scaling, default for config 2); tiles = row bands, "
+                         "voxelisation replicated; trishard = triangle ranges + NCCL all-reduce of the accumulator; shard = triangle "
+                         "ranges reduced into every rank's accumulator by multimem.red inside the shading kernel + row bands")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
                     help="BASELINE.json config: 2 = headline (default); 3 = 512^3 fp16 grid, 4K, 9+1 cones, row bands; "
                          "4 = dynamic 1M-triangle mesh re-voxelised every frame, triangle-sharded + all-reduce")
@@ -53,9 +56,9 @@ def parse():
     if a.config == 3:
         a.grid, a.width, a.height = 512, 3840, 2160
         a.cones = a.cones or "9+1"
-        a.mode = a.mode or "tiles"
+        a.mode = a.mode or ("shard" if a.gpus > 1 else "views")
     elif a.config == 4:
-        a.mode = a.mode or "trishard"
+        a.mode = a.mode or ("shard" if a.gpus > 1 else "views")
     a.cones = a.cones or "6+1"
     a.mode = a.mode or "views"
     return a
@@ -165,15 +168,16 @@ def run_ours(args):
     ctx.set_uniforms(u)
     ctx.load_scene(sc)
     H = args.height
-    if args.mode == "tiles" and world > 1:
+    if args.mode in ("tiles", "shard") and world > 1:
         b0, b1 = parallel.row_band(H, rank, world)
         ctx.set_i("RowBegin", b0); ctx.set_i("RowEnd", b1)
     ctx.draw_depth()                                # static light: once, like the reference's init
     ctx.sync()
-    tri_rng = parallel.triangle_range(sc.n_tris, rank, world) if args.mode == "trishard" else None
+    tri_rng = parallel.triangle_range(sc.n_tris, rank, world) if args.mode in ("trishard", "shard") else None
+    shared = parallel.SharedAccumulator(ctx, dev) if args.mode == "shard" else None
     acc = parallel.accumulator_tensor(ctx, dev) if args.mode == "trishard" else None
     gather_buf = None
-    if args.mode == "tiles" and world > 1:
+    if args.mode in ("tiles", "shard") and world > 1:
         fptr, fbytes = ctx.frame_buffer()
         frame_t = torch.as_tensor(parallel._DevicePointer(fptr, fbytes, "|u1"), device=dev)
         gather_buf = frame_t
@@ -201,7 +205,11 @@ def run_ours(args):
             ctx.resolve_and_mip()
             ctx.render(host_out)
         else:
-            ctx.frame(host_out)
+            if args.mode == "shard":
+                shared.frame_voxels(tri_rng[0], tri_rng[1])   # exchange fused into the shading kernel (multimem.red)
+                ctx.render(None)
+            else:
+                ctx.frame(None if gather_buf is not None else host_out)
             if gather_buf is not None:              # row bands -> every rank holds the full frame
                 b0, b1 = parallel.row_band(H, rank, world)
                 rows = [gather_buf[parallel.row_band(H, r, world)[0] * args.width * 4:
@@ -211,6 +219,11 @@ def run_ours(args):
                 else:
                     for r in range(world):
                         dist.broadcast(rows[r], src=r)
+                if host_out is not None:
+                    host_out.view(-1).copy_(gather_buf, non_blocking=False)
+            elif host_out is not None and args.mode == "shard":
+                ctx.sync()
+                host_out.copy_(torch.from_numpy(ctx.read_frame()))
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if args.flush else None   # > 126 MB L2
 

@@ -114,9 +114,10 @@ int vct_resolve_and_mip(vct_handle h);   /* dense resolve of the whole accumulat
 
 /* Fused form of the same exchange over NVLink / NVSwitch (one process per GPU): the accumulator lives in a
  * symmetric allocation (same size on every rank, e.g. torch symmetric memory) that is also mapped through a
- * MULTICAST address; the voxel-shading kernel reduces each fragment straight into EVERY rank's accumulator with
- * multimem.red (one instruction, reduced in the switch), so there is no separate all-reduce: after a cross-rank
- * barrier every rank resolves its own full copy.  Layout of the buffer: [16 B * V^3 accumulator][V^3 / 8 B occupancy
+ * MULTICAST address.  Each rank voxelises its triangle range into its private accumulator and then adds every voxel
+ * it touched straight into EVERY rank's symmetric accumulator with multimem.red (reduced in the switch), so there
+ * is no separate all-reduce and the exchange volume is the touched voxels, not V^3: after a cross-rank barrier every
+ * rank resolves its own full copy.  Layout of the buffer: [16 B * V^3 accumulator][V^3 / 8 B occupancy
  * bit mask].  With multicast_ptr == NULL (single GPU, or no multicast) plain local atomics are used.
  *   per frame:  vct_voxelize_shared(range of this rank) -> barrier -> vct_resolve_shared() -> barrier */
 int vct_shared_accum_bytes(vct_handle h, size_t* bytes);

@@ -470,7 +470,7 @@ int vct_destroy(vct_handle c) {
   cudaFree(c->d_verts); cudaFree(c->d_idx); cudaFree(c->d_trimat); cudaFree(c->d_materials);
   if (c->depth_tex) cudaDestroyTextureObject(c->depth_tex);
   if (c->depth_array) cudaFreeArray(c->depth_array);
-  cudaFree(c->mask_prev[0]); cudaFree(c->mask_prev[1]);
+  cudaFree(c->mask_prev[0]); cudaFree(c->mask_prev[1]); cudaFree(c->d_push_list); cudaFree(c->d_push_count);
   cudaFree(c->d_voxrec); cudaFree(c->d_depth); cudaFree(c->d_frags); cudaFree(c->d_items); cudaFree(c->d_counters);
   cudaFree(c->d_vis2[0]); cudaFree(c->d_vis2[1]); cudaFree(c->d_frame);
   for (int k = 0; k < 2; ++k) if (c->slot_read_done[k]) cudaEventDestroy(c->slot_read_done[k]);

@@ -135,7 +135,9 @@ struct vct_context {
   unsigned long long* shared_local = nullptr; unsigned long long* shared_mc = nullptr;
   uint32_t* mask_prev[2] = {nullptr, nullptr}; int mask_prev_V = 0;   // occupancy mask of what each slot's level 0 holds
   bool mask_valid[2] = {false, false};                                // ... and whether it is exact
-  int accum_list_slot = -1;                    // slot whose touched list describes the accumulator's non-zero cells; -1 = dense dirty
+  uint32_t* d_push_list = nullptr; unsigned int* d_push_count = nullptr; size_t push_cap = 0;   // voxels this rank touched
+  int accum_list_slot = -1;                    // slot whose touched list describes the accumulator's non-zero cells;
+                                               // -1 = dense dirty, -2 = all zero (left so by vox_push_shared)
 
   void* d_voxrec = nullptr; size_t voxrec_nt = 0;   // per-triangle voxelisation records (vct_voxelize.cu)
 

@@ -208,17 +208,18 @@ __device__ __forceinline__ void append_first_touch(bool& pending, unsigned long 
 }
 
 // multimem.red: one reduction instruction applied to the same offset of every rank's copy, performed in the NVSwitch
-__device__ __forceinline__ void multimem_add_u64(unsigned long long* mc_addr, unsigned long long v) {
-  asm volatile("multimem.red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(mc_addr), "l"(v) : "memory");
+// The symmetric accumulator holds (r, g, b, count) as four fp32 per voxel: every value is an integer below 2^24
+// (<= 65 793 fragments of 255 per voxel), so fp32 addition is exact and order independent, and one 16-byte vector
+// reduction carries a whole voxel.
+__device__ __forceinline__ void multimem_add_v4f32(float4* mc_addr, float4 v) {
+  asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ void multimem_or_b32(uint32_t* mc_addr, uint32_t v) {
   asm volatile("multimem.red.relaxed.sys.global.or.b32 [%0], %1;" ::"l"(mc_addr), "r"(v) : "memory");
 }
 
-// SHARED = 0: private accumulator + touched list.  SHARED = 1: symmetric accumulator + occupancy bit mask, plain
-// atomics on the local copy.  SHARED = 2: the same through the multicast mapping (all ranks' copies at once).
 // ---------------------------------------------------------------------------------------------------
-template <int SHARED>
 __global__ void __launch_bounds__(256) vox_shade(Params P, const VoxRecord* __restrict__ rec,
                                                  const MaterialDev* __restrict__ mats,
                                                  const uint32_t* __restrict__ depth, cudaTextureObject_t depth_tex,
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(256) vox_shade(Params P, const VoxRecord* __re
       fr_next = frags[f + stride];
       asm volatile("prefetch.global.L1 [%0];" ::"l"(&rec[fr_next.x]));
     }
-    if (SHARED == 0) append_first_touch(pending, pend_old, pend_voxel, touched, n_touched);
+    append_first_touch(pending, pend_old, pend_voxel, touched, n_touched);
     const uint32_t tri = fr.x;
     const int i = (int)(fr.y & 0xFFFFu), j = (int)(fr.y >> 16);
     VoxTri s;
@@ -297,28 +298,15 @@ __global__ void __launch_bounds__(256) vox_shade(Params P, const VoxRecord* __re
       bc = cg::reduce(same, bc, cg::plus<unsigned long long>());
     }
     if (same.thread_rank() == 0) {
-      if (SHARED == 0) {
-        atomicAdd(&accum[2 * (size_t)voxel], rg);
-        // The returned old count is consumed one iteration later (append_first_touch at the loop top), so the
-        // warp does not sit on the L2 round trip of this atomic.
-        pend_old = atomicAdd(&accum[2 * (size_t)voxel + 1], bc);
-        pend_voxel = voxel;
-        pending = true;
-      } else {
-        uint32_t* mask = reinterpret_cast<uint32_t*>(accum + 2 * (size_t)V * V * V);
-        if (SHARED == 2) {
-          multimem_add_u64(&accum[2 * (size_t)voxel], rg);
-          multimem_add_u64(&accum[2 * (size_t)voxel + 1], bc);
-          multimem_or_b32(&mask[voxel >> 5], 1u << (voxel & 31));
-        } else {
-          atomicAdd(&accum[2 * (size_t)voxel], rg);
-          atomicAdd(&accum[2 * (size_t)voxel + 1], bc);
-          atomicOr(&mask[voxel >> 5], 1u << (voxel & 31));
-        }
-      }
+      atomicAdd(&accum[2 * (size_t)voxel], rg);
+      // The returned old count is consumed one iteration later (append_first_touch at the loop top), so the
+      // warp does not sit on the L2 round trip of this atomic.
+      pend_old = atomicAdd(&accum[2 * (size_t)voxel + 1], bc);
+      pend_voxel = voxel;
+      pending = true;
     }
   }
-  if (SHARED == 0) append_first_touch(pending, pend_old, pend_voxel, touched, n_touched);
+  append_first_touch(pending, pend_old, pend_voxel, touched, n_touched);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -463,18 +451,11 @@ static int voxelize_impl(vct_context* c, size_t tb, size_t te, int shared) {
   }
   {
     PassTimer timer(c, VCT_PASS_VOX_SHADE);
-    if (shared == 0)
-      vox_shade<0><<<148 * 8, 256, 0, c->stream>>>(c->P, (const VoxRecord*)c->d_voxrec, c->d_materials, c->d_depth,
-                                                   c->depth_tex, c->d_frags, (uint32_t)c->frags_cap, c->d_accum,
-                                                   c->grid[c->cur].touched, c->grid[c->cur].n_touched, c->d_counters);
-    else if (shared == 1)
-      vox_shade<1><<<148 * 8, 256, 0, c->stream>>>(c->P, (const VoxRecord*)c->d_voxrec, c->d_materials, c->d_depth,
-                                                   c->depth_tex, c->d_frags, (uint32_t)c->frags_cap, c->shared_local,
-                                                   nullptr, nullptr, c->d_counters);
-    else
-      vox_shade<2><<<148 * 8, 256, 0, c->stream>>>(c->P, (const VoxRecord*)c->d_voxrec, c->d_materials, c->d_depth,
-                                                   c->depth_tex, c->d_frags, (uint32_t)c->frags_cap, c->shared_mc,
-                                                   nullptr, nullptr, c->d_counters);
+    uint32_t* list = shared ? c->d_push_list : c->grid[c->cur].touched;
+    unsigned int* n_list = shared ? c->d_push_count : c->grid[c->cur].n_touched;
+    vox_shade<<<148 * 8, 256, 0, c->stream>>>(c->P, (const VoxRecord*)c->d_voxrec, c->d_materials, c->d_depth,
+                                              c->depth_tex, c->d_frags, (uint32_t)c->frags_cap, c->d_accum, list, n_list,
+                                              c->d_counters);
     c->launches += 1;
   }
   VCT_CUDA(c, cudaGetLastError());
@@ -483,10 +464,69 @@ static int voxelize_impl(vct_context* c, size_t tb, size_t te, int shared) {
 
 int launch_voxelize(vct_context* c, size_t tb, size_t te) { return voxelize_impl(c, tb, te, 0); }
 
+// The exchange step of triangle-sharded voxelisation, fused over NVSwitch: every voxel this rank touched is added
+// into the same cell of EVERY rank's symmetric accumulator (and its bit set in every rank's occupancy mask) by
+// multimem.red on the multicast mapping -- three switch-side reductions per touched voxel, no all-reduce, no staging
+// copy.  The private cells are zeroed on the way, so the private accumulator is clean for the next frame.
+template <bool MULTICAST>
+__global__ void vox_push_shared(unsigned long long* __restrict__ accum, const uint32_t* __restrict__ list,
+                                const unsigned int* __restrict__ n_list, float4* shared, int V) {
+  const uint32_t n = *n_list;
+  uint32_t* mask = reinterpret_cast<uint32_t*>(shared + (size_t)V * V * V);
+  const uint32_t n_round = (n + 31u) & ~31u;      // whole warps stay in the loop for the match below
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_round; k += gridDim.x * blockDim.x) {
+    const bool live = k < n;
+    const uint32_t v = live ? list[k] : 0xFFFFFFFFu;
+    if (live) {
+      ulonglong2* cell = reinterpret_cast<ulonglong2*>(&accum[2 * (size_t)v]);
+      const ulonglong2 a = *cell;
+      *cell = make_ulonglong2(0ull, 0ull);
+      const float4 f = make_float4((float)(unsigned)(a.x >> 32), (float)(unsigned)a.x, (float)(unsigned)(a.y >> 32),
+                                   (float)(unsigned)a.y);
+      if (MULTICAST) multimem_add_v4f32(&shared[v], f);
+      else {
+        atomicAdd(&shared[v].x, f.x); atomicAdd(&shared[v].y, f.y); atomicAdd(&shared[v].z, f.z); atomicAdd(&shared[v].w, f.w);
+      }
+    }
+    // occupancy bits: lanes whose voxels share a 32-voxel mask word issue one OR
+    const uint32_t word = live ? (v >> 5) : 0xFFFFFFFFu;
+    const unsigned peers = __match_any_sync(0xffffffffu, word);
+    uint32_t bits = live ? (1u << (v & 31)) : 0u;
+    // OR-reduce the bits over the peer group (at most 32 lanes; groups are small in practice)
+    uint32_t acc = 0;
+    for (unsigned m = peers; m; m &= m - 1) acc |= __shfl_sync(peers, bits, __ffs(m) - 1);
+    if (live && (int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+      if (MULTICAST) multimem_or_b32(&mask[word], acc);
+      else atomicOr(&mask[word], acc);
+    }
+  }
+}
+
 int launch_voxelize_shared(vct_context* c, size_t tb, size_t te) {
   if (!c->shared_local) return set_error(c, VCT_ERR_STATE, "vct_voxelize_shared: call vct_set_shared_accum first");
-  PassTimer* none = nullptr; (void)none;
-  return voxelize_impl(c, tb, te, c->shared_mc ? 2 : 1);
+  int rc = ensure_grid(c); if (rc) return rc;
+  const size_t n = (size_t)c->P.V * c->P.V * c->P.V;
+  if (c->push_cap != n) {
+    cudaFree(c->d_push_list); cudaFree(c->d_push_count); c->d_push_list = nullptr; c->d_push_count = nullptr;
+    VCT_CUDA(c, cudaMalloc(&c->d_push_list, n * 4));
+    VCT_CUDA(c, cudaMalloc(&c->d_push_count, 128));
+    c->push_cap = n;
+  }
+  if (c->accum_list_slot != -2)      // the private accumulator must start all zero; vox_push_shared leaves it that way
+    VCT_CUDA(c, cudaMemsetAsync(c->d_accum, 0, n * 16, c->stream));
+  c->accum_list_slot = -2;
+  VCT_CUDA(c, cudaMemsetAsync(c->d_push_count, 0, 4, c->stream));
+  rc = voxelize_impl(c, tb, te, 1); if (rc) return rc;
+  {
+    PassTimer timer(c, VCT_PASS_VOX_CLEAR);   // reported under "vox_clear": the push replaces the clear in this mode
+    if (c->shared_mc)
+      vox_push_shared<true><<<148 * 8, 256, 0, c->stream>>>(c->d_accum, c->d_push_list, c->d_push_count, (float4*)c->shared_mc, c->P.V);
+    else
+      vox_push_shared<false><<<148 * 8, 256, 0, c->stream>>>(c->d_accum, c->d_push_list, c->d_push_count, (float4*)c->shared_local, c->P.V);
+    c->launches += 1;
+  }
+  VCT_CUDA(c, cudaGetLastError());
+  return VCT_OK;
 }
 
 // Mask-driven resolve of the symmetric accumulator into the current slot: one thread per 32-voxel mask word.
@@ -494,28 +534,36 @@ int launch_voxelize_shared(vct_context* c, size_t tb, size_t te) {
 // longer occupied, and leaves accumulator cells and mask word zeroed for the next frame.
 __global__ void vox_resolve_shared(unsigned long long* __restrict__ accum, uint32_t* __restrict__ mask,
                                    uint32_t* __restrict__ mask_prev, cudaSurfaceObject_t level0, int V, int f16) {
+  // warp-cooperative: a warp loads 32 mask words at once, then walks only the non-zero ones with lane b handling
+  // bit b of the word (a word is 32 consecutive voxels along x: one 128 B / 256 B run of level 0)
   const size_t n_words = ((size_t)V * V * V) >> 5;
-  for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (size_t)gridDim.x * blockDim.x) {
-    const uint32_t now = mask[w], before = mask_prev[w];
-    if (!(now | before)) continue;
-    uint32_t bits = now | before;
-    while (bits) {
-      const int b = __ffs(bits) - 1;
-      bits &= bits - 1;
-      const size_t v = (w << 5) + b;
+  const unsigned lane = threadIdx.x & 31;
+  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t base = warp0 * 32; base < n_words; base += n_warps * 32) {
+    const size_t w = base + lane;
+    uint32_t now = 0, before = 0;
+    if (w < n_words) { now = mask[w]; before = mask_prev[w]; }
+    if (w < n_words && (now | before)) { mask_prev[w] = now; mask[w] = 0u; }
+    unsigned todo = __ballot_sync(0xffffffffu, (now | before) != 0u);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t wn = __shfl_sync(0xffffffffu, now, src), wb = __shfl_sync(0xffffffffu, before, src);
+      const size_t v = ((base + src) << 5) + lane;
       const int x = (int)(v % V), y = (int)((v / V) % V), z = (int)(v / ((size_t)V * V));
-      if ((now >> b) & 1u) {
-        const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(&accum[2 * v]);
-        if (f16) surf3Dwrite(resolve_cell16(a.x, a.y), level0, x * 8, y, z);
-        else surf3Dwrite(resolve_cell(a.x, a.y), level0, x * 4, y, z);
-        accum[2 * v] = 0ull; accum[2 * v + 1] = 0ull;
-      } else {
+      if ((wn >> lane) & 1u) {
+        float4* cell = reinterpret_cast<float4*>(accum) + v;
+        const float4 f = *cell;                       // exact integers (see multimem_add_v4f32)
+        *cell = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        const unsigned long long rg = ((unsigned long long)(unsigned)f.x << 32) | (unsigned)f.y;
+        const unsigned long long bc = ((unsigned long long)(unsigned)f.z << 32) | (unsigned)f.w;
+        if (f16) surf3Dwrite(resolve_cell16(rg, bc), level0, x * 8, y, z);
+        else surf3Dwrite(resolve_cell(rg, bc), level0, x * 4, y, z);
+      } else if ((wb >> lane) & 1u) {
         if (f16) surf3Dwrite(make_uint2(0u, 0u), level0, x * 8, y, z);
         else surf3Dwrite(make_uchar4(0, 0, 0, 0), level0, x * 4, y, z);
       }
     }
-    mask_prev[w] = now;
-    mask[w] = 0u;
   }
 }
 
