@@ -78,8 +78,10 @@ def make_scene_and_uniforms(args):
 
 def camera_for(step, rank):
     """Per-step input: a slow camera pan (every step has a new view matrix, as the reference's loop does)."""
-    yaw = -90.0 + 0.05 * step + 37.0 * rank
-    pos = (0.0 + 3.0 * rank, 4.0, 0.0)
+    # every rank renders its own stream of frames: the same pan, 17 steps apart per rank (distinct frames of
+    # near-identical cost, so that per-GPU work stays fixed as N grows = weak scaling)
+    yaw = -90.0 + 0.05 * (step + 17 * rank)
+    pos = (0.0, 4.0, 0.0)
     return pos, yaw
 
 
