@@ -512,11 +512,8 @@ int vct_set_i(vct_handle c, const char* name, int v) {
   else if (k == "MaxTileItems") { if (v < 1024) return set_error(c, VCT_ERR_INVALID, "MaxTileItems too small"); c->max_items = (size_t)v; }
   else if (k == "RowBegin") { if (v < 0) return set_error(c, VCT_ERR_INVALID, "RowBegin < 0"); P.row_begin = v; }
   else if (k == "RowEnd") { if (v < 0) return set_error(c, VCT_ERR_INVALID, "RowEnd < 0"); P.row_end = v; }
-  else if (k == "DebugLaneMap") c->debug_lane_map = v;
-  else if (k == "ConeSmemPad") { if (v < 0 || v > 90000) return set_error(c, VCT_ERR_INVALID, "ConeSmemPad out of range"); c->debug_cone_smem_pad = v; }
   else if (k == "OverlapVisibility") c->overlap_visibility = v != 0;
   else if (k == "PipelineFrames") c->pipeline_frames = v != 0;
-  else if (k == "DebugFlags") P.debug_flags = v;
   else if (k == "DebugSpecAhead") c->debug_spec_ahead = v;
   else if (k == "DenseResolve") c->dense_resolve = v != 0;
   else if (k == "Profile") c->profile = v != 0;

@@ -393,12 +393,10 @@ __global__ void __launch_bounds__(64, 8) cone_trace(Params P, VertexCache vc,
                                                   const uint32_t* __restrict__ depth,
                                                   const unsigned long long* __restrict__ vis,
                                                   cudaTextureObject_t grid, uchar4* __restrict__ frame,
-                                                  Counters* __restrict__ ctr, int y_begin, int y_end, int lane_map) {
+                                                  Counters* __restrict__ ctr, int y_begin, int y_end) {
   extern __shared__ float s_dirs[];   // [3][NC][blockDim.x]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int lx, ly;
-  if (lane_map == 1) { lx = (lane & 1) | ((lane >> 1) & 6); ly = ((lane >> 1) & 1) | ((lane >> 3) & 2); }   // 2x2 quads in 8x4
-  else { lx = lane & 7; ly = lane >> 3; }                                                                     // rows of 8
+  const int lx = lane & 7, ly = lane >> 3;    // 8x4 pixel tile per warp (a 2x2-quad lane order measured the same)
   const int i = blockIdx.x * 8 + lx;
   const int j = y_begin + blockIdx.y * 8 + warp * 4 + ly;
   unsigned samples = 0;
@@ -533,12 +531,9 @@ int launch_cone(vct_context* c) {
   const int y0 = c->P.row_begin, y1 = (c->P.row_end > 0 && c->P.row_end < c->P.H) ? c->P.row_end : c->P.H;
   if (y0 >= y1) return VCT_OK;
   dim3 b(64), g((c->P.W + 7) / 8, (y1 - y0 + 7) / 8);
-  if (c->debug_cone_smem_pad > 40000) {
-    cudaFuncSetAttribute(cone_trace<6, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  }
 #define VCT_LAUNCH_CONE(NC, SU)                                                                                   \
-  cone_trace<NC, SU><<<g, b, 3 * NC * 64 * sizeof(float) + (size_t)c->debug_cone_smem_pad, c->stream>>>(c->P, c->vcache2[c->cur], c->d_idx, c->d_trimat, \
-      c->d_materials, c->d_depth, c->d_vis2[c->cur], c->grid[c->cur].tex, c->d_frame, c->d_counters, y0, y1, c->debug_lane_map)
+  cone_trace<NC, SU><<<g, b, 3 * NC * 64 * sizeof(float), c->stream>>>(c->P, c->vcache2[c->cur], c->d_idx, c->d_trimat, \
+      c->d_materials, c->d_depth, c->d_vis2[c->cur], c->grid[c->cur].tex, c->d_frame, c->d_counters, y0, y1)
   const int su = c->debug_spec_ahead;
   if (c->P.n_cones <= 6) {
     if (su == 1) VCT_LAUNCH_CONE(6, 1); else if (su == 2) VCT_LAUNCH_CONE(6, 2); else VCT_LAUNCH_CONE(6, 4);

@@ -35,7 +35,6 @@ struct Params {
   int coverage;          // 0 CENTER, 1 MSAA4_ANY, 2 CONSERVATIVE
   int bounces;
   int row_begin, row_end;   // rows of the frame this context renders (row-band sharding); row_end 0 = H
-  int debug_flags;          // diagnostics only (tools/): bit0 skip voxel atomics, bit1 skip voxel PCF, bit2 skip albedo fetch
 };
 
 struct MaterialDev {
@@ -89,9 +88,6 @@ struct vct_context {
   bool profile = true;
   int dense_resolve = 0;
   int grid_format = 0;
-  int debug_lane_map = 1;
-  int debug_cone_smem_pad = 0;   // extra dynamic smem per cone_trace block: limits its blocks/SM so that the
-                                 // voxel/visibility stages of the next frame can be co-resident (pipelined frames)
   int debug_spec_ahead = 4;   // specular steps fetched ahead per iteration (1, 2, 4)
   size_t max_fragments = 16u << 20;
   size_t max_items = 4u << 20;
