@@ -97,10 +97,11 @@ int vct_render(vct_handle h, uint8_t* host_rgba);
 int vct_frame(vct_handle h, uint8_t* host_rgba);
 
 /* Pipelined form of vct_frame for render loops (the reference's loop is glClear -> Render -> glfwSwapBuffers,
- * main.cpp:77-94; swapping is what lets a GL driver overlap frames).  vct_frame_async renders into one of two
- * device frame buffers and queues the device->host copy of that frame to host_rgba on a separate copy stream;
- * it returns without waiting.  vct_frame_wait blocks until the OLDEST frame still in flight has fully arrived
- * in its host buffer (at most two frames are in flight; a third vct_frame_async waits for the oldest itself).
+ * main.cpp:77-94; swapping is what lets a GL driver overlap frames).  vct_frame_async renders into one of a ring
+ * of three device frame buffers and queues the device->host copy of that frame to host_rgba on a separate copy
+ * stream; it returns without waiting.  vct_frame_wait blocks until the OLDEST frame still in flight has fully
+ * arrived in its host buffer (at most three frames are in flight; a fourth vct_frame_async waits for the oldest
+ * itself).  Keeping two frames queued lets the next frame's voxel stages start beside the current cone_trace.
  * host_rgba should be pinned memory for the copy to overlap. */
 int vct_frame_async(vct_handle h, uint8_t* host_rgba);
 int vct_frame_wait(vct_handle h);

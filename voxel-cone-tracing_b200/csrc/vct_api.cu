@@ -475,7 +475,7 @@ int vct_destroy(vct_handle c) {
   cudaFree(c->d_vis2[0]); cudaFree(c->d_vis2[1]); cudaFree(c->d_frame);
   for (int k = 0; k < 2; ++k) if (c->slot_read_done[k]) cudaEventDestroy(c->slot_read_done[k]);
   if (c->stream_vox) { cudaStreamDestroy(c->stream_vox); cudaEventDestroy(c->ev_vox_done); cudaEventDestroy(c->ev_vtx_done); }
-  for (int k = 0; k < 2; ++k) { cudaFree(c->d_frame2[k]); if (c->ev_rendered[k]) cudaEventDestroy(c->ev_rendered[k]); if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]); }
+  for (int k = 0; k < 3; ++k) { cudaFree(c->d_frame2[k]); if (c->ev_rendered[k]) cudaEventDestroy(c->ev_rendered[k]); if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]); }
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->stream2) { cudaStreamDestroy(c->stream2); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
   cudaFree(c->d_items_vis); cudaFree(c->d_counters_vis);
@@ -859,34 +859,40 @@ int vct_frame(vct_handle c, uint8_t* host_rgba) {
   return VCT_OK;
 }
 
+constexpr int VCT_ASYNC_FRAMES = 3;
+
 static int ensure_async(vct_context* c) {
   if (!c->copy_stream) {
     VCT_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < VCT_ASYNC_FRAMES; ++k) {
       VCT_CUDA(c, cudaEventCreateWithFlags(&c->ev_rendered[k], cudaEventDisableTiming));
       VCT_CUDA(c, cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
     }
   }
   if (c->frame2_W != c->P.W || c->frame2_H != c->P.H || !c->d_frame2[0]) {
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < VCT_ASYNC_FRAMES; ++k) {
       if (c->in_flight[k]) { cudaEventSynchronize(c->ev_copied[k]); c->in_flight[k] = false; }
       cudaFree(c->d_frame2[k]); c->d_frame2[k] = nullptr;
       VCT_CUDA(c, cudaMalloc(&c->d_frame2[k], (size_t)c->P.W * c->P.H * 4));
     }
     c->frame2_W = c->P.W; c->frame2_H = c->P.H;
+    c->frame_oldest = c->frame_seq;
   }
   return VCT_OK;
 }
 
+// blocks until the OLDEST frame still in flight has fully arrived in its host buffer
 int vct_frame_wait(vct_handle c) {
   NEED(c);
-  // oldest in-flight slot: frames alternate slots, so it is the one the NEXT frame would use if both are busy,
-  // otherwise whichever is busy
-  const int next = c->frame_seq & 1;
-  int slot = c->in_flight[next] ? next : (c->in_flight[next ^ 1] ? (next ^ 1) : -1);
-  if (slot < 0) return VCT_OK;
-  VCT_CUDA(c, cudaEventSynchronize(c->ev_copied[slot]));
-  c->in_flight[slot] = false;
+  while (c->frame_oldest != c->frame_seq) {
+    const int slot = c->frame_oldest % VCT_ASYNC_FRAMES;
+    c->frame_oldest++;
+    if (c->in_flight[slot]) {
+      VCT_CUDA(c, cudaEventSynchronize(c->ev_copied[slot]));
+      c->in_flight[slot] = false;
+      return VCT_OK;
+    }
+  }
   return VCT_OK;
 }
 
@@ -895,10 +901,11 @@ int vct_frame_async(vct_handle c, uint8_t* host_rgba) {
   if (!host_rgba) return set_error(c, VCT_ERR_INVALID, "vct_frame_async: host buffer required");
   int rc = ensure_frame(c); if (rc) return rc;
   rc = ensure_async(c); if (rc) return rc;
-  const int slot = c->frame_seq & 1;
-  if (c->in_flight[slot]) {                       // this device buffer is still being copied out
+  const int slot = c->frame_seq % VCT_ASYNC_FRAMES;
+  if (c->in_flight[slot]) {                       // ring full: this device buffer is still being copied out
     VCT_CUDA(c, cudaEventSynchronize(c->ev_copied[slot]));
     c->in_flight[slot] = false;
+    if (c->frame_oldest + VCT_ASYNC_FRAMES == c->frame_seq) c->frame_oldest++;
   }
   uchar4* saved = c->d_frame;
   c->d_frame = c->d_frame2[slot];                 // render straight into the slot

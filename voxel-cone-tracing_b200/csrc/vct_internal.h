@@ -150,10 +150,10 @@ struct vct_context {
 
   // frame
   unsigned long long* d_vis2[2] = {nullptr, nullptr}; uchar4* d_frame = nullptr; int frame_W = 0, frame_H = 0;
-  // double-buffered frames for vct_frame_async
-  uchar4* d_frame2[2] = {nullptr, nullptr}; int frame2_W = 0, frame2_H = 0;
-  cudaStream_t copy_stream = nullptr; cudaEvent_t ev_rendered[2]{}, ev_copied[2]{}; bool in_flight[2] = {false, false};
-  unsigned frame_seq = 0;
+  // ring of device frame buffers for vct_frame_async (up to VCT_ASYNC_FRAMES frames in flight)
+  uchar4* d_frame2[3] = {nullptr, nullptr, nullptr}; int frame2_W = 0, frame2_H = 0;
+  cudaStream_t copy_stream = nullptr; cudaEvent_t ev_rendered[3]{}, ev_copied[3]{}; bool in_flight[3] = {false, false, false};
+  unsigned frame_seq = 0, frame_oldest = 0;
   uint8_t* h_frame_pinned = nullptr; size_t h_frame_bytes = 0;
 
   // timing
