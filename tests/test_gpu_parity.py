@@ -339,6 +339,33 @@ def test_config2_properties(gpu_ctx, atrium_full):
     assert np.array_equal(out, frame)
 
 
+def test_config2_full_size_vs_oracle(gpu_ctx, oracle, atrium_full):
+    """The headline configuration itself (259 608 triangles, 256^3, 1920x1080, conservative coverage) against the
+    oracle: shadow map, occupancy and fragment counts bit-exact; radiance and the frame within the north_star bar."""
+    sc = atrium_full
+    u = _cfg2(sc)
+    run_gpu(gpu_ctx, sc, u)
+    run_oracle(oracle, sc, u)
+    assert np.array_equal(gpu_ctx.depth(), oracle.depth())
+    cg, co = gpu_ctx.counts(), oracle.counts()
+    assert np.array_equal(cg, co) and cg.sum() > 1_500_000
+    for l in range(9):
+        g, o = gpu_ctx.grid(l), oracle.grid(l)
+        assert np.array_equal(g[..., 3] > 0, o[..., 3] > 0)
+        assert np.abs(g.astype(int) - o.astype(int)).max() <= LSB_TOL, f"level {l}"
+    vis_g, vis_o = gpu_ctx.visibility(), oracle.visibility()
+    assert (vis_g != vis_o).mean() <= 1e-4
+    fg, fo = gpu_ctx.read_frame(), oracle.frame()
+    assert psnr(fg[..., :3], fo[..., :3]) >= PSNR_MIN and frac_within(fg, fo, LSB_TOL) >= FRAC_MIN
+    assert abs(gpu_ctx.cone_samples() - oracle.cone_samples()) <= 2e-4 * oracle.cone_samples()
+    # pipelined frames (three streams, alternating slots) reproduce the same frame
+    out = np.zeros_like(fg)
+    for _ in range(3):
+        gpu_ctx.frame()
+    gpu_ctx.frame(out)
+    assert np.array_equal(out, fg)
+
+
 def test_dynamic_positions_round_trip(gpu_ctx):
     sc = scenes.dynamic_knot(nu=256, nv=128)
     u = uniforms.scene_uniforms(sc, V=128, width=320, height=180, shadow_map_size=1024, coverage="conservative")
