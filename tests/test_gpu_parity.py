@@ -577,3 +577,36 @@ def test_fused_sharded_voxelisation_two_gpus():
            "--master-port", "29533", os.path.join(HERE, "mgpu_shared_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
     assert "MGPU_SHARED_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+
+
+def test_pipelined_frames_with_a_moving_mesh_and_camera(gpu_ctx):
+    """vct_frame overlaps frame i+1's voxel / visibility stages with frame i's cone_trace; device-side input changes
+    (positions, shadow map) between frames must still be honoured.  Compare against the unpipelined, unoverlapped path."""
+    import vct_b200.glmath as gm
+    sc = scenes.dynamic_knot(nu=192, nv=96)
+    u = uniforms.scene_uniforms(sc, V=64, width=256, height=144, shadow_map_size=1024, coverage="conservative")
+    c = gpu_ctx
+    c.set_uniforms(u); c.load_scene(sc)
+
+    def run(pipe, overlap):
+        c.set_i("PipelineFrames", pipe); c.set_i("OverlapVisibility", overlap)
+        frames, grids = [], []
+        for i in range(6):
+            if i % 2 == 0:      # the mesh moves every other frame; the camera every frame
+                P = scenes.torus_knot_positions(192, 96, t=0.4 * i).reshape(-1, 3) * 20.0
+                c.update_positions(P.astype(np.float32)); c.draw_depth()
+            view = gm.view_matrix(sc.camera_pos, sc.yaw + 3.0 * i, sc.pitch)
+            c.set_mat4("ModelViewMatrix", gm.colmajor((view @ gm.scale(0.05)).astype(np.float32)))
+            c.frame()
+            if i in (1, 3, 5):
+                c.sync(); frames.append(c.read_frame()); grids.append(c.grid(0))
+            else:
+                c.frame()       # a second frame with unchanged device inputs: this one pipelines
+        c.sync()
+        return frames, grids
+
+    fa, ga = run(0, 0)
+    fb, gb = run(1, 1)
+    for k in range(3):
+        assert np.array_equal(fa[k], fb[k]) and np.array_equal(ga[k], gb[k]), k
+    assert not np.array_equal(ga[0], ga[2])
