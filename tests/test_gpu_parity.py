@@ -610,3 +610,20 @@ def test_pipelined_frames_with_a_moving_mesh_and_camera(gpu_ctx):
     for k in range(3):
         assert np.array_equal(fa[k], fb[k]) and np.array_equal(ga[k], gb[k]), k
     assert not np.array_equal(ga[0], ga[2])
+
+
+def test_specular_fetch_ahead_depth_does_not_change_results(gpu_ctx):
+    """cone_trace fetches 4 specular steps ahead and composites them in order; 1, 2 and 4 must agree bit for bit
+    (guards the ordering logic and the nvcc issue noted in DESIGN.md)."""
+    sc = scenes.atrium(detail=0.1, tex_size=32)
+    u = uniforms.scene_uniforms(sc, V=32, width=96, height=54, shadow_map_size=512, coverage="conservative")
+    c = gpu_ctx
+    c.set_uniforms(u); c.load_scene(sc)
+    c.draw_depth(); c.draw_voxels()
+    out = {}
+    for su in (1, 2, 4):
+        c.set_i("DebugSpecAhead", su)
+        c.render(); c.sync()
+        out[su] = (c.read_frame(), c.cone_samples())
+    assert np.array_equal(out[1][0], out[2][0]) and np.array_equal(out[1][0], out[4][0])
+    assert out[1][1] == out[2][1] == out[4][1]
