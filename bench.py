@@ -383,6 +383,14 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
+def host_cores():
+    """threads the OpenMP oracle actually gets (affinity mask), not the machine total"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count()
+
+
 def cpu_baseline(args, sc, u, budget_s):
     """The oracle ("port": the reference's GLSL cannot run here) timed on the host cores, on a
     bounded sample of the same workload: as many full config frames as fit in ~budget_s (at least one)."""
@@ -396,7 +404,7 @@ def cpu_baseline(args, sc, u, budget_s):
             break
     dt = time.perf_counter() - t0
     o.close()
-    return {"value": round(n / dt, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+    return {"value": round(n / dt, 4), "unit": UNIT, "cores": host_cores(), "kind": "port",
             "sample": f"{n} full frame(s) of the same workload (voxelize+mip+cone-trace) in {dt:.1f} s, OpenMP over all host cores"}
 
 
@@ -427,12 +435,12 @@ def run_reference(args):
     frame_s = tv / K + (tr / K) * (H / rows)        # time of a full frame extrapolated from the row band
     value = 1.0 / frame_s
     sample = (f"each step = full voxelize+mip ({tv / K * 1e3:.0f} ms) + cone trace of {rows} of {H} rows "
-              f"({tr / K * 1e3:.0f} ms), extrapolated linearly to the full frame; CPU oracle (port), OpenMP, {os.cpu_count()} cores")
+              f"({tr / K * 1e3:.0f} ms), extrapolated linearly to the full frame; CPU oracle (port), OpenMP, {host_cores()} cores")
     out = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(frame_s * 1e3, 2), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 grid, f32 shading", "data": "synthetic",
            "config": {"workload": WORKLOAD, "mode": "cpu"},
-           "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": host_cores(), "kind": "port", "sample": sample},
            "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
