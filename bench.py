@@ -39,7 +39,10 @@ def parse():
     ap.add_argument("--mode", default=None, choices=["views", "tiles", "trishard", "shard"],
                     help="N>1: views = one camera per rank, grid replicated (weak scaling, default for config 2); tiles = row bands, "
                          "voxelisation replicated; trishard = triangle ranges + NCCL all-reduce of the accumulator; shard = triangle "
-                         "ranges reduced into every rank's accumulator by multimem.red inside the shading kernel + row bands")
+                         "ranges exchanged over NVSwitch multicast by the library's own kernels (see --exchange) + row bands")
+    ap.add_argument("--exchange", default="inbox", choices=["inbox", "reduce"],
+                    help="--mode shard: inbox = touched voxels multicast as records (multimem.st) and merged locally; reduce = "
+                         "multimem.red into a dense symmetric accumulator (reduced in the switch)")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
                     help="BASELINE.json config: 2 = headline (default); 3 = 512^3 fp16 grid, 4K, 9+1 cones, row bands; "
                          "4 = dynamic 1M-triangle mesh re-voxelised every frame, triangle-sharded + all-reduce")
@@ -176,7 +179,7 @@ def run_ours(args):
     ctx.draw_depth()                                # static light: once, like the reference's init
     ctx.sync()
     tri_rng = parallel.triangle_range(sc.n_tris, rank, world) if args.mode in ("trishard", "shard") else None
-    shared = parallel.SharedAccumulator(ctx, dev) if args.mode == "shard" else None
+    shared = parallel.SharedAccumulator(ctx, dev, exchange=args.exchange) if args.mode == "shard" else None
     acc = parallel.accumulator_tensor(ctx, dev) if args.mode == "trishard" else None
     gather_buf = None
     if args.mode in ("tiles", "shard") and world > 1:
@@ -208,7 +211,7 @@ def run_ours(args):
             ctx.render(host_out)
         else:
             if args.mode == "shard":
-                shared.frame_voxels(tri_rng[0], tri_rng[1])   # exchange fused into the shading kernel (multimem.red)
+                shared.frame_voxels(tri_rng[0], tri_rng[1])   # exchange over NVSwitch multicast (multimem.st inbox / multimem.red)
                 ctx.render(None)
             else:
                 ctx.frame(None if gather_buf is not None else host_out)
@@ -345,7 +348,7 @@ def run_ours(args):
         "scaling": "weak" if args.mode == "views" else "strong", "vs_baseline": None, "dtype": "u8/u32 grid, f32 shading",
         "data": "synthetic",
         "config": {"workload": WORKLOAD if (args.config == 2 and args.detail == 1.0 and args.grid == 256) else f"config{args.config}: {sc.name} {sc.n_tris} tris, V={args.grid} {'RGBA16F' if args.config == 3 else 'RGBA8'}, {args.width}x{args.height}, cones {args.cones}",
-                   "mode": args.mode, "l2": ("flushed between steps by an untimed 256 MiB write; frames not pipelined" if args.flush else "no flush: per-frame working set ~220 MB (64 MiB level 0 + mips, shadow texels, accumulator lines, queues, vertex cache, visibility) in two alternating frame slots exceeds the 126 MB L2"),
+                   "mode": args.mode + ("/" + args.exchange if args.mode == "shard" else ""), "l2": ("flushed between steps by an untimed 256 MiB write; frames not pipelined" if args.flush else "no flush: per-frame working set ~220 MB (64 MiB level 0 + mips, shadow texels, accumulator lines, queues, vertex cache, visibility) in two alternating frame slots exceeds the 126 MB L2"),
                    "timing": "one CUDA-event pair around the K steps on the launching stream, barrier+synchronize both sides; max over ranks",
                    "step": "clear+voxelize+resolve+mip+visibility+cone-trace (shadow map static, drawn once)"},
         "clocks": clocks,

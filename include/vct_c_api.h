@@ -113,14 +113,20 @@ int vct_voxelize_range(vct_handle h, size_t tri_begin, size_t tri_end, int clear
 int vct_accum_buffer(vct_handle h, void** device_ptr, size_t* n_uint32);
 int vct_resolve_and_mip(vct_handle h);   /* dense resolve of the whole accumulator, then mip */
 
-/* Fused form of the same exchange over NVLink / NVSwitch (one process per GPU): the accumulator lives in a
- * symmetric allocation (same size on every rank, e.g. torch symmetric memory) that is also mapped through a
- * MULTICAST address.  Each rank voxelises its triangle range into its private accumulator and then adds every voxel
- * it touched straight into EVERY rank's symmetric accumulator with multimem.red (reduced in the switch), so there
- * is no separate all-reduce and the exchange volume is the touched voxels, not V^3: after a cross-rank barrier every
- * rank resolves its own full copy.  Layout of the buffer: [16 B * V^3 accumulator][V^3 / 8 B occupancy
- * bit mask].  With multicast_ptr == NULL (single GPU, or no multicast) plain local atomics are used.
- *   per frame:  vct_voxelize_shared(range of this rank) -> barrier -> vct_resolve_shared() -> barrier */
+/* Fused form of the same exchange over NVLink / NVSwitch (one process per GPU).  The caller provides ONE symmetric
+ * allocation per rank (same size everywhere, e.g. torch symmetric memory) that is also mapped through a MULTICAST
+ * address.  Set SharedWorld / SharedRank (vct_set_i) first; vct_shared_accum_bytes gives the size.  Two flavours
+ * (vct_set_i "SharedExchange"):
+ *   0 (default) inbox: every rank voxelises its triangle range privately, then multicasts one 32-byte record per
+ *     voxel it touched (index, integer sums, count) with multimem.st into its row of every rank's inbox; after the
+ *     barrier each rank adds the other rows into its private accumulator -- which then equals a single-GPU
+ *     voxelisation bit for bit -- and the ordinary sparse resolve + mip follow.  Exchange volume = touched voxels.
+ *   1 in-switch reduction: the accumulator itself is the symmetric buffer ([16 B * V^3][V^3/8 B occupancy mask]) and
+ *     every touched voxel is added into all copies at once with multimem.red.add.v4.f32 (reduced in the switch),
+ *     followed by a mask-driven resolve.
+ * With multicast_ptr == NULL (single GPU) plain local stores / atomics are used.
+ *   per frame:  vct_voxelize_shared(range of this rank) -> cross-rank barrier -> vct_resolve_shared()
+ *   (flavour 1 needs a second barrier after vct_resolve_shared) */
 int vct_shared_accum_bytes(vct_handle h, size_t* bytes);
 int vct_set_shared_accum(vct_handle h, void* local_ptr, void* multicast_ptr);
 int vct_voxelize_shared(vct_handle h, size_t tri_begin, size_t tri_end);

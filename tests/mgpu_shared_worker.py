@@ -34,7 +34,7 @@ def main():
     ref_grid = [c.grid(l) for l in range(8)]
     ref_frame = c.read_frame()
     # fused sharded path, three frames (exercises the mask-driven clear / stale-voxel removal on both slots)
-    shared = parallel.SharedAccumulator(c, dev)
+    shared = parallel.SharedAccumulator(c, dev, exchange=sys.argv[1] if len(sys.argv) > 1 else "inbox")
     tb, te = parallel.triangle_range(sc.n_tris, rank, world)
     ok = True
     for it in range(3):

@@ -537,8 +537,9 @@ def test_fp16_bounce_extension_vs_oracle(gpu_ctx, oracle):
 
 # ------------------------------------------------------------------------------------------ fused sharded voxelisation
 def test_shared_accumulator_path_single_rank(gpu_ctx):
-    """vct_voxelize_shared / vct_resolve_shared with a one-rank accumulator (plain atomics + occupancy mask): identical
-    to vct_draw_voxels, also across frames, a moving mesh and a switch back to the private path."""
+    """In-switch-reduction flavour of vct_voxelize_shared / vct_resolve_shared with a one-rank accumulator (plain atomics
+    + occupancy mask): identical to vct_draw_voxels, also across frames, a moving mesh and a switch back to the private
+    path."""
     import torch
     from vct_b200 import parallel
     sc = scenes.dynamic_knot(nu=256, nv=128)
@@ -546,7 +547,7 @@ def test_shared_accumulator_path_single_rank(gpu_ctx):
     c = gpu_ctx
     run_gpu(c, sc, u)
     g_ref = [c.grid(l) for l in range(8)]
-    shared = parallel.SharedAccumulator(c, torch.device("cuda", 0))
+    shared = parallel.SharedAccumulator(c, torch.device("cuda", 0), exchange="reduce")
     n = sc.n_tris
     for it in range(3):
         c.voxelize_shared(0, n // 2)          # two ranges into the same accumulator = what two ranks would add
@@ -563,10 +564,76 @@ def test_shared_accumulator_path_single_rank(gpu_ctx):
     c.update_positions(sc.verts[:, :3]); c.draw_depth()
     c.voxelize_shared(0, n); c.resolve_shared(); c.sync()
     assert np.array_equal(c.grid(0), g_ref[0]) and np.array_equal(c.grid(3), g_ref[3])     # stale voxels removed
+    del shared
 
 
-def test_fused_sharded_voxelisation_two_gpus():
-    """multimem.red path over NVSwitch multicast: needs two GPUs on the box (skipped otherwise)."""
+def test_inbox_exchange_two_contexts_one_gpu(gpu_ctx):
+    """Inbox flavour (default): two handles on ONE device act as ranks 0 and 1 of a world of two and share one exchange
+    buffer (no multicast mapping -> plain stores).  After push / merge both hold the single-GPU grid bit for bit, over
+    several frames, with a moving mesh, after a switch to the private path and back, and an undersized inbox is
+    reported as an overflow."""
+    import torch
+    sc = scenes.dynamic_knot(nu=256, nv=128)
+    u = uniforms.scene_uniforms(sc, V=128, width=320, height=180, shadow_map_size=1024, coverage="conservative")
+    a = gpu_ctx
+    run_gpu(a, sc, u)
+    g_ref = [a.grid(l) for l in range(8)]
+    b = vct_b200.Context(0)
+    b.set_uniforms(u); b.load_scene(sc); b.draw_depth(); b.sync()
+    for rank, c in enumerate((a, b)):
+        c.set_i("SharedExchange", 0); c.set_i("SharedWorld", 2); c.set_i("SharedRank", rank)
+    nbytes = a.shared_accum_bytes()
+    assert nbytes == b.shared_accum_bytes()
+    buf = torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device="cuda:0")
+    a.set_shared_accum(buf.data_ptr(), 0); b.set_shared_accum(buf.data_ptr(), 0)
+    n = sc.n_tris
+    cut = n // 3                                  # unequal shares
+
+    def exchange():
+        a.voxelize_shared(0, cut); b.voxelize_shared(cut, n)
+        a.sync(); b.sync()                        # the cross-rank barrier
+        a.resolve_shared(); b.resolve_shared()
+        a.sync(); b.sync()
+
+    for it in range(3):
+        exchange()
+        for l in range(8):
+            assert np.array_equal(a.grid(l), g_ref[l]), (it, l)
+            assert np.array_equal(b.grid(l), g_ref[l]), (it, l)
+    assert a.occupied_voxels() == int((g_ref[0][..., 3] > 0).sum())
+    P1 = scenes.torus_knot_positions(256, 128, t=0.9).reshape(-1, 3) * 20.0
+    for c in (a, b):
+        c.update_positions(P1.astype(np.float32)); c.draw_depth()
+    exchange()
+    moved = a.grid(0)
+    assert np.array_equal(b.grid(0), moved)
+    a.draw_voxels(); a.sync()                     # private path on the same mesh
+    assert np.array_equal(a.grid(0), moved) and not np.array_equal(moved, g_ref[0])
+    for c in (a, b):
+        c.update_positions(sc.verts[:, :3]); c.draw_depth()
+    exchange()
+    for c in (a, b):
+        assert np.array_equal(c.grid(0), g_ref[0]) and np.array_equal(c.grid(3), g_ref[3])   # stale voxels removed
+    # frames rendered from the merged grid equal the single-GPU frame
+    a.draw_voxels(); a.render(); a.sync(); f_ref = a.read_frame()
+    exchange(); b.render(); b.sync()
+    assert np.array_equal(b.read_frame(), f_ref)
+    # an inbox smaller than the touched set is an error, not a silent truncation
+    for c in (a, b):
+        c.set_i("MaxExchangeVoxels", 1024)
+    small = torch.zeros((a.shared_accum_bytes() + 7) // 8, dtype=torch.int64, device="cuda:0")
+    a.set_shared_accum(small.data_ptr(), 0); b.set_shared_accum(small.data_ptr(), 0)
+    a.voxelize_shared(0, cut); b.voxelize_shared(cut, n); a.sync(); b.sync()
+    a.resolve_shared()
+    with pytest.raises(vct_b200.VctError):
+        a.sync()
+    b.close() if hasattr(b, "close") else None
+
+
+@pytest.mark.parametrize("exchange", ["inbox", "reduce"])
+def test_fused_sharded_voxelisation_two_gpus(exchange):
+    """multimem.st inbox / multimem.red in-switch reduction over NVSwitch multicast: needs two GPUs on the box (skipped
+    otherwise)."""
     import subprocess
     import sys
     import torch
@@ -574,7 +641,7 @@ def test_fused_sharded_voxelisation_two_gpus():
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(HERE)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(HERE, "mgpu_shared_worker.py")]
+           "--master-port", "29533", os.path.join(HERE, "mgpu_shared_worker.py"), exchange]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
     assert "MGPU_SHARED_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
 

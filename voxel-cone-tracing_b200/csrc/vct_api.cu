@@ -193,7 +193,7 @@ int check_overflow(vct_context* c) {
   if (ov || ov2) {
     cudaMemsetAsync(&c->d_counters->overflow, 0, 4, c->stream);
     if (c->d_counters_vis) cudaMemset(&c->d_counters_vis->overflow, 0, 4);
-    return set_error(c, VCT_ERR_OVERFLOW, "device work queue overflow: raise MaxFragments / MaxTileItems");
+    return set_error(c, VCT_ERR_OVERFLOW, "device work queue overflow: raise MaxFragments / MaxTileItems (or MaxExchangeVoxels for vct_voxelize_shared)");
   }
   return VCT_OK;
 }
@@ -513,6 +513,10 @@ int vct_set_i(vct_handle c, const char* name, int v) {
   else if (k == "RowBegin") { if (v < 0) return set_error(c, VCT_ERR_INVALID, "RowBegin < 0"); P.row_begin = v; }
   else if (k == "RowEnd") { if (v < 0) return set_error(c, VCT_ERR_INVALID, "RowEnd < 0"); P.row_end = v; }
   else if (k == "OverlapVisibility") c->overlap_visibility = v != 0;
+  else if (k == "SharedExchange") { if (v != 0 && v != 1) return set_error(c, VCT_ERR_INVALID, "SharedExchange: 0 inbox, 1 in-switch reduction"); c->shared_exchange = v; }
+  else if (k == "SharedWorld") { if (v < 1 || v > 16) return set_error(c, VCT_ERR_INVALID, "SharedWorld out of range"); c->shared_world = v; }
+  else if (k == "SharedRank") { if (v < 0 || v > 15) return set_error(c, VCT_ERR_INVALID, "SharedRank out of range"); c->shared_rank = v; }
+  else if (k == "MaxExchangeVoxels") { if (v < 1024) return set_error(c, VCT_ERR_INVALID, "MaxExchangeVoxels too small"); c->exchange_cap_user = (size_t)v; }
   else if (k == "PipelineFrames") c->pipeline_frames = v != 0;
   else if (k == "DebugSpecAhead") c->debug_spec_ahead = v;
   else if (k == "DenseResolve") c->dense_resolve = v != 0;
@@ -717,10 +721,18 @@ int vct_voxelize_range(vct_handle c, size_t tb, size_t te, int clear_first) {
   return rc;
 }
 
+static size_t exchange_capacity(const vct_context* c) {
+  const size_t n = (size_t)c->P.V * c->P.V * c->P.V;
+  const size_t cap = c->exchange_cap_user ? c->exchange_cap_user : 32 * (size_t)c->P.V * c->P.V;
+  return cap < n ? cap : n;
+}
+
 int vct_shared_accum_bytes(vct_handle c, size_t* bytes) {
   NEED(c);
   const size_t n = (size_t)c->P.V * c->P.V * c->P.V;
-  if (bytes) *bytes = n * 16 + n / 8;
+  c->exchange_cap = exchange_capacity(c);
+  if (bytes) *bytes = c->shared_exchange == 1 ? n * 16 + n / 8
+                                              : 4096 + 2 * (size_t)c->shared_world * c->exchange_cap * 32;
   return VCT_OK;
 }
 
@@ -728,6 +740,8 @@ int vct_set_shared_accum(vct_handle c, void* local_ptr, void* multicast_ptr) {
   NEED(c);
   c->shared_local = (unsigned long long*)local_ptr;
   c->shared_mc = (unsigned long long*)multicast_ptr;
+  c->exchange_parity = 0;
+  c->exchange_cap = exchange_capacity(c);   // the size vct_shared_accum_bytes reported for the current settings
   c->scene_epoch++;
   return VCT_OK;
 }

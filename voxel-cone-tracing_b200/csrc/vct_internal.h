@@ -132,6 +132,10 @@ struct vct_context {
   uint32_t* mask_prev[2] = {nullptr, nullptr}; int mask_prev_V = 0;   // occupancy mask of what each slot's level 0 holds
   bool mask_valid[2] = {false, false};                                // ... and whether it is exact
   uint32_t* d_push_list = nullptr; unsigned int* d_push_count = nullptr; size_t push_cap = 0;   // voxels this rank touched
+  // exchange flavour: 0 = inbox (records multicast with multimem.st, merged locally; default), 1 = in-switch reduction
+  // (multimem.red into a dense symmetric accumulator + occupancy mask)
+  int shared_exchange = 0, shared_world = 1, shared_rank = 0, exchange_parity = 0;
+  size_t exchange_cap = 0, exchange_cap_user = 0; // records per rank and parity in the inbox (user 0 = auto: min(V^3, 32 V^2))
   int accum_list_slot = -1;                    // slot whose touched list describes the accumulator's non-zero cells;
                                                // -1 = dense dirty, -2 = all zero (left so by vox_push_shared)
 

@@ -218,6 +218,14 @@ __device__ __forceinline__ void multimem_add_v4f32(float4* mc_addr, float4 v) {
 __device__ __forceinline__ void multimem_or_b32(uint32_t* mc_addr, uint32_t v) {
   asm volatile("multimem.red.relaxed.sys.global.or.b32 [%0], %1;" ::"l"(mc_addr), "r"(v) : "memory");
 }
+// multicast store: one 16-byte store lands at the same offset on every rank
+__device__ __forceinline__ void multimem_st_v4(void* mc_addr, uint4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)) : "memory");
+}
+__device__ __forceinline__ void multimem_st_u32(uint32_t* mc_addr, uint32_t v) {
+  asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(mc_addr), "r"(v) : "memory");
+}
 
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) vox_shade(Params P, const VoxRecord* __restrict__ rec,
@@ -502,7 +510,61 @@ __global__ void vox_push_shared(unsigned long long* __restrict__ accum, const ui
   }
 }
 
+// ---- inbox exchange -------------------------------------------------------------------------------------------
+// Symmetric buffer: [4096 B header: count[parity][rank]] [records: (parity, rank, k) -> 32 B].  Every rank multicasts
+// the voxels it touched (index + integer sums + count) into ITS row of every rank's inbox; after the barrier each
+// rank adds the other rows into its private accumulator, which then equals a single-GPU voxelisation exactly, and
+// the ordinary sparse resolve / mip / clear machinery applies unchanged.
+constexpr size_t EXCH_HEADER = 4096;
+__host__ __device__ inline size_t exch_record_offset(int parity, int world, int rank, size_t cap, size_t k) {
+  return EXCH_HEADER + ((((size_t)parity * world + rank) * cap) + k) * 32;
+}
+
+template <bool MULTICAST>
+__global__ void vox_push_inbox(const unsigned long long* __restrict__ accum, const uint32_t* __restrict__ list,
+                               const unsigned int* __restrict__ n_list, unsigned char* dst, int parity, int world, int rank,
+                               uint32_t cap) {
+  const uint32_t n = min(*n_list, cap);
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const uint32_t v = list[k];
+    const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(&accum[2 * (size_t)v]);
+    unsigned char* rec = dst + exch_record_offset(parity, world, rank, cap, k);
+    const uint4 lo = make_uint4(v, 0u, (uint32_t)a.x, (uint32_t)(a.x >> 32));
+    const uint4 hi = make_uint4((uint32_t)a.y, (uint32_t)(a.y >> 32), 0u, 0u);
+    if (MULTICAST) { multimem_st_v4(rec, lo); multimem_st_v4(rec + 16, hi); }
+    else { *reinterpret_cast<uint4*>(rec) = lo; *reinterpret_cast<uint4*>(rec + 16) = hi; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(dst) + (parity * 16 + rank);
+    if (MULTICAST) multimem_st_u32(cnt, n); else *cnt = n;
+  }
+}
+
+__global__ void vox_merge_inbox(unsigned long long* __restrict__ accum, const unsigned char* __restrict__ inbox, int parity,
+                                int world, int rank, uint32_t cap, uint32_t* __restrict__ touched,
+                                unsigned int* __restrict__ n_touched, Counters* __restrict__ ctr, const unsigned int* own_n) {
+  const uint32_t* counts = reinterpret_cast<const uint32_t*>(inbox) + parity * 16;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && *own_n > cap) ctr->overflow = 1;   // this rank touched more voxels than fit
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) continue;
+    const uint32_t n = min(counts[r], cap);
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+      const unsigned char* rec = inbox + exch_record_offset(parity, world, r, cap, k);
+      const uint4 lo = *reinterpret_cast<const uint4*>(rec), hi = *reinterpret_cast<const uint4*>(rec + 16);
+      const uint32_t v = lo.x;
+      atomicAdd(&accum[2 * (size_t)v], ((unsigned long long)lo.w << 32) | lo.z);
+      const unsigned long long old = atomicAdd(&accum[2 * (size_t)v + 1], ((unsigned long long)hi.y << 32) | hi.x);
+      bool pending = true;
+      append_first_touch(pending, old, v, touched, n_touched);
+    }
+  }
+}
+
+static int voxelize_inbox(vct_context* c, size_t tb, size_t te);
+static int resolve_inbox(vct_context* c);
+
 int launch_voxelize_shared(vct_context* c, size_t tb, size_t te) {
+  if (c->shared_local && c->shared_exchange == 0) return voxelize_inbox(c, tb, te);
   if (!c->shared_local) return set_error(c, VCT_ERR_STATE, "vct_voxelize_shared: call vct_set_shared_accum first");
   int rc = ensure_grid(c); if (rc) return rc;
   const size_t n = (size_t)c->P.V * c->P.V * c->P.V;
@@ -569,6 +631,7 @@ __global__ void vox_resolve_shared(unsigned long long* __restrict__ accum, uint3
 
 int launch_resolve_shared(vct_context* c) {
   if (!c->shared_local) return set_error(c, VCT_ERR_STATE, "vct_resolve_shared: call vct_set_shared_accum first");
+  if (c->shared_exchange == 0) return resolve_inbox(c);
   int rc = ensure_grid(c); if (rc) return rc;
   const int V = c->P.V;
   const size_t n_words = ((size_t)V * V * V) >> 5;
@@ -596,6 +659,42 @@ int launch_resolve_shared(vct_context* c) {
   // this slot must start from a dense zero, and mask_prev stays exact as long as only this path writes the slot
   g.list_valid = false;
   c->mask_valid[c->cur] = true;
+  VCT_CUDA(c, cudaGetLastError());
+  return VCT_OK;
+}
+
+static int voxelize_inbox(vct_context* c, size_t tb, size_t te) {
+  int rc = ensure_grid(c); if (rc) return rc;
+  rc = begin_voxel_slot(c); if (rc) return rc;
+  rc = launch_voxel_clear(c); if (rc) return rc;             // ordinary sparse clear (lists describe ALL voxels)
+  rc = launch_voxelize(c, tb, te); if (rc) return rc;         // this rank's triangles -> private accumulator + list
+  vct_context::GridBuf& g = c->grid[c->cur];
+  const uint32_t cap = (uint32_t)c->exchange_cap;
+  if (c->shared_mc)
+    vox_push_inbox<true><<<148 * 4, 256, 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, (unsigned char*)c->shared_mc,
+                                                         c->exchange_parity, c->shared_world, c->shared_rank, cap);
+  else
+    vox_push_inbox<false><<<148 * 4, 256, 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, (unsigned char*)c->shared_local,
+                                                          c->exchange_parity, c->shared_world, c->shared_rank, cap);
+  // own record count, needed by the merge for the overflow check (the list keeps growing during the merge)
+  if (!c->d_push_count) VCT_CUDA(c, cudaMalloc(&c->d_push_count, 128));
+  VCT_CUDA(c, cudaMemcpyAsync(c->d_push_count, g.n_touched, 4, cudaMemcpyDeviceToDevice, c->stream));
+  c->launches += 1;
+  VCT_CUDA(c, cudaGetLastError());
+  return VCT_OK;
+}
+
+static int resolve_inbox(vct_context* c) {
+  vct_context::GridBuf& g = c->grid[c->cur];
+  {
+    PassTimer timer(c, VCT_PASS_REINJECT);   // reported under "reinject" slot: the merge of the other ranks' voxels
+    vox_merge_inbox<<<148 * 4, 256, 0, c->stream>>>(c->d_accum, (const unsigned char*)c->shared_local, c->exchange_parity,
+                                                    c->shared_world, c->shared_rank, (uint32_t)c->exchange_cap, g.touched,
+                                                    g.n_touched, c->d_counters, c->d_push_count);
+    c->launches += 1;
+  }
+  c->exchange_parity ^= 1;
+  int rc = launch_resolve(c, false); if (rc) return rc;
   VCT_CUDA(c, cudaGetLastError());
   return VCT_OK;
 }

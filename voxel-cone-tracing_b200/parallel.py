@@ -74,19 +74,25 @@ def unpack_accumulator(acc: np.ndarray):
 
 
 class SharedAccumulator:
-    """Symmetric accumulator for the fused triangle-sharded voxelisation (vct_voxelize_shared / vct_resolve_shared).
+    """Symmetric exchange buffer for the fused triangle-sharded voxelisation (vct_voxelize_shared / vct_resolve_shared).
 
     Plumbing only: the memory comes from torch symmetric memory (same allocation size on every rank, mapped on the
     peers and through an NVSwitch multicast address), the barrier is the symmetric-memory signal-pad barrier on the
-    current stream.  With world size 1 it is a plain zeroed device buffer and the barrier is a no-op."""
+    current stream.  With world size 1 it is a plain zeroed device buffer and the barrier is a no-op.
+    exchange = "inbox" (default) or "reduce" (multimem.red into a dense symmetric accumulator)."""
 
-    def __init__(self, ctx, device, group=None):
+    def __init__(self, ctx, device, group=None, exchange="inbox"):
         import torch
         import torch.distributed as dist
         self.ctx = ctx
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.reduce = exchange == "reduce"
+        ctx.set_i("SharedExchange", 1 if self.reduce else 0)
+        ctx.set_i("SharedWorld", self.world)
+        ctx.set_i("SharedRank", self.rank)
         nbytes = ctx.shared_accum_bytes()
         n64 = (nbytes + 7) // 8
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.hdl = None
         if self.world > 1:
             import torch.distributed._symmetric_memory as symm_mem
@@ -109,9 +115,11 @@ class SharedAccumulator:
             self.hdl.barrier()
 
     def frame_voxels(self, tri_begin, tri_end):
-        """One sharded voxelisation: reduce this rank's triangle range into every rank's accumulator, barrier,
-        resolve + mip the local copy, barrier (so nobody adds into an accumulator that is still being resolved)."""
+        """One sharded voxelisation: voxelise this rank's triangle range and multicast what it touched, barrier, merge /
+        resolve + mip the local copy.  (The inbox is double buffered by frame parity, so one barrier per frame is
+        enough; the in-switch reduction needs a second one before the next frame may add into the accumulator.)"""
         self.ctx.voxelize_shared(tri_begin, tri_end)
         self.barrier()
         self.ctx.resolve_shared()
-        self.barrier()
+        if self.reduce:
+            self.barrier()
