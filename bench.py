@@ -30,7 +30,7 @@ WORKLOAD = ("config2: synthetic Sponza-scale atrium 259608 tris (seed 1234), 256
             "4096^2 shadow map")
 
 
-def parse():
+def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=300)
@@ -40,6 +40,7 @@ def parse():
                     help="N>1: views = one camera per rank, grid replicated (weak scaling, default for config 2); tiles = row bands, "
                          "voxelisation replicated; trishard = triangle ranges + NCCL all-reduce of the accumulator; shard = triangle "
                          "ranges exchanged over NVSwitch multicast by the library's own kernels (see --exchange) + row bands")
+    ap.add_argument("--contiguous", action="store_true", help="triangle sharding by contiguous ranges instead of interleaved blocks")
     ap.add_argument("--exchange", default="inbox", choices=["inbox", "reduce"],
                     help="--mode shard: inbox = touched voxels multicast as records (multimem.st) and merged locally; reduce = "
                          "multimem.red into a dense symmetric accumulator (reduced in the switch)")
@@ -55,7 +56,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--flush", action="store_true", help="flush L2 between timed steps (per-step events, frames not pipelined); "
                     "default: no flush -- the per-frame working set (~220 MB, two alternating frame slots) exceeds the 126 MB L2")
-    a = ap.parse_args()
+    a = ap.parse_args(argv)
     if a.config == 3:
         a.grid, a.width, a.height = 512, 3840, 2160
         a.cones = a.cones or "9+1"
@@ -178,7 +179,8 @@ def run_ours(args):
         ctx.set_i("RowBegin", b0); ctx.set_i("RowEnd", b1)
     ctx.draw_depth()                                # static light: once, like the reference's init
     ctx.sync()
-    tri_rng = parallel.triangle_range(sc.n_tris, rank, world) if args.mode in ("trishard", "shard") else None
+    tri_rng = (parallel.triangle_share(ctx, sc.n_tris, rank, world, interleave=not args.contiguous)
+               if args.mode in ("trishard", "shard") else None)
     shared = parallel.SharedAccumulator(ctx, dev, exchange=args.exchange) if args.mode == "shard" else None
     acc = parallel.accumulator_tensor(ctx, dev) if args.mode == "trishard" else None
     gather_buf = None
@@ -276,6 +278,8 @@ def run_ours(args):
     # (2) per-pass breakdown and the dominant kernel's average duration: same steps again with pass events on
     ctx.set_i("Profile", 1)
     pass_names = ["vox_clear", "vox_cover", "vox_shade", "resolve", "mip", "visibility", "cone"]
+    if args.mode == "shard" and args.exchange == "inbox":
+        pass_names.insert(3, "reinject")             # the timer slot the inbox merge reports under
     pass_sum = {p: 0.0 for p in pass_names}
     samples_sum = 0
     n_prof = min(args.steps, 30)
@@ -292,6 +296,11 @@ def run_ours(args):
         samples_sum += ctx.cone_samples()
     ctx.set_i("Profile", 0)
     barrier()
+    passes_max = None
+    if world > 1 and args.mode != "views":         # sharded work: the slowest rank sets the pace of every phase
+        mine = torch.tensor([pass_sum[p] / n_prof for p in pass_names], dtype=torch.float64, device=dev)
+        dist.all_reduce(mine, op=dist.ReduceOp.MAX)
+        passes_max = {("merge" if p == "reinject" else p): round(float(v), 2) for p, v in zip(pass_names, mine.tolist())}
 
     # ---- end to end through the public API with HOST frame buffers (pinned); every frame's D2H copy is inside
     # the timed region.  Render loops use the pipelined call (vct_frame_async / vct_frame_wait: double-buffered,
@@ -356,7 +365,8 @@ def run_ours(args):
                 "d2h_bytes_per_step": args.width * args.height * 4,
                 "note": "vct_frame_async(host_rgba)+vct_frame_wait, three pinned host frame buffers (two frames queued), every frame copied to the host inside the timed region; per-step input = view matrix + camera position (kernel parameters)"},
         "gpu_launches": int(launches),
-        "passes_us": {p: round(pass_sum[p] / n_prof, 2) for p in pass_names},
+        "passes_us": {("merge" if (p == "reinject" and args.mode == "shard") else p): round(pass_sum[p] / n_prof, 2) for p in pass_names},
+        "passes_us_max_over_ranks": passes_max,
         "cone_samples_per_frame": int(samples_per_launch),
         "gcone_samples_per_s": round(achieved_gs, 2),
         # dominant kernel.  It is bound by the texture pipe (tex3DLod wavefronts), not by HBM (28 MB of DRAM traffic per

@@ -58,6 +58,9 @@ const char* vct_version(void);
  *   int   : VoxelDimensions ShadowMapSize screen_width screen_height PcfRadius CoveragePolicy
  *           Bounces NumDiffuseCones GridFormat MaxFragments MaxTileItems DenseResolve Profile
  *           RowBegin RowEnd (rows [RowBegin, RowEnd) of the frame are rendered; RowEnd 0 = all: row-band sharding)
+ *           TriangleInterleave TrianglePhase (voxelisation takes every TriangleInterleave-th block of 128 triangles of
+ *             the requested range, starting at block TrianglePhase: balanced triangle sharding, one phase per rank)
+ *           SharedExchange SharedWorld SharedRank MaxExchangeVoxels (fused sharded voxelisation, see below)
  *           ShadowMap VoxelTexture (texture-unit numbers: accepted and ignored)
  *   float : VoxelGridWorldSize ambientFactor DiffuseTanHalfAngle SpecularTanHalfAngle StepMultiplier
  *           MaxDistance MaxAlpha ShadowBias
@@ -117,8 +120,8 @@ int vct_resolve_and_mip(vct_handle h);   /* dense resolve of the whole accumulat
  * allocation per rank (same size everywhere, e.g. torch symmetric memory) that is also mapped through a MULTICAST
  * address.  Set SharedWorld / SharedRank (vct_set_i) first; vct_shared_accum_bytes gives the size.  Two flavours
  * (vct_set_i "SharedExchange"):
- *   0 (default) inbox: every rank voxelises its triangle range privately, then multicasts one 32-byte record per
- *     voxel it touched (index, integer sums, count) with multimem.st into its row of every rank's inbox; after the
+ *   0 (default) inbox: every rank voxelises its triangle range privately, then multicasts one record per
+ *     voxel it touched (one 16-byte record: index, 24-bit integer sums, 24-bit count) with multimem.st into its row of every rank's inbox; after the
  *     barrier each rank adds the other rows into its private accumulator -- which then equals a single-GPU
  *     voxelisation bit for bit -- and the ordinary sparse resolve + mip follow.  Exchange volume = touched voxels.
  *   1 in-switch reduction: the accumulator itself is the symmetric buffer ([16 B * V^3][V^3/8 B occupancy mask]) and

@@ -35,9 +35,9 @@ def main():
     ref_frame = c.read_frame()
     # fused sharded path, three frames (exercises the mask-driven clear / stale-voxel removal on both slots)
     shared = parallel.SharedAccumulator(c, dev, exchange=sys.argv[1] if len(sys.argv) > 1 else "inbox")
-    tb, te = parallel.triangle_range(sc.n_tris, rank, world)
     ok = True
-    for it in range(3):
+    for it in range(4):
+        tb, te = parallel.triangle_share(c, sc.n_tris, rank, world, interleave=it >= 2)   # contiguous, then interleaved
         shared.frame_voxels(tb, te)
         c.sync()
         for l in range(8):

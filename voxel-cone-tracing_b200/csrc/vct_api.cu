@@ -514,6 +514,8 @@ int vct_set_i(vct_handle c, const char* name, int v) {
   else if (k == "RowEnd") { if (v < 0) return set_error(c, VCT_ERR_INVALID, "RowEnd < 0"); P.row_end = v; }
   else if (k == "OverlapVisibility") c->overlap_visibility = v != 0;
   else if (k == "SharedExchange") { if (v != 0 && v != 1) return set_error(c, VCT_ERR_INVALID, "SharedExchange: 0 inbox, 1 in-switch reduction"); c->shared_exchange = v; }
+  else if (k == "TriangleInterleave") { if (v < 1) return set_error(c, VCT_ERR_INVALID, "TriangleInterleave < 1"); c->tri_interleave = v; c->scene_epoch++; }
+  else if (k == "TrianglePhase") { if (v < 0) return set_error(c, VCT_ERR_INVALID, "TrianglePhase < 0"); c->tri_phase = v; c->scene_epoch++; }
   else if (k == "SharedWorld") { if (v < 1 || v > 16) return set_error(c, VCT_ERR_INVALID, "SharedWorld out of range"); c->shared_world = v; }
   else if (k == "SharedRank") { if (v < 0 || v > 15) return set_error(c, VCT_ERR_INVALID, "SharedRank out of range"); c->shared_rank = v; }
   else if (k == "MaxExchangeVoxels") { if (v < 1024) return set_error(c, VCT_ERR_INVALID, "MaxExchangeVoxels too small"); c->exchange_cap_user = (size_t)v; }
@@ -732,7 +734,7 @@ int vct_shared_accum_bytes(vct_handle c, size_t* bytes) {
   const size_t n = (size_t)c->P.V * c->P.V * c->P.V;
   c->exchange_cap = exchange_capacity(c);
   if (bytes) *bytes = c->shared_exchange == 1 ? n * 16 + n / 8
-                                              : 4096 + 2 * (size_t)c->shared_world * c->exchange_cap * 32;
+                                              : 4096 + 2 * (size_t)c->shared_world * c->exchange_cap * 16;
   return VCT_OK;
 }
 

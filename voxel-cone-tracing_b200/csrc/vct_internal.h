@@ -135,6 +135,7 @@ struct vct_context {
   // exchange flavour: 0 = inbox (records multicast with multimem.st, merged locally; default), 1 = in-switch reduction
   // (multimem.red into a dense symmetric accumulator + occupancy mask)
   int shared_exchange = 0, shared_world = 1, shared_rank = 0, exchange_parity = 0;
+  int tri_interleave = 1, tri_phase = 0;         // voxelisation takes every tri_interleave-th block of 128 triangles
   size_t exchange_cap = 0, exchange_cap_user = 0; // records per rank and parity in the inbox (user 0 = auto: min(V^3, 32 V^2))
   int accum_list_slot = -1;                    // slot whose touched list describes the accumulator's non-zero cells;
                                                // -1 = dense dirty, -2 = all zero (left so by vox_push_shared)

@@ -26,8 +26,11 @@ constexpr int ITEM_TILES = 16;
 template <class Pass>
 __global__ void __launch_bounds__(128, 5) raster_small(Pass pass, uint32_t tri_begin, uint32_t tri_end,
                                                     TileItem* __restrict__ items, uint32_t items_cap,
-                                                    Counters* __restrict__ ctr) {
-  uint32_t tri = tri_begin + blockIdx.x * blockDim.x + threadIdx.x;
+                                                    Counters* __restrict__ ctr, uint32_t interleave = 1,
+                                                    uint32_t phase = 0) {
+  // interleave > 1: this launch owns every interleave-th block of 128 triangles of [tri_begin, tri_end), starting at
+  // block `phase` (triangle sharding across ranks: contiguous ranges of a mesh differ a lot in fragments per triangle)
+  uint32_t tri = tri_begin + (blockIdx.x * interleave + phase) * blockDim.x + threadIdx.x;
   bool live = tri < tri_end;
   typename Pass::Setup s;
   int i0 = 0, i1 = -1, j0 = 0, j1 = -1;

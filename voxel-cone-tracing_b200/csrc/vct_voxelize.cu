@@ -452,8 +452,11 @@ static int voxelize_impl(vct_context* c, size_t tb, size_t te, int shared) {
     VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_fragments, 0, sizeof(unsigned int), c->stream));
     VoxCoverPass pass{c->P, c->vcache2[c->cur], c->d_idx, c->d_trimat, c->d_materials, (VoxRecord*)c->d_voxrec, c->d_frags, (uint32_t)c->frags_cap, c->d_counters};
     const uint32_t n = (uint32_t)(te - tb);
-    raster_small<VoxCoverPass><<<(n + 127) / 128, 128, 0, c->stream>>>(pass, (uint32_t)tb, (uint32_t)te, c->d_items,
-                                                                        (uint32_t)c->items_cap, c->d_counters);
+    const uint32_t n_blocks = (n + 127) / 128, il = (uint32_t)c->tri_interleave, ph = (uint32_t)c->tri_phase % il;
+    const uint32_t own_blocks = n_blocks > ph ? (n_blocks - ph + il - 1) / il : 0;
+    if (own_blocks)
+      raster_small<VoxCoverPass><<<own_blocks, 128, 0, c->stream>>>(pass, (uint32_t)tb, (uint32_t)te, c->d_items,
+                                                                    (uint32_t)c->items_cap, c->d_counters, il, ph);
     raster_tiles<VoxCoverPass><<<148 * 4, 256, 0, c->stream>>>(pass, c->d_items, (uint32_t)c->items_cap, c->d_counters);
     c->launches += 2;
   }
@@ -511,28 +514,32 @@ __global__ void vox_push_shared(unsigned long long* __restrict__ accum, const ui
 }
 
 // ---- inbox exchange -------------------------------------------------------------------------------------------
-// Symmetric buffer: [4096 B header: count[parity][rank]] [records: (parity, rank, k) -> 32 B].  Every rank multicasts
+// Symmetric buffer: [4096 B header: count[parity][rank]] [records: (parity, rank, k) -> 16 B].  Every rank multicasts
 // the voxels it touched (index + integer sums + count) into ITS row of every rank's inbox; after the barrier each
 // rank adds the other rows into its private accumulator, which then equals a single-GPU voxelisation exactly, and
 // the ordinary sparse resolve / mip / clear machinery applies unchanged.
-constexpr size_t EXCH_HEADER = 4096;
+// Record = uint4 {r | c0<<24, g | c1<<24, b | c2<<24, voxel}: 24-bit channel sums and a 24-bit count (bytes c0..c2).
+// A sum of 2^24 or more (> 65 793 fragments in one voxel from one rank) does not fit and is reported as an overflow.
+constexpr size_t EXCH_HEADER = 4096, EXCH_RECORD = 16;
 __host__ __device__ inline size_t exch_record_offset(int parity, int world, int rank, size_t cap, size_t k) {
-  return EXCH_HEADER + ((((size_t)parity * world + rank) * cap) + k) * 32;
+  return EXCH_HEADER + ((((size_t)parity * world + rank) * cap) + k) * EXCH_RECORD;
 }
 
 template <bool MULTICAST>
 __global__ void vox_push_inbox(const unsigned long long* __restrict__ accum, const uint32_t* __restrict__ list,
                                const unsigned int* __restrict__ n_list, unsigned char* dst, int parity, int world, int rank,
-                               uint32_t cap) {
+                               uint32_t cap, Counters* __restrict__ ctr) {
   const uint32_t n = min(*n_list, cap);
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const uint32_t v = list[k];
     const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(&accum[2 * (size_t)v]);
     unsigned char* rec = dst + exch_record_offset(parity, world, rank, cap, k);
-    const uint4 lo = make_uint4(v, 0u, (uint32_t)a.x, (uint32_t)(a.x >> 32));
-    const uint4 hi = make_uint4((uint32_t)a.y, (uint32_t)(a.y >> 32), 0u, 0u);
-    if (MULTICAST) { multimem_st_v4(rec, lo); multimem_st_v4(rec + 16, hi); }
-    else { *reinterpret_cast<uint4*>(rec) = lo; *reinterpret_cast<uint4*>(rec + 16) = hi; }
+    // accumulator cell: a.x = r << 32 | g, a.y = b << 32 | count
+    const uint32_t r = (uint32_t)(a.x >> 32), g = (uint32_t)a.x, b = (uint32_t)(a.y >> 32), n_frag = (uint32_t)a.y;
+    if ((r | g | b | n_frag) >> 24) ctr->overflow = 1;
+    const uint4 q = make_uint4((r & 0xFFFFFFu) | (n_frag << 24), (g & 0xFFFFFFu) | ((n_frag >> 8) << 24),
+                               (b & 0xFFFFFFu) | ((n_frag >> 16) << 24), v);
+    if (MULTICAST) multimem_st_v4(rec, q); else *reinterpret_cast<uint4*>(rec) = q;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     uint32_t* cnt = reinterpret_cast<uint32_t*>(dst) + (parity * 16 + rank);
@@ -550,10 +557,10 @@ __global__ void vox_merge_inbox(unsigned long long* __restrict__ accum, const un
     const uint32_t n = min(counts[r], cap);
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
       const unsigned char* rec = inbox + exch_record_offset(parity, world, r, cap, k);
-      const uint4 lo = *reinterpret_cast<const uint4*>(rec), hi = *reinterpret_cast<const uint4*>(rec + 16);
-      const uint32_t v = lo.x;
-      atomicAdd(&accum[2 * (size_t)v], ((unsigned long long)lo.w << 32) | lo.z);
-      const unsigned long long old = atomicAdd(&accum[2 * (size_t)v + 1], ((unsigned long long)hi.y << 32) | hi.x);
+      const uint4 q = *reinterpret_cast<const uint4*>(rec);
+      const uint32_t v = q.w, n_frag = (q.x >> 24) | ((q.y >> 24) << 8) | ((q.z >> 24) << 16);
+      atomicAdd(&accum[2 * (size_t)v], ((unsigned long long)(q.x & 0xFFFFFFu) << 32) | (q.y & 0xFFFFFFu));
+      const unsigned long long old = atomicAdd(&accum[2 * (size_t)v + 1], ((unsigned long long)(q.z & 0xFFFFFFu) << 32) | n_frag);
       bool pending = true;
       append_first_touch(pending, old, v, touched, n_touched);
     }
@@ -672,10 +679,10 @@ static int voxelize_inbox(vct_context* c, size_t tb, size_t te) {
   const uint32_t cap = (uint32_t)c->exchange_cap;
   if (c->shared_mc)
     vox_push_inbox<true><<<148 * 4, 256, 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, (unsigned char*)c->shared_mc,
-                                                         c->exchange_parity, c->shared_world, c->shared_rank, cap);
+                                                         c->exchange_parity, c->shared_world, c->shared_rank, cap, c->d_counters);
   else
     vox_push_inbox<false><<<148 * 4, 256, 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, (unsigned char*)c->shared_local,
-                                                          c->exchange_parity, c->shared_world, c->shared_rank, cap);
+                                                          c->exchange_parity, c->shared_world, c->shared_rank, cap, c->d_counters);
   // own record count, needed by the merge for the overflow check (the list keeps growing during the merge)
   if (!c->d_push_count) VCT_CUDA(c, cudaMalloc(&c->d_push_count, 128));
   VCT_CUDA(c, cudaMemcpyAsync(c->d_push_count, g.n_touched, 4, cudaMemcpyDeviceToDevice, c->stream));

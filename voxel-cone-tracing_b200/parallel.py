@@ -18,6 +18,17 @@ def triangle_range(n_tris: int, rank: int, world: int):
     return b, b + base + (1 if rank < rem else 0)
 
 
+def triangle_share(ctx, n_tris: int, rank: int, world: int, interleave: bool = True):
+    """Triangle share of `rank` for sharded voxelisation; returns the [begin, end) to pass to voxelize_range /
+    voxelize_shared.  interleave=True deals blocks of 128 triangles round-robin (TriangleInterleave / TrianglePhase):
+    contiguous ranges of a real mesh differ several-fold in fragments per triangle, interleaved shares do not."""
+    if interleave:
+        ctx.set_i("TriangleInterleave", world); ctx.set_i("TrianglePhase", rank)
+        return 0, int(n_tris)
+    ctx.set_i("TriangleInterleave", 1); ctx.set_i("TrianglePhase", 0)
+    return triangle_range(n_tris, rank, world)
+
+
 def row_band(height: int, rank: int, world: int, align: int = 8):
     """[begin, end) rows of the frame for `rank`; bands are multiples of `align` rows (cone_trace's warp
     tile height) except possibly the last."""
