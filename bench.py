@@ -309,6 +309,12 @@ def run_ours(args):
     pipelined = args.mode == "views"
     for i in range(3):
         step(i, hosts[0])
+    if pipelined:                                   # warm the asynchronous path too (ring buffers, copy stream)
+        for i in range(6):
+            ctx.frame_async(hosts[i % 3])
+            if i >= 2:
+                ctx.frame_wait()
+        ctx.frame_wait(); ctx.frame_wait()
     barrier()
     t0 = time.perf_counter()
     h2d = 0

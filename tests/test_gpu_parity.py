@@ -567,6 +567,31 @@ def test_shared_accumulator_path_single_rank(gpu_ctx):
     del shared
 
 
+@pytest.mark.parametrize("grid_format,bounces", [(0, 2), (1, 2), (0, 3)])
+def test_sparse_mip_build_tracks_a_moving_mesh(gpu_ctx, grid_format, bounces):
+    """The pyramid is rebuilt only above level-0 bricks that changed (dirty flags set by the sparse clear and resolve).
+    Over frames of a moving mesh -- both frame slots, stale voxels disappearing, switches to the dense path and back --
+    every level must equal what the dense build (DenseResolve=1: dense clear, resolve and mip) produces."""
+    sc = scenes.dynamic_knot(nu=192, nv=96)
+    u = uniforms.scene_uniforms(sc, V=128, width=64, height=64, shadow_map_size=1024, coverage="conservative",
+                                grid_format=grid_format)
+    c = gpu_ctx
+    c.set_uniforms(u); c.load_scene(sc); c.set_i("Bounces", bounces)
+    levels = 8
+    for frame in range(7):
+        P = scenes.torus_knot_positions(192, 96, t=0.35 * frame).reshape(-1, 3) * 20.0
+        c.update_positions(P.astype(np.float32)); c.draw_depth()
+        c.set_i("DenseResolve", 0)
+        c.draw_voxels(); c.sync()
+        sparse = [c.grid(l) for l in range(levels)]
+        if frame in (0, 1, 3, 6):              # the dense build of the same frame (also leaves a densely written slot behind)
+            c.set_i("DenseResolve", 1)
+            c.draw_voxels(); c.sync()
+            for l in range(levels):
+                assert np.array_equal(c.grid(l), sparse[l]), (frame, l)
+        assert (sparse[0][..., 3] > 0).sum() > 1000 and sparse[levels - 1].max() > 0
+
+
 def test_interleaved_triangle_shares_sum_to_the_whole(gpu_ctx):
     """TriangleInterleave / TrianglePhase: the three interleaved shares of a mesh, accumulated, give exactly the
     accumulator (counts and sums) of one full voxelisation."""

@@ -617,6 +617,7 @@ int launch_reinject(vct_context* c) {
   reinject_gather<<<g, b, 0, c->stream>>>(c->P, c->grid[c->cur].tex, c->grid[c->cur].surf[0], staged, c->grid_format);
   reinject_commit<<<g, b, 0, c->stream>>>(staged, c->grid[c->cur].surf[0], V, c->grid_format);
   c->launches += 2;
+  c->grid[c->cur].mips_current = false;   // level 0 changed (occupied voxels only: inside the bricks already flagged)
   VCT_CUDA(c, cudaFreeAsync(staged, c->stream));
   VCT_CUDA(c, cudaGetLastError());
   return VCT_OK;

@@ -125,6 +125,11 @@ struct vct_context {
     uint32_t* touched = nullptr;               // voxels whose level-0 texel may be non-zero (exact when list_valid)
     unsigned int* n_touched = nullptr;         // device counter
     bool list_valid = true;                    // false: level 0 was written densely, a dense clear is needed before reuse
+    // sparse mip build: one flag per 32x8x8 brick of level 0 (= one mip_fused3 block).  While dirty_valid, the flags
+    // cover every brick whose level-0 texels changed since this slot's pyramid was last built (mips_current), so the
+    // fine levels are rebuilt for flagged bricks only -- cost follows the occupied surface, not V^3.
+    unsigned char* dirty = nullptr;
+    bool dirty_valid = false, mips_current = false;
   } grid[2];
   size_t touched_cap = 0;
   // fused sharded voxelisation: external symmetric accumulator + occupancy mask (local view and multicast view)
@@ -224,6 +229,13 @@ __device__ __forceinline__ F4 mul_mat_vec(const float* __restrict__ m, float x, 
   r.w = ((m[3] * x + m[7] * y) + m[11] * z) + m[15] * w;
   return r;
 }
+
+// index of the 32x8x8 level-0 brick holding voxel (x, y, z)
+__host__ __device__ inline uint32_t brick_of(int x, int y, int z, int V) {
+  return ((uint32_t)(z >> 3) * (uint32_t)(V >> 3) + (uint32_t)(y >> 3)) * (uint32_t)(V >> 5) + (uint32_t)(x >> 5);
+}
+
+inline size_t dirty_bytes(int V) { size_t n = (size_t)(V >> 5) * (V >> 3) * (V >> 3); return n ? n : 1; }
 
 constexpr int SUBPIX = 256;
 constexpr float SNAP_LIMIT = 8388608.0f;

@@ -321,9 +321,16 @@ __global__ void __launch_bounds__(256) vox_shade(Params P, const VoxRecord* __re
 // Sparse clear before a voxelisation into slot B: (1) zero the accumulator cells named by the list of the previous
 // voxelisation (slot A), (2) zero the level-0 texels of slot B named by slot B's own old list (what the frame before
 // last left there).  Cost is proportional to the occupied voxels, not to V^3.
+// Thousands of voxels share a brick: test first so that almost all of them issue a (cached) load instead of a store to
+// the same few L2 lines.  A stale 0 only costs a redundant store.
+__device__ __forceinline__ void mark_dirty(unsigned char* __restrict__ dirty, uint32_t brick) {
+  if (dirty[brick] == 0) dirty[brick] = 1;
+}
+
 __global__ void vox_clear_sparse(unsigned long long* __restrict__ accum, const uint32_t* __restrict__ listA,
                                  const unsigned int* __restrict__ nA, cudaSurfaceObject_t level0B,
-                                 const uint32_t* __restrict__ listB, const unsigned int* __restrict__ nB, int V, int f16) {
+                                 const uint32_t* __restrict__ listB, const unsigned int* __restrict__ nB, int V, int f16,
+                                 unsigned char* __restrict__ dirty) {
   const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
   if (listA) {
     const uint32_t n = *nA;
@@ -340,6 +347,7 @@ __global__ void vox_clear_sparse(unsigned long long* __restrict__ accum, const u
       int x = v % V, y = (v / V) % V, z = v / (V * V);
       if (f16) surf3Dwrite(make_uint2(0u, 0u), level0B, x * 8, y, z);
       else surf3Dwrite(make_uchar4(0, 0, 0, 0), level0B, x * 4, y, z);
+      mark_dirty(dirty, brick_of(x, y, z, V));      // the pyramid above this brick must be rebuilt
     }
   }
 }
@@ -373,7 +381,7 @@ __device__ __forceinline__ uint2 resolve_cell16(unsigned long long rg, unsigned 
 
 __global__ void vox_resolve_sparse(const unsigned long long* __restrict__ accum,
                                    const uint32_t* __restrict__ touched, const unsigned int* __restrict__ n_touched,
-                                   cudaSurfaceObject_t level0, int V, int f16) {
+                                   cudaSurfaceObject_t level0, int V, int f16, unsigned char* __restrict__ dirty) {
   const uint32_t n = *n_touched;
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     uint32_t v = touched[k];
@@ -381,6 +389,7 @@ __global__ void vox_resolve_sparse(const unsigned long long* __restrict__ accum,
     int x = v % V, y = (v / V) % V, z = v / (V * V);
     if (f16) surf3Dwrite(resolve_cell16(a.x, a.y), level0, x * 8, y, z);
     else surf3Dwrite(resolve_cell(a.x, a.y), level0, x * 4, y, z);
+    mark_dirty(dirty, brick_of(x, y, z, V));
   }
 }
 
@@ -411,6 +420,13 @@ int launch_voxel_clear(vct_context* c) {
   vct_context::GridBuf& g = c->grid[c->cur];
   const bool accum_sparse = c->accum_list_slot >= 0 && !c->dense_resolve;
   if (!accum_sparse) VCT_CUDA(c, cudaMemsetAsync(c->d_accum, 0, (size_t)V * V * V * 16, c->stream));
+  if (g.list_valid && g.mips_current) {      // a new tracking period for the sparse mip build starts here
+    VCT_CUDA(c, cudaMemsetAsync(g.dirty, 0, dirty_bytes(V), c->stream));
+    g.dirty_valid = true;
+  } else if (!g.list_valid) {
+    g.dirty_valid = false;                   // dense zero below: which bricks changed is unknown
+  }                                          // else: level 0 changed again before its pyramid was built, keep the flags
+  g.mips_current = false;
   if (!g.list_valid) {              // level 0 of this slot was written densely: zero all of it
     dim3 b(32, 8), gr((V + 31) / 32, (V + 7) / 8, V);
     zero_level0<<<gr, b, 0, c->stream>>>(g.surf[0], V, c->grid_format);
@@ -419,7 +435,7 @@ int launch_voxel_clear(vct_context* c) {
   if (accum_sparse || g.list_valid) {
     const vct_context::GridBuf* a = accum_sparse ? &c->grid[c->accum_list_slot] : nullptr;
     vox_clear_sparse<<<148 * 8, 256, 0, c->stream>>>(c->d_accum, a ? a->touched : nullptr, a ? a->n_touched : nullptr,
-                                                     g.surf[0], g.list_valid ? g.touched : nullptr, g.n_touched, V, c->grid_format);
+                                                     g.surf[0], g.list_valid ? g.touched : nullptr, g.n_touched, V, c->grid_format, g.dirty);
     c->launches += 1;
   }
   VCT_CUDA(c, cudaMemsetAsync(g.n_touched, 0, sizeof(unsigned int), c->stream));
@@ -665,6 +681,7 @@ int launch_resolve_shared(vct_context* c) {
   // the slot is now described by mask_prev, not by a touched list: a later private-accumulator voxelisation into
   // this slot must start from a dense zero, and mask_prev stays exact as long as only this path writes the slot
   g.list_valid = false;
+  g.dirty_valid = false; g.mips_current = false;
   c->mask_valid[c->cur] = true;
   VCT_CUDA(c, cudaGetLastError());
   return VCT_OK;
@@ -715,11 +732,13 @@ int launch_resolve(vct_context* c, bool dense) {
     dim3 b(32, 8), gr((V + 31) / 32, (V + 7) / 8, V);
     vox_resolve_dense<<<gr, b, 0, c->stream>>>(c->d_accum, g.surf[0], V, c->grid_format);
     g.list_valid = false;           // every texel was rewritten from the accumulator, the list was not maintained
+    g.dirty_valid = false;
     c->mask_valid[c->cur] = false;
     c->accum_list_slot = -1;
   } else {
-    vox_resolve_sparse<<<148 * 8, 256, 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, g.surf[0], V, c->grid_format);
+    vox_resolve_sparse<<<148 * 8, 256, 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, g.surf[0], V, c->grid_format, g.dirty);
   }
+  g.mips_current = false;
   c->launches += 1;
   VCT_CUDA(c, cudaGetLastError());
   return VCT_OK;
