@@ -174,9 +174,11 @@ def run_ours(args):
     ctx.set_uniforms(u)
     ctx.load_scene(sc)
     H = args.height
+    band = None
     if args.mode in ("tiles", "shard") and world > 1:
-        b0, b1 = parallel.row_band(H, rank, world)
+        b0, b1, per = parallel.row_band_equal(H, rank, world)     # equal nominal bands: ONE all-gather per frame
         ctx.set_i("RowBegin", b0); ctx.set_i("RowEnd", b1)
+        band = (b0, b1, per)
     ctx.draw_depth()                                # static light: once, like the reference's init
     ctx.sync()
     tri_rng = (parallel.triangle_share(ctx, sc.n_tris, rank, world, interleave=not args.contiguous)
@@ -184,10 +186,13 @@ def run_ours(args):
     shared = parallel.SharedAccumulator(ctx, dev, exchange=args.exchange) if args.mode == "shard" else None
     acc = parallel.accumulator_tensor(ctx, dev) if args.mode == "trishard" else None
     gather_buf = None
-    if args.mode in ("tiles", "shard") and world > 1:
+    if band is not None:
         fptr, fbytes = ctx.frame_buffer()
         frame_t = torch.as_tensor(parallel._DevicePointer(fptr, fbytes, "|u1"), device=dev)
-        gather_buf = frame_t
+        chunk = band[2] * args.width * 4
+        gather_buf = torch.zeros(world * chunk, dtype=torch.uint8, device=dev)    # bands in frame order, padded at the end
+        mine = torch.zeros(chunk, dtype=torch.uint8, device=dev)
+        own0, own1 = band[0] * args.width * 4, band[1] * args.width * 4
 
     dyn = None
     if args.config == 4:
@@ -197,15 +202,19 @@ def run_ours(args):
         phase = (base[:, 0] * 0.004 + base[:, 2] * 0.003)
         dyn = (base, nrm, phase, torch.empty_like(base))
 
-    def step(i, host_out=None):
+    def prepare(i):
+        """Per-step input: the camera (configs 2, 3) or the re-generated mesh and its shadow map (config 4)."""
         cam_rank = rank if args.mode == "views" else 0
         if args.config != 4:
-            set_camera(ctx, args, i, cam_rank)
-        if dyn is not None:
-            base, nrm, phase, out = dyn
-            torch.add(base, nrm * (12.0 * torch.sin(phase + 0.21 * i)).unsqueeze(1), out=out)
-            ctx.update_positions(device_ptr=out.data_ptr(), n_verts=out.shape[0])
-            ctx.draw_depth()                        # the light-space depth map follows the mesh
+            return set_camera(ctx, args, i, cam_rank)
+        base, nrm, phase, out = dyn
+        torch.add(base, nrm * (12.0 * torch.sin(phase + 0.21 * i)).unsqueeze(1), out=out)
+        ctx.update_positions(device_ptr=out.data_ptr(), n_verts=out.shape[0])
+        ctx.draw_depth()                            # the light-space depth map follows the mesh
+        return 4                                    # the time parameter; the mesh itself is generated on the device
+
+    def step(i, host_out=None):
+        prepare(i)
         if args.mode == "trishard":
             ctx.voxelize_range(tri_rng[0], tri_rng[1], clear_first=True)
             parallel.allreduce_accumulator(acc)
@@ -218,16 +227,10 @@ def run_ours(args):
             else:
                 ctx.frame(None if gather_buf is not None else host_out)
             if gather_buf is not None:              # row bands -> every rank holds the full frame
-                b0, b1 = parallel.row_band(H, rank, world)
-                rows = [gather_buf[parallel.row_band(H, r, world)[0] * args.width * 4:
-                                   parallel.row_band(H, r, world)[1] * args.width * 4] for r in range(world)]
-                if len({r.numel() for r in rows}) == 1:
-                    dist.all_gather(rows, rows[rank].clone())
-                else:
-                    for r in range(world):
-                        dist.broadcast(rows[r], src=r)
+                mine[:own1 - own0].copy_(frame_t[own0:own1])
+                dist.all_gather_into_tensor(gather_buf, mine)
                 if host_out is not None:
-                    host_out.view(-1).copy_(gather_buf, non_blocking=False)
+                    host_out.view(-1).copy_(gather_buf[:H * args.width * 4], non_blocking=False)
             elif host_out is not None and args.mode == "shard":
                 ctx.sync()
                 host_out.copy_(torch.from_numpy(ctx.read_frame()))
@@ -321,12 +324,12 @@ def run_ours(args):
     cam_rank = rank if args.mode == "views" else 0
     for i in range(args.steps):
         if pipelined:
-            h2d = set_camera(ctx, args, args.warmup + i, cam_rank)
+            h2d = prepare(args.warmup + i)
             ctx.frame_async(hosts[i % 3])
             if i >= 2:
                 ctx.frame_wait()                    # frame i-2 has arrived in host memory (two frames stay queued)
         else:
-            h2d = set_camera(ctx, args, args.warmup + i, cam_rank)
+            h2d = 76 if args.config != 4 else 4
             step(args.warmup + i, hosts[i % 3])     # returns after the frame is in host memory
     if pipelined:
         ctx.frame_wait(); ctx.frame_wait()

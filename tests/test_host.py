@@ -110,3 +110,18 @@ def test_uniform_names_match_the_reference_shader_interface():
               "LightDirection", "ambientFactor"):                        # Voxel_Cone_Tracing.h:167-187,224-243
         assert k in u
     assert u["VoxelDimensions"] == 128 and u["ShadowMapSize"] == 4096 and u["VoxelGridWorldSize"] == 150.0
+
+
+def test_equal_row_bands_tile_the_frame():
+    """row_band_equal: equal nominal bands (multiples of 8 rows) that cover the frame once; later bands are clipped."""
+    from vct_b200 import parallel
+    for H in (1080, 2160, 720, 64, 9):
+        for world in (1, 2, 3, 4, 8):
+            rows, per_all = [], set()
+            for r in range(world):
+                b0, b1, per = parallel.row_band_equal(H, r, world)
+                assert 0 <= b0 <= b1 <= H and per % 8 == 0 and b1 - b0 <= per
+                assert b0 == min(r * per, H)
+                rows += list(range(b0, b1)); per_all.add(per)
+            assert rows == list(range(H)) and len(per_all) == 1
+            assert per_all.pop() * world >= H

@@ -67,7 +67,7 @@ static void free_grid(vct_context* c) {
     for (auto s : g.surf) cudaDestroySurfaceObject(s);
     g.surf.clear();
     if (g.array) cudaFreeMipmappedArray(g.array);
-    cudaFree(g.touched); cudaFree(g.n_touched); cudaFree(g.dirty);
+    cudaFree(g.touched); cudaFree(g.n_touched); cudaFree(g.dirty_now); cudaFree(g.dirty_prev);
     g = vct_context::GridBuf();
   }
   cudaFree(c->d_accum);
@@ -91,8 +91,10 @@ int ensure_grid(vct_context* c) {
     VCT_CUDA(c, cudaMalloc(&g.touched, n * 4));
     VCT_CUDA(c, cudaMalloc(&g.n_touched, 128));
     VCT_CUDA(c, cudaMemsetAsync(g.n_touched, 0, 128, c->stream));
-    VCT_CUDA(c, cudaMalloc(&g.dirty, dirty_bytes(V)));
-    VCT_CUDA(c, cudaMemsetAsync(g.dirty, 0, dirty_bytes(V), c->stream));
+    VCT_CUDA(c, cudaMalloc(&g.dirty_now, dirty_bytes(V)));
+    VCT_CUDA(c, cudaMalloc(&g.dirty_prev, dirty_bytes(V)));
+    VCT_CUDA(c, cudaMemsetAsync(g.dirty_now, 0, dirty_bytes(V), c->stream));
+    VCT_CUDA(c, cudaMemsetAsync(g.dirty_prev, 0, dirty_bytes(V), c->stream));
     VCT_CUDA(c, cudaMallocMipmappedArray(&g.array, &desc, make_cudaExtent(V, V, V), c->P.levels, cudaArraySurfaceLoadStore));
     for (int l = 0; l < c->P.levels; ++l) {
       cudaArray_t lvl;
@@ -130,6 +132,7 @@ int ensure_grid(vct_context* c) {
     rc = launch_mip(c); if (rc) return rc;
     c->grid[k].list_valid = true;     // all zero: the (empty) list is exact
     c->grid[k].dirty_valid = true;    // ... no brick differs from the pyramid just built
+    c->grid[k].occ_valid = true;      // ... and no brick holds a non-zero texel (flags all zero)
   }
   c->cur = 0;
   c->accum_list_slot = 0;             // accumulator all zero, slot 0's empty list describes it
@@ -981,7 +984,7 @@ int vct_upload_grid_level0(vct_handle c, const uint8_t* rgba) {
   p.kind = cudaMemcpyHostToDevice;
   VCT_CUDA(c, cudaMemcpy3DAsync(&p, c->stream));
   c->grid[c->cur].list_valid = false;   // level 0 no longer matches the touched list
-  c->grid[c->cur].dirty_valid = false; c->grid[c->cur].mips_current = false;
+  c->grid[c->cur].dirty_valid = false; c->grid[c->cur].occ_valid = false; c->grid[c->cur].mips_current = false;
   c->mask_valid[c->cur] = false;
   c->scene_epoch++;
   return check_cuda(c, cudaStreamSynchronize(c->stream), "sync");

@@ -125,11 +125,13 @@ struct vct_context {
     uint32_t* touched = nullptr;               // voxels whose level-0 texel may be non-zero (exact when list_valid)
     unsigned int* n_touched = nullptr;         // device counter
     bool list_valid = true;                    // false: level 0 was written densely, a dense clear is needed before reuse
-    // sparse mip build: one flag per 32x8x8 brick of level 0 (= one mip_fused3 block).  While dirty_valid, the flags
-    // cover every brick whose level-0 texels changed since this slot's pyramid was last built (mips_current), so the
-    // fine levels are rebuilt for flagged bricks only -- cost follows the occupied surface, not V^3.
-    unsigned char* dirty = nullptr;
-    bool dirty_valid = false, mips_current = false;
+    // sparse mip build: one flag per 32x8x8 brick of level 0 (= one mip_fused3 block).  dirty_now is set by the sparse
+    // resolve for every brick that holds a non-zero texel (exact superset while occ_valid); dirty_prev is the same for
+    // the content this slot held before the current voxelisation, i.e. the bricks the sparse clear zeroed.  While
+    // dirty_valid, now | prev covers every brick that changed since the slot's pyramid was last built (mips_current),
+    // and only those are re-filtered -- the cost follows the occupied surface, not V^3.
+    unsigned char* dirty_now = nullptr; unsigned char* dirty_prev = nullptr;
+    bool dirty_valid = false, occ_valid = false, mips_current = false;
   } grid[2];
   size_t touched_cap = 0;
   // fused sharded voxelisation: external symmetric accumulator + occupancy mask (local view and multicast view)

@@ -27,11 +27,15 @@ __device__ __forceinline__ uint32_t finish_px(uint32_t even, uint32_t odd) {
 // block = (8,4,4) threads, covers 32x8x8 texels of `src`
 __global__ void __launch_bounds__(128) mip_fused3(cudaSurfaceObject_t src, cudaSurfaceObject_t d1,
                                                   cudaSurfaceObject_t d2, cudaSurfaceObject_t d3,
-                                                  const unsigned char* __restrict__ dirty) {
+                                                  const unsigned char* __restrict__ dirty,
+                                                  const unsigned char* __restrict__ dirty_prev) {
   __shared__ uint32_t s1[4][4][16];
   __shared__ uint32_t s2[2][2][8];
   // sparse build (level 0 only): this block's 32x8x8 source brick did not change since the pyramid was last built
-  if (dirty && !dirty[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x]) return;
+  if (dirty) {
+    const uint32_t brick = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (!(dirty[brick] | dirty_prev[brick])) return;
+  }
   const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
   const int bx = blockIdx.x * 32, by = blockIdx.y * 8, bz = blockIdx.z * 8;
   uint32_t e0 = 0, o0 = 0, e1 = 0, o1 = 0;
@@ -136,11 +140,14 @@ __global__ void mip_one(cudaSurfaceObject_t src, cudaSurfaceObject_t dst, int h)
 // row 2y+dy, slice 2z+dz), times 0.125, rounded to half.  One thread per child texel; every level is read once and
 // written once (1.29 x level 0 in total), which is what bounds it: HBM.
 __global__ void mip_level_f16(cudaSurfaceObject_t src, cudaSurfaceObject_t dst, int h, const unsigned char* __restrict__ dirty,
-                              int shift, int V) {
+                              const unsigned char* __restrict__ dirty_prev, int shift, int V) {
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, z = blockIdx.z;
   if (x >= h || y >= h) return;
   // sparse build (child levels 1..3: a child texel lies inside one 32x8x8 level-0 brick)
-  if (dirty && !dirty[brick_of(x << shift, y << shift, z << shift, V)]) return;
+  if (dirty) {
+    const uint32_t brick = brick_of(x << shift, y << shift, z << shift, V);
+    if (!(dirty[brick] | dirty_prev[brick])) return;
+  }
   float acc[4];
 #pragma unroll
   for (int dz = 0; dz < 2; ++dz)
@@ -166,13 +173,13 @@ int launch_mip(vct_context* c) {
   PassTimer timer(c, VCT_PASS_MIP);
   const int levels = c->P.levels;
   vct_context::GridBuf& gb = c->grid[c->cur];
-  const unsigned char* dirty = (gb.dirty_valid && c->P.V >= 32 && !c->dense_resolve) ? gb.dirty : nullptr;
+  const unsigned char* dirty = (gb.dirty_valid && c->P.V >= 32 && !c->dense_resolve) ? gb.dirty_now : nullptr;
   gb.mips_current = true;
   if (c->grid_format == 1) {
     for (int l = 0, n = c->P.V; l + 1 < levels; ++l, n >>= 1) {
       const int h = n >> 1;
       dim3 b(32, 4), g((h + 31) / 32, (h + 3) / 4, h);
-      mip_level_f16<<<g, b, 0, c->stream>>>(gb.surf[l], gb.surf[l + 1], h, l + 1 <= 3 ? dirty : nullptr, l + 1, c->P.V);
+      mip_level_f16<<<g, b, 0, c->stream>>>(gb.surf[l], gb.surf[l + 1], h, l + 1 <= 3 ? dirty : nullptr, gb.dirty_prev, l + 1, c->P.V);
       c->launches += 1;
     }
     VCT_CUDA(c, cudaGetLastError());
@@ -181,7 +188,7 @@ int launch_mip(vct_context* c) {
   int l = 0, n = c->P.V;
   while (n >= 32 && l + 3 < levels) {
     dim3 b(8, 4, 4), g(n / 32, n / 8, n / 8);
-    mip_fused3<<<g, b, 0, c->stream>>>(gb.surf[l], gb.surf[l + 1], gb.surf[l + 2], gb.surf[l + 3], l == 0 ? dirty : nullptr);
+    mip_fused3<<<g, b, 0, c->stream>>>(gb.surf[l], gb.surf[l + 1], gb.surf[l + 2], gb.surf[l + 3], l == 0 ? dirty : nullptr, gb.dirty_prev);
     c->launches += 1;
     l += 3; n >>= 3;
   }

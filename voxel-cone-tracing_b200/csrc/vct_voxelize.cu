@@ -321,16 +321,18 @@ __global__ void __launch_bounds__(256) vox_shade(Params P, const VoxRecord* __re
 // Sparse clear before a voxelisation into slot B: (1) zero the accumulator cells named by the list of the previous
 // voxelisation (slot A), (2) zero the level-0 texels of slot B named by slot B's own old list (what the frame before
 // last left there).  Cost is proportional to the occupied voxels, not to V^3.
-// Thousands of voxels share a brick: test first so that almost all of them issue a (cached) load instead of a store to
-// the same few L2 lines.  A stale 0 only costs a redundant store.
-__device__ __forceinline__ void mark_dirty(unsigned char* __restrict__ dirty, uint32_t brick) {
-  if (dirty[brick] == 0) dirty[brick] = 1;
+// Thousands of voxels share a brick and neighbours in the touched list are neighbours in space: a lane stores only
+// if its brick differs from the previous lane's (plain byte stores from every thread to the same few L2 sectors cost
+// ~10 us per pass).  Called from grid-stride loops over a list: the active lanes are a prefix of the warp.
+__device__ __forceinline__ void mark_dirty(unsigned char* dirty, uint32_t brick) {
+  const unsigned active = __activemask();
+  const uint32_t up = __shfl_up_sync(active, brick, 1);
+  if ((threadIdx.x & 31) == 0 || up != brick) dirty[brick] = 1;
 }
 
 __global__ void vox_clear_sparse(unsigned long long* __restrict__ accum, const uint32_t* __restrict__ listA,
                                  const unsigned int* __restrict__ nA, cudaSurfaceObject_t level0B,
-                                 const uint32_t* __restrict__ listB, const unsigned int* __restrict__ nB, int V, int f16,
-                                 unsigned char* __restrict__ dirty) {
+                                 const uint32_t* __restrict__ listB, const unsigned int* __restrict__ nB, int V, int f16) {
   const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
   if (listA) {
     const uint32_t n = *nA;
@@ -347,7 +349,6 @@ __global__ void vox_clear_sparse(unsigned long long* __restrict__ accum, const u
       int x = v % V, y = (v / V) % V, z = v / (V * V);
       if (f16) surf3Dwrite(make_uint2(0u, 0u), level0B, x * 8, y, z);
       else surf3Dwrite(make_uchar4(0, 0, 0, 0), level0B, x * 4, y, z);
-      mark_dirty(dirty, brick_of(x, y, z, V));      // the pyramid above this brick must be rebuilt
     }
   }
 }
@@ -420,12 +421,17 @@ int launch_voxel_clear(vct_context* c) {
   vct_context::GridBuf& g = c->grid[c->cur];
   const bool accum_sparse = c->accum_list_slot >= 0 && !c->dense_resolve;
   if (!accum_sparse) VCT_CUDA(c, cudaMemsetAsync(c->d_accum, 0, (size_t)V * V * V * 16, c->stream));
-  if (g.list_valid && g.mips_current) {      // a new tracking period for the sparse mip build starts here
-    VCT_CUDA(c, cudaMemsetAsync(g.dirty, 0, dirty_bytes(V), c->stream));
+  if (g.list_valid && g.occ_valid && g.mips_current) {
+    // a new tracking period for the sparse mip build: the bricks of the content about to be zeroed become "prev"
+    std::swap(g.dirty_now, g.dirty_prev);
+    VCT_CUDA(c, cudaMemsetAsync(g.dirty_now, 0, dirty_bytes(V), c->stream));
     g.dirty_valid = true;
-  } else if (!g.list_valid) {
-    g.dirty_valid = false;                   // dense zero below: which bricks changed is unknown
-  }                                          // else: level 0 changed again before its pyramid was built, keep the flags
+  } else if (g.list_valid && g.occ_valid && g.dirty_valid) {
+    // level 0 changes again before its pyramid was built: keep accumulating into the same flags
+  } else {
+    VCT_CUDA(c, cudaMemsetAsync(g.dirty_now, 0, dirty_bytes(V), c->stream));
+    g.dirty_valid = false;                   // which bricks differ from the pyramid is unknown: next build is dense
+  }
   g.mips_current = false;
   if (!g.list_valid) {              // level 0 of this slot was written densely: zero all of it
     dim3 b(32, 8), gr((V + 31) / 32, (V + 7) / 8, V);
@@ -435,7 +441,7 @@ int launch_voxel_clear(vct_context* c) {
   if (accum_sparse || g.list_valid) {
     const vct_context::GridBuf* a = accum_sparse ? &c->grid[c->accum_list_slot] : nullptr;
     vox_clear_sparse<<<148 * 8, 256, 0, c->stream>>>(c->d_accum, a ? a->touched : nullptr, a ? a->n_touched : nullptr,
-                                                     g.surf[0], g.list_valid ? g.touched : nullptr, g.n_touched, V, c->grid_format, g.dirty);
+                                                     g.surf[0], g.list_valid ? g.touched : nullptr, g.n_touched, V, c->grid_format);
     c->launches += 1;
   }
   VCT_CUDA(c, cudaMemsetAsync(g.n_touched, 0, sizeof(unsigned int), c->stream));
@@ -563,23 +569,26 @@ __global__ void vox_push_inbox(const unsigned long long* __restrict__ accum, con
   }
 }
 
+// One launch per remote rank, in stream order.  A rank's records name distinct voxels and nothing else writes the
+// accumulator between the barrier and the resolve, so each record is a plain 16-byte read-modify-write of its cell
+// (no atomics); the cell read also tells whether the voxel is new to this rank's touched list.
 __global__ void vox_merge_inbox(unsigned long long* __restrict__ accum, const unsigned char* __restrict__ inbox, int parity,
-                                int world, int rank, uint32_t cap, uint32_t* __restrict__ touched,
+                                int world, int src_rank, uint32_t cap, uint32_t* __restrict__ touched,
                                 unsigned int* __restrict__ n_touched, Counters* __restrict__ ctr, const unsigned int* own_n) {
   const uint32_t* counts = reinterpret_cast<const uint32_t*>(inbox) + parity * 16;
   if (blockIdx.x == 0 && threadIdx.x == 0 && *own_n > cap) ctr->overflow = 1;   // this rank touched more voxels than fit
-  for (int r = 0; r < world; ++r) {
-    if (r == rank) continue;
-    const uint32_t n = min(counts[r], cap);
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-      const unsigned char* rec = inbox + exch_record_offset(parity, world, r, cap, k);
-      const uint4 q = *reinterpret_cast<const uint4*>(rec);
-      const uint32_t v = q.w, n_frag = (q.x >> 24) | ((q.y >> 24) << 8) | ((q.z >> 24) << 16);
-      atomicAdd(&accum[2 * (size_t)v], ((unsigned long long)(q.x & 0xFFFFFFu) << 32) | (q.y & 0xFFFFFFu));
-      const unsigned long long old = atomicAdd(&accum[2 * (size_t)v + 1], ((unsigned long long)(q.z & 0xFFFFFFu) << 32) | n_frag);
-      bool pending = true;
-      append_first_touch(pending, old, v, touched, n_touched);
-    }
+  const uint32_t n = min(counts[src_rank], cap);
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const uint4 q = *reinterpret_cast<const uint4*>(inbox + exch_record_offset(parity, world, src_rank, cap, k));
+    const uint32_t v = q.w, n_frag = (q.x >> 24) | ((q.y >> 24) << 8) | ((q.z >> 24) << 16);
+    ulonglong2* cell = reinterpret_cast<ulonglong2*>(&accum[2 * (size_t)v]);
+    ulonglong2 a = *cell;
+    const unsigned long long old = a.y;
+    a.x += ((unsigned long long)(q.x & 0xFFFFFFu) << 32) | (q.y & 0xFFFFFFu);
+    a.y += ((unsigned long long)(q.z & 0xFFFFFFu) << 32) | n_frag;
+    *cell = a;
+    bool pending = true;
+    append_first_touch(pending, old, v, touched, n_touched);
   }
 }
 
@@ -681,7 +690,7 @@ int launch_resolve_shared(vct_context* c) {
   // the slot is now described by mask_prev, not by a touched list: a later private-accumulator voxelisation into
   // this slot must start from a dense zero, and mask_prev stays exact as long as only this path writes the slot
   g.list_valid = false;
-  g.dirty_valid = false; g.mips_current = false;
+  g.dirty_valid = false; g.occ_valid = false; g.mips_current = false;
   c->mask_valid[c->cur] = true;
   VCT_CUDA(c, cudaGetLastError());
   return VCT_OK;
@@ -712,10 +721,13 @@ static int resolve_inbox(vct_context* c) {
   vct_context::GridBuf& g = c->grid[c->cur];
   {
     PassTimer timer(c, VCT_PASS_REINJECT);   // reported under "reinject" slot: the merge of the other ranks' voxels
-    vox_merge_inbox<<<148 * 4, 256, 0, c->stream>>>(c->d_accum, (const unsigned char*)c->shared_local, c->exchange_parity,
-                                                    c->shared_world, c->shared_rank, (uint32_t)c->exchange_cap, g.touched,
-                                                    g.n_touched, c->d_counters, c->d_push_count);
-    c->launches += 1;
+    for (int r = 0; r < c->shared_world; ++r) {
+      if (r == c->shared_rank) continue;
+      vox_merge_inbox<<<148 * 4, 256, 0, c->stream>>>(c->d_accum, (const unsigned char*)c->shared_local, c->exchange_parity,
+                                                      c->shared_world, r, (uint32_t)c->exchange_cap, g.touched, g.n_touched,
+                                                      c->d_counters, c->d_push_count);
+      c->launches += 1;
+    }
   }
   c->exchange_parity ^= 1;
   int rc = launch_resolve(c, false); if (rc) return rc;
@@ -732,11 +744,12 @@ int launch_resolve(vct_context* c, bool dense) {
     dim3 b(32, 8), gr((V + 31) / 32, (V + 7) / 8, V);
     vox_resolve_dense<<<gr, b, 0, c->stream>>>(c->d_accum, g.surf[0], V, c->grid_format);
     g.list_valid = false;           // every texel was rewritten from the accumulator, the list was not maintained
-    g.dirty_valid = false;
+    g.dirty_valid = false; g.occ_valid = false;
     c->mask_valid[c->cur] = false;
     c->accum_list_slot = -1;
   } else {
-    vox_resolve_sparse<<<148 * 8, 256, 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, g.surf[0], V, c->grid_format, g.dirty);
+    vox_resolve_sparse<<<148 * 8, 256, 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, g.surf[0], V, c->grid_format, g.dirty_now);
+    g.occ_valid = g.list_valid;
   }
   g.mips_current = false;
   c->launches += 1;

@@ -37,6 +37,14 @@ def row_band(height: int, rank: int, world: int, align: int = 8):
     return min(b0 * align, height), min(b1 * align, height)
 
 
+def row_band_equal(height: int, rank: int, world: int, align: int = 8):
+    """Row bands of EQUAL nominal size (a multiple of `align`), the last ones clipped to the frame: what a single
+    all-gather of the bands needs.  Returns (begin, end, rows_per_band)."""
+    blocks = (height + align - 1) // align
+    per = ((blocks + world - 1) // world) * align
+    return min(rank * per, height), min((rank + 1) * per, height), per
+
+
 def views_for_rank(n_views: int, rank: int, world: int):
     """Round-robin view assignment (light-probe bake, BASELINE config 5)."""
     return list(range(rank, n_views, world))
