@@ -191,7 +191,7 @@ def run_ours(args):
         frame_t = torch.as_tensor(parallel._DevicePointer(fptr, fbytes, "|u1"), device=dev)
         chunk = band[2] * args.width * 4
         gather_buf = torch.zeros(world * chunk, dtype=torch.uint8, device=dev)    # bands in frame order, padded at the end
-        mine = torch.zeros(chunk, dtype=torch.uint8, device=dev)
+        my_band = torch.zeros(chunk, dtype=torch.uint8, device=dev)
         own0, own1 = band[0] * args.width * 4, band[1] * args.width * 4
 
     dyn = None
@@ -227,8 +227,8 @@ def run_ours(args):
             else:
                 ctx.frame(None if gather_buf is not None else host_out)
             if gather_buf is not None:              # row bands -> every rank holds the full frame
-                mine[:own1 - own0].copy_(frame_t[own0:own1])
-                dist.all_gather_into_tensor(gather_buf, mine)
+                my_band[:own1 - own0].copy_(frame_t[own0:own1])
+                dist.all_gather_into_tensor(gather_buf, my_band)
                 if host_out is not None:
                     host_out.view(-1).copy_(gather_buf[:H * args.width * 4], non_blocking=False)
             elif host_out is not None and args.mode == "shard":
@@ -301,9 +301,9 @@ def run_ours(args):
     barrier()
     passes_max = None
     if world > 1 and args.mode != "views":         # sharded work: the slowest rank sets the pace of every phase
-        mine = torch.tensor([pass_sum[p] / n_prof for p in pass_names], dtype=torch.float64, device=dev)
-        dist.all_reduce(mine, op=dist.ReduceOp.MAX)
-        passes_max = {("merge" if p == "reinject" else p): round(float(v), 2) for p, v in zip(pass_names, mine.tolist())}
+        pass_t = torch.tensor([pass_sum[p] / n_prof for p in pass_names], dtype=torch.float64, device=dev)
+        dist.all_reduce(pass_t, op=dist.ReduceOp.MAX)
+        passes_max = {("merge" if p == "reinject" else p): round(float(v), 2) for p, v in zip(pass_names, pass_t.tolist())}
 
     # ---- end to end through the public API with HOST frame buffers (pinned); every frame's D2H copy is inside
     # the timed region.  Render loops use the pipelined call (vct_frame_async / vct_frame_wait: double-buffered,

@@ -1,7 +1,8 @@
 N=${1:-2}
-python -m pytest tests -x -q -m gpu -k "fused_sharded" 2>&1 | tail -3
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus $N --steps 100 --warmup 10"
-run() { echo "== $*"; $TR "$@" 2>&1 | tail -1 | python -c "
+STEPS=${2:-60}
+[ "$N" = "2" ] && python -m pytest tests -x -q -m gpu -k "fused_sharded or sparse_mip" 2>&1 | tail -3
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus $N --steps $STEPS --warmup 10"
+run() { echo "== $*"; $TR "$@" > /tmp/bench_out.txt 2>&1; grep -m3 "Error" /tmp/bench_out.txt; tail -1 /tmp/bench_out.txt | python -c "
 import sys,json
 l=sys.stdin.read().strip()
 try:
@@ -9,7 +10,7 @@ try:
 except Exception as e: print('ERR', l[-1500:])
 "; }
 run --config 3 --mode shard
-run --config 3 --mode shard --contiguous
 run --config 3 --mode tiles
 run --config 4 --mode shard
 run --config 2 --mode shard
+[ "$N" != "2" ] && run --config 2 --mode views
