@@ -44,9 +44,10 @@ def parse(argv=None):
     ap.add_argument("--exchange", default="inbox", choices=["inbox", "reduce"],
                     help="--mode shard: inbox = touched voxels multicast as records (multimem.st) and merged locally; reduce = "
                          "multimem.red into a dense symmetric accumulator (reduced in the switch)")
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
                     help="BASELINE.json config: 2 = headline (default); 3 = 512^3 fp16 grid, 4K, 9+1 cones, row bands; "
-                         "4 = dynamic 1M-triangle mesh re-voxelised every frame, triangle-sharded + all-reduce")
+                         "4 = dynamic 1M-triangle mesh re-voxelised every frame, triangle-sharded + all-reduce; 5 = light-probe bake: 64 "
+                         "camera views at 1024^2 from one 3-bounce voxelisation per bake, views round-robin over the ranks")
     ap.add_argument("--detail", type=float, default=1.0, help="scene tessellation scale (1.0 = config 2)")
     ap.add_argument("--grid", type=int, default=256)
     ap.add_argument("--width", type=int, default=1920)
@@ -63,6 +64,8 @@ def parse(argv=None):
         a.mode = a.mode or ("shard" if a.gpus > 1 else "views")
     elif a.config == 4:
         a.mode = a.mode or ("shard" if a.gpus > 1 else "views")
+    elif a.config == 5:
+        a.width, a.height, a.mode = 1024, 1024, "probes"
     a.cones = a.cones or "6+1"
     a.mode = a.mode or "views"
     return a
@@ -76,7 +79,8 @@ def make_scene_and_uniforms(args):
     else:
         sc = scenes.atrium(detail=args.detail)
     u = uniforms.scene_uniforms(sc, V=args.grid, width=args.width, height=args.height, shadow_map_size=4096,
-                                coverage=args.coverage, cones=args.cones, grid_format=1 if args.config == 3 else 0)
+                                coverage=args.coverage, cones=args.cones, grid_format=1 if args.config == 3 else 0,
+                                bounces=3 if args.config == 5 else 2)
     return sc, u
 
 
@@ -202,9 +206,30 @@ def run_ours(args):
         phase = (base[:, 0] * 0.004 + base[:, 2] * 0.003)
         dyn = (base, nrm, phase, torch.empty_like(base))
 
+    probes = None
+    if args.config == 5:
+        import vct_b200.glmath as gm
+        from vct_b200 import scenes as _scenes
+        cams = _scenes.probe_cameras(64)
+        probes = []
+        for k in parallel.views_for_rank(len(cams), rank, world):
+            pos, yaw, pitch = cams[k]
+            view = gm.view_matrix(pos, yaw, pitch)
+            probes.append((gm.colmajor((view @ gm.scale(0.05)).astype(np.float32)), tuple(float(x) for x in pos)))
+        probe_hosts = [torch.empty((args.height, args.width, 4), dtype=torch.uint8).pin_memory() for _ in range(2)]
+
+    def bake(to_host):
+        """Config 5: one 3-bounce voxelisation, then this rank's probe views rendered from it."""
+        ctx.draw_voxels()
+        for n, (mv, pos) in enumerate(probes):
+            ctx.set_mat4("ModelViewMatrix", mv); ctx.set_3f("CameraPosition", pos)
+            ctx.render(probe_hosts[n & 1] if to_host else None)
+
     def prepare(i):
         """Per-step input: the camera (configs 2, 3) or the re-generated mesh and its shadow map (config 4)."""
         cam_rank = rank if args.mode == "views" else 0
+        if args.config == 5:
+            return 76 * len(probes)
         if args.config != 4:
             return set_camera(ctx, args, i, cam_rank)
         base, nrm, phase, out = dyn
@@ -215,6 +240,9 @@ def run_ours(args):
 
     def step(i, host_out=None):
         prepare(i)
+        if probes is not None:
+            bake(host_out is not None)
+            return
         if args.mode == "trishard":
             ctx.voxelize_range(tri_rng[0], tri_rng[1], clear_first=True)
             parallel.allreduce_accumulator(acc)
@@ -276,7 +304,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    frames = args.steps * (world if args.mode == "views" else 1)
+    frames = args.steps * (world if args.mode == "views" else 64 if args.mode == "probes" else 1)
     value = frames / (total_ms * 1e-3)
     # (2) per-pass breakdown and the dominant kernel's average duration: same steps again with pass events on
     ctx.set_i("Profile", 1)
@@ -329,7 +357,7 @@ def run_ours(args):
             if i >= 2:
                 ctx.frame_wait()                    # frame i-2 has arrived in host memory (two frames stay queued)
         else:
-            h2d = 76 if args.config != 4 else 4
+            h2d = 76 * len(probes) if probes is not None else 76 if args.config != 4 else 4
             step(args.warmup + i, hosts[i % 3])     # returns after the frame is in host memory
     if pipelined:
         ctx.frame_wait(); ctx.frame_wait()
@@ -363,15 +391,16 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
         "ms_per_step": round(total_ms / K, 4), "higher_is_better": True,
-        "scaling": "weak" if args.mode == "views" else "strong", "vs_baseline": None, "dtype": "u8/u32 grid, f32 shading",
+        "scaling": "weak" if args.mode == "views" else "strong",     # probes / tiles / shards: total work fixed "vs_baseline": None, "dtype": "u8/u32 grid, f32 shading",
         "data": "synthetic",
         "config": {"workload": WORKLOAD if (args.config == 2 and args.detail == 1.0 and args.grid == 256) else f"config{args.config}: {sc.name} {sc.n_tris} tris, V={args.grid} {'RGBA16F' if args.config == 3 else 'RGBA8'}, {args.width}x{args.height}, cones {args.cones}",
                    "mode": args.mode + ("/" + args.exchange if args.mode == "shard" else ""), "l2": ("flushed between steps by an untimed 256 MiB write; frames not pipelined" if args.flush else "no flush: per-frame working set ~220 MB (64 MiB level 0 + mips, shadow texels, accumulator lines, queues, vertex cache, visibility) in two alternating frame slots exceeds the 126 MB L2"),
                    "timing": "one CUDA-event pair around the K steps on the launching stream, barrier+synchronize both sides; max over ranks",
-                   "step": "clear+voxelize+resolve+mip+visibility+cone-trace (shadow map static, drawn once)"},
+                   "step": ("one bake = clear+voxelize+resolve+mip+reinject+mip once, then visibility+cone-trace of 64 probe views (round-robin over ranks); value counts views"
+                            if args.mode == "probes" else "clear+voxelize+resolve+mip+visibility+cone-trace (shadow map static, drawn once)")},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": args.width * args.height * 4,
+                "d2h_bytes_per_step": args.width * args.height * 4 * (len(probes) if probes is not None else 1),
                 "note": "vct_frame_async(host_rgba)+vct_frame_wait, three pinned host frame buffers (two frames queued), every frame copied to the host inside the timed region; per-step input = view matrix + camera position (kernel parameters)"},
         "gpu_launches": int(launches),
         "passes_us": {("merge" if (p == "reinject" and args.mode == "shard") else p): round(pass_sum[p] / n_prof, 2) for p in pass_names},

@@ -397,6 +397,29 @@ def test_bounce_extension_vs_oracle(gpu_ctx, oracle):
     assert_frame_close(gpu_ctx.read_frame(), oracle_frame_with(oracle, u), "bounces=3", FRAC_MIN_SMALL)
 
 
+def test_config5_light_probe_views_vs_oracle(gpu_ctx, oracle):
+    """BASELINE config 5 in small: one voxelisation with Bounces = 3 (re-injection, extension), then several cameras of
+    the 4x4x4 probe lattice -- arbitrary position, yaw and pitch inside the atrium -- rendered from that grid."""
+    sc = scenes.atrium(detail=0.2, tex_size=64)
+    cams = scenes.probe_cameras(64)
+    assert len(cams) == 64 and len({c[0] for c in cams}) == 64
+    base = dict(V=64, width=192, height=192, shadow_map_size=1024, coverage="conservative", bounces=3)
+    u0 = uniforms.scene_uniforms(sc, **base)
+    c = gpu_ctx
+    c.set_uniforms(u0); c.load_scene(sc); c.draw_depth(); c.draw_voxels(); c.sync()
+    oracle.set_uniforms(u0); oracle.load_scene(sc); oracle.draw_depth(); oracle.draw_voxels()
+    g, o = c.grid(0), oracle.grid(0)
+    assert np.array_equal(g[..., 3], o[..., 3])
+    assert np.abs(g.astype(int) - o.astype(int)).max() <= LSB_TOL
+    for k in (5, 22, 47):
+        pos, yaw, pitch = cams[k]
+        u = uniforms.scene_uniforms(sc, camera_pos=pos, yaw=yaw, pitch=pitch, **base)
+        c.set_uniforms(u); c.render(); c.sync()
+        oracle.set_uniforms(u); oracle.render()
+        assert_frame_close(c.read_frame(), oracle.frame(), f"probe {k}", FRAC_MIN_SMALL)
+    assert np.array_equal(c.grid(0), g)          # rendering views does not touch the grid
+
+
 def oracle_frame_with(oracle, u):
     oracle.set_uniforms(u)
     oracle.draw_voxels()
