@@ -277,3 +277,72 @@ def test_texture_channel_rules(oracle):
     np.testing.assert_allclose(oracle.sample_texture(0, 0.75, 0.25, 0.0), [1, 0, 0, 1], atol=1e-6)
     np.testing.assert_allclose(oracle.sample_texture(0, 0.5, 0.5, 1.0), [191 / 255, 0, 0, 1], atol=1e-6)  # (765+2)>>2
     np.testing.assert_allclose(oracle.sample_texture(0, 0.5, 0.5, 0.0), [0.75, 0, 0, 1], atol=1e-6)       # bilinear centre
+
+
+# --- accumulator resolve (DESIGN.md "Defined semantics"; Voxelization.fs:88 writes alpha 1) ---------------------
+def test_resolve_rule_from_a_hand_set_accumulator(oracle):
+    V = 8
+    setup(oracle, V=V)
+    counts = np.zeros((V, V, V), dtype=np.uint32); sums = np.zeros((V, V, V, 3), dtype=np.uint32)
+    counts[1, 2, 3], sums[1, 2, 3] = 3, (10, 11, 765)        # 10/3 = 3.33 -> 3, 11/3 = 3.67 -> 4, 765/3 = 255
+    counts[0, 0, 0], sums[0, 0, 0] = 2, (1, 3, 255)          # ties round up: (1+1)/2 = 1, (3+1)/2 = 2, (255+1)/2 = 128
+    oracle.set_accum(counts, sums); oracle.resolve_and_mip()
+    g = oracle.grid(0)
+    assert tuple(g[1, 2, 3]) == (3, 4, 255, 255)
+    assert tuple(g[0, 0, 0]) == (1, 2, 128, 255)
+    assert int(g[..., 3].astype(int).sum()) == 2 * 255       # every other voxel stays (0, 0, 0, 0)
+    # level 1 = (sum of 8 + 4) >> 3 per channel, alpha included
+    assert tuple(oracle.grid(1)[0, 0, 0]) == ((1 + 4) >> 3, (2 + 4) >> 3, (128 + 4) >> 3, (255 + 4) >> 3)
+
+
+def test_fp16_resolve_and_mip_order(oracle):
+    """RGBA16F grid (BASELINE config 3): level 0 = half(sum / (count * 255)), alpha = 1; a mip texel is the fp32 sum of the
+    eight parents in the order ((a00 + a10) + a01) + a11 over (y, z) of the x-pair sums, times 0.125, rounded to half."""
+    V = 4
+    setup(oracle, V=V, grid_format=1)
+    counts = np.zeros((V, V, V), dtype=np.uint32); sums = np.zeros((V, V, V, 3), dtype=np.uint32)
+    counts[0, 0, 0], sums[0, 0, 0] = 3, (100, 200, 765)
+    counts[1, 1, 1], sums[1, 1, 1] = 1, (255, 1, 0)
+    oracle.set_accum(counts, sums); oracle.resolve_and_mip()
+    g0 = oracle.grid(0)
+    assert g0.dtype == np.float16
+    exp = np.array([np.float32(100) / np.float32(765), np.float32(200) / np.float32(765), 1.0, 1.0], dtype=np.float32).astype(np.float16)
+    assert np.array_equal(g0[0, 0, 0], exp)
+    assert np.array_equal(g0[1, 1, 1], np.array([1.0, np.float32(1) / np.float32(255), 0.0, 1.0], dtype=np.float32).astype(np.float16))
+    p = g0[:2, :2, :2].astype(np.float32)                    # [z][y][x][c]
+    pair = p[:, :, 0] + p[:, :, 1]                           # x pairs, fp32
+    s = ((pair[0, 0] + pair[0, 1]) + pair[1, 0]) + pair[1, 1]
+    assert np.array_equal(oracle.grid(1)[0, 0, 0], (s * np.float32(0.125)).astype(np.float16))
+    assert not oracle.grid(1)[1:, 1:, 1:].any()
+
+
+# --- sharding hooks of the oracle are exact restatements of the unsharded passes ---------------------------------
+def test_row_bands_and_triangle_ranges_reproduce_the_whole(oracle):
+    sc = scenes.cornell()
+    u = uniforms.scene_uniforms(sc, V=32, width=64, height=48, shadow_map_size=256)
+    oracle.set_uniforms(u); oracle.load_scene(sc); oracle.draw_depth(); oracle.draw_voxels(); oracle.render()
+    frame, counts, sums, g1 = oracle.frame().copy(), oracle.counts().copy(), oracle.sums().copy(), oracle.grid(1).copy()
+    n = sc.n_tris
+    oracle.draw_voxels_range(0, n // 3, clear_first=True)
+    oracle.draw_voxels_range(n // 3, n, clear_first=False)
+    oracle.resolve_and_mip()
+    assert np.array_equal(oracle.counts(), counts) and np.array_equal(oracle.sums(), sums)
+    assert np.array_equal(oracle.grid(1), g1)
+    for y0, y1 in ((0, 16), (16, 40), (40, 48)):      # a band call renders only its rows (the bench extrapolates from one)
+        oracle.render_rows(y0, y1)
+        assert np.array_equal(oracle.frame()[y0:y1], frame[y0:y1])
+
+
+def test_extra_bounce_only_adds_light_and_keeps_occupancy(oracle):
+    """Bounces = 3 (extension, README.md:14 claims it, no reference code): re-injection adds gathered radiance to
+    occupied voxels only; alpha (occupancy) is untouched."""
+    sc = scenes.cornell()
+    u2 = uniforms.scene_uniforms(sc, V=32, width=32, height=32, shadow_map_size=256, bounces=2)
+    oracle.set_uniforms(u2); oracle.load_scene(sc); oracle.draw_depth(); oracle.draw_voxels()
+    g2 = oracle.grid(0).astype(int)
+    u3 = dict(u2); u3["Bounces"] = 3
+    oracle.set_uniforms(u3); oracle.draw_voxels()
+    g3 = oracle.grid(0).astype(int)
+    assert np.array_equal(g2[..., 3], g3[..., 3])
+    assert np.all(g3[..., :3] >= g2[..., :3]) and g3[..., :3].sum() > g2[..., :3].sum()
+    assert not g3[g3[..., 3] == 0].any()
