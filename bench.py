@@ -309,8 +309,10 @@ def run_ours(args):
     # (2) per-pass breakdown and the dominant kernel's average duration: same steps again with pass events on
     ctx.set_i("Profile", 1)
     pass_names = ["vox_clear", "vox_cover", "vox_shade", "resolve", "mip", "visibility", "cone"]
-    if args.mode == "shard" and args.exchange == "inbox":
-        pass_names.insert(3, "reinject")             # the timer slot the inbox merge reports under
+    if args.mode == "shard":
+        pass_names.insert(3, "exchange_push")
+        if args.exchange == "inbox":
+            pass_names.insert(4, "exchange_merge")
     pass_sum = {p: 0.0 for p in pass_names}
     samples_sum = 0
     n_prof = min(args.steps, 30)
@@ -331,7 +333,7 @@ def run_ours(args):
     if world > 1 and args.mode != "views":         # sharded work: the slowest rank sets the pace of every phase
         pass_t = torch.tensor([pass_sum[p] / n_prof for p in pass_names], dtype=torch.float64, device=dev)
         dist.all_reduce(pass_t, op=dist.ReduceOp.MAX)
-        passes_max = {("merge" if p == "reinject" else p): round(float(v), 2) for p, v in zip(pass_names, pass_t.tolist())}
+        passes_max = {p: round(float(v), 2) for p, v in zip(pass_names, pass_t.tolist())}
 
     # ---- end to end through the public API with HOST frame buffers (pinned); every frame's D2H copy is inside
     # the timed region.  Render loops use the pipelined call (vct_frame_async / vct_frame_wait: double-buffered,
@@ -403,7 +405,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": args.width * args.height * 4 * (len(probes) if probes is not None else 1),
                 "note": "vct_frame_async(host_rgba)+vct_frame_wait, three pinned host frame buffers (two frames queued), every frame copied to the host inside the timed region; per-step input = view matrix + camera position (kernel parameters)"},
         "gpu_launches": int(launches),
-        "passes_us": {("merge" if (p == "reinject" and args.mode == "shard") else p): round(pass_sum[p] / n_prof, 2) for p in pass_names},
+        "passes_us": {p: round(pass_sum[p] / n_prof, 2) for p in pass_names},
         "passes_us_max_over_ranks": passes_max,
         "cone_samples_per_frame": int(samples_per_launch),
         "gcone_samples_per_s": round(achieved_gs, 2),

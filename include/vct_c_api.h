@@ -42,7 +42,9 @@ typedef enum vct_pass {
   VCT_PASS_CONE = 7,        /* VoxelConeTracing.fs                      Shader/VoxelConeTracing.fs:165-229 */
   VCT_PASS_FRAME = 8,       /* whole vct_frame() call                                               */
   VCT_PASS_REINJECT = 9,    /* Bounces >= 3 extension                                               */
-  VCT_PASS_COUNT = 10
+  VCT_PASS_EXCHANGE_PUSH = 10,  /* vct_voxelize_shared: multicast of the touched voxels (multimem.st / multimem.red) */
+  VCT_PASS_EXCHANGE_MERGE = 11, /* vct_resolve_shared (inbox): the other ranks' records added to the accumulator     */
+  VCT_PASS_COUNT = 12
 } vct_pass;
 
 /* ---- lifetime.  Replaces Voxel_Cone_Tracing::Voxel_Cone_Tracing + init_voxel_cone_tracing resource

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libvct_b200.so")
 
 PASSES = {"depth": 0, "vox_clear": 1, "vox_cover": 2, "vox_shade": 3, "resolve": 4, "mip": 5,
-          "visibility": 6, "cone": 7, "frame": 8, "reinject": 9}
+          "visibility": 6, "cone": 7, "frame": 8, "reinject": 9, "exchange_push": 10, "exchange_merge": 11}
 
 # every symbol include/vct_c_api.h declares (tests check the library exports all of them)
 SYMBOLS = [

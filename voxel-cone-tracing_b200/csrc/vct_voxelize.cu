@@ -612,7 +612,7 @@ int launch_voxelize_shared(vct_context* c, size_t tb, size_t te) {
   VCT_CUDA(c, cudaMemsetAsync(c->d_push_count, 0, 4, c->stream));
   rc = voxelize_impl(c, tb, te, 1); if (rc) return rc;
   {
-    PassTimer timer(c, VCT_PASS_VOX_CLEAR);   // reported under "vox_clear": the push replaces the clear in this mode
+    PassTimer timer(c, VCT_PASS_EXCHANGE_PUSH);
     if (c->shared_mc)
       vox_push_shared<true><<<148 * 8, 256, 0, c->stream>>>(c->d_accum, c->d_push_list, c->d_push_count, (float4*)c->shared_mc, c->P.V);
     else
@@ -703,6 +703,7 @@ static int voxelize_inbox(vct_context* c, size_t tb, size_t te) {
   rc = launch_voxelize(c, tb, te); if (rc) return rc;         // this rank's triangles -> private accumulator + list
   vct_context::GridBuf& g = c->grid[c->cur];
   const uint32_t cap = (uint32_t)c->exchange_cap;
+  PassTimer timer(c, VCT_PASS_EXCHANGE_PUSH);
   if (c->shared_mc)
     vox_push_inbox<true><<<148 * 4, 256, 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, (unsigned char*)c->shared_mc,
                                                          c->exchange_parity, c->shared_world, c->shared_rank, cap, c->d_counters);
@@ -720,7 +721,7 @@ static int voxelize_inbox(vct_context* c, size_t tb, size_t te) {
 static int resolve_inbox(vct_context* c) {
   vct_context::GridBuf& g = c->grid[c->cur];
   {
-    PassTimer timer(c, VCT_PASS_REINJECT);   // reported under "reinject" slot: the merge of the other ranks' voxels
+    PassTimer timer(c, VCT_PASS_EXCHANGE_MERGE);
     for (int r = 0; r < c->shared_world; ++r) {
       if (r == c->shared_rank) continue;
       vox_merge_inbox<<<148 * 4, 256, 0, c->stream>>>(c->d_accum, (const unsigned char*)c->shared_local, c->exchange_parity,
