@@ -66,3 +66,80 @@ def test_triangle_sharded_voxelisation_allreduce_is_bit_exact(tmp_path, oracle_m
     assert np.array_equal(got["grid0"], o.grid(0)) and np.array_equal(got["grid3"], o.grid(3))
     assert np.array_equal(got["frame"], o.frame())
     assert got["counts"].sum() > 1000
+
+
+def _worker_inbox(rank, world, port, out_dir):
+    """CPU model of the fused exchange (vct_voxelize_shared / vct_resolve_shared, inbox flavour): interleaved triangle
+    shares, every rank sends 16-byte records of the voxels it touched to all others, merges what it receives, resolves
+    locally; equal row bands gathered by ONE all-gather."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import vct_b200  # noqa: F401
+    from vct_b200 import parallel, scenes, uniforms
+    from oracle.oracle_py import Oracle
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    sc = scenes.atrium(detail=0.12, tex_size=32)
+    H = W = 72
+    u = uniforms.scene_uniforms(sc, V=32, width=W, height=H, shadow_map_size=256, coverage="conservative")
+    o = Oracle(); o.set_uniforms(u); o.load_scene(sc)
+    o.draw_depth()
+    first = True
+    for b0 in range(rank * 128, sc.n_tris, world * 128):      # TriangleInterleave = world, TrianglePhase = rank
+        o.draw_voxels_range(b0, min(b0 + 128, sc.n_tris), clear_first=first)
+        first = False
+    counts, sums = o.counts().copy(), o.sums().copy()
+    mine = parallel.pack_exchange_records(counts, sums)
+    n = torch.tensor([len(mine)], dtype=torch.int64)
+    ns = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(ns, n)
+    cap = int(max(int(x) for x in ns))
+    padded = torch.zeros((cap, 4), dtype=torch.int32)
+    padded[:len(mine)] = torch.from_numpy(mine.view(np.int32))
+    inbox = [torch.zeros((cap, 4), dtype=torch.int32) for _ in range(world)]
+    dist.all_gather(inbox, padded)                            # = the multicast store into every rank's inbox row
+    for r in range(world):
+        if r != rank:
+            parallel.merge_exchange_records(counts, sums, inbox[r].numpy().view(np.uint32)[:int(ns[r])])
+    o.set_accum(counts, sums)
+    o.resolve_and_mip()
+    o.render()
+    y0, y1, per = parallel.row_band_equal(H, rank, world)
+    band = torch.zeros((per, W, 4), dtype=torch.uint8)
+    band[:y1 - y0] = torch.from_numpy(o.frame()[y0:y1].copy())
+    full = torch.zeros((world * per, W, 4), dtype=torch.uint8)
+    dist.all_gather_into_tensor(full, band)
+    np.savez(os.path.join(out_dir, f"inbox_{rank}.npz"), counts=counts, sums=sums, grid0=o.grid(0), grid3=o.grid(3),
+             frame=full.numpy()[:H], n_records=np.array([int(x) for x in ns]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_inbox_exchange_model_is_bit_exact_on_every_rank(tmp_path, oracle_mod):
+    import torch.multiprocessing as mp
+    from vct_b200 import parallel, scenes, uniforms
+    port = _free_port()
+    mp.spawn(_worker_inbox, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    sc = scenes.atrium(detail=0.12, tex_size=32)
+    u = uniforms.scene_uniforms(sc, V=32, width=72, height=72, shadow_map_size=256, coverage="conservative")
+    o = oracle_mod.Oracle(); o.set_uniforms(u); o.load_scene(sc)
+    o.draw_depth(); o.draw_voxels(); o.render()
+    for rank in range(2):
+        got = np.load(tmp_path / f"inbox_{rank}.npz")
+        assert np.array_equal(got["counts"], o.counts()) and np.array_equal(got["sums"], o.sums())
+        assert np.array_equal(got["grid0"], o.grid(0)) and np.array_equal(got["grid3"], o.grid(3))
+        assert np.array_equal(got["frame"], o.frame())
+        assert 0 < got["n_records"].min() and got["n_records"].sum() >= int((o.counts() > 0).sum())
+    # record format: round trip and the 24-bit limit
+    c = np.zeros(8, dtype=np.uint32); s = np.zeros((8, 3), dtype=np.uint32)
+    c[3], s[3] = 65793, (65793 * 255, 1, 0)
+    rec = parallel.pack_exchange_records(c, s)
+    assert rec.shape == (1, 4) and rec[0, 3] == 3
+    c2 = np.zeros(8, dtype=np.uint32); s2 = np.zeros((8, 3), dtype=np.uint32)
+    parallel.merge_exchange_records(c2, s2, rec)
+    assert np.array_equal(c2, c) and np.array_equal(s2, s)
+    c[3], s[3] = 65794, (65794 * 255, 0, 0)                   # 16 777 470 >= 2^24
+    with pytest.raises(OverflowError):
+        parallel.pack_exchange_records(c, s)

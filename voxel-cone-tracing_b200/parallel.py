@@ -92,6 +92,37 @@ def unpack_accumulator(acc: np.ndarray):
     return counts, sums
 
 
+def pack_exchange_records(counts, sums):
+    """Host mirror of the inbox record format (vox_push_inbox, csrc/vct_voxelize.cu): one uint32[4] per voxel with
+    count > 0 = {r | c0<<24, g | c1<<24, b | c2<<24, voxel}, 24-bit channel sums and a 24-bit count split into bytes
+    c0..c2.  Values of 2^24 or more do not fit (the library reports VCT_ERR_OVERFLOW; here OverflowError)."""
+    c = np.ascontiguousarray(counts, dtype=np.uint32).reshape(-1)
+    s = np.ascontiguousarray(sums, dtype=np.uint32).reshape(-1, 3)
+    v = np.nonzero(c)[0].astype(np.uint32)
+    cc, ss = c[v], s[v]
+    if (cc >> 24).any() or (ss >> 24).any():
+        raise OverflowError("a voxel sum or count needs more than 24 bits")
+    rec = np.empty((len(v), 4), dtype=np.uint32)
+    for ch in range(3):
+        rec[:, ch] = ss[:, ch] | (((cc >> (8 * ch)) & 0xFF) << 24)
+    rec[:, 3] = v
+    return rec
+
+
+def merge_exchange_records(counts, sums, records):
+    """Adds another rank's records into (counts, sums) in place (vox_merge_inbox): a rank's records name distinct
+    voxels, so plain indexed adds suffice."""
+    r = np.asarray(records, dtype=np.uint32).reshape(-1, 4)
+    c = counts.reshape(-1); s = sums.reshape(-1, 3)
+    v = r[:, 3]
+    assert len(np.unique(v)) == len(v)
+    n = (r[:, 0] >> 24) | ((r[:, 1] >> 24) << 8) | ((r[:, 2] >> 24) << 16)
+    c[v] += n
+    for ch in range(3):
+        s[v, ch] += r[:, ch] & 0xFFFFFF
+    return counts, sums
+
+
 class SharedAccumulator:
     """Symmetric exchange buffer for the fused triangle-sharded voxelisation (vct_voxelize_shared / vct_resolve_shared).
 
