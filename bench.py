@@ -40,6 +40,8 @@ def parse(argv=None):
                     help="N>1: views = one camera per rank, grid replicated (weak scaling, default for config 2); tiles = row bands, "
                          "voxelisation replicated; trishard = triangle ranges + NCCL all-reduce of the accumulator; shard = triangle "
                          "ranges exchanged over NVSwitch multicast by the library's own kernels (see --exchange) + row bands")
+    ap.add_argument("--serial-shard", action="store_true", help="--mode shard: voxelise / exchange / trace back to back on one stream "
+                    "instead of the pipelined vct_frame_shared_begin/_end")
     ap.add_argument("--contiguous", action="store_true", help="triangle sharding by contiguous ranges instead of interleaved blocks")
     ap.add_argument("--exchange", default="inbox", choices=["inbox", "reduce"],
                     help="--mode shard: inbox = touched voxels multicast as records (multimem.st) and merged locally; reduce = "
@@ -250,8 +252,11 @@ def run_ours(args):
             ctx.render(host_out)
         else:
             if args.mode == "shard":
-                shared.frame_voxels(tri_rng[0], tri_rng[1])   # exchange over NVSwitch multicast (multimem.st inbox / multimem.red)
-                ctx.render(None)
+                if args.exchange == "inbox" and not args.serial_shard:
+                    shared.frame(tri_rng[0], tri_rng[1])      # pipelined: exchange on the library's voxel stream
+                else:
+                    shared.frame_voxels(tri_rng[0], tri_rng[1])   # exchange over NVSwitch multicast (multimem.st inbox / multimem.red)
+                    ctx.render(None)
             else:
                 ctx.frame(None if gather_buf is not None else host_out)
             if gather_buf is not None:              # row bands -> every rank holds the full frame

@@ -136,6 +136,15 @@ int vct_shared_accum_bytes(vct_handle h, size_t* bytes);
 int vct_set_shared_accum(vct_handle h, void* local_ptr, void* multicast_ptr);
 int vct_voxelize_shared(vct_handle h, size_t tri_begin, size_t tri_end);
 int vct_resolve_shared(vct_handle h);
+/* The same frame, pipelined like vct_frame (inbox flavour only).  begin: this rank's share is voxelised and multicast on
+ * the library's voxel stream while primary visibility runs on a second stream; the caller then enqueues its cross-rank
+ * barrier ON vct_exchange_stream (stream order is the only synchronisation needed); end: merge + resolve + mip on the
+ * voxel stream and cone_trace (rows RowBegin..RowEnd) on the main stream after both.  With PipelineFrames = 1 the
+ * voxel / exchange / visibility stages of frame i+1 overlap cone_trace of frame i -- the replicated part of a sharded
+ * frame (clear, merge, resolve, mip) hides behind the sharded one.  Replaces main.cpp:81-92 for a multi-GPU loop. */
+int vct_frame_shared_begin(vct_handle h, size_t tri_begin, size_t tri_end);
+int vct_exchange_stream(vct_handle h, void** cuda_stream);
+int vct_frame_shared_end(vct_handle h, uint8_t* host_rgba_or_null);
 
 /* ---- read-back (the reference reads nothing back; these exist for parity checks and hosts) */
 int vct_readback_depth(vct_handle h, uint32_t* d24 /* S*S */);

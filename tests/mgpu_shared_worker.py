@@ -55,6 +55,15 @@ def main():
             bands[r] = band
     frame = torch.cat(bands, 0).cpu().numpy()
     ok &= bool(np.array_equal(frame, ref_frame))
+    if not shared.reduce:
+        # pipelined sharded frames (vct_frame_shared_begin / barrier on the exchange stream / _end)
+        c.set_i("PipelineFrames", 1)
+        for it in range(4):
+            shared.frame(tb, te)
+        c.sync()
+        ok &= bool(np.array_equal(c.read_frame()[b0:b1], ref_frame[b0:b1]))
+        for l in range(8):
+            ok &= bool(np.array_equal(c.grid(l), ref_grid[l]))
     ok &= bool(ref_counts_occ.sum() > 10000)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

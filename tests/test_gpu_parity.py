@@ -709,6 +709,60 @@ def test_inbox_exchange_two_contexts_one_gpu(gpu_ctx):
     b.close()
 
 
+def test_pipelined_shared_frames_match_plain_frames(gpu_ctx):
+    """vct_frame_shared_begin / _end (the pipelined sharded frame) with a world of one, and with two handles acting as
+    two ranks on one device: frames and grids equal those of the plain path while the mesh and the camera move."""
+    import torch
+    import vct_b200.glmath as gm
+    from vct_b200 import parallel
+    sc = scenes.dynamic_knot(nu=192, nv=96)
+    u = uniforms.scene_uniforms(sc, V=64, width=256, height=144, shadow_map_size=1024, coverage="conservative")
+    a = gpu_ctx
+    a.set_uniforms(u); a.load_scene(sc)
+    b = capi.Context(0)
+    b.set_uniforms(u); b.load_scene(sc)
+    n = sc.n_tris
+
+    def inputs(c, i):
+        if i % 2 == 0:      # the mesh moves every other frame (ordered path); the camera every frame (pipelined path)
+            P = scenes.torus_knot_positions(192, 96, t=0.4 * i).reshape(-1, 3) * 20.0
+            c.update_positions(P.astype(np.float32)); c.draw_depth()
+        view = gm.view_matrix(sc.camera_pos, sc.yaw + 3.0 * i, sc.pitch)
+        c.set_mat4("ModelViewMatrix", gm.colmajor((view @ gm.scale(0.05)).astype(np.float32)))
+
+    a.set_i("PipelineFrames", 0); a.set_i("OverlapVisibility", 0)
+    ref = []
+    for i in range(6):
+        inputs(a, i); a.frame(); a.sync()
+        ref.append((a.read_frame(), a.grid(0), a.grid(2)))
+    a.set_i("PipelineFrames", 1); a.set_i("OverlapVisibility", 1)
+    # (1) a world of one
+    shared = parallel.SharedAccumulator(a, torch.device("cuda", 0))
+    for i in range(6):
+        inputs(a, i); shared.frame(0, n); a.sync()
+        assert np.array_equal(a.read_frame(), ref[i][0]), i
+        assert np.array_equal(a.grid(0), ref[i][1]) and np.array_equal(a.grid(2), ref[i][2]), i
+    with pytest.raises(capi.VctError):
+        a.frame_shared_end()                         # nothing begun
+    # (2) two handles = two ranks sharing one inbox; the device-wide synchronize stands in for the cross-rank barrier
+    b.set_i("PipelineFrames", 1)
+    for rank, c in enumerate((a, b)):
+        c.set_i("SharedWorld", 2); c.set_i("SharedRank", rank)
+        c.set_i("TriangleInterleave", 2); c.set_i("TrianglePhase", rank)
+    buf = torch.zeros((a.shared_accum_bytes() + 7) // 8, dtype=torch.int64, device="cuda:0")
+    a.set_shared_accum(buf.data_ptr(), 0); b.set_shared_accum(buf.data_ptr(), 0)
+    for i in range(6):
+        inputs(a, i); inputs(b, i)
+        a.frame_shared_begin(0, n); b.frame_shared_begin(0, n)
+        torch.cuda.synchronize()
+        a.frame_shared_end(); b.frame_shared_end()
+        a.sync(); b.sync()
+        for c in (a, b):
+            assert np.array_equal(c.read_frame(), ref[i][0]), i
+            assert np.array_equal(c.grid(0), ref[i][1]) and np.array_equal(c.grid(2), ref[i][2]), i
+    b.close()
+
+
 @pytest.mark.parametrize("exchange", ["inbox", "reduce"])
 def test_fused_sharded_voxelisation_two_gpus(exchange):
     """multimem.st inbox / multimem.red in-switch reduction over NVSwitch multicast: needs two GPUs on the box (skipped

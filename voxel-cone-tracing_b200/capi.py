@@ -19,7 +19,7 @@ SYMBOLS = [
     "vct_set_mat4", "vct_get_i", "vct_get_f", "vct_set_cones", "vct_upload_texture", "vct_set_material",
     "vct_upload_mesh", "vct_update_positions", "vct_draw_depth", "vct_draw_voxels", "vct_render", "vct_frame", "vct_frame_async", "vct_frame_wait",
     "vct_voxelize_range", "vct_accum_buffer", "vct_resolve_and_mip", "vct_shared_accum_bytes", "vct_set_shared_accum",
-    "vct_voxelize_shared", "vct_resolve_shared", "vct_readback_depth", "vct_readback_counts",
+    "vct_voxelize_shared", "vct_resolve_shared", "vct_frame_shared_begin", "vct_exchange_stream", "vct_frame_shared_end", "vct_readback_depth", "vct_readback_counts",
     "vct_readback_sums", "vct_readback_grid", "vct_upload_grid_level0", "vct_build_mips", "vct_readback_visibility",
     "vct_readback_frame", "vct_frame_buffer", "vct_cone_samples", "vct_fragment_count", "vct_occupied_voxels", "vct_debug_counter",
     "vct_trace_cones", "vct_sample_voxels", "vct_set_stream", "vct_use_own_stream", "vct_sync", "vct_pass_time_us", "vct_kernel_launches", "vct_bench_tex3d",
@@ -60,6 +60,8 @@ def load_library(path=None):
         "vct_accum_buffer": [vp, C.POINTER(vp), C.POINTER(sz)], "vct_resolve_and_mip": [vp],
         "vct_shared_accum_bytes": [vp, C.POINTER(sz)], "vct_set_shared_accum": [vp, vp, vp],
         "vct_voxelize_shared": [vp, sz, sz], "vct_resolve_shared": [vp],
+        "vct_frame_shared_begin": [vp, sz, sz], "vct_exchange_stream": [vp, C.POINTER(C.c_void_p)],
+        "vct_frame_shared_end": [vp, C.c_void_p],
         "vct_readback_depth": [vp, vp], "vct_readback_counts": [vp, vp], "vct_readback_sums": [vp, vp],
         "vct_readback_grid": [vp, i, vp], "vct_upload_grid_level0": [vp, vp], "vct_build_mips": [vp],
         "vct_readback_visibility": [vp, vp], "vct_readback_frame": [vp, vp],
@@ -237,6 +239,17 @@ class Context:
 
     def resolve_shared(self):
         self._ck(self.L.vct_resolve_shared(self.h))
+
+    def frame_shared_begin(self, tb, te):
+        self._ck(self.L.vct_frame_shared_begin(self.h, int(tb), int(te)))
+
+    def exchange_stream(self):
+        s = C.c_void_p()
+        self._ck(self.L.vct_exchange_stream(self.h, C.byref(s)))
+        return int(s.value or 0)
+
+    def frame_shared_end(self, host_rgba=None):
+        self._ck(self.L.vct_frame_shared_end(self.h, None if host_rgba is None else _host_ptr(host_rgba)))
 
     # ---- read-back
     def depth(self):

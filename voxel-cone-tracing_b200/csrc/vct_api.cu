@@ -773,6 +773,77 @@ int vct_resolve_shared(vct_handle c) {
   return VCT_OK;
 }
 
+static int ensure_overlap(vct_context* c);
+
+// Pipelined form of one sharded frame (inbox flavour).  begin: the rank's triangle share is voxelised and multicast on
+// the library's voxel stream, primary visibility runs on the visibility stream; the HOST then enqueues its cross-rank
+// barrier on vct_exchange_stream; end: merge + resolve + mip on the voxel stream, cone_trace on the main stream after
+// both.  As in vct_frame, with PipelineFrames the voxel/visibility stages of frame i+1 run beside cone_trace of frame i.
+int vct_frame_shared_begin(vct_handle c, size_t tb, size_t te) {
+  NEED(c);
+  if (!c->shared_local) return set_error(c, VCT_ERR_STATE, "vct_frame_shared_begin: call vct_set_shared_accum first");
+  if (c->shared_exchange != 0) return set_error(c, VCT_ERR_STATE, "vct_frame_shared_begin: needs SharedExchange = 0 (inbox)");
+  if (c->shared_frame_open) return set_error(c, VCT_ERR_STATE, "vct_frame_shared_begin: previous frame not ended");
+  int rc = ensure_grid(c); if (rc) return rc;
+  rc = ensure_frame(c); if (rc) return rc;
+  rc = ensure_queues(c); if (rc) return rc;
+  rc = sync_materials(c); if (rc) return rc;
+  rc = ensure_overlap(c); if (rc) return rc;
+  const bool ordered = !c->pipeline_frames || c->scene_epoch != c->frame_epoch;
+  cudaStream_t main_stream = c->stream; TileItem* main_items = c->d_items; Counters* main_ctr = c->d_counters;
+  if (ordered) VCT_CUDA(c, cudaEventRecord(c->ev_fork, main_stream));
+  c->stream = c->stream_vox;
+  rc = VCT_OK;
+  if (ordered) rc = check_cuda(c, cudaStreamWaitEvent(c->stream_vox, c->ev_fork, 0), "wait fork");
+  if (!rc) rc = begin_voxel_slot(c);
+  if (!rc) rc = ensure_vertex_cache(c);
+  if (!rc) rc = check_cuda(c, cudaEventRecord(c->ev_vtx_done, c->stream_vox), "record vtx");
+  if (!rc) rc = launch_voxelize_inbox_into_slot(c, tb, te);
+  if (!rc) {
+    c->stream = c->stream2; c->d_items = c->d_items_vis; c->d_counters = c->d_counters_vis;
+    rc = check_cuda(c, cudaStreamWaitEvent(c->stream2, c->ev_vtx_done, 0), "wait vtx");
+    if (!rc) rc = launch_visibility(c);
+    if (!rc) rc = check_cuda(c, cudaEventRecord(c->ev_join, c->stream2), "record join");
+  }
+  c->stream = main_stream; c->d_items = main_items; c->d_counters = main_ctr;
+  if (rc) return rc;
+  c->shared_frame_open = true;
+  return VCT_OK;
+}
+
+int vct_exchange_stream(vct_handle c, void** cuda_stream) {
+  NEED(c);
+  int rc = ensure_overlap(c); if (rc) return rc;
+  if (cuda_stream) *cuda_stream = (void*)c->stream_vox;
+  return VCT_OK;
+}
+
+int vct_frame_shared_end(vct_handle c, uint8_t* host_rgba) {
+  NEED(c);
+  if (!c->shared_frame_open) return set_error(c, VCT_ERR_STATE, "vct_frame_shared_end: no frame begun");
+  c->shared_frame_open = false;
+  cudaStream_t main_stream = c->stream;
+  c->stream = c->stream_vox;
+  int rc = launch_resolve_shared(c);
+  if (!rc) rc = launch_mip(c);
+  for (int b = 3; !rc && b <= c->P.bounces; ++b) {
+    rc = launch_reinject(c);
+    if (!rc) rc = launch_mip(c);
+  }
+  if (!rc) rc = check_cuda(c, cudaEventRecord(c->ev_vox_done, c->stream_vox), "record vox");
+  c->stream = main_stream;
+  if (rc) return rc;
+  VCT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_vox_done, 0));
+  VCT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  c->frame_epoch = c->scene_epoch;
+  rc = launch_cone(c); if (rc) return rc;
+  if (host_rgba) {
+    VCT_CUDA(c, cudaMemcpyAsync(host_rgba, c->d_frame, (size_t)c->P.W * c->P.H * 4, cudaMemcpyDeviceToHost, c->stream));
+    VCT_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return VCT_OK;
+}
+
 int vct_accum_buffer(vct_handle c, void** p, size_t* n) {
   NEED(c);
   int rc = ensure_grid(c); if (rc) return rc;

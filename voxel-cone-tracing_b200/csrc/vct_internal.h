@@ -142,6 +142,7 @@ struct vct_context {
   // exchange flavour: 0 = inbox (records multicast with multimem.st, merged locally; default), 1 = in-switch reduction
   // (multimem.red into a dense symmetric accumulator + occupancy mask)
   int shared_exchange = 0, shared_world = 1, shared_rank = 0, exchange_parity = 0;
+  bool shared_frame_open = false;                // vct_frame_shared_begin issued, vct_frame_shared_end pending
   int tri_interleave = 1, tri_phase = 0;         // voxelisation takes every tri_interleave-th block of 128 triangles
   size_t exchange_cap = 0, exchange_cap_user = 0; // records per rank and parity in the inbox (user 0 = auto: min(V^3, 32 V^2))
   int accum_list_slot = -1;                    // slot whose touched list describes the accumulator's non-zero cells;
@@ -211,6 +212,7 @@ int launch_voxelize(vct_context* c, size_t tb, size_t te);
 int launch_resolve(vct_context* c, bool dense);
 int launch_voxelize_shared(vct_context* c, size_t tb, size_t te);
 int launch_resolve_shared(vct_context* c);
+int launch_voxelize_inbox_into_slot(vct_context* c, size_t tb, size_t te);   // inbox flavour, slot already chosen
 int launch_mip(vct_context* c);
 int launch_visibility(vct_context* c);
 int launch_cone(vct_context* c);

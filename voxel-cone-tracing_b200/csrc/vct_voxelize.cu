@@ -592,11 +592,11 @@ __global__ void vox_merge_inbox(unsigned long long* __restrict__ accum, const un
   }
 }
 
-static int voxelize_inbox(vct_context* c, size_t tb, size_t te);
+static int voxelize_inbox(vct_context* c, size_t tb, size_t te, bool slot_ready);
 static int resolve_inbox(vct_context* c);
 
 int launch_voxelize_shared(vct_context* c, size_t tb, size_t te) {
-  if (c->shared_local && c->shared_exchange == 0) return voxelize_inbox(c, tb, te);
+  if (c->shared_local && c->shared_exchange == 0) return voxelize_inbox(c, tb, te, false);
   if (!c->shared_local) return set_error(c, VCT_ERR_STATE, "vct_voxelize_shared: call vct_set_shared_accum first");
   int rc = ensure_grid(c); if (rc) return rc;
   const size_t n = (size_t)c->P.V * c->P.V * c->P.V;
@@ -696,9 +696,12 @@ int launch_resolve_shared(vct_context* c) {
   return VCT_OK;
 }
 
-static int voxelize_inbox(vct_context* c, size_t tb, size_t te) {
+// slot_ready: the caller (vct_frame_shared_begin) already switched to the slot to build into
+int launch_voxelize_inbox_into_slot(vct_context* c, size_t tb, size_t te) { return voxelize_inbox(c, tb, te, true); }
+
+static int voxelize_inbox(vct_context* c, size_t tb, size_t te, bool slot_ready) {
   int rc = ensure_grid(c); if (rc) return rc;
-  rc = begin_voxel_slot(c); if (rc) return rc;
+  if (!slot_ready) { rc = begin_voxel_slot(c); if (rc) return rc; }
   rc = launch_voxel_clear(c); if (rc) return rc;             // ordinary sparse clear (lists describe ALL voxels)
   rc = launch_voxelize(c, tb, te); if (rc) return rc;         // this rank's triangles -> private accumulator + list
   vct_context::GridBuf& g = c->grid[c->cur];

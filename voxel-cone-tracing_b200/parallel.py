@@ -138,6 +138,7 @@ class SharedAccumulator:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.reduce = exchange == "reduce"
+        self._xstream = None
         ctx.set_i("SharedExchange", 1 if self.reduce else 0)
         ctx.set_i("SharedWorld", self.world)
         ctx.set_i("SharedRank", self.rank)
@@ -163,6 +164,19 @@ class SharedAccumulator:
     def barrier(self):
         if self.hdl is not None:
             self.hdl.barrier()
+
+    def frame(self, tri_begin, tri_end, host_rgba=None):
+        """One sharded frame, pipelined (vct_frame_shared_begin / _end; inbox exchange only): the cross-rank barrier is
+        enqueued on the library's exchange stream, so the voxel / exchange / visibility stages of the next frame run
+        beside this frame's cone_trace.  Renders rows RowBegin..RowEnd of this rank."""
+        import torch
+        self.ctx.frame_shared_begin(tri_begin, tri_end)
+        if self.hdl is not None:
+            if self._xstream is None:
+                self._xstream = torch.cuda.ExternalStream(self.ctx.exchange_stream(), device=self.buf.device)
+            with torch.cuda.stream(self._xstream):
+                self.hdl.barrier()
+        self.ctx.frame_shared_end(host_rgba)
 
     def frame_voxels(self, tri_begin, tri_end):
         """One sharded voxelisation: voxelise this rank's triangle range and multicast what it touched, barrier, merge /
