@@ -408,7 +408,8 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": args.width * args.height * 4 * (len(probes) if probes is not None else 1),
-                "note": "vct_frame_async(host_rgba)+vct_frame_wait, three pinned host frame buffers (two frames queued), every frame copied to the host inside the timed region; per-step input = view matrix + camera position (kernel parameters)"},
+                "note": ("vct_frame_async(host_rgba)+vct_frame_wait, three pinned host frame buffers (two frames queued), every frame copied to the host inside the timed region; per-step input = view matrix + camera position (kernel parameters)"
+                         if pipelined else "each step returns after its frame(s) reached pinned host memory (synchronous copy inside the timed region)")},
         "gpu_launches": int(launches),
         "passes_us": {p: round(pass_sum[p] / n_prof, 2) for p in pass_names},
         "passes_us_max_over_ranks": passes_max,
