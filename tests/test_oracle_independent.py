@@ -1,0 +1,490 @@
+"""Second, independent restatement of the arithmetic-heavy pieces of the path, in float64 numpy / exact Python
+integers, written from the GLSL and the GL 4.3 filtering rules rather than from the C++ oracle, and compared with
+the oracle on random inputs.  The reference has no tests of its own (parity is unpinned); these
+cross-checks, the hand-derived vectors in test_oracle_kat.py and the golden fixtures are what pins the oracle.
+
+  * SampleVoxels / textureLod        VoxelConeTracing.fs:59-66, GL 4.3 8.14 (weighted-sum form, float64)
+  * Voxel_Cone_Tracing loop          VoxelConeTracing.fs:82-107
+  * PCF_Shadow_Mapping               Voxelization.fs:18-52 (bilinear GL_LINEAR taps, CLAMP_TO_EDGE)
+  * ortho rasteriser coverage        GL 4.3 14.6.1: interior / exterior / shared-edge exactly-once, exact integers
+"""
+import numpy as np
+import pytest
+
+from vct_b200 import scenes, uniforms
+from test_oracle_kat import quad_mesh, setup
+
+G = 150.0
+
+
+# ---------------------------------------------------------------------------------------------- voxel texture
+def mip_chain(g0):
+    """(sum of 8 + 4) >> 3 per channel (defined semantics) -- integer, so exact."""
+    levels = [g0.astype(np.int64)]
+    while levels[-1].shape[0] > 1:
+        p = levels[-1]
+        n = p.shape[0] // 2
+        levels.append((p.reshape(n, 2, n, 2, n, 2, 4).sum((1, 3, 5)) + 4) >> 3)
+    return [l.astype(np.float64) / 255.0 for l in levels]
+
+
+def sample_level(level, uvw):
+    """GL_LINEAR on a 3D level with GL_REPEAT: eight texels weighted by the products of (1 - f) / f."""
+    n = level.shape[0]
+    t = np.asarray(uvw, dtype=np.float64) * n - 0.5
+    i0 = np.floor(t).astype(int)
+    f = t - i0
+    out = np.zeros(4)
+    for dz in (0, 1):
+        for dy in (0, 1):
+            for dx in (0, 1):
+                w = (f[0] if dx else 1 - f[0]) * (f[1] if dy else 1 - f[1]) * (f[2] if dz else 1 - f[2])
+                out += w * level[(i0[2] + dz) % n, (i0[1] + dy) % n, (i0[0] + dx) % n]
+    return out
+
+
+def sample_voxels(levels, pos, lod):
+    uvw = np.asarray(pos, dtype=np.float64) / (G / 2) * 0.5 + 0.5       # VoxelConeTracing.fs:61-63
+    lod = min(max(lod, 0.0), len(levels) - 1.0)
+    l0 = int(np.floor(lod))
+    f = lod - l0
+    a = sample_level(levels[l0], uvw)
+    if f > 0 and l0 + 1 < len(levels):
+        a = (1 - f) * a + f * sample_level(levels[l0 + 1], uvw)
+    return a
+
+
+def cone(levels, V, start, direction, tan_half, max_dist=75.0, max_alpha=0.95):
+    """VoxelConeTracing.fs:82-107 in float64; also returns how close alpha came to the exit threshold."""
+    vws = G / V
+    dist, alpha, occ, color, n, margin = vws, 0.0, 0.0, np.zeros(3), 0, 1.0
+    start, direction = np.asarray(start, dtype=np.float64), np.asarray(direction, dtype=np.float64)
+    while dist < max_dist and alpha < max_alpha:
+        diameter = max(vws, 2 * tan_half * dist)
+        s = sample_voxels(levels, start + dist * direction, np.log2(diameter / vws))
+        color += (1 - alpha) * s[:3]
+        occ += (1 - alpha) * s[3] / (1 + 0.03 * diameter)
+        alpha += (1 - alpha) * s[3]
+        dist += diameter
+        n += 1
+        margin = min(margin, abs(alpha - max_alpha), abs(dist - max_dist) / max_dist)
+    return np.append(color, occ), n, margin
+
+
+def random_grid(V, rng, fill=0.08):
+    g = np.zeros((V, V, V, 4), dtype=np.uint8)
+    occ = rng.random((V, V, V)) < fill
+    g[occ, :3] = rng.integers(0, 256, (int(occ.sum()), 3))
+    g[occ, 3] = 255
+    return g
+
+
+@pytest.mark.parametrize("V", [16, 32])
+def test_sample_voxels_against_float64_weighted_sum(oracle, V):
+    rng = np.random.default_rng(V)
+    u = setup(oracle, V=V)
+    u["FilterMode"] = 0                      # fp32 filter weights (mode 1 models the 8-bit hardware weights)
+    oracle.set_uniforms(u)
+    g = random_grid(V, rng, fill=0.3)
+    oracle.set_grid_level0(g)
+    levels = mip_chain(g)
+    for l in range(len(levels)):             # the oracle's own pyramid is the integer one
+        assert np.array_equal(np.rint(levels[l] * 255).astype(np.uint8), oracle.grid(l))
+    worst = 0.0
+    for _ in range(300):
+        pos = rng.uniform(-110, 110, 3)      # beyond +-75: GL_REPEAT wraps (the reference never sets a wrap mode)
+        lod = float(rng.uniform(-0.5, np.log2(V) + 0.5))
+        worst = max(worst, np.abs(oracle.sample_voxels(pos, lod) - sample_voxels(levels, pos, lod)).max())
+    assert worst < 3e-6, worst
+
+
+def test_quantised_filter_mode_stays_within_one_weight_step(oracle):
+    """FilterMode 1 (default; 8-bit weights, LOD fraction truncated to 1/256 as measured on the texture hardware) differs
+    from the exact filter by at most the weight quantisation: 3 axes * 1/512 + the LOD step 1/256."""
+    V = 16
+    rng = np.random.default_rng(5)
+    u = setup(oracle, V=V)
+    g = random_grid(V, rng, fill=0.3)
+    levels = mip_chain(g)
+    oracle.set_grid_level0(g)
+    worst = 0.0
+    for _ in range(300):
+        pos = rng.uniform(-75, 75, 3)
+        lod = float(rng.uniform(0, np.log2(V)))
+        worst = max(worst, np.abs(oracle.sample_voxels(pos, lod) - sample_voxels(levels, pos, lod)).max())
+    assert 1e-5 < worst <= 3 / 512 + 1 / 256 + 1e-6, worst
+
+
+@pytest.mark.parametrize("tan_half", [0.577, 0.07])
+def test_cone_march_against_float64_loop(oracle, tan_half):
+    V = 32
+    rng = np.random.default_rng(int(tan_half * 1000))
+    u = setup(oracle, V=V)
+    u["FilterMode"] = 0
+    oracle.set_uniforms(u)
+    g = random_grid(V, rng, fill=0.02)
+    oracle.set_grid_level0(g)
+    levels = mip_chain(g)
+    checked = 0
+    for _ in range(60):
+        start = rng.uniform(-60, 60, 3)
+        d = rng.normal(size=3); d /= np.linalg.norm(d)
+        want, n_want, margin = cone(levels, V, start, d, tan_half)
+        if margin < 1e-4:                    # a float32/float64 difference could add or drop a whole step here
+            continue
+        got, n_got = oracle.cone(start, d.astype(np.float32), tan_half)
+        assert n_got == n_want
+        assert np.abs(got - want).max() < 2e-5 * max(1, n_want), (got, want)
+        checked += 1
+    assert checked > 40
+    # step counts on an empty grid: distances 75/16 * (1 + 2 tan)^k style growth until 75
+    oracle.set_grid_level0(np.zeros_like(g))
+    _, n_empty = oracle.cone((0, 0, 0), (0, 0, 1), tan_half)
+    _, n_want, _ = cone(mip_chain(np.zeros_like(g)), V, (0, 0, 0), (0, 0, 1), tan_half)
+    assert n_empty == n_want
+
+
+# ---------------------------------------------------------------------------------------------------- PCF
+def test_pcf_against_numpy_bilinear_taps(oracle):
+    S = 64
+    u = setup(oracle, V=32, shadow_map_size=S)
+    # two overlapping tilted quads so that the map holds a depth discontinuity
+    # (wound to face the light at +y: the shadow pass culls back faces, Voxel_Cone_Tracing.h:198-199)
+    v1, i1 = quad_mesh((-70, -10, -60), (-70, 0, 60), (70, 6, 60), (70, -4, -60))
+    v2, i2 = quad_mesh((-25, 20, -25), (-28, 26, 22), (26, 30, 28), (30, 24, -20))
+    oracle.upload_mesh(np.concatenate([v1, v2]), np.concatenate([i1, i2 + 4]))
+    oracle.draw_depth()
+    d24 = oracle.depth().astype(np.float64)                  # [row][col] of D24 integers
+    assert (d24 < 0xFFFFFF).sum() > 500
+    tex = d24 / 16777215.0
+
+    def bilinear(uv):
+        x, y = uv[0] * S - 0.5, uv[1] * S - 0.5
+        i, j = int(np.floor(x)), int(np.floor(y))
+        a, b = x - i, y - j
+        cl = lambda k: min(max(k, 0), S - 1)                 # CLAMP_TO_EDGE, Voxel_Cone_Tracing.h:95-96
+        t = lambda ii, jj: tex[cl(jj), cl(ii)]
+        return (1 - b) * ((1 - a) * t(i, j) + a * t(i + 1, j)) + b * ((1 - a) * t(i, j + 1) + a * t(i + 1, j + 1))
+
+    rng = np.random.default_rng(3)
+    checked = 0
+    for _ in range(400):
+        dc = np.array([rng.uniform(-0.05, 1.05), rng.uniform(-0.05, 1.05), rng.uniform(0.2, 0.8), 1.0])
+        cur = dc[2] / dc[3]
+        lit, safe = 0, True
+        for x in range(-2, 3):                               # Voxelization.fs:32-44
+            for y in range(-2, 3):
+                closest = bilinear((dc[0] + x / S, dc[1] + y / S))
+                if abs((cur - 0.002) - closest) < 1e-5:
+                    safe = False
+                lit += (cur - 0.002) <= closest
+        if not safe:
+            continue
+        assert oracle.pcf(dc) == pytest.approx(lit / 25.0, abs=1e-6)
+        checked += 1
+    assert checked > 300
+
+
+# ------------------------------------------------------------------------------------------------ rasteriser
+def edge(a, b, p):
+    return (b[0] - a[0]) * (p[1] - a[1]) - (b[1] - a[1]) * (p[0] - a[0])
+
+
+def classify(tri, p):
+    """+1 strictly inside, 0 on the boundary, -1 outside; exact integers"""
+    e = [edge(tri[k], tri[(k + 1) % 3], p) for k in range(3)]
+    if edge(tri[0], tri[1], tri[2]) < 0:
+        e = [-x for x in e]
+    if min(e) > 0:
+        return 1
+    return 0 if min(e) == 0 else -1
+
+
+def test_center_coverage_of_random_triangle_pairs_exact(oracle):
+    """Pixel-centre coverage (CoveragePolicy 0) of two triangles sharing an edge, vertices on the 1/256-pixel lattice so
+    that the snap is exact: strictly interior centres are hit, exterior ones are not, centres on the shared edge are
+    hit exactly once, centres on the outer boundary at most once (GL 4.3 14.6.1; no reliance on which edge owns)."""
+    V = 32
+    rng = np.random.default_rng(11)
+    sub = 256
+    for trial in range(25):
+        setup(oracle, V=V, coverage="center")
+        # convex quad A-B-D-C in window lattice units, split along B-C; some vertices ON pixel centres
+        while True:
+            q = rng.integers(2 * sub, (V - 2) * sub, (4, 2))
+            if trial % 3 == 0:
+                q = (q // sub) * sub + sub // 2
+            A, B, C, D = [tuple(int(x) for x in p) for p in q]
+            o1, o2 = edge(A, B, C), edge(C, B, D)
+            if o1 != 0 and o2 != 0 and (o1 > 0) == (o2 > 0) and (edge(A, B, D) > 0) == (o1 > 0) and (edge(A, D, C) < 0) == (o1 < 0):
+                break
+        z_world = 75.0 - (rng.integers(0, V) + 0.5) * G / V   # mid-voxel plane: the slice index is unambiguous
+        to_world = lambda p: (p[0] / sub * G / V - 75.0, p[1] / sub * G / V - 75.0, z_world)
+        verts = np.zeros((4, 14), dtype=np.float32)
+        verts[:, :3] = np.array([to_world(p) for p in (A, B, C, D)]) * 20.0
+        verts[:, 3:6] = (0, 0, 1); verts[:, 8:11] = (1, 0, 0); verts[:, 11:14] = (0, 1, 0)
+        oracle.upload_mesh(verts, np.array([[0, 1, 2], [2, 1, 3]], dtype=np.uint32))
+        oracle.draw_depth(); oracle.draw_voxels()
+        c = oracle.counts()
+        zs = np.nonzero(c.sum((1, 2)))[0]
+        assert len(zs) == 1 and zs[0] == int(np.floor((z_world / G + 0.5) * V))
+        cov = c[zs[0]]                                        # [y][x]
+        t1, t2 = (A, B, C), (C, B, D)
+        n_inside = 0
+        for j in range(V):
+            for i in range(V):
+                p = (i * sub + sub // 2, j * sub + sub // 2)
+                k1, k2 = classify(t1, p), classify(t2, p)
+                got = int(cov[j, i])
+                if k1 == 1 or k2 == 1:
+                    assert got == 1, (trial, i, j)
+                    n_inside += 1
+                elif k1 == -1 and k2 == -1:
+                    assert got == 0, (trial, i, j)
+                elif k1 == 0 and k2 == 0 and edge(B, C, p) == 0 and p not in (B, C):
+                    assert got == 1, ("shared edge", trial, i, j)
+                else:
+                    assert got in (0, 1), (trial, i, j)
+        assert n_inside == 0 or cov.sum() >= n_inside
+
+
+# ------------------------------------------------------------------------------------------ material textures
+def test_material_texture_trilinear_repeat_against_float64(oracle):
+    """texture()/textureLod on a 2D material texture: RGBA8 + 2x2 box mips (sum of 4 + 2) >> 2, GL_REPEAT, trilinear
+    (Model.h:172-175).  Quantised hardware-style weights (FilterMode 1) stay within the weight step of the exact filter."""
+    rng = np.random.default_rng(21)
+    tex = rng.integers(0, 256, (16, 32, 4), dtype=np.uint8)          # h = 16, w = 32
+    u = setup(oracle, V=16)
+    levels = [tex.astype(np.int64)]
+    while levels[-1].shape[0] > 1 or levels[-1].shape[1] > 1:
+        p = levels[-1]
+        h, w = max(p.shape[0] // 2, 1), max(p.shape[1] // 2, 1)
+        if p.shape[0] == 1:
+            p = np.concatenate([p, p], 0)
+        if p.shape[1] == 1:
+            p = np.concatenate([p, p], 1)
+        levels.append((p.reshape(h, 2, w, 2, 4).sum((1, 3)) + 2) >> 2)
+    levels = [l.astype(np.float64) / 255.0 for l in levels]
+
+    def sample2d(level, s, t):
+        h, w = level.shape[:2]
+        x, y = s * w - 0.5, t * h - 0.5
+        i, j = int(np.floor(x)), int(np.floor(y))
+        a, b = x - i, y - j
+        at = lambda ii, jj: level[jj % h, ii % w]
+        return (1 - b) * ((1 - a) * at(i, j) + a * at(i + 1, j)) + b * ((1 - a) * at(i, j + 1) + a * at(i + 1, j + 1))
+
+    for mode, tol in ((0, 3e-6), (1, 2 / 512 + 1 / 256 + 1e-6)):
+        u["FilterMode"] = mode
+        oracle.set_uniforms(u)
+        oracle.upload_texture(3, tex)
+        worst = 0.0
+        for _ in range(300):
+            s, t = rng.uniform(-2, 3, 2)
+            lod = float(rng.uniform(0, len(levels) - 1))
+            l0 = int(np.floor(lod)); f = lod - l0
+            want = sample2d(levels[l0], s, t)
+            if f > 0 and l0 + 1 < len(levels):
+                want = (1 - f) * want + f * sample2d(levels[l0 + 1], s, t)
+            worst = max(worst, np.abs(oracle.sample_texture(3, s, t, lod) - want).max())
+        assert worst <= tol, (mode, worst)
+
+
+# ------------------------------------------------------------------------------------------ primary visibility
+def test_visibility_against_float64_ray_casting(oracle):
+    """S2 (VoxelConeTracing.vs + GL raster, depth test LESS, back-face culling): the triangle the oracle's homogeneous
+    rasteriser finds per pixel must be the nearest front-facing triangle hit by the ray through the pixel centre."""
+    sc = scenes.cornell()
+    W, H = 80, 64
+    u = uniforms.scene_uniforms(sc, V=32, width=W, height=H, shadow_map_size=256)
+    oracle.set_uniforms(u); oracle.load_scene(sc); oracle.draw_depth(); oracle.draw_voxels(); oracle.render()
+    vis = oracle.visibility()                                   # [row][col], row 0 = bottom (GL window order)
+    MV = np.asarray(u["ModelViewMatrix"], dtype=np.float64).reshape(4, 4).T     # column-major -> maths form
+    P = np.asarray(u["ProjectionMatrix"], dtype=np.float64).reshape(4, 4).T
+    inv = np.linalg.inv(P @ MV)
+    pos = sc.verts[:, :3].astype(np.float64)
+    tri = pos[sc.idx.astype(np.int64)]                          # [nt][3][3], model space
+    e1, e2 = tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]
+    nrm = np.cross(e1, e2)
+    mism = total = 0
+    for j in range(H):
+        for i in range(W):
+            ndc = np.array([(i + 0.5) / W * 2 - 1, (j + 0.5) / H * 2 - 1])
+            a = inv @ np.array([ndc[0], ndc[1], -1.0, 1.0]); b = inv @ np.array([ndc[0], ndc[1], 1.0, 1.0])
+            o, d = a[:3] / a[3], b[:3] / b[3] - a[:3] / a[3]
+            # Moeller-Trumbore for all triangles at once
+            pv = np.cross(d, e2)
+            det = (e1 * pv).sum(1)
+            ok = np.abs(det) > 1e-12
+            inv_det = np.where(ok, 1.0 / np.where(ok, det, 1.0), 0.0)
+            tv = o - tri[:, 0]
+            uu = (tv * pv).sum(1) * inv_det
+            qv = np.cross(tv, e1)
+            vv = (qv * d).sum(1) * inv_det
+            tt = (qv * e2).sum(1) * inv_det
+            eps = 1e-4
+            live = ok & (tt > 0) & (tt < 1) & ((nrm * d).sum(1) < 0)      # between the planes, front facing (CCW)
+            hit = live & (uu > eps) & (vv > eps) & (uu + vv < 1 - eps)
+            edge_case = live & (uu > -eps) & (vv > -eps) & (uu + vv < 1 + eps) & ~hit
+            if edge_case.any():
+                continue                                        # on or next to an edge: the fill rule decides
+            want = 0xFFFFFFFF
+            if hit.any():
+                cand = np.nonzero(hit)[0]
+                t_min = tt[cand].min()
+                near = cand[tt[cand] < t_min + 1e-9]
+                if len(near) > 1:
+                    continue                                    # coplanar duplicates: tie broken by triangle id
+                want = int(near[0])
+            total += 1
+            mism += int(vis[j, i]) != want
+    assert total > 0.8 * W * H
+    assert mism == 0, (mism, total)
+
+
+# ------------------------------------------------------------------------------------- whole fragment shader
+def pcf_lit_taps(tex, S, dc, bias=0.002):
+    """Voxelization.fs:18-52 / VoxelConeTracing.fs:132-163 without the final normalisation; also says whether any tap
+    sits on the compare threshold."""
+    def bilinear(s, t):
+        x, y = s * S - 0.5, t * S - 0.5
+        i, j = int(np.floor(x)), int(np.floor(y))
+        a, b = x - i, y - j
+        cl = lambda k: min(max(k, 0), S - 1)
+        at = lambda ii, jj: tex[cl(jj), cl(ii)]
+        return (1 - b) * ((1 - a) * at(i, j) + a * at(i + 1, j)) + b * ((1 - a) * at(i, j + 1) + a * at(i + 1, j + 1))
+    cur = dc[2] / dc[3]
+    lit, safe = 0, True
+    for x in range(-2, 3):
+        for y in range(-2, 3):
+            closest = bilinear(dc[0] + x / S, dc[1] + y / S)
+            safe &= abs((cur - bias) - closest) > 2e-6
+            lit += (cur - bias) <= closest
+    return lit, safe
+
+
+def test_fragment_shader_against_float64_restatement(oracle):
+    """VoxelConeTracing.fs main() (:165-229) restated in float64 for pixels of the Cornell box: TBN = inverse(transpose(
+    mat3(T, B, N))) with the un-normalised world-space frame (length 0.05), cone start offset Normal_world * voxel size,
+    PCF gain 0.111 (range [0, 2.775]), six weighted diffuse cones + one specular cone, specColor.rrra for single-channel
+    maps, ambient 0.1; compared with the oracle's frame to 1 LSB."""
+    sc = scenes.cornell()
+    W, H, V, S = 48, 40, 32, 256
+    u = uniforms.scene_uniforms(sc, V=V, width=W, height=H, shadow_map_size=S)
+    u["FilterMode"] = 0
+    oracle.set_uniforms(u); oracle.load_scene(sc); oracle.draw_depth(); oracle.draw_voxels(); oracle.render()
+    frame, vis = oracle.frame(), oracle.visibility()
+    levels = mip_chain(oracle.grid(0))
+    shadow_tex = oracle.depth().astype(np.float64) / 16777215.0
+    col = lambda name: np.asarray(u[name], dtype=np.float64).reshape(4, 4).T
+    M, MV, P, DMVP = col("ModelMatrix"), col("ModelViewMatrix"), col("ProjectionMatrix"), col("DepthModelViewProjectionMatrix")
+    inv = np.linalg.inv(P @ MV)
+    cam = np.asarray(u["CameraPosition"], dtype=np.float64)
+    L = np.asarray(u["LightDirection"], dtype=np.float64); L /= np.linalg.norm(L)
+    dirs = np.asarray(u["ConeDirections"], dtype=np.float64).reshape(-1, 3)
+    wts = np.asarray(u["ConeWeights"], dtype=np.float64)
+    assert len(dirs) == 6 and wts[0] == pytest.approx(0.25)
+    norm = lambda v: v / np.linalg.norm(v)
+
+    def texel(tex_id):
+        t = sc.textures[tex_id].reshape(-1).astype(np.float64) / 255.0      # all 1x1 here
+        return np.array([t[0], 0, 0, 1.0]) if len(t) == 1 else np.append(t[:3], 1.0 if len(t) == 3 else t[3])
+
+    checked = 0
+    rng = np.random.default_rng(2)
+    for _ in range(400):
+        i, j = int(rng.integers(0, W)), int(rng.integers(0, H))
+        tri_id = int(vis[j, i])
+        if tri_id == 0xFFFFFFFF:
+            continue
+        ndc = np.array([(i + 0.5) / W * 2 - 1, (j + 0.5) / H * 2 - 1])
+        a, b = inv @ np.array([*ndc, -1.0, 1.0]), inv @ np.array([*ndc, 1.0, 1.0])
+        o, d = a[:3] / a[3], b[:3] / b[3] - a[:3] / a[3]
+        idx = sc.idx[tri_id].astype(int)
+        p0, p1, p2 = sc.verts[idx, :3].astype(np.float64)
+        e1, e2 = p1 - p0, p2 - p0
+        pv = np.cross(d, e2); det = e1 @ pv
+        tv = o - p0; bu = (tv @ pv) / det; qv = np.cross(tv, e1); bv = (qv @ d) / det
+        if min(bu, bv, 1 - bu - bv) < 0.02:
+            continue                                            # keep away from edges (visibility ties)
+        bary = np.array([1 - bu - bv, bu, bv])
+        attr = lambda lo, hi: bary @ sc.verts[idx, lo:hi].astype(np.float64)
+        Pw = (M @ np.append(bary @ np.stack([p0, p1, p2]), 1.0))[:3]       # VoxelConeTracing.vs:27-34
+        Nw, Tw, Bw = (M[:3, :3] @ attr(3, 6)), (M[:3, :3] @ attr(8, 11)), (M[:3, :3] @ attr(11, 14))
+        Pd = DMVP @ np.append(bary @ np.stack([p0, p1, p2]), 1.0); Pd[:3] = Pd[:3] * 0.5 + 0.5
+        mat = sc.materials[int(sc.tri_material[tri_id])]
+        albedo, spec_c = texel(mat[0]), texel(mat[1])
+        TBN = np.linalg.inv(np.stack([Tw, Bw, Nw]))             # inverse(transpose(mat3(T, B, N))), :175
+        N = norm(TBN @ np.array([0.0, 0.0, 1.0]))               # flat height map: bump normal (0, 0, 1), :110-128
+        E = norm(cam - Pw)
+        lit, safe = pcf_lit_taps(shadow_tex, S, Pd)
+        if not safe:
+            continue
+        shadow = lit * 0.111                                     # :160
+        start = Pw + Nw * (G / V)                                # :92, Normal_world is NOT normalised
+        ind, margin = np.zeros(4), 1.0
+        for k in range(6):
+            c4, _, m = cone(levels, V, start, norm(TBN @ dirs[k]), 0.577)
+            ind += wts[k] * c4; margin = min(margin, m)
+        occlusion = 1 - ind[3]
+        diffuse = (shadow * max(N @ L, 0.0) + occlusion * ind[:3]) * albedo[:3]
+        if np.linalg.norm(spec_c[1:3]) == 0:
+            spec_c = np.array([spec_c[0]] * 3 + [spec_c[3]])     # specColor.rrra, :208
+        R = norm(2 * (N @ L) * N - L)                            # reflect(-L, N)
+        direct_spec = max(E @ R, 0.0) ** mat[3] * shadow
+        isp, _, m = cone(levels, V, start, norm(2 * (N @ E) * N - E), 0.07)
+        margin = min(margin, m)
+        if margin < 1e-4:
+            continue                                             # a cone exit sits on its threshold
+        specular = (isp[:3] + (1 - isp[3]) * direct_spec) * spec_c[:3]
+        rgb = 0.1 * albedo[:3] * occlusion + diffuse + specular
+        want = np.rint(np.clip(np.append(rgb, albedo[3]), 0, 1) * 255)
+        got = frame[j, i].astype(np.float64)
+        assert np.abs(got - want).max() <= 1, ((i, j), got, want)
+        checked += 1
+    assert checked > 150
+
+
+# ------------------------------------------------------------------------------- voxelisation light injection
+def test_light_injection_of_a_floor_under_an_occluder(oracle):
+    """Voxelization.{vs,gs,fs}: a floor quad (normal +y => projected along Y, Voxelization.gs:36) partly shadowed by a
+    smaller quad above it.  Every floor voxel gets one fragment at its pixel centre (centre coverage); its value is
+    unorm8(albedo * lit_taps / 25) with the taps of Voxelization.fs:18-52 evaluated in float64 on the oracle's depth map,
+    stored at voxel (x, y, V-1-j) per the un-swizzle of Voxelization.fs:77-82."""
+    V, S = 32, 512
+    u = setup(oracle, V=V, coverage="center", shadow_map_size=S)
+    oracle.upload_texture(0, np.array([[[200, 100, 50]]], dtype=np.uint8))
+    y_floor, y_occ = -20.3, 11.1
+    v1, i1 = quad_mesh((-60, y_floor, -60), (-60, y_floor, 60), (60, y_floor, 60), (60, y_floor, -60))
+    v2, i2 = quad_mesh((-22, y_occ, -17), (-22, y_occ, 23), (18, y_occ, 23), (18, y_occ, -17))
+    oracle.upload_mesh(np.concatenate([v1, v2]), np.concatenate([i1, i2 + 4]))
+    oracle.draw_depth(); oracle.draw_voxels()
+    g, c = oracle.grid(0), oracle.counts()
+    tex = oracle.depth().astype(np.float64) / 16777215.0
+    DMVP = np.asarray(u["DepthModelViewProjectionMatrix"], dtype=np.float64).reshape(4, 4).T
+    yv = int(np.floor((y_floor / G + 0.5) * V))
+    albedo = np.array([200, 100, 50]) / 255.0
+    checked = shadowed = partial = 0
+    for j in range(V):
+        for i in range(V):
+            xw = ((i + 0.5) / V * 2 - 1) * 75.0                  # ProjY: x_ndc = x_w / 75, y_ndc = -z_w / 75
+            zw = -((j + 0.5) / V * 2 - 1) * 75.0
+            inside = abs(xw) < 60 - 1e-6 and abs(zw) < 60 - 1e-6
+            voxel = (V - 1 - j, yv, i)                           # [z][y][x]
+            if not inside:
+                if abs(abs(xw) - 60) > 1e-3 and abs(abs(zw) - 60) > 1e-3:
+                    assert c[voxel] == 0
+                continue
+            assert c[voxel] == 1, (i, j)
+            dc = DMVP @ np.array([xw * 20.0, y_floor * 20.0, zw * 20.0, 1.0])
+            dc[:3] = dc[:3] * 0.5 + 0.5                          # Voxelization.vs:19-20
+            lit, safe = pcf_lit_taps(tex, S, dc)
+            if not safe:
+                continue
+            val = albedo * (lit / 25.0) * 255.0
+            if np.any(np.abs(val - np.floor(val) - 0.5) < 1e-3):
+                continue
+            assert np.array_equal(g[voxel][:3], np.rint(val).astype(np.uint8)), ((i, j), lit, g[voxel])
+            assert g[voxel][3] == 255
+            checked += 1; shadowed += lit == 0; partial += 0 < lit < 25
+    assert checked > 500 and shadowed > 20 and partial > 5
