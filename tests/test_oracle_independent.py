@@ -488,3 +488,50 @@ def test_light_injection_of_a_floor_under_an_occluder(oracle):
             assert g[voxel][3] == 255
             checked += 1; shadowed += lit == 0; partial += 0 < lit < 25
     assert checked > 500 and shadowed > 20 and partial > 5
+
+
+# ------------------------------------------------------------------------------------------------ shadow map
+def test_shadow_map_depths_of_a_tilted_plane(oracle):
+    """DrawDepthTexture (Voxel_Cone_Tracing.h:192-211, Shadow.vs): the ortho light projection is affine, so the window
+    depth over a tilted quad is a plane in texel coordinates; every covered texel must hold rint(z * (2^24 - 1)) of that
+    plane at the texel centre (float32 interpolation: +-2 units), uncovered texels the clear value."""
+    S = 128
+    u = setup(oracle, V=32, shadow_map_size=S)
+    p00, e1, e2 = np.array([-50.4, -30.0, -40.1]), np.array([6.0, 35.0, 92.0]), np.array([96.0, 9.0, -8.0])
+    quad = [tuple(p00), tuple(p00 + e1), tuple(p00 + e1 + e2), tuple(p00 + e2)]   # planar; cross(e1, e2) faces the light
+    v, idx = quad_mesh(*quad)
+    oracle.upload_mesh(v, idx)
+    oracle.draw_depth()
+    d = oracle.depth().astype(np.int64)
+    DMVP = np.asarray(u["DepthModelViewProjectionMatrix"], dtype=np.float64).reshape(4, 4).T
+    win = []
+    for p in quad:
+        c = DMVP @ np.array([p[0] * 20.0, p[1] * 20.0, p[2] * 20.0, 1.0])
+        win.append(((c[0] * 0.5 + 0.5) * S, (c[1] * 0.5 + 0.5) * S, c[2] * 0.5 + 0.5))
+    win = np.array(win)
+    # vertex positions are snapped to 1/256 texel before set-up and attributes are interpolated over the snapped
+    # triangle (GL 4.3 14.6.1 allows it; DESIGN.md defines 8 sub-pixel bits): up to 1/512 texel * slope = ~200 units here
+    assert np.abs(win[:, :2] * 256 - np.rint(win[:, :2] * 256)).max() < 0.49
+    win[:, :2] = np.rint(win[:, :2] * 256) / 256
+    A = np.column_stack([win[:3, 0], win[:3, 1], np.ones(3)])
+    coef = np.linalg.solve(A, win[:3, 2])                       # z = a x + b y + c through three corners
+    assert abs(coef @ np.array([win[3, 0], win[3, 1], 1.0]) - win[3, 2]) < 2e-5   # planar up to the snap
+    covered = d < 0xFFFFFF
+    assert covered.sum() > 1500
+    jj, ii = np.nonzero(covered)
+    want = np.rint((coef[0] * (ii + 0.5) + coef[1] * (jj + 0.5) + coef[2]) * 16777215.0)
+    # the second triangle's plane differs from the first's by the snap of the fourth corner: compare each texel with
+    # the nearer of the two planes
+    A2 = np.column_stack([win[[0, 2, 3], 0], win[[0, 2, 3], 1], np.ones(3)])
+    coef2 = np.linalg.solve(A2, win[[0, 2, 3], 2])
+    want2 = np.rint((coef2[0] * (ii + 0.5) + coef2[1] * (jj + 0.5) + coef2[2]) * 16777215.0)
+    assert np.minimum(np.abs(d[jj, ii] - want), np.abs(d[jj, ii] - want2)).max() <= 3
+    # coverage: texel centres strictly inside the projected quad are covered, those outside are not
+    def side(a, b, px, py):
+        return (b[0] - a[0]) * (py - a[1]) - (b[1] - a[1]) * (px - a[0])
+    X, Y = np.meshgrid(np.arange(S) + 0.5, np.arange(S) + 0.5)
+    e = np.stack([side(win[k], win[(k + 1) % 4], X, Y) for k in range(4)])
+    if e[:, S // 2, S // 2].sum() < 0:
+        e = -e
+    inside, outside = (e > 1e-3).all(0), (e < -1e-3).any(0)
+    assert covered[inside].all() and not covered[outside].any()
