@@ -535,3 +535,78 @@ def test_shadow_map_depths_of_a_tilted_plane(oracle):
         e = -e
     inside, outside = (e > 1e-3).all(0), (e < -1e-3).any(0)
     assert covered[inside].all() and not covered[outside].any()
+
+
+# ------------------------------------------------------------------------------- other coverage policies
+def _random_lattice_triangle(rng, V, sub=256, min_area=None):
+    while True:
+        q = rng.integers(2 * sub, (V - 2) * sub, (3, 2))
+        t = [tuple(int(x) for x in p) for p in q]
+        a = edge(t[0], t[1], t[2])
+        if abs(a) > (min_area or sub * sub):
+            return t
+
+
+def _voxelise_window_triangle(oracle, V, tri, rng, sub=256):
+    z_world = 75.0 - (rng.integers(0, V) + 0.5) * G / V
+    verts = np.zeros((3, 14), dtype=np.float32)
+    verts[:, :3] = np.array([(p[0] / sub * G / V - 75.0, p[1] / sub * G / V - 75.0, z_world) for p in tri]) * 20.0
+    verts[:, 3:6] = (0, 0, 1); verts[:, 8:11] = (1, 0, 0); verts[:, 11:14] = (0, 1, 0)
+    oracle.upload_mesh(verts, np.array([[0, 1, 2]], dtype=np.uint32))
+    oracle.draw_depth(); oracle.draw_voxels()
+    c = oracle.counts()
+    zs = np.nonzero(c.sum((1, 2)))[0]
+    assert len(zs) == 1
+    return c[zs[0]]
+
+
+def test_conservative_coverage_is_exact_open_square_overlap(oracle):
+    """CoveragePolicy 2 (the policy of every BASELINE config): a pixel yields a fragment iff the OPEN pixel square and the
+    OPEN triangle intersect.  Exact separating-axis test in integers (axes: the square's two and the triangle's three)."""
+    V, sub = 32, 256
+    rng = np.random.default_rng(17)
+    for trial in range(20):
+        setup(oracle, V=V, coverage="conservative")
+        tri = _random_lattice_triangle(rng, V)
+        if trial % 4 == 0:                                     # vertices on pixel corners: touching squares do not count
+            tri = [((p[0] // sub) * sub, (p[1] // sub) * sub) for p in tri]
+            if edge(*tri) == 0:
+                continue
+        cov = _voxelise_window_triangle(oracle, V, tri, rng)
+        axes = [(1, 0), (0, 1)] + [(-(tri[(k + 1) % 3][1] - tri[k][1]), tri[(k + 1) % 3][0] - tri[k][0]) for k in range(3)]
+        for j in range(V):
+            for i in range(V):
+                sq = [(i * sub, j * sub), ((i + 1) * sub, j * sub), ((i + 1) * sub, (j + 1) * sub), (i * sub, (j + 1) * sub)]
+                overlap = True
+                for ax in axes:
+                    pt = [ax[0] * p[0] + ax[1] * p[1] for p in tri]
+                    ps = [ax[0] * p[0] + ax[1] * p[1] for p in sq]
+                    if not (max(pt) > min(ps) and max(ps) > min(pt)):
+                        overlap = False
+                        break
+                assert int(cov[j, i]) == int(overlap), (trial, i, j, tri)
+
+
+def test_msaa4_any_coverage_against_sample_classification(oracle):
+    """CoveragePolicy 1 (the reference's 4x MSAA window, main.cpp:30): fragment iff any of the four samples of the D3D
+    pattern (+-1/8, +-3/8 rotated grid) is covered.  A sample strictly inside forces a fragment; all four strictly
+    outside forbid it; samples exactly on an edge are left to the fill rule."""
+    V, sub = 32, 256
+    rng = np.random.default_rng(23)
+    offs = [(-2, -6), (6, -2), (-6, 2), (2, 6)]                 # 1/16 pixel units
+    seen_partial = 0
+    for trial in range(20):
+        setup(oracle, V=V, coverage="msaa4")
+        tri = _random_lattice_triangle(rng, V)
+        cov = _voxelise_window_triangle(oracle, V, tri, rng)
+        for j in range(V):
+            for i in range(V):
+                ks = [classify(tri, (i * sub + sub // 2 + ox * sub // 16, j * sub + sub // 2 + oy * sub // 16)) for ox, oy in offs]
+                if max(ks) == 1:
+                    assert cov[j, i] == 1, (trial, i, j)
+                    seen_partial += min(ks) == -1
+                elif max(ks) == -1:
+                    assert cov[j, i] == 0, (trial, i, j)
+                else:
+                    assert cov[j, i] in (0, 1)
+    assert seen_partial > 50
