@@ -610,3 +610,64 @@ def test_msaa4_any_coverage_against_sample_classification(oracle):
                 else:
                     assert cov[j, i] in (0, 1)
     assert seen_partial > 50
+
+
+# ------------------------------------------------------------------- dominant-axis projection of tilted triangles
+def test_tilted_triangles_land_in_the_voxels_of_their_world_positions(oracle):
+    """Voxelization.gs:34-47 + Voxelization.fs:58-86 for general triangles: whatever axis is chosen and however the
+    fragment coordinates are un-swizzled, a fragment generated at a pixel centre must be stored in the voxel that
+    contains its world-space position, floor((world / 150 + 0.5) * V) per component.  Float64 plane
+    intersection per pixel centre of the dominant-axis projection; centres near edges or slice boundaries are skipped."""
+    V = 32
+    rng = np.random.default_rng(29)
+    per_axis = [0, 0, 0]
+    for trial in range(45):
+        setup(oracle, V=V, coverage="center")
+        while True:
+            w = rng.uniform(-60, 60, (3, 3))
+            n = np.cross(w[1] - w[0], w[2] - w[0])
+            an = np.abs(n)
+            axis = int(np.argmax(an))
+            if np.linalg.norm(n) > 800 and an[axis] > 1.3 * np.sort(an)[1] and axis == trial % 3:
+                break
+        verts = np.zeros((3, 14), dtype=np.float32)
+        verts[:, :3] = w * 20.0
+        verts[:, 3:6] = n / np.linalg.norm(n); verts[:, 8:11] = (1, 0, 0); verts[:, 11:14] = (0, 1, 0)
+        w = verts[:, :3].astype(np.float64) * np.float64(np.float32(0.05))      # what the shader sees after ModelMatrix
+        oracle.upload_mesh(verts, np.array([[0, 1, 2]], dtype=np.uint32))
+        oracle.draw_depth(); oracle.draw_voxels()
+        c = oracle.counts()
+        # the two in-plane world axes of each projection as (component, sign): window x, window y   (SURVEY.md A.1)
+        plane = {0: ((2, -1), (1, 1)), 1: ((0, 1), (2, -1)), 2: ((0, 1), (1, 1))}[axis]
+        (cx, sx), (cy, sy) = plane
+        win = np.stack([(sx * w[:, cx] / 75 * 0.5 + 0.5) * V, (sy * w[:, cy] / 75 * 0.5 + 0.5) * V], 1)
+        d = n @ w[0]
+        expected = set()
+        for j in range(V):
+            for i in range(V):
+                p = np.array([i + 0.5, j + 0.5])
+                e = np.array([(win[(k + 1) % 3, 0] - win[k, 0]) * (p[1] - win[k, 1]) - (win[(k + 1) % 3, 1] - win[k, 1]) * (p[0] - win[k, 0])
+                              for k in range(3)])
+                if e.sum() < 0:
+                    e = -e
+                if e.min() < 0.02 * abs(e.sum()):
+                    continue                                    # outside, or too close to an edge to call
+                pos = np.zeros(3)
+                pos[cx] = sx * ((i + 0.5) / V * 2 - 1) * 75.0
+                pos[cy] = sy * ((j + 0.5) / V * 2 - 1) * 75.0
+                pos[axis] = (d - n[cx] * pos[cx] - n[cy] * pos[cy]) / n[axis]
+                f = (pos / G + 0.5) * V
+                if abs(f[axis] - np.rint(f[axis])) < 2e-3:
+                    continue                                    # on a slice boundary
+                vx, vy, vz = np.floor(f).astype(int)
+                assert c[vz, vy, vx] >= 1, (trial, axis, (i, j), (vx, vy, vz))
+                expected.add((vz, vy, vx))
+        assert len(expected) > 5
+        per_axis[axis] += 1
+        # nothing far from the triangle: every occupied voxel lies within one voxel of its world-space bounding box
+        zz, yy, xx = np.nonzero(c)
+        lo = np.floor((w.min(0) / G + 0.5) * V) - 1
+        hi = np.floor((w.max(0) / G + 0.5) * V) + 1
+        assert np.all(xx >= lo[0]) and np.all(xx <= hi[0]) and np.all(yy >= lo[1]) and np.all(yy <= hi[1])
+        assert np.all(zz >= lo[2]) and np.all(zz <= hi[2])
+    assert per_axis == [15, 15, 15]
