@@ -363,12 +363,21 @@ def pcf_lit_taps(tex, S, dc, bias=0.002):
     return lit, safe
 
 
-def test_fragment_shader_against_float64_restatement(oracle):
-    """VoxelConeTracing.fs main() (:165-229) restated in float64 for pixels of the Cornell box: TBN = inverse(transpose(
-    mat3(T, B, N))) with the un-normalised world-space frame (length 0.05), cone start offset Normal_world * voxel size,
-    PCF gain 0.111 (range [0, 2.775]), six weighted diffuse cones + one specular cone, specColor.rrra for single-channel
-    maps, ambient 0.1; compared with the oracle's frame to 1 LSB."""
-    sc = scenes.cornell()
+def bilinear_repeat(tex, s, t):
+    """level 0 of a material texture, GL_LINEAR + GL_REPEAT; channel rules of Model.h:159-169 (RED -> (r,0,0,1), RGB -> a=1)"""
+    h, w = tex.shape[:2]
+    x, y = s * w - 0.5, t * h - 0.5
+    i, j = int(np.floor(x)), int(np.floor(y))
+    a, b = x - i, y - j
+    at = lambda ii, jj: tex[jj % h, ii % w].astype(np.float64) / 255.0
+    c = (1 - b) * ((1 - a) * at(i, j) + a * at(i + 1, j)) + b * ((1 - a) * at(i, j + 1) + a * at(i + 1, j + 1))
+    c = np.atleast_1d(c)
+    if len(c) == 1:
+        return np.array([c[0], 0.0, 0.0, 1.0])
+    return np.append(c[:3], 1.0) if len(c) == 3 else c
+
+
+def _check_fragment_shader(oracle, sc, min_checked):
     W, H, V, S = 48, 40, 32, 256
     u = uniforms.scene_uniforms(sc, V=V, width=W, height=H, shadow_map_size=S)
     u["FilterMode"] = 0
@@ -386,36 +395,51 @@ def test_fragment_shader_against_float64_restatement(oracle):
     assert len(dirs) == 6 and wts[0] == pytest.approx(0.25)
     norm = lambda v: v / np.linalg.norm(v)
 
-    def texel(tex_id):
-        t = sc.textures[tex_id].reshape(-1).astype(np.float64) / 255.0      # all 1x1 here
-        return np.array([t[0], 0, 0, 1.0]) if len(t) == 1 else np.append(t[:3], 1.0 if len(t) == 3 else t[3])
-
-    checked = 0
-    rng = np.random.default_rng(2)
-    for _ in range(400):
-        i, j = int(rng.integers(0, W)), int(rng.integers(0, H))
-        tri_id = int(vis[j, i])
-        if tri_id == 0xFFFFFFFF:
-            continue
+    def hit(i, j, p0, e1, e2):
+        """ray through the centre of pixel (i, j) against the triangle's plane: barycentrics (perspective correct)"""
         ndc = np.array([(i + 0.5) / W * 2 - 1, (j + 0.5) / H * 2 - 1])
         a, b = inv @ np.array([*ndc, -1.0, 1.0]), inv @ np.array([*ndc, 1.0, 1.0])
         o, d = a[:3] / a[3], b[:3] / b[3] - a[:3] / a[3]
+        pv = np.cross(d, e2); det = e1 @ pv
+        tv = o - p0; bu = (tv @ pv) / det; bv = (np.cross(tv, e1) @ d) / det
+        return np.array([1 - bu - bv, bu, bv])
+
+    checked = 0
+    rng = np.random.default_rng(2)
+    for _ in range(600):
+        i, j = int(rng.integers(0, W - 1)), int(rng.integers(0, H - 1))
+        tri_id = int(vis[j, i])
+        if tri_id == 0xFFFFFFFF:
+            continue
         idx = sc.idx[tri_id].astype(int)
         p0, p1, p2 = sc.verts[idx, :3].astype(np.float64)
-        e1, e2 = p1 - p0, p2 - p0
-        pv = np.cross(d, e2); det = e1 @ pv
-        tv = o - p0; bu = (tv @ pv) / det; qv = np.cross(tv, e1); bv = (qv @ d) / det
-        if min(bu, bv, 1 - bu - bv) < 0.02:
+        bary = hit(i, j, p0, p1 - p0, p2 - p0)
+        if bary.min() < 0.02:
             continue                                            # keep away from edges (visibility ties)
-        bary = np.array([1 - bu - bv, bu, bv])
-        attr = lambda lo, hi: bary @ sc.verts[idx, lo:hi].astype(np.float64)
-        Pw = (M @ np.append(bary @ np.stack([p0, p1, p2]), 1.0))[:3]       # VoxelConeTracing.vs:27-34
-        Nw, Tw, Bw = (M[:3, :3] @ attr(3, 6)), (M[:3, :3] @ attr(8, 11)), (M[:3, :3] @ attr(11, 14))
-        Pd = DMVP @ np.append(bary @ np.stack([p0, p1, p2]), 1.0); Pd[:3] = Pd[:3] * 0.5 + 0.5
+        attr = lambda bb, lo, hi: bb @ sc.verts[idx, lo:hi].astype(np.float64)
+        uv = attr(bary, 6, 8)
         mat = sc.materials[int(sc.tri_material[tri_id])]
-        albedo, spec_c = texel(mat[0]), texel(mat[1])
+        t_diff, t_spec, t_height = (sc.textures[mat[k]] for k in range(3))
+        # implicit LOD (GL 4.3 8.14) from forward differences of uv: only magnified pixels (lambda <= 0 -> level 0) are compared
+        uvx, uvy = attr(hit(i + 1, j, p0, p1 - p0, p2 - p0), 6, 8), attr(hit(i, j + 1, p0, p1 - p0, p2 - p0), 6, 8)
+        rho = 0.0
+        for t in (t_diff, t_spec, t_height):
+            size = np.array([t.shape[1], t.shape[0]], dtype=np.float64)
+            rho = max(rho, np.linalg.norm((uvx - uv) * size), np.linalg.norm((uvy - uv) * size))
+        if max(t.shape[0] * t.shape[1] for t in (t_diff, t_spec, t_height)) > 1 and rho > 0.85:
+            continue
+        Pm = bary @ np.stack([p0, p1, p2])
+        Pw = (M @ np.append(Pm, 1.0))[:3]                       # VoxelConeTracing.vs:27-34
+        Nw, Tw, Bw = (M[:3, :3] @ attr(bary, 3, 6)), (M[:3, :3] @ attr(bary, 8, 11)), (M[:3, :3] @ attr(bary, 11, 14))
+        Pd = DMVP @ np.append(Pm, 1.0); Pd[:3] = Pd[:3] * 0.5 + 0.5
+        albedo, spec_c = bilinear_repeat(t_diff, *uv), bilinear_repeat(t_spec, *uv)
         TBN = np.linalg.inv(np.stack([Tw, Bw, Nw]))             # inverse(transpose(mat3(T, B, N))), :175
-        N = norm(TBN @ np.array([0.0, 0.0, 1.0]))               # flat height map: bump normal (0, 0, 1), :110-128
+        offx, offy = 1.0 / t_height.shape[1], 1.0 / t_height.shape[0]      # CalcBumpNormal, :110-128
+        h0 = bilinear_repeat(t_height, *uv)[0]
+        dx = bilinear_repeat(t_height, uv[0] + offx, uv[1])[0] - h0
+        dy = bilinear_repeat(t_height, uv[0], uv[1] + offy)[0] - h0
+        bump = norm(np.cross(norm(np.array([1.0, 0.0, dx])), norm(np.array([0.0, 1.0, dy]))))
+        N = norm(TBN @ bump)
         E = norm(cam - Pw)
         lit, safe = pcf_lit_taps(shadow_tex, S, Pd)
         if not safe:
@@ -438,11 +462,33 @@ def test_fragment_shader_against_float64_restatement(oracle):
             continue                                             # a cone exit sits on its threshold
         specular = (isp[:3] + (1 - isp[3]) * direct_spec) * spec_c[:3]
         rgb = 0.1 * albedo[:3] * occlusion + diffuse + specular
-        want = np.rint(np.clip(np.append(rgb, albedo[3]), 0, 1) * 255)
+        want = np.clip(np.append(rgb, albedo[3]), 0, 1) * 255
         got = frame[j, i].astype(np.float64)
-        assert np.abs(got - want).max() <= 1, ((i, j), got, want)
+        assert np.abs(got - want).max() <= 1.0, ((i, j), got, want)
         checked += 1
-    assert checked > 150
+    assert checked > min_checked, checked
+
+
+def test_fragment_shader_against_float64_restatement(oracle):
+    """VoxelConeTracing.fs main() (:165-229) restated in float64 for pixels of the Cornell box: TBN = inverse(transpose(
+    mat3(T, B, N))) with the un-normalised world-space frame (length 0.05), cone start offset Normal_world * voxel size,
+    PCF gain 0.111 (range [0, 2.775]), six weighted diffuse cones + one specular cone, specColor.rrra for single-channel
+    maps, ambient 0.1; compared with the oracle's frame to 1 LSB."""
+    _check_fragment_shader(oracle, scenes.cornell(), 150)
+
+
+def test_fragment_shader_with_textures_and_bump_mapping(oracle):
+    """The same with multi-texel albedo / specular / height maps on every surface: bilinear REPEAT fetches, the three-tap
+    CalcBumpNormal (:110-128) pushed through the TBN, RGB specular maps used as they are.  Only magnified pixels are
+    compared (implicit LOD <= 0 from forward differences of the interpolated uv)."""
+    sc = scenes.cornell()
+    rng = np.random.default_rng(8)
+    tex = [rng.integers(40, 256, (8, 8, 3), dtype=np.uint8) for _ in range(3)]          # albedo per material
+    spec = rng.integers(0, 256, (4, 8, 3), dtype=np.uint8)
+    height = rng.integers(0, 256, (8, 4, 1), dtype=np.uint8)
+    sc.textures = tex + [spec, height]
+    sc.materials = [(0, 3, 4, 20.0), (1, 3, 4, 20.0), (2, 3, 4, 20.0)]
+    _check_fragment_shader(oracle, sc, 100)
 
 
 # ------------------------------------------------------------------------------- voxelisation light injection
@@ -671,3 +717,65 @@ def test_tilted_triangles_land_in_the_voxels_of_their_world_positions(oracle):
         assert np.all(xx >= lo[0]) and np.all(xx <= hi[0]) and np.all(yy >= lo[1]) and np.all(yy <= hi[1])
         assert np.all(zz >= lo[2]) and np.all(zz <= hi[2])
     assert per_axis == [15, 15, 15]
+
+
+# ------------------------------------------------------------------------------------------- alpha cut-outs
+def test_alpha_discard_reveals_the_surface_behind(oracle):
+    """VoxelConeTracing.fs:167-172: fragments whose albedo alpha is below 0.5 are discarded before the depth write, so
+    the nearest OPAQUE fragment wins.  A card with a 4x4 alpha pattern in front of a wall: per pixel, the bilinear alpha
+    at the ray's hit point decides whether the card or the wall is visible."""
+    rng = np.random.default_rng(31)
+    W, H = 64, 48
+    card_tex = np.zeros((4, 4, 4), dtype=np.uint8)
+    card_tex[..., :3] = 180
+    card_tex[..., 3] = np.where(rng.random((4, 4)) < 0.5, 0, 255)
+    assert 3 < (card_tex[..., 3] == 0).sum() < 13
+    wall_tex = np.array([[[90, 120, 200]]], dtype=np.uint8)
+    flat = np.array([[[128]]], dtype=np.uint8)
+    cv, ci = quad_mesh((-30, -25, 20), (30, -25, 20), (30, 25, 20), (-30, 25, 20))        # card, normal +z
+    wv, wi = quad_mesh((-70, -60, -40), (70, -60, -40), (70, 60, -40), (-70, 60, -40))    # wall behind it
+    sc = scenes.Scene("card", np.concatenate([cv, wv]), np.concatenate([ci, wi + 4]).astype(np.uint32),
+                      np.array([0, 0, 1, 1], dtype=np.uint16), [card_tex, wall_tex, flat],
+                      [(0, 2, 2, 20.0), (1, 2, 2, 20.0)], camera_pos=(6.0, 3.0, 140.0), yaw=-92.0, pitch=-1.0)
+    u = uniforms.scene_uniforms(sc, V=32, width=W, height=H, shadow_map_size=256)
+    u["FilterMode"] = 0
+    oracle.set_uniforms(u); oracle.load_scene(sc); oracle.draw_depth(); oracle.draw_voxels(); oracle.render()
+    vis, frame = oracle.visibility(), oracle.frame()
+    col = lambda name: np.asarray(u[name], dtype=np.float64).reshape(4, 4).T
+    inv = np.linalg.inv(col("ProjectionMatrix") @ col("ModelViewMatrix"))
+    seen = {"card": 0, "hole": 0}
+    for j in range(H):
+        for i in range(W):
+            ndc = np.array([(i + 0.5) / W * 2 - 1, (j + 0.5) / H * 2 - 1])
+            a, b = inv @ np.array([*ndc, -1.0, 1.0]), inv @ np.array([*ndc, 1.0, 1.0])
+            o, d = a[:3] / a[3], b[:3] / b[3] - a[:3] / a[3]
+            hits = []
+            for t_id in range(4):
+                p0, p1, p2 = sc.verts[sc.idx[t_id].astype(int), :3].astype(np.float64)
+                e1, e2 = p1 - p0, p2 - p0
+                pv = np.cross(d, e2); det = e1 @ pv
+                tv = o - p0; bu = (tv @ pv) / det; qv = np.cross(tv, e1); bv = (qv @ d) / det
+                bary = np.array([1 - bu - bv, bu, bv])
+                hits.append((t_id, bary, (qv @ e2) / det))
+            if any(-0.03 < h[1].min() < 0.03 for h in hits):
+                continue                                        # near an edge or a diagonal of either quad
+            want = 0xFFFFFFFF
+            for t_id, bary, _ in sorted((h for h in hits if h[1].min() > 0), key=lambda h: h[2]):
+                if t_id < 2:
+                    uv = bary @ sc.verts[sc.idx[t_id].astype(int), 6:8].astype(np.float64)
+                    alpha = bilinear_repeat(card_tex, *uv)[3]
+                    if abs(alpha - 0.5) < 0.03:
+                        want = None
+                        break
+                    if alpha < 0.5:
+                        seen["hole"] += 1
+                        continue                                # discarded: look further along the ray
+                    seen["card"] += 1
+                want = t_id
+                break
+            if want is None:
+                continue
+            assert int(vis[j, i]) == want, ((i, j), int(vis[j, i]), want)
+            if want == 0xFFFFFFFF:
+                assert tuple(frame[j, i]) == (128, 128, 128, 255)      # glClearColor 0.5 grey, Voxel_Cone_Tracing.h:156-159
+    assert seen["card"] > 100 and seen["hole"] > 100
