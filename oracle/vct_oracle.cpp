@@ -1,7 +1,11 @@
 /*
  * vct_oracle.cpp -- CPU ORACLE: scalar restatement of the reference's three passes.
  *
- * TEST INFRASTRUCTURE ONLY (see vct_oracle.h).  PARITY UNPINNED by the reference (it has no tests).
+ * TEST INFRASTRUCTURE ONLY (see vct_oracle.h).  PARITY UNPINNED by the reference (it has no tests,
+ * cannot be built here and reads nothing back).  What pins this file instead: the hand-derived
+ * known-answer tests (tests/test_oracle_kat.py), the committed golden fixtures (tests/golden/) and a
+ * second, independent restatement of the same shader lines in float64 numpy / exact integers
+ * (tests/test_oracle_independent.py).
  *
  * Each function cites the reference file:line it restates; paths are relative to
  * /root/reference/Voxel_Cone_Tracing_Final/.  Where the reference leans on GL fixed function
