@@ -779,3 +779,44 @@ def test_alpha_discard_reveals_the_surface_behind(oracle):
             if want == 0xFFFFFFFF:
                 assert tuple(frame[j, i]) == (128, 128, 128, 255)      # glClearColor 0.5 grey, Voxel_Cone_Tracing.h:156-159
     assert seen["card"] > 100 and seen["hole"] > 100
+
+
+# ------------------------------------------------------------------------------- Bounces >= 3 (extension)
+def test_reinjection_bounce_against_float64_gather(oracle):
+    """Bounces = 3 (DESIGN.md "Bounces"; the reference only claims it, README.md:14): every occupied voxel gathers one
+    diffuse-aperture cone along each of +-X, +-Y, +-Z from one voxel outside its centre through the pyramid of the
+    previous bounce, averages them, and stores min(old + gathered * old, 1); alpha is untouched."""
+    V = 16
+    rng = np.random.default_rng(41)
+    u = setup(oracle, V=V)
+    u["FilterMode"] = 0
+    oracle.set_uniforms(u)
+    counts = (rng.random((V, V, V)) < 0.06).astype(np.uint32) * rng.integers(1, 4, (V, V, V)).astype(np.uint32)
+    sums = (rng.integers(20, 256, (V, V, V, 3)) * counts[..., None]).astype(np.uint32)
+    oracle.set_accum(counts, sums); oracle.resolve_and_mip()
+    g2 = oracle.grid(0).copy()
+    levels = mip_chain(g2)
+    u["Bounces"] = 3
+    oracle.set_uniforms(u)
+    oracle.set_accum(counts, sums); oracle.resolve_and_mip()
+    g3 = oracle.grid(0)
+    assert np.array_equal(g3[..., 3], g2[..., 3])
+    vws = G / V
+    checked = brighter = 0
+    for z, y, x in zip(*np.nonzero(counts)):
+        centre = (np.array([x, y, z]) + 0.5) * vws - G / 2
+        acc, margin = np.zeros(3), 1.0
+        for axis in range(3):
+            for sign in (1.0, -1.0):
+                d = np.zeros(3); d[axis] = sign
+                c4, _, m = cone(levels, V, centre + d * vws, d, 0.577)
+                acc += c4[:3] / 6.0; margin = min(margin, m)
+        if margin < 1e-4:
+            continue
+        base = g2[z, y, x, :3].astype(np.float64) / 255.0
+        val = np.minimum(base + acc * base, 1.0) * 255.0
+        if np.any(np.abs(val - np.floor(val) - 0.5) < 2e-3):
+            continue
+        assert np.array_equal(g3[z, y, x, :3], np.rint(val).astype(np.uint8)), ((x, y, z), g3[z, y, x], val)
+        checked += 1; brighter += bool((g3[z, y, x, :3] > g2[z, y, x, :3]).any())
+    assert checked > 150 and brighter > 50
