@@ -377,7 +377,30 @@ def bilinear_repeat(tex, s, t):
     return np.append(c[:3], 1.0) if len(c) == 3 else c
 
 
-def _check_fragment_shader(oracle, sc, min_checked):
+def material_levels(tex):
+    """RGBA8 + 2x2 box mips (sum of 4 + 2) >> 2 (glGenerateMipmap on the material textures, Model.h:171)"""
+    levels = [tex.astype(np.int64)]
+    while levels[-1].shape[0] > 1 or levels[-1].shape[1] > 1:
+        p = levels[-1]
+        h, w = max(p.shape[0] // 2, 1), max(p.shape[1] // 2, 1)
+        if p.shape[0] == 1:
+            p = np.concatenate([p, p], 0)
+        if p.shape[1] == 1:
+            p = np.concatenate([p, p], 1)
+        levels.append((p.reshape(h, 2, w, 2, -1).sum((1, 3)) + 2) >> 2)
+    return [l.astype(np.uint8) for l in levels]
+
+
+def trilinear_repeat(levels, s, t, lod):
+    lod = min(max(lod, 0.0), len(levels) - 1.0)
+    l0 = int(np.floor(lod)); f = lod - l0
+    c = bilinear_repeat(levels[l0], s, t)
+    if f > 0 and l0 + 1 < len(levels):
+        c = (1 - f) * c + f * bilinear_repeat(levels[l0 + 1], s, t)
+    return c
+
+
+def _check_fragment_shader(oracle, sc, min_checked, use_lod=False, tol=1.0):
     W, H, V, S = 48, 40, 32, 256
     u = uniforms.scene_uniforms(sc, V=V, width=W, height=H, shadow_map_size=S)
     u["FilterMode"] = 0
@@ -422,22 +445,28 @@ def _check_fragment_shader(oracle, sc, min_checked):
         t_diff, t_spec, t_height = (sc.textures[mat[k]] for k in range(3))
         # implicit LOD (GL 4.3 8.14) from forward differences of uv: only magnified pixels (lambda <= 0 -> level 0) are compared
         uvx, uvy = attr(hit(i + 1, j, p0, p1 - p0, p2 - p0), 6, 8), attr(hit(i, j + 1, p0, p1 - p0, p2 - p0), 6, 8)
-        rho = 0.0
+        rho, lods = 0.0, []
         for t in (t_diff, t_spec, t_height):
             size = np.array([t.shape[1], t.shape[0]], dtype=np.float64)
-            rho = max(rho, np.linalg.norm((uvx - uv) * size), np.linalg.norm((uvy - uv) * size))
-        if max(t.shape[0] * t.shape[1] for t in (t_diff, t_spec, t_height)) > 1 and rho > 0.85:
+            r = max(np.linalg.norm((uvx - uv) * size), np.linalg.norm((uvy - uv) * size))
+            lods.append(np.log2(max(r, 1e-12)))
+            rho = max(rho, r)
+        if not use_lod and max(t.shape[0] * t.shape[1] for t in (t_diff, t_spec, t_height)) > 1 and rho > 0.85:
             continue
+        if use_lod:                                             # minified too: trilinear with the implicit LOD
+            sample = lambda t, k, s_, t_: trilinear_repeat(material_levels(t), s_, t_, lods[k])
+        else:
+            sample = lambda t, k, s_, t_: bilinear_repeat(t, s_, t_)
         Pm = bary @ np.stack([p0, p1, p2])
         Pw = (M @ np.append(Pm, 1.0))[:3]                       # VoxelConeTracing.vs:27-34
         Nw, Tw, Bw = (M[:3, :3] @ attr(bary, 3, 6)), (M[:3, :3] @ attr(bary, 8, 11)), (M[:3, :3] @ attr(bary, 11, 14))
         Pd = DMVP @ np.append(Pm, 1.0); Pd[:3] = Pd[:3] * 0.5 + 0.5
-        albedo, spec_c = bilinear_repeat(t_diff, *uv), bilinear_repeat(t_spec, *uv)
+        albedo, spec_c = sample(t_diff, 0, *uv), sample(t_spec, 1, *uv)
         TBN = np.linalg.inv(np.stack([Tw, Bw, Nw]))             # inverse(transpose(mat3(T, B, N))), :175
         offx, offy = 1.0 / t_height.shape[1], 1.0 / t_height.shape[0]      # CalcBumpNormal, :110-128
-        h0 = bilinear_repeat(t_height, *uv)[0]
-        dx = bilinear_repeat(t_height, uv[0] + offx, uv[1])[0] - h0
-        dy = bilinear_repeat(t_height, uv[0], uv[1] + offy)[0] - h0
+        h0 = sample(t_height, 2, *uv)[0]
+        dx = sample(t_height, 2, uv[0] + offx, uv[1])[0] - h0
+        dy = sample(t_height, 2, uv[0], uv[1] + offy)[0] - h0
         bump = norm(np.cross(norm(np.array([1.0, 0.0, dx])), norm(np.array([0.0, 1.0, dy]))))
         N = norm(TBN @ bump)
         E = norm(cam - Pw)
@@ -464,7 +493,7 @@ def _check_fragment_shader(oracle, sc, min_checked):
         rgb = 0.1 * albedo[:3] * occlusion + diffuse + specular
         want = np.clip(np.append(rgb, albedo[3]), 0, 1) * 255
         got = frame[j, i].astype(np.float64)
-        assert np.abs(got - want).max() <= 1.0, ((i, j), got, want)
+        assert np.abs(got - want).max() <= tol, ((i, j), got, want)
         checked += 1
     assert checked > min_checked, checked
 
@@ -489,6 +518,17 @@ def test_fragment_shader_with_textures_and_bump_mapping(oracle):
     sc.textures = tex + [spec, height]
     sc.materials = [(0, 3, 4, 20.0), (1, 3, 4, 20.0), (2, 3, 4, 20.0)]
     _check_fragment_shader(oracle, sc, 100)
+
+
+def test_fragment_shader_with_minified_textures_and_implicit_lod(oracle):
+    """32x32 maps on a 48x40 frame: most pixels minify.  The implicit LOD (GL 4.3 8.14: log2 of the longer of the two
+    texel-space forward differences of the interpolated uv, per texture size) selects two box-filtered mip levels."""
+    sc = scenes.cornell()
+    rng = np.random.default_rng(9)
+    smooth = lambda c: np.clip(rng.integers(60, 200, (32, 32, c)) + rng.integers(-40, 40, (32, 32, c)), 0, 255).astype(np.uint8)
+    sc.textures = [smooth(3), smooth(3), smooth(3), smooth(3), smooth(1)]
+    sc.materials = [(0, 3, 4, 20.0), (1, 3, 4, 20.0), (2, 3, 4, 20.0)]
+    _check_fragment_shader(oracle, sc, 100, use_lod=True, tol=2.0)
 
 
 # ------------------------------------------------------------------------------- voxelisation light injection
