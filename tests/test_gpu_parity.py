@@ -473,18 +473,63 @@ def test_pipelined_frames_equal_synchronous_frames(gpu_ctx):
         assert np.array_equal(hosts[i].numpy(), ref[i])
 
 
-def test_cpp_facade_with_the_reference_class_surface_runs():
-    """host/Voxel_Cone_Tracing.h (same struct / method names as the reference) driven by host/facade_demo.cpp."""
+def test_cpp_facade_with_the_reference_class_surface_runs(gpu_ctx, oracle, tmp_path):
+    """host/Voxel_Cone_Tracing.h (same struct / method names as the reference) driven by host/facade_demo.cpp.  The
+    demo dumps its flattened scene, the uniforms of each frame and the frames; the same inputs replayed through the
+    ctypes binding must give the same bytes, and the oracle the same frame within the bar."""
     import subprocess
     root = os.path.dirname(HERE)
     exe = os.path.join(root, "voxel-cone-tracing_b200", "lib", "facade_demo")
     if not os.path.exists(exe):
         import __graft_entry__
         __graft_entry__.build()
-    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    out = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     sums = [int(l.split()[-1]) for l in out.stdout.splitlines() if l.startswith("frame")]
     assert len(sums) == 3 and all(s > 256 * 256 * 4 * 20 for s in sums) and len(set(sums)) == 3   # three different views
+    rd = lambda name, dt: np.fromfile(os.path.join(str(tmp_path), name), dtype=dt)
+    verts, idx, trimat = rd("verts.f32", np.float32).reshape(-1, 14), rd("idx.u32", np.uint32).reshape(-1, 3), rd("trimat.u16", np.uint16)
+    tex = [np.full((1, 1, 3), c, np.uint8) for c in ((200, 200, 200), (200, 30, 30), (30, 200, 30))] + \
+          [np.full((1, 1), 128, np.uint8), np.full((1, 1, 3), 128, np.uint8)]
+    sc = scenes.Scene("facade", verts, idx, trimat, tex, [(0, 3, 4, 20.0), (1, 3, 4, 20.0), (2, 3, 4, 20.0)])
+    names = ["ModelViewMatrix", "ProjectionMatrix", "DepthModelViewProjectionMatrix", "ProjX", "ProjY", "ProjZ"]
+    for f in range(3):
+        raw = rd(f"uniforms_{f}.f32", np.float32)
+        u = uniforms.reference_uniforms(V=64, width=256, height=256, shadow_map_size=4096, coverage="msaa4")
+        for k, name in enumerate(names):
+            u[name] = raw[16 * k:16 * k + 16].copy()
+        u["CameraPosition"] = raw[96:99].copy()
+        want = rd(f"frame_{f}.rgba", np.uint8).reshape(256, 256, 4)
+        run_gpu(gpu_ctx, sc, u)
+        assert np.array_equal(gpu_ctx.read_frame(), want), f"frame {f}: C++ facade and ctypes binding disagree"
+        assert int(want.astype(np.uint64).sum()) == sums[f]
+        run_oracle(oracle, sc, u)
+        assert_frame_close(want, oracle.frame(), f"facade frame {f} vs oracle")
+
+
+def test_tile_item_queue_overflow_is_detected_and_harmless(gpu_ctx):
+    """MaxTileItems too small for the scene's large triangles: the pass must report VCT_ERR_OVERFLOW (not fault on the
+    stale part of the queue) and the context must keep working once the queue is large enough."""
+    sc = scenes.cornell()
+    u = uniforms.scene_uniforms(sc, V=256, width=512, height=512, shadow_map_size=2048)
+    c = gpu_ctx
+    c.set_uniforms(u); c.load_scene(sc)
+    c.draw_depth(); c.draw_voxels(); c.render(); c.sync()
+    good_counts, good_frame = c.counts(), c.read_frame()
+    assert c.debug_counter(0) > 0
+    c.set_i("MaxTileItems", 1024)
+    c.draw_depth()                                # 2048^2 shadow map: one wall triangle alone needs ~1024 items
+    with pytest.raises(capi.VctError) as e:
+        c.sync()
+    assert e.value.code == -4
+    c.draw_depth()
+    out = np.zeros_like(good_frame)
+    with pytest.raises(capi.VctError) as e:
+        c.frame(out)                              # the synchronous host-buffer path reports the truncated pass too
+    assert e.value.code == -4
+    c.set_i("MaxTileItems", 4 << 20)
+    c.draw_depth(); c.draw_voxels(); c.render(); c.sync()
+    assert np.array_equal(c.counts(), good_counts) and np.array_equal(c.read_frame(), good_frame)
 
 
 # ------------------------------------------------------------------------------------------ RGBA16F grid (config 3)

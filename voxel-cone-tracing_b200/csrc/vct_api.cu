@@ -187,6 +187,14 @@ int ensure_queues(vct_context* c) {
   return VCT_OK;
 }
 
+int sync_all_streams(vct_context* c) {
+  VCT_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->stream_vox) VCT_CUDA(c, cudaStreamSynchronize(c->stream_vox));
+  if (c->stream2) VCT_CUDA(c, cudaStreamSynchronize(c->stream2));
+  if (c->copy_stream) VCT_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+  return VCT_OK;
+}
+
 int check_overflow(vct_context* c) {
   unsigned int ov = 0, ov2 = 0;
   VCT_CUDA(c, cudaMemcpyAsync(&ov, &c->d_counters->overflow, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -312,6 +320,7 @@ int sync_materials(vct_context* c) {
     host[i].shininess = m.shininess;
     host[i].alpha_test = alpha ? 1 : 0;
   }
+  if (c->d_materials) { int rc = sync_all_streams(c); if (rc) return rc; }   // in-flight kernels read the table
   if (c->n_materials_dev < n) {
     cudaFree(c->d_materials); c->d_materials = nullptr;
     VCT_CUDA(c, cudaMalloc(&c->d_materials, n * sizeof(MaterialDev)));
@@ -483,6 +492,7 @@ int vct_destroy(vct_handle c) {
   if (c->stream_vox) { cudaStreamDestroy(c->stream_vox); cudaEventDestroy(c->ev_vox_done); cudaEventDestroy(c->ev_vtx_done); }
   for (int k = 0; k < 3; ++k) { cudaFree(c->d_frame2[k]); if (c->ev_rendered[k]) cudaEventDestroy(c->ev_rendered[k]); if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]); }
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->h_overflow) cudaFreeHost(c->h_overflow);
   if (c->stream2) { cudaStreamDestroy(c->stream2); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
   cudaFree(c->d_items_vis); cudaFree(c->d_counters_vis);
   for (int p = 0; p < VCT_PASS_COUNT; ++p) { cudaEventDestroy(c->ev_begin[p]); cudaEventDestroy(c->ev_end[p]); }
@@ -621,6 +631,8 @@ int vct_upload_texture(vct_handle c, int id, int w, int h, int ch, const uint8_t
   if (id < 0 || id > 65535 || w < 1 || h < 1 || w > 32768 || h > 32768 || (ch != 1 && ch != 3 && ch != 4) || !px)
     return set_error(c, VCT_ERR_INVALID, "vct_upload_texture: bad arguments");
   if ((int)c->textures.size() <= id) c->textures.resize(id + 1);
+  // frames queued by vct_frame(NULL) / vct_frame_async / vct_frame_shared_begin may still sample the old texture
+  if (c->textures[id].tex) { int rc = sync_all_streams(c); if (rc) return rc; }
   free_texture(c->textures[id]);
   c->materials_dirty = true;
   c->scene_epoch++;
@@ -644,6 +656,7 @@ int vct_upload_mesh(vct_handle c, const float* verts, size_t nv, const uint32_t*
   for (size_t i = 0; i < nt * 3; ++i)
     if (idx[i] >= nv) return set_error(c, VCT_ERR_INVALID, "vct_upload_mesh: index out of range");
   if (tm) for (size_t i = 0; i < nt; ++i) max_mat = tm[i] > max_mat ? tm[i] : max_mat;
+  if (c->d_verts) { int rc = sync_all_streams(c); if (rc) return rc; }
   cudaFree(c->d_verts); cudaFree(c->d_idx); cudaFree(c->d_trimat);
   c->d_verts = nullptr; c->d_idx = nullptr; c->d_trimat = nullptr; c->nv = c->nt = 0;
   VCT_CUDA(c, cudaMalloc(&c->d_verts, nv * 14 * sizeof(float)));
@@ -746,6 +759,8 @@ int vct_shared_accum_bytes(vct_handle c, size_t* bytes) {
 
 int vct_set_shared_accum(vct_handle c, void* local_ptr, void* multicast_ptr) {
   NEED(c);
+  if (c->shared_frame_open) return set_error(c, VCT_ERR_STATE, "vct_set_shared_accum: a shared frame is open (call vct_frame_shared_end first)");
+  if (c->shared_local) { int rc = sync_all_streams(c); if (rc) return rc; }   // queued exchange kernels use the old buffer
   c->shared_local = (unsigned long long*)local_ptr;
   c->shared_mc = (unsigned long long*)multicast_ptr;
   c->exchange_parity = 0;
@@ -840,6 +855,7 @@ int vct_frame_shared_end(vct_handle c, uint8_t* host_rgba) {
   if (host_rgba) {
     VCT_CUDA(c, cudaMemcpyAsync(host_rgba, c->d_frame, (size_t)c->P.W * c->P.H * 4, cudaMemcpyDeviceToHost, c->stream));
     VCT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return check_overflow(c);       // a truncated queue must not pass for a frame (device-only paths: vct_sync)
   }
   return VCT_OK;
 }
@@ -872,6 +888,7 @@ int vct_render(vct_handle c, uint8_t* host_rgba) {
   if (host_rgba) {
     VCT_CUDA(c, cudaMemcpyAsync(host_rgba, c->d_frame, (size_t)c->P.W * c->P.H * 4, cudaMemcpyDeviceToHost, c->stream));
     VCT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return check_overflow(c);       // a truncated queue must not pass for a frame (device-only paths: vct_sync)
   }
   return VCT_OK;
 }
@@ -948,6 +965,7 @@ int vct_frame(vct_handle c, uint8_t* host_rgba) {
   if (host_rgba) {
     VCT_CUDA(c, cudaMemcpyAsync(host_rgba, c->d_frame, (size_t)c->P.W * c->P.H * 4, cudaMemcpyDeviceToHost, c->stream));
     VCT_CUDA(c, cudaStreamSynchronize(c->stream));
+    return check_overflow(c);       // a truncated queue must not pass for a frame (device-only paths: vct_sync)
   }
   return VCT_OK;
 }
@@ -961,6 +979,8 @@ static int ensure_async(vct_context* c) {
       VCT_CUDA(c, cudaEventCreateWithFlags(&c->ev_rendered[k], cudaEventDisableTiming));
       VCT_CUDA(c, cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
     }
+    VCT_CUDA(c, cudaMallocHost(&c->h_overflow, VCT_ASYNC_FRAMES * 2 * sizeof(unsigned int)));
+    std::memset(c->h_overflow, 0, VCT_ASYNC_FRAMES * 2 * sizeof(unsigned int));
   }
   if (c->frame2_W != c->P.W || c->frame2_H != c->P.H || !c->d_frame2[0]) {
     for (int k = 0; k < VCT_ASYNC_FRAMES; ++k) {
@@ -974,6 +994,16 @@ static int ensure_async(vct_context* c) {
   return VCT_OK;
 }
 
+// the overflow words that travelled to the host behind frame `slot` (a truncated queue must not pass for a frame)
+static int async_overflow(vct_context* c, int slot) {
+  unsigned int* f = c->h_overflow + 2 * slot;
+  if (!(f[0] | f[1])) return VCT_OK;
+  f[0] = f[1] = 0;
+  cudaMemsetAsync(&c->d_counters->overflow, 0, 4, c->stream);
+  if (c->d_counters_vis) cudaMemsetAsync(&c->d_counters_vis->overflow, 0, 4, c->stream);
+  return set_error(c, VCT_ERR_OVERFLOW, "device work queue overflow in an asynchronous frame: raise MaxFragments / MaxTileItems / MaxExchangeVoxels");
+}
+
 // blocks until the OLDEST frame still in flight has fully arrived in its host buffer
 int vct_frame_wait(vct_handle c) {
   NEED(c);
@@ -983,7 +1013,7 @@ int vct_frame_wait(vct_handle c) {
     if (c->in_flight[slot]) {
       VCT_CUDA(c, cudaEventSynchronize(c->ev_copied[slot]));
       c->in_flight[slot] = false;
-      return VCT_OK;
+      return async_overflow(c, slot);
     }
   }
   return VCT_OK;
@@ -999,6 +1029,7 @@ int vct_frame_async(vct_handle c, uint8_t* host_rgba) {
     VCT_CUDA(c, cudaEventSynchronize(c->ev_copied[slot]));
     c->in_flight[slot] = false;
     if (c->frame_oldest + VCT_ASYNC_FRAMES == c->frame_seq) c->frame_oldest++;
+    rc = async_overflow(c, slot); if (rc) return rc;
   }
   uchar4* saved = c->d_frame;
   c->d_frame = c->d_frame2[slot];                 // render straight into the slot
@@ -1008,6 +1039,9 @@ int vct_frame_async(vct_handle c, uint8_t* host_rgba) {
   VCT_CUDA(c, cudaEventRecord(c->ev_rendered[slot], c->stream));
   VCT_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_rendered[slot], 0));
   VCT_CUDA(c, cudaMemcpyAsync(host_rgba, c->d_frame2[slot], (size_t)c->P.W * c->P.H * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+  VCT_CUDA(c, cudaMemcpyAsync(c->h_overflow + 2 * slot, &c->d_counters->overflow, 4, cudaMemcpyDeviceToHost, c->copy_stream));
+  if (c->d_counters_vis)
+    VCT_CUDA(c, cudaMemcpyAsync(c->h_overflow + 2 * slot + 1, &c->d_counters_vis->overflow, 4, cudaMemcpyDeviceToHost, c->copy_stream));
   VCT_CUDA(c, cudaEventRecord(c->ev_copied[slot], c->copy_stream));
   c->in_flight[slot] = true;
   c->frame_seq++;

@@ -206,8 +206,7 @@ int launch_visibility(vct_context* c) {
   PassTimer timer(c, VCT_PASS_VISIBILITY);
   const size_t n = (size_t)c->P.W * c->P.H;
   fill_u64<<<148 * 4, 256, 0, c->stream>>>(c->d_vis2[c->cur], n, ~0ull);
-  VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_items, 0, sizeof(unsigned int), c->stream));
-    VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->next_item, 0, sizeof(unsigned int), c->stream));
+  VCT_CUDA(c, reset_item_queue(c));
   VisibilityPass pass{c->P, c->vcache2[c->cur], c->d_idx, c->d_trimat, c->d_materials, c->d_vis2[c->cur]};
   const uint32_t nt = (uint32_t)c->nt;
   raster_small<VisibilityPass><<<(nt + 127) / 128, 128, 0, c->stream>>>(pass, 0, nt, c->d_items,

@@ -56,11 +56,13 @@ struct MaterialHost { int d = -1, s = -1, h = -1; float shininess = 20.0f; };
 // Device counters, one cache line each to keep unrelated atomics apart.
 struct Counters {
   unsigned int n_fragments;   unsigned int pad0[31];
-  unsigned int n_items;       unsigned int pad1[31];
+  // tile-item queue of the current raster pass: written by raster_small, consumed by raster_tiles (stream order), so
+  // the three words share a line and are reset by ONE 12-byte memset per pass (reset_item_queue).  items_overflow is
+  // the per-pass twin of the sticky `overflow`: when set, raster_tiles consumes nothing (the queue holds stale items).
+  unsigned int n_items, next_item, items_overflow; unsigned int pad1[29];
   unsigned int n_touched;     unsigned int pad2[31];
-  unsigned int overflow;      unsigned int pad3[31];
+  unsigned int overflow;      unsigned int pad3[31];   // sticky until read by check_overflow
   unsigned long long cone_samples; unsigned int pad4[30];
-  unsigned int next_item;     unsigned int pad5[31];
 };
 
 // Per-vertex transform cache written once per frame by vertex_pass -- the vertex-shader stage of the three
@@ -154,7 +156,7 @@ struct vct_context {
   uint2* d_frags = nullptr; size_t frags_cap = 0;
   vct::TileItem* d_items = nullptr; size_t items_cap = 0;
   vct::Counters* d_counters = nullptr;
-  vct::Counters* h_counters = nullptr;          // pinned mirror
+  unsigned int* h_overflow = nullptr;           // pinned [VCT_ASYNC_FRAMES][2]: overflow words copied out behind each async frame
 
   // second stream: the visibility pass is independent of voxelisation + mip and runs beside them in vct_frame
   cudaStream_t stream2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -218,6 +220,8 @@ int launch_visibility(vct_context* c);
 int launch_cone(vct_context* c);
 int launch_reinject(vct_context* c);
 int check_overflow(vct_context* c);
+int sync_all_streams(vct_context* c);      // main + voxel + visibility + copy streams idle (before freeing what frames in flight read)
+inline cudaError_t reset_item_queue(vct_context* c) { return cudaMemsetAsync(&c->d_counters->n_items, 0, 3 * sizeof(unsigned int), c->stream); }
 
 // ------------------------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__

@@ -45,7 +45,10 @@ __global__ void __launch_bounds__(128, 5) raster_small(Pass pass, uint32_t tri_b
     uint32_t nitems = (ntiles + ITEM_TILES - 1) / ITEM_TILES;
     uint32_t base = atomicAdd(&ctr->n_items, nitems);
     if (base + nitems > items_cap) {
+      // Nothing of this triangle is queued and n_items now overstates what was written: raster_tiles must not
+      // touch the queue at all (slots past the last complete write hold stale or uninitialised items).
       ctr->overflow = 1;
+      ctr->items_overflow = 1;
     } else {
       for (uint32_t k = 0; k < nitems; ++k) {
         TileItem it;
@@ -60,7 +63,7 @@ __global__ void __launch_bounds__(128, 5) raster_small(Pass pass, uint32_t tri_b
 template <class Pass>
 __global__ void __launch_bounds__(256) raster_tiles(Pass pass, const TileItem* __restrict__ items,
                                                     uint32_t items_cap, Counters* __restrict__ ctr) {
-  const uint32_t n_items = min(ctr->n_items, items_cap);
+  const uint32_t n_items = ctr->items_overflow ? 0u : min(ctr->n_items, items_cap);
   const uint32_t lane = threadIdx.x & 31;
   // dynamic distribution: item costs vary by orders of magnitude (slivers vs. screen-filling triangles), so
   // each warp takes the next item from a ticket counter instead of a static stride

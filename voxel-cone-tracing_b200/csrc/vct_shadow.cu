@@ -74,8 +74,7 @@ int launch_shadow(vct_context* c) {
   PassTimer timer(c, VCT_PASS_DEPTH);
   const size_t n = (size_t)c->P.S * c->P.S;
   fill_u32<<<148 * 8, 256, 0, c->stream>>>(c->d_depth, n, 0xFFFFFFu);
-  VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_items, 0, sizeof(unsigned int), c->stream));
-    VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->next_item, 0, sizeof(unsigned int), c->stream));
+  VCT_CUDA(c, reset_item_queue(c));
   ShadowPass pass{c->P, c->d_verts, c->d_idx, c->d_depth};
   const uint32_t nt = (uint32_t)c->nt;
   raster_small<ShadowPass><<<(nt + 127) / 128, 128, 0, c->stream>>>(pass, 0, nt, c->d_items,

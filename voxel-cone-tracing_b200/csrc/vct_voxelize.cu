@@ -323,11 +323,16 @@ __global__ void __launch_bounds__(256) vox_shade(Params P, const VoxRecord* __re
 // last left there).  Cost is proportional to the occupied voxels, not to V^3.
 // Thousands of voxels share a brick and neighbours in the touched list are neighbours in space: a lane stores only
 // if its brick differs from the previous lane's (plain byte stores from every thread to the same few L2 sectors cost
-// ~10 us per pass).  Called from grid-stride loops over a list: the active lanes are a prefix of the warp.
+// ~10 us per pass).  The leader and every lane's predecessor are derived from the active mask itself (independent
+// thread scheduling does not promise that the callers' lanes are a converged prefix of the warp): the lowest active
+// lane always stores, any other lane compares with the nearest active lane below it.
 __device__ __forceinline__ void mark_dirty(unsigned char* dirty, uint32_t brick) {
   const unsigned active = __activemask();
-  const uint32_t up = __shfl_up_sync(active, brick, 1);
-  if ((threadIdx.x & 31) == 0 || up != brick) dirty[brick] = 1;
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned below = active & ((1u << lane) - 1u);
+  const int prev = below ? 31 - __clz(below) : (int)lane;         // self for the leader: shuffle source stays in the mask
+  const uint32_t up = __shfl_sync(active, brick, prev);
+  if (!below || up != brick) dirty[brick] = 1;
 }
 
 __global__ void vox_clear_sparse(unsigned long long* __restrict__ accum, const uint32_t* __restrict__ listA,
@@ -469,8 +474,7 @@ static int voxelize_impl(vct_context* c, size_t tb, size_t te, int shared) {
   if (tb >= te) return VCT_OK;
   {
     PassTimer timer(c, VCT_PASS_VOX_COVER);
-    VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_items, 0, sizeof(unsigned int), c->stream));
-    VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->next_item, 0, sizeof(unsigned int), c->stream));
+    VCT_CUDA(c, reset_item_queue(c));
     VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_fragments, 0, sizeof(unsigned int), c->stream));
     VoxCoverPass pass{c->P, c->vcache2[c->cur], c->d_idx, c->d_trimat, c->d_materials, (VoxRecord*)c->d_voxrec, c->d_frags, (uint32_t)c->frags_cap, c->d_counters};
     const uint32_t n = (uint32_t)(te - tb);

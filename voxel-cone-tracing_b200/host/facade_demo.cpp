@@ -1,8 +1,12 @@
 // facade_demo.cpp -- the reference's main.cpp:23-94 with the window stripped: construct, init, render a few frames.
 // Builds a small Cornell-style room in code, renders it through the C++ facade and prints a checksum per frame.
 // Needs a CUDA device to run; compiling and linking it is part of build().
+//   facade_demo [dump_dir]   with a directory: also writes the flattened scene (verts.f32, idx.u32, trimat.u16), the
+//   uniforms of every frame (uniforms_<f>.f32: ModelView, Projection, DepthMVP, ProjX, ProjY, ProjZ, camera) and the
+//   frames (frame_<f>.rgba), so that a test can replay the same inputs through another binding and compare bytes.
 #include <cstdio>
 #include <cstring>
+#include <string>
 
 #include "Voxel_Cone_Tracing.h"
 
@@ -29,7 +33,12 @@ static void add_quad(Model& m, const float p[4][3], int mat) {
   m.triangle_material.push_back((uint16_t)mat);
 }
 
-int main() {
+static void dump(const std::string& path, const void* p, size_t bytes) {
+  if (FILE* f = std::fopen(path.c_str(), "wb")) { std::fwrite(p, 1, bytes, f); std::fclose(f); }
+}
+
+int main(int argc, char** argv) {
+  const std::string dir = argc > 1 ? std::string(argv[1]) + "/" : std::string();
   Model m;
   const float s = 60.0f;
   const float floor_[4][3] = {{-s, -s, s}, {s, -s, s}, {s, -s, -s}, {-s, -s, -s}};
@@ -45,6 +54,11 @@ int main() {
     voxel_cone_tracing.VoxelDimensions = 64;
     camera = Camera(vec3(0.0f, 0.0f, 205.0f));
     voxel_cone_tracing.init_voxel_cone_tracing(m);
+    if (!dir.empty()) {
+      dump(dir + "verts.f32", m.vertices.data(), m.vertices.size() * sizeof(Vertex));
+      dump(dir + "idx.u32", m.indices.data(), m.indices.size() * sizeof(unsigned));
+      dump(dir + "trimat.u16", m.triangle_material.data(), m.triangle_material.size() * sizeof(uint16_t));
+    }
     std::vector<uint8_t> frame(256 * 256 * 4);
     for (int f = 0; f < 3; ++f) {
       camera.Yaw = -90.0f + 2.0f * f;
@@ -52,6 +66,18 @@ int main() {
       unsigned long long sum = 0;
       for (uint8_t b : frame) sum += b;
       std::printf("frame %d checksum %llu\n", f, sum);
+      if (!dir.empty()) {
+        const mat4 mMat = vctm::scale(mat4(1.0f), vec3(0.05f, 0.05f, 0.05f));
+        const mat4 mv = camera.GetViewMatrix() * mMat, pr = vctm::perspective(vctm::radians(camera.Zoom), 1.0f, 0.1f, 1000.0f),
+                   dm = voxel_cone_tracing.DepthViewProjectionMatrix * mMat;
+        std::vector<float> u;
+        const mat4* mats[6] = {&mv, &pr, &dm, &voxel_cone_tracing.ProjX, &voxel_cone_tracing.ProjY, &voxel_cone_tracing.ProjZ};
+        for (const mat4* q : mats)
+          u.insert(u.end(), q->data(), q->data() + 16);
+        u.push_back(camera.position.x); u.push_back(camera.position.y); u.push_back(camera.position.z);
+        dump(dir + "uniforms_" + std::to_string(f) + ".f32", u.data(), u.size() * sizeof(float));
+        dump(dir + "frame_" + std::to_string(f) + ".rgba", frame.data(), frame.size());
+      }
     }
   } catch (const std::exception& e) {
     std::printf("error: %s\n", e.what());
