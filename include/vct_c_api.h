@@ -146,6 +146,46 @@ int vct_frame_shared_begin(vct_handle h, size_t tri_begin, size_t tri_end);
 int vct_exchange_stream(vct_handle h, void** cuda_stream);
 int vct_frame_shared_end(vct_handle h, uint8_t* host_rgba_or_null);
 
+/* ---- multi-GPU, owned by the library (SURVEY.md 8b "pass entry points": vct_create_multi; 8e).  The reference is one
+ * GL context on one GPU (main.cpp:44); a sharded frame replaces its loop body glClear -> Render -> glfwSwapBuffers
+ * (main.cpp:81-92).  No torch, NCCL or MPI is involved: the library allocates one symmetric segment per rank
+ * (cuMemCreate), maps every rank's segment on every rank (NVLink peer access) and binds them to one NVSwitch multicast
+ * object (cuMulticastCreate / cuMulticastBindMem), passes the handles between processes itself (POSIX file descriptors
+ * over an abstract unix socket named after `session`; rank 0 is the hub) and synchronises ranks with a device-side
+ * barrier kernel enqueued in stream order.  One node only.
+ *
+ *   one process per GPU:   vct_create(device) ; set uniforms + scene (identical on every rank) ; vct_draw_depth ;
+ *                          vct_comm_init(h, rank, world, session, flags) ; loop { vct_frame_sharded(h, host) } ;
+ *                          vct_frame_sharded_wait(h)
+ *   one process, n GPUs:   vct_create_multi(devices, n, hs) ; same set-up on every handle ; vct_comm_init_multi(hs, n, flags) ;
+ *                          loop { vct_frame_sharded_multi(hs, n, host) } ; vct_frame_sharded_wait(hs[r]) for every r
+ *
+ * vct_comm_init sizes the segment from the CURRENT VoxelDimensions / screen size / MaxExchangeVoxels (call it again after
+ * changing them) and, unless VCT_COMM_KEEP_SHARES is given, deals the work: triangles in blocks of 128 round-robin
+ * (TriangleInterleave / TrianglePhase) and equal row bands (RowBegin / RowEnd).  All ranks must call it with the same
+ * world, session and settings; it blocks until every rank has joined (120 s limit). */
+#define VCT_COMM_NO_MULTICAST 1   /* do not create a multicast object: exchange by one peer store per rank */
+#define VCT_COMM_KEEP_SHARES  2   /* leave TriangleInterleave / TrianglePhase / RowBegin / RowEnd as the caller set them */
+int vct_comm_init(vct_handle h, int rank, int world, const char* session, int flags);
+int vct_comm_destroy(vct_handle h);
+int vct_comm_info(vct_handle h, int* rank, int* world, int* multicast, size_t* segment_bytes);
+int vct_comm_barrier(vct_handle h);     /* enqueue the device-side cross-rank barrier on the context's stream */
+/* One sharded frame: this rank voxelises its triangle share and multicasts the voxels it touched (multimem.st), merges
+ * the other ranks' records after a device barrier, builds the pyramid, traces its row band and writes the pixels
+ * straight into RANK 0's frame ring over NVLink (cone_trace's own epilogue -- no staging copy, no collective call).
+ * Rank 0 then queues the device->host copy of the assembled frame into host_rgba (pinned memory recommended; NULL
+ * keeps the frame on the device; ignored on other ranks).  Returns without waiting: up to three frames are in flight
+ * and the voxel stages of frame i+1 run beside cone_trace of frame i.  vct_frame_sharded_wait blocks until every frame
+ * issued so far is complete on this rank (rank 0: has arrived in host memory) and reports queue overflows and barrier
+ * time-outs. */
+int vct_frame_sharded(vct_handle h, uint8_t* host_rgba);
+int vct_frame_sharded_wait(vct_handle h);
+int vct_comm_frame_buffer(vct_handle h, void** device_ptr, size_t* n_bytes);   /* rank 0: the last assembled frame */
+/* the same for one process that drives n devices (out / hs: arrays of n handles; rank = array index) */
+int vct_create_multi(const int* devices, int n, vct_handle* out);
+int vct_comm_init_multi(vct_handle* hs, int n, int flags);
+int vct_frame_sharded_multi(vct_handle* hs, int n, uint8_t* host_rgba);
+
 /* ---- read-back (the reference reads nothing back; these exist for parity checks and hosts) */
 int vct_readback_depth(vct_handle h, uint32_t* d24 /* S*S */);
 int vct_readback_counts(vct_handle h, uint32_t* counts /* V^3, (z*V+y)*V+x */);
@@ -185,6 +225,13 @@ int vct_kernel_launches(vct_handle h, uint64_t* n);        /* kernels launched b
  * coherent cone-like walks, 1 = random.  Returns giga-samples/s. */
 int vct_bench_tex3d(vct_handle h, int V, uint64_t n_samples, int pattern, float lod, int iters,
                     float* gsamples_per_s);
+/* the same on a pyramid of the given GridFormat (0 = RGBA8, 1 = RGBA16F: 8 B texels, BASELINE config 3); V also sets
+ * the residency: 64^3 RGBA8 = 1 MiB (L1/L2), 256^3 = 73 MiB (L2), 512^3 RGBA16F = 1.17 GiB (HBM) */
+int vct_bench_tex3d_format(vct_handle h, int V, int grid_format, uint64_t n_samples, int pattern, float lod, int iters,
+                           float* gsamples_per_s);
+/* 64-bit atomicAdd rate of the voxel accumulation (two atomics per fragment, vox_shade) on the voxel population of
+ * the last voxelisation with its mean fragments-per-voxel multiplicity.  Returns giga-atomics/s. */
+int vct_bench_atomics(vct_handle h, uint64_t n_fragments, int iters, float* gatomics_per_s);
 
 #ifdef __cplusplus
 }

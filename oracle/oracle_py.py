@@ -64,6 +64,11 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
+def set_num_threads(n=0):
+    """OpenMP threads of the oracle (n > 0 sets them); returns the number in effect."""
+    return int(lib().orc_set_num_threads(int(n)))
+
+
 class Oracle:
     def __init__(self):
         self.L = lib()

@@ -1280,6 +1280,11 @@ extern "C" int orc_debug_pixel(orc_ctx* o, int i, int j, float* out110, uint8_t*
 extern "C" uint64_t orc_cone_samples(orc_ctx* o) { return o->cone_samples; }
 extern "C" uint64_t orc_fragment_count(orc_ctx* o) { return o->fragments; }
 
+extern "C" int orc_set_num_threads(int n) {
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+}
+
 extern "C" void orc_sample_voxels(orc_ctx* o, const float pos[3], float lod, float out[4]) {
   ensure_grid(o);
   sample_voxels(o, {pos[0], pos[1], pos[2]}, lod, out);

@@ -89,6 +89,9 @@ int orc_get_visibility(orc_ctx*, uint32_t* tri_id);         /* H*W, 0xFFFFFFFF =
 int orc_get_frame(orc_ctx*, uint8_t* rgba);                 /* H*W*4, row 0 = bottom (GL window coords) */
 uint64_t orc_cone_samples(orc_ctx*);
 uint64_t orc_fragment_count(orc_ctx*);                      /* voxel fragments of the last draw_voxels */
+/* OpenMP threads of the oracle's parallel loops: n > 0 sets them (torchrun exports OMP_NUM_THREADS=1, which would
+ * silently turn the CPU baseline into a one-thread run); returns the number in effect. */
+int orc_set_num_threads(int n);
 
 /* point probes for known-answer tests */
 void orc_sample_voxels(orc_ctx*, const float world_pos[3], float lod, float out_rgba[4]);

@@ -615,7 +615,7 @@ def test_shared_accumulator_path_single_rank(gpu_ctx):
     c = gpu_ctx
     run_gpu(c, sc, u)
     g_ref = [c.grid(l) for l in range(8)]
-    shared = parallel.SharedAccumulator(c, torch.device("cuda", 0), exchange="reduce")
+    shared = parallel.SharedAccumulator(c, rank=0, world=1, session="t_reduce1", exchange="reduce")
     n = sc.n_tris
     for it in range(3):
         c.voxelize_shared(0, n // 2)          # two ranges into the same accumulator = what two ranks would add
@@ -632,7 +632,7 @@ def test_shared_accumulator_path_single_rank(gpu_ctx):
     c.update_positions(sc.verts[:, :3]); c.draw_depth()
     c.voxelize_shared(0, n); c.resolve_shared(); c.sync()
     assert np.array_equal(c.grid(0), g_ref[0]) and np.array_equal(c.grid(3), g_ref[3])     # stale voxels removed
-    del shared
+    shared.close()
 
 
 @pytest.mark.parametrize("grid_format,bounces", [(0, 2), (1, 2), (0, 3)])
@@ -781,14 +781,18 @@ def test_pipelined_shared_frames_match_plain_frames(gpu_ctx):
         inputs(a, i); a.frame(); a.sync()
         ref.append((a.read_frame(), a.grid(0), a.grid(2)))
     a.set_i("PipelineFrames", 1); a.set_i("OverlapVisibility", 1)
-    # (1) a world of one
-    shared = parallel.SharedAccumulator(a, torch.device("cuda", 0))
+    # (1) a world of one through the library's own multi-GPU layer (vct_comm_init / vct_frame_sharded)
+    shared = parallel.SharedAccumulator(a, rank=0, world=1, session="t_pipe1")
+    host = np.zeros_like(ref[0][0])
     for i in range(6):
-        inputs(a, i); shared.frame(0, n); a.sync()
-        assert np.array_equal(a.read_frame(), ref[i][0]), i
+        inputs(a, i); shared.frame(host); shared.wait()
+        assert np.array_equal(host, ref[i][0]) and np.array_equal(a.read_frame(), ref[i][0]), i
         assert np.array_equal(a.grid(0), ref[i][1]) and np.array_equal(a.grid(2), ref[i][2]), i
     with pytest.raises(capi.VctError):
         a.frame_shared_end()                         # nothing begun
+    with pytest.raises(capi.VctError):
+        a.set_shared_accum(0, 0)                     # the exchange buffer belongs to the library now
+    shared.close()
     # (2) two handles = two ranks sharing one inbox; the device-wide synchronize stands in for the cross-rank barrier
     b.set_i("PipelineFrames", 1)
     for rank, c in enumerate((a, b)):
@@ -808,20 +812,85 @@ def test_pipelined_shared_frames_match_plain_frames(gpu_ctx):
     b.close()
 
 
-@pytest.mark.parametrize("exchange", ["inbox", "reduce"])
-def test_fused_sharded_voxelisation_two_gpus(exchange):
-    """multimem.st inbox / multimem.red in-switch reduction over NVSwitch multicast: needs two GPUs on the box (skipped
-    otherwise)."""
+def _run_ranks(world, devices, extra=(), timeout=600):
+    """Launches `world` processes of tests/mgpu_comm_worker.py (plain subprocesses: the library does its own bootstrap)."""
     import subprocess
     import sys
+    import uuid
+    root = os.path.dirname(HERE)
+    session = "t_" + uuid.uuid4().hex[:12]
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "mgpu_comm_worker.py"), str(r), str(world), session,
+                               str(devices[r]), *extra], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=root)
+             for r in range(world)]
+    outs = []
+    for p in procs:
+        try:
+            o, _ = p.communicate(timeout=timeout)
+        except subprocess.TimeoutExpired:
+            p.kill(); o, _ = p.communicate()
+        outs.append(o)
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"MGPU_COMM_OK {r}" in o, f"rank {r} rc={p.returncode}\n" + o[-3000:]
+    return outs
+
+
+def test_library_comm_two_processes_one_gpu():
+    """The library's own bootstrap (handle exchange over a unix socket, peer mapping, device barrier, frame gather into
+    rank 0, asynchronous host ring) with two PROCESSES acting as two ranks on device 0: no multicast object (one device
+    cannot join a team twice), so the records travel as peer stores (vox_push_inbox<2>)."""
+    _run_ranks(2, [0, 0], extra=("nomc",))
+
+
+@pytest.mark.parametrize("extra", [(), ("nomc",), ("reduce",)])
+def test_library_comm_two_gpus(extra):
+    """Two processes on two GPUs: multimem.st inbox through the library's multicast mapping, the same without a multicast
+    object, and the multimem.red flavour.  Needs two GPUs on the box (skipped otherwise)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    root = os.path.dirname(HERE)
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(HERE, "mgpu_shared_worker.py"), exchange]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
-    assert "MGPU_SHARED_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+    outs = _run_ranks(2, [0, 1], extra=extra)
+    if "nomc" not in extra:
+        assert "multicast=True" in outs[0]
+
+
+def test_one_process_driving_several_devices(gpu_ctx):
+    """vct_create_multi / vct_comm_init_multi / vct_frame_sharded_multi: one host thread, n handles.  On a one-GPU box the
+    two handles share device 0 (peer stores instead of multicast); with two GPUs the multicast path runs."""
+    import torch
+    import vct_b200.glmath as gm
+    devices = [0, 1] if torch.cuda.device_count() >= 2 else [0, 0]
+    sc = scenes.atrium(detail=0.25, tex_size=64)
+    H, W = 288, 512
+    u = uniforms.scene_uniforms(sc, V=128, width=W, height=H, shadow_map_size=2048, coverage="conservative")
+
+    def camera(c, i):
+        view = gm.view_matrix(sc.camera_pos, sc.yaw + 5.0 * i, sc.pitch)
+        c.set_mat4("ModelViewMatrix", gm.colmajor((view @ gm.scale(0.05)).astype(np.float32)))
+
+    ref = []
+    gpu_ctx.set_uniforms(u); gpu_ctx.load_scene(sc); gpu_ctx.draw_depth()
+    for i in range(4):
+        camera(gpu_ctx, i); gpu_ctx.frame(); gpu_ctx.sync()
+        ref.append(gpu_ctx.read_frame())
+    ref_grid = [gpu_ctx.grid(l) for l in range(8)]
+    m = capi.MultiContext(devices)
+    for c in m.ctx:
+        c.set_uniforms(u); c.load_scene(sc); c.draw_depth()
+    m.comm_init()
+    assert m.ctx[0].comm_info()["multicast"] == (devices[0] != devices[1])
+    assert m.ctx[1].get_i("RowBegin") == H // 2 and m.ctx[0].get_i("RowEnd") == H // 2
+    hosts = [np.zeros((H, W, 4), np.uint8) for _ in range(4)]
+    for i in range(4):
+        for c in m.ctx:
+            camera(c, i)
+        m.frame_sharded(hosts[i])
+    m.wait()
+    for i in range(4):
+        assert np.array_equal(hosts[i], ref[i]), f"frame {i}"
+    for c in m.ctx:
+        for l in range(8):
+            assert np.array_equal(c.grid(l), ref_grid[l]), l
+    m.close()
 
 
 def test_pipelined_frames_with_a_moving_mesh_and_camera(gpu_ctx):

@@ -23,7 +23,12 @@ SYMBOLS = [
     "vct_readback_sums", "vct_readback_grid", "vct_upload_grid_level0", "vct_build_mips", "vct_readback_visibility",
     "vct_readback_frame", "vct_frame_buffer", "vct_cone_samples", "vct_fragment_count", "vct_occupied_voxels", "vct_debug_counter",
     "vct_trace_cones", "vct_sample_voxels", "vct_set_stream", "vct_use_own_stream", "vct_sync", "vct_pass_time_us", "vct_kernel_launches", "vct_bench_tex3d",
+    "vct_bench_tex3d_format", "vct_bench_atomics",
+    "vct_comm_init", "vct_comm_destroy", "vct_comm_info", "vct_comm_barrier", "vct_frame_sharded", "vct_frame_sharded_wait",
+    "vct_comm_frame_buffer", "vct_create_multi", "vct_comm_init_multi", "vct_frame_sharded_multi",
 ]
+
+COMM_NO_MULTICAST, COMM_KEEP_SHARES = 1, 2
 
 
 class VctError(RuntimeError):
@@ -70,6 +75,14 @@ def load_library(path=None):
         "vct_trace_cones": [vp, sz, vp, vp, vp, vp, vp], "vct_sample_voxels": [vp, sz, vp, vp, vp], "vct_set_stream": [vp, vp], "vct_use_own_stream": [vp], "vct_sync": [vp], "vct_pass_time_us": [vp, i, C.POINTER(f)],
         "vct_kernel_launches": [vp, C.POINTER(C.c_uint64)],
         "vct_bench_tex3d": [vp, i, C.c_uint64, i, f, i, C.POINTER(f)],
+        "vct_bench_tex3d_format": [vp, i, i, C.c_uint64, i, f, i, C.POINTER(f)],
+        "vct_bench_atomics": [vp, C.c_uint64, i, C.POINTER(f)],
+        "vct_comm_init": [vp, i, i, cp, i], "vct_comm_destroy": [vp],
+        "vct_comm_info": [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(sz)], "vct_comm_barrier": [vp],
+        "vct_frame_sharded": [vp, vp], "vct_frame_sharded_wait": [vp],
+        "vct_comm_frame_buffer": [vp, C.POINTER(vp), C.POINTER(sz)],
+        "vct_create_multi": [C.POINTER(i), i, C.POINTER(vp)], "vct_comm_init_multi": [C.POINTER(vp), i, i],
+        "vct_frame_sharded_multi": [C.POINTER(vp), i, vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(L, name)
@@ -87,8 +100,11 @@ def _ptr(a):
 class Context:
     """Thin object wrapper over a vct_handle."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, handle=None):
         self.L = load_library()
+        if handle is not None:          # adopt a handle made by vct_create_multi
+            self.h, self.device = handle, device
+            return
         h = C.c_void_p()
         rc = self.L.vct_create(int(device), C.byref(h))
         if rc:
@@ -251,6 +267,32 @@ class Context:
     def frame_shared_end(self, host_rgba=None):
         self._ck(self.L.vct_frame_shared_end(self.h, None if host_rgba is None else _host_ptr(host_rgba)))
 
+    # ---- multi-GPU owned by the library (vct_comm.cu)
+    def comm_init(self, rank, world, session, flags=0):
+        self._ck(self.L.vct_comm_init(self.h, int(rank), int(world), str(session).encode(), int(flags)))
+
+    def comm_destroy(self):
+        self._ck(self.L.vct_comm_destroy(self.h))
+
+    def comm_info(self):
+        r, w, m, n = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+        self._ck(self.L.vct_comm_info(self.h, C.byref(r), C.byref(w), C.byref(m), C.byref(n)))
+        return {"rank": r.value, "world": w.value, "multicast": bool(m.value), "segment_bytes": n.value}
+
+    def comm_barrier(self):
+        self._ck(self.L.vct_comm_barrier(self.h))
+
+    def frame_sharded(self, host_rgba=None):
+        self._ck(self.L.vct_frame_sharded(self.h, None if host_rgba is None else _host_ptr(host_rgba)))
+
+    def frame_sharded_wait(self):
+        self._ck(self.L.vct_frame_sharded_wait(self.h))
+
+    def comm_frame_buffer(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(self.L.vct_comm_frame_buffer(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
     # ---- read-back
     def depth(self):
         S = self.get_i("ShadowMapSize")
@@ -356,9 +398,15 @@ class Context:
         self._ck(self.L.vct_pass_time_us(self.h, PASSES[name] if isinstance(name, str) else int(name), C.byref(v)))
         return v.value
 
-    def bench_tex3d(self, V=256, n_samples=1 << 28, pattern=0, lod=0.5, iters=5):
+    def bench_tex3d(self, V=256, n_samples=1 << 28, pattern=0, lod=0.5, iters=5, grid_format=0):
         v = C.c_float()
-        self._ck(self.L.vct_bench_tex3d(self.h, int(V), int(n_samples), int(pattern), float(lod), int(iters), C.byref(v)))
+        self._ck(self.L.vct_bench_tex3d_format(self.h, int(V), int(grid_format), int(n_samples), int(pattern), float(lod),
+                                               int(iters), C.byref(v)))
+        return v.value
+
+    def bench_atomics(self, n_fragments, iters=5):
+        v = C.c_float()
+        self._ck(self.L.vct_bench_atomics(self.h, int(n_fragments), int(iters), C.byref(v)))
         return v.value
 
 
@@ -369,3 +417,42 @@ def _host_ptr(out):
     if hasattr(out, "data_ptr"):
         return C.c_void_p(out.data_ptr())
     return _ptr(out)
+
+
+
+class MultiContext:
+    """One process driving n devices (vct_create_multi / vct_comm_init_multi / vct_frame_sharded_multi)."""
+
+    def __init__(self, devices):
+        self.L = load_library()
+        n = len(devices)
+        self._arr = (C.c_void_p * n)()
+        rc = self.L.vct_create_multi((C.c_int * n)(*[int(d) for d in devices]), n, self._arr)
+        if rc:
+            raise VctError(rc, self.L.vct_last_error(None).decode())
+        self.ctx = [Context(int(d), handle=C.c_void_p(self._arr[k])) for k, d in enumerate(devices)]
+
+    def __len__(self):
+        return len(self.ctx)
+
+    def each(self, fn):
+        return [fn(c) for c in self.ctx]
+
+    def comm_init(self, flags=0):
+        rc = self.L.vct_comm_init_multi(self._arr, len(self.ctx), int(flags))
+        if rc:
+            raise VctError(rc, self.L.vct_last_error(self.ctx[0].h).decode())
+
+    def frame_sharded(self, host_rgba=None):
+        rc = self.L.vct_frame_sharded_multi(self._arr, len(self.ctx), None if host_rgba is None else _host_ptr(host_rgba))
+        if rc:
+            for c in self.ctx:
+                c._ck(rc)
+
+    def wait(self):
+        for c in self.ctx:
+            c.frame_sharded_wait()
+
+    def close(self):
+        for c in self.ctx:
+            c.close()

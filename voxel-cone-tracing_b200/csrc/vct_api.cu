@@ -170,6 +170,7 @@ int ensure_frame(vct_context* c) {
   VCT_CUDA(c, cudaMalloc(&c->d_vis2[1], n * 8));
   VCT_CUDA(c, cudaMalloc(&c->d_frame, n * 4));
   c->frame_W = c->P.W; c->frame_H = c->P.H;
+  c->last_frame = nullptr;
   return VCT_OK;
 }
 
@@ -409,12 +410,25 @@ int begin_voxel_slot(vct_context* c) {
 }
 
 // ------------------------------------------------------------------------------------------ tex bench
-__global__ void fill_level_random(cudaSurfaceObject_t s, int n, unsigned seed) {
+__global__ void fill_level_random(cudaSurfaceObject_t s, int n, unsigned seed, int f16) {
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, z = blockIdx.z;
   if (x >= n || y >= n) return;
   unsigned h = (unsigned)(x * 73856093) ^ (unsigned)(y * 19349663) ^ (unsigned)(z * 83492791) ^ seed;
   h ^= h >> 13; h *= 0x5bd1e995u; h ^= h >> 15;
-  surf3Dwrite(h, s, x * 4, y, z);
+  if (f16) surf3Dwrite(make_uint2(h & 0x3BFF3BFFu, (h >> 3) & 0x3BFF3BFFu), s, x * 8, y, z);   // four finite halves in [0, 1)
+  else surf3Dwrite(h, s, x * 4, y, z);
+}
+
+// Atomics micro-benchmark (roofline denominator of vox_shade's accumulation): the same two 64-bit atomicAdds per
+// fragment, on the voxel population of the last voxelisation (touched list), `mult` consecutive fragments per voxel --
+// the measured mean multiplicity -- so that the warp-level and L2-level collision profile resembles the real pass.
+__global__ void __launch_bounds__(256) atomics_bench(unsigned long long* __restrict__ accum, const uint32_t* __restrict__ touched,
+                                                     uint32_t n_touched, uint32_t n_frag, uint32_t mult) {
+  for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < n_frag; f += gridDim.x * blockDim.x) {
+    const uint32_t v = touched[(f / mult) % n_touched];
+    atomicAdd(&accum[2 * (size_t)v], 0x0000000100000001ull);
+    atomicAdd(&accum[2 * (size_t)v + 1], 0x0000000100000001ull);
+  }
 }
 
 // each thread marches `steps` samples; a warp covers an 8x4 patch of start points (as cone_trace does)
@@ -477,6 +491,7 @@ int vct_destroy(vct_handle c) {
   if (!c) return VCT_ERR_INVALID;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  comm_release_for_destroy(c);
   free_grid(c);
   free_vertex_cache(c);
   for (auto& t : c->textures) free_texture(t);
@@ -760,7 +775,9 @@ int vct_shared_accum_bytes(vct_handle c, size_t* bytes) {
 int vct_set_shared_accum(vct_handle c, void* local_ptr, void* multicast_ptr) {
   NEED(c);
   if (c->shared_frame_open) return set_error(c, VCT_ERR_STATE, "vct_set_shared_accum: a shared frame is open (call vct_frame_shared_end first)");
+  if (c->comm) return set_error(c, VCT_ERR_STATE, "vct_set_shared_accum: the exchange buffer belongs to vct_comm_init (call vct_comm_destroy first)");
   if (c->shared_local) { int rc = sync_all_streams(c); if (rc) return rc; }   // queued exchange kernels use the old buffer
+  c->shared_peers = nullptr; c->shared_seg = 0;
   c->shared_local = (unsigned long long*)local_ptr;
   c->shared_mc = (unsigned long long*)multicast_ptr;
   c->exchange_parity = 0;
@@ -1119,7 +1136,10 @@ int vct_readback_visibility(vct_handle c, uint32_t* tri) {
 int vct_readback_frame(vct_handle c, uint8_t* rgba) {
   NEED(c);
   if (!c->d_frame || !rgba) return set_error(c, VCT_ERR_STATE, "no frame rendered");
-  VCT_CUDA(c, cudaMemcpyAsync(rgba, c->d_frame, (size_t)c->P.W * c->P.H * 4, cudaMemcpyDeviceToHost, c->stream));
+  // the most recent frame, wherever it was rendered (vct_render / vct_frame: d_frame; vct_frame_async and
+  // vct_frame_sharded: a ring slot -- on ranks other than 0 of a sharded frame only the own rows are meaningful)
+  const uchar4* src = c->last_frame ? c->last_frame : c->d_frame;
+  VCT_CUDA(c, cudaMemcpyAsync(rgba, src, (size_t)c->P.W * c->P.H * 4, cudaMemcpyDeviceToHost, c->stream));
   return check_cuda(c, cudaStreamSynchronize(c->stream), "sync");
 }
 
@@ -1201,6 +1221,7 @@ int vct_sync(vct_handle c) {
   NEED(c);
   int rc = check_cuda(c, cudaStreamSynchronize(c->stream), "cudaStreamSynchronize");
   if (rc) return rc;
+  rc = comm_check(c); if (rc) return rc;
   return check_overflow(c);
 }
 
@@ -1217,12 +1238,11 @@ int vct_pass_time_us(vct_handle c, int pass, float* us) {
 
 int vct_kernel_launches(vct_handle c, uint64_t* n) { NEED(c); if (n) *n = c->launches; return VCT_OK; }
 
-int vct_bench_tex3d(vct_handle c, int V, uint64_t n_samples, int pattern, float lod, int iters, float* gsps) {
-  NEED(c);
+static int bench_tex3d(vct_context* c, int V, int f16, uint64_t n_samples, int pattern, float lod, int iters, float* gsps) {
   if (V < 8 || V > 1024 || (V & (V - 1)) || iters < 1 || !gsps) return set_error(c, VCT_ERR_INVALID, "vct_bench_tex3d: bad arguments");
   const int levels = ilog2(V) + 1;
   cudaMipmappedArray_t arr = nullptr;
-  cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
+  cudaChannelFormatDesc desc = f16 ? cudaCreateChannelDescHalf4() : cudaCreateChannelDesc<uchar4>();
   VCT_CUDA(c, cudaMallocMipmappedArray(&arr, &desc, make_cudaExtent(V, V, V), levels, cudaArraySurfaceLoadStore));
   for (int l = 0; l < levels; ++l) {
     cudaArray_t lvl;
@@ -1232,7 +1252,7 @@ int vct_bench_tex3d(vct_handle c, int V, uint64_t n_samples, int pattern, float 
     cudaCreateSurfaceObject(&s, &rd);
     int n = V >> l;
     dim3 b(32, 8), g((n + 31) / 32, (n + 7) / 8, n);
-    fill_level_random<<<g, b, 0, c->stream>>>(s, n, 1234u + l);
+    fill_level_random<<<g, b, 0, c->stream>>>(s, n, 1234u + l, f16);
     cudaStreamSynchronize(c->stream);
     cudaDestroySurfaceObject(s);
   }
@@ -1240,7 +1260,7 @@ int vct_bench_tex3d(vct_handle c, int V, uint64_t n_samples, int pattern, float 
   cudaTextureDesc td{};
   td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeWrap;
   td.filterMode = cudaFilterModeLinear; td.mipmapFilterMode = cudaFilterModeLinear;
-  td.readMode = cudaReadModeNormalizedFloat; td.normalizedCoords = 1; td.maxMipmapLevelClamp = (float)(levels - 1);
+  td.readMode = f16 ? cudaReadModeElementType : cudaReadModeNormalizedFloat; td.normalizedCoords = 1; td.maxMipmapLevelClamp = (float)(levels - 1);
   cudaTextureObject_t tex;
   VCT_CUDA(c, cudaCreateTextureObject(&tex, &rd, &td, nullptr));
   const int Wp = 1920, Hp = 1080, steps = (int)((n_samples + (uint64_t)Wp * Hp - 1) / ((uint64_t)Wp * Hp));
@@ -1264,6 +1284,51 @@ int vct_bench_tex3d(vct_handle c, int V, uint64_t n_samples, int pattern, float 
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   cudaDestroyTextureObject(tex); cudaFreeMipmappedArray(arr); cudaFree(sink);
   return check_cuda(c, cudaGetLastError(), "vct_bench_tex3d");
+}
+
+int vct_bench_tex3d(vct_handle c, int V, uint64_t n_samples, int pattern, float lod, int iters, float* gsps) {
+  NEED(c);
+  return bench_tex3d(c, V, 0, n_samples, pattern, lod, iters, gsps);
+}
+
+int vct_bench_tex3d_format(vct_handle c, int V, int grid_format, uint64_t n_samples, int pattern, float lod, int iters,
+                           float* gsps) {
+  NEED(c);
+  if (grid_format != 0 && grid_format != 1) return set_error(c, VCT_ERR_INVALID, "vct_bench_tex3d_format: 0 = RGBA8, 1 = RGBA16F");
+  return bench_tex3d(c, V, grid_format, n_samples, pattern, lod, iters, gsps);
+}
+
+int vct_bench_atomics(vct_handle c, uint64_t n_fragments, int iters, float* gatomics_per_s) {
+  NEED(c);
+  if (!gatomics_per_s || iters < 1 || n_fragments < 1 || n_fragments > 0xFFFFFFFFull) return set_error(c, VCT_ERR_INVALID, "vct_bench_atomics: bad arguments");
+  int rc = ensure_grid(c); if (rc) return rc;
+  rc = sync_all_streams(c); if (rc) return rc;
+  unsigned int n_touched = 0;
+  VCT_CUDA(c, cudaMemcpy(&n_touched, c->grid[c->cur].n_touched, 4, cudaMemcpyDeviceToHost));
+  if (!n_touched || !c->grid[c->cur].list_valid) return set_error(c, VCT_ERR_STATE, "vct_bench_atomics: voxelise first (needs the touched-voxel list)");
+  // a scratch accumulator: the context's own one must stay consistent with its lists
+  unsigned long long* scratch = nullptr;
+  const size_t n = (size_t)c->P.V * c->P.V * c->P.V;
+  VCT_CUDA(c, cudaMalloc(&scratch, n * 16));
+  VCT_CUDA(c, cudaMemsetAsync(scratch, 0, n * 16, c->stream));
+  uint32_t mult = (uint32_t)((n_fragments + n_touched - 1) / n_touched);
+  if (mult < 1) mult = 1;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  atomics_bench<<<148 * 8, 256, 0, c->stream>>>(scratch, c->grid[c->cur].touched, n_touched, (uint32_t)n_fragments, mult);
+  float best = 1e30f;
+  for (int it = 0; it < iters; ++it) {
+    cudaEventRecord(e0, c->stream);
+    atomics_bench<<<148 * 8, 256, 0, c->stream>>>(scratch, c->grid[c->cur].touched, n_touched, (uint32_t)n_fragments, mult);
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    best = ms < best ? ms : best;
+  }
+  c->launches += iters + 1;
+  *gatomics_per_s = (float)(2.0 * (double)n_fragments / (best * 1e-3) * 1e-9);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(scratch);
+  return check_cuda(c, cudaGetLastError(), "vct_bench_atomics");
 }
 
 }  // extern "C"

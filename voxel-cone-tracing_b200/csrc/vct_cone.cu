@@ -541,6 +541,7 @@ int launch_cone(vct_context* c) {
   }
 #undef VCT_LAUNCH_CONE
   c->launches += 1;
+  c->last_frame = c->d_frame;
   mark_slot_read(c);
   VCT_CUDA(c, cudaGetLastError());
   return VCT_OK;

@@ -138,6 +138,9 @@ struct vct_context {
   size_t touched_cap = 0;
   // fused sharded voxelisation: external symmetric accumulator + occupancy mask (local view and multicast view)
   unsigned long long* shared_local = nullptr; unsigned long long* shared_mc = nullptr;
+  // library-owned multi-GPU state (vct_comm.cu): symmetric segments, multicast mapping, bootstrap sockets.  When the
+  // segments are mapped without a multicast object, shared_peers + r * shared_seg is rank r's inbox (unicast stores).
+  void* comm = nullptr; unsigned char* shared_peers = nullptr; size_t shared_seg = 0;
   uint32_t* mask_prev[2] = {nullptr, nullptr}; int mask_prev_V = 0;   // occupancy mask of what each slot's level 0 holds
   bool mask_valid[2] = {false, false};                                // ... and whether it is exact
   uint32_t* d_push_list = nullptr; unsigned int* d_push_count = nullptr; size_t push_cap = 0;   // voxels this rank touched
@@ -165,6 +168,7 @@ struct vct_context {
 
   // frame
   unsigned long long* d_vis2[2] = {nullptr, nullptr}; uchar4* d_frame = nullptr; int frame_W = 0, frame_H = 0;
+  uchar4* last_frame = nullptr;   // where the most recent cone_trace wrote (d_frame, an async ring slot or a sharded-frame slot)
   // ring of device frame buffers for vct_frame_async (up to VCT_ASYNC_FRAMES frames in flight)
   uchar4* d_frame2[3] = {nullptr, nullptr, nullptr}; int frame2_W = 0, frame2_H = 0;
   cudaStream_t copy_stream = nullptr; cudaEvent_t ev_rendered[3]{}, ev_copied[3]{}; bool in_flight[3] = {false, false, false};
@@ -220,6 +224,9 @@ int launch_visibility(vct_context* c);
 int launch_cone(vct_context* c);
 int launch_reinject(vct_context* c);
 int check_overflow(vct_context* c);
+int comm_barrier(vct_context* c, int channel, cudaStream_t stream);   // device-side cross-rank barrier, in stream order
+int comm_check(vct_context* c);                                        // barrier time-outs -> VCT_ERR_STATE
+void comm_release_for_destroy(vct_context* c);
 int sync_all_streams(vct_context* c);      // main + voxel + visibility + copy streams idle (before freeing what frames in flight read)
 inline cudaError_t reset_item_queue(vct_context* c) { return cudaMemsetAsync(&c->d_counters->n_items, 0, 3 * sizeof(unsigned int), c->stream); }
 

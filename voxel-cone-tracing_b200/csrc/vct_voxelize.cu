@@ -551,25 +551,32 @@ __host__ __device__ inline size_t exch_record_offset(int parity, int world, int 
   return EXCH_HEADER + ((((size_t)parity * world + rank) * cap) + k) * EXCH_RECORD;
 }
 
-template <bool MULTICAST>
+// MODE 0: plain store into one buffer (single GPU, or several handles sharing one buffer); 1: multimem.st through the
+// multicast mapping (one store lands in every rank's inbox, replicated by the NVSwitch); 2: no multicast object --
+// one peer store per rank into the mapped segments (dst + r * seg is rank r's inbox).
+template <int MODE>
 __global__ void vox_push_inbox(const unsigned long long* __restrict__ accum, const uint32_t* __restrict__ list,
-                               const unsigned int* __restrict__ n_list, unsigned char* dst, int parity, int world, int rank,
-                               uint32_t cap, Counters* __restrict__ ctr) {
+                               const unsigned int* __restrict__ n_list, unsigned char* dst, size_t seg, int parity, int world,
+                               int rank, uint32_t cap, Counters* __restrict__ ctr) {
   const uint32_t n = min(*n_list, cap);
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const uint32_t v = list[k];
     const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(&accum[2 * (size_t)v]);
-    unsigned char* rec = dst + exch_record_offset(parity, world, rank, cap, k);
+    const size_t off = exch_record_offset(parity, world, rank, cap, k);
     // accumulator cell: a.x = r << 32 | g, a.y = b << 32 | count
     const uint32_t r = (uint32_t)(a.x >> 32), g = (uint32_t)a.x, b = (uint32_t)(a.y >> 32), n_frag = (uint32_t)a.y;
     if ((r | g | b | n_frag) >> 24) ctr->overflow = 1;
     const uint4 q = make_uint4((r & 0xFFFFFFu) | (n_frag << 24), (g & 0xFFFFFFu) | ((n_frag >> 8) << 24),
                                (b & 0xFFFFFFu) | ((n_frag >> 16) << 24), v);
-    if (MULTICAST) multimem_st_v4(rec, q); else *reinterpret_cast<uint4*>(rec) = q;
+    if (MODE == 1) multimem_st_v4(dst + off, q);
+    else if (MODE == 2) { for (int p = 0; p < world; ++p) if (p != rank) *reinterpret_cast<uint4*>(dst + (size_t)p * seg + off) = q; }
+    else *reinterpret_cast<uint4*>(dst + off) = q;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(dst) + (parity * 16 + rank);
-    if (MULTICAST) multimem_st_u32(cnt, n); else *cnt = n;
+    const size_t off = (size_t)(parity * 16 + rank) * 4;
+    if (MODE == 1) multimem_st_u32(reinterpret_cast<uint32_t*>(dst + off), n);
+    else if (MODE == 2) { for (int p = 0; p < world; ++p) *reinterpret_cast<uint32_t*>(dst + (size_t)p * seg + off) = n; }
+    else *reinterpret_cast<uint32_t*>(dst + off) = n;
   }
 }
 
@@ -601,7 +608,9 @@ static int resolve_inbox(vct_context* c);
 
 int launch_voxelize_shared(vct_context* c, size_t tb, size_t te) {
   if (c->shared_local && c->shared_exchange == 0) return voxelize_inbox(c, tb, te, false);
-  if (!c->shared_local) return set_error(c, VCT_ERR_STATE, "vct_voxelize_shared: call vct_set_shared_accum first");
+  if (!c->shared_local) return set_error(c, VCT_ERR_STATE, "vct_voxelize_shared: call vct_comm_init or vct_set_shared_accum first");
+  if (c->comm && c->shared_world > 1 && !c->shared_mc)
+    return set_error(c, VCT_ERR_STATE, "vct_voxelize_shared: SharedExchange = 1 (in-switch reduction) needs the multicast mapping");
   int rc = ensure_grid(c); if (rc) return rc;
   const size_t n = (size_t)c->P.V * c->P.V * c->P.V;
   if (c->push_cap != n) {
@@ -712,11 +721,14 @@ static int voxelize_inbox(vct_context* c, size_t tb, size_t te, bool slot_ready)
   const uint32_t cap = (uint32_t)c->exchange_cap;
   PassTimer timer(c, VCT_PASS_EXCHANGE_PUSH);
   if (c->shared_mc)
-    vox_push_inbox<true><<<148 * 4, 256, 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, (unsigned char*)c->shared_mc,
-                                                         c->exchange_parity, c->shared_world, c->shared_rank, cap, c->d_counters);
+    vox_push_inbox<1><<<148 * 4, 256, 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, (unsigned char*)c->shared_mc, 0,
+                                                      c->exchange_parity, c->shared_world, c->shared_rank, cap, c->d_counters);
+  else if (c->shared_peers && c->shared_world > 1)
+    vox_push_inbox<2><<<148 * 4, 256, 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, c->shared_peers, c->shared_seg,
+                                                      c->exchange_parity, c->shared_world, c->shared_rank, cap, c->d_counters);
   else
-    vox_push_inbox<false><<<148 * 4, 256, 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, (unsigned char*)c->shared_local,
-                                                          c->exchange_parity, c->shared_world, c->shared_rank, cap, c->d_counters);
+    vox_push_inbox<0><<<148 * 4, 256, 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, (unsigned char*)c->shared_local, 0,
+                                                      c->exchange_parity, c->shared_world, c->shared_rank, cap, c->d_counters);
   // own record count, needed by the merge for the overflow check (the list keeps growing during the merge)
   if (!c->d_push_count) VCT_CUDA(c, cudaMalloc(&c->d_push_count, 128));
   VCT_CUDA(c, cudaMemcpyAsync(c->d_push_count, g.n_touched, 4, cudaMemcpyDeviceToDevice, c->stream));

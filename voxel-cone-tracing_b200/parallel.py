@@ -123,67 +123,51 @@ def merge_exchange_records(counts, sums, records):
     return counts, sums
 
 
+def default_session():
+    """A session name every rank of one launch agrees on (torchrun exports MASTER_ADDR / MASTER_PORT)."""
+    import os
+    return f"{os.environ.get('MASTER_ADDR', 'local')}_{os.environ.get('MASTER_PORT', '0')}"
+
+
 class SharedAccumulator:
-    """Symmetric exchange buffer for the fused triangle-sharded voxelisation (vct_voxelize_shared / vct_resolve_shared).
+    """Sharded voxelisation / sharded frames through the LIBRARY's multi-GPU layer (vct_comm_init, csrc/vct_comm.cu):
+    symmetric segments, NVSwitch multicast mapping, handle exchange between the processes and the device-side barrier
+    all live behind the C ABI; nothing here touches torch.  rank / world default to the torchrun environment
+    (RANK / WORLD_SIZE), a world of one works on a single GPU.
+    exchange = "inbox" (default; touched voxels as records, multimem.st) or "reduce" (multimem.red into a dense
+    symmetric accumulator).  flags: capi.COMM_NO_MULTICAST, capi.COMM_KEEP_SHARES."""
 
-    Plumbing only: the memory comes from torch symmetric memory (same allocation size on every rank, mapped on the
-    peers and through an NVSwitch multicast address), the barrier is the symmetric-memory signal-pad barrier on the
-    current stream.  With world size 1 it is a plain zeroed device buffer and the barrier is a no-op.
-    exchange = "inbox" (default) or "reduce" (multimem.red into a dense symmetric accumulator)."""
-
-    def __init__(self, ctx, device, group=None, exchange="inbox"):
-        import torch
-        import torch.distributed as dist
+    def __init__(self, ctx, device=None, group=None, exchange="inbox", rank=None, world=None, session=None, flags=0):
+        import os
         self.ctx = ctx
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.rank = int(os.environ.get("RANK", 0)) if rank is None else int(rank)
+        self.world = int(os.environ.get("WORLD_SIZE", 1)) if world is None else int(world)
         self.reduce = exchange == "reduce"
-        self._xstream = None
         ctx.set_i("SharedExchange", 1 if self.reduce else 0)
-        ctx.set_i("SharedWorld", self.world)
-        ctx.set_i("SharedRank", self.rank)
-        nbytes = ctx.shared_accum_bytes()
-        n64 = (nbytes + 7) // 8
-        self.hdl = None
-        if self.world > 1:
-            import torch.distributed._symmetric_memory as symm_mem
-            self.buf = symm_mem.empty(n64, dtype=torch.int64, device=device)
-            g = group or dist.group.WORLD
-            self.hdl = symm_mem.rendezvous(self.buf, group=g.group_name if hasattr(g, "group_name") else g)
-            self.buf.zero_()
-            torch.cuda.synchronize(device)
-            self.hdl.barrier()
-            mc = int(self.hdl.multicast_ptr or 0)
-            if not mc:
-                raise RuntimeError("no multicast mapping for symmetric memory on this system")
-            ctx.set_shared_accum(self.buf.data_ptr(), mc)
-        else:
-            self.buf = torch.zeros(n64, dtype=torch.int64, device=device)
-            ctx.set_shared_accum(self.buf.data_ptr(), 0)
+        ctx.comm_init(self.rank, self.world, session or default_session(), flags)
+        self.info = ctx.comm_info()
 
     def barrier(self):
-        if self.hdl is not None:
-            self.hdl.barrier()
+        self.ctx.comm_barrier()
 
-    def frame(self, tri_begin, tri_end, host_rgba=None):
-        """One sharded frame, pipelined (vct_frame_shared_begin / _end; inbox exchange only): the cross-rank barrier is
-        enqueued on the library's exchange stream, so the voxel / exchange / visibility stages of the next frame run
-        beside this frame's cone_trace.  Renders rows RowBegin..RowEnd of this rank."""
-        import torch
-        self.ctx.frame_shared_begin(tri_begin, tri_end)
-        if self.hdl is not None:
-            if self._xstream is None:
-                self._xstream = torch.cuda.ExternalStream(self.ctx.exchange_stream(), device=self.buf.device)
-            with torch.cuda.stream(self._xstream):
-                self.hdl.barrier()
-        self.ctx.frame_shared_end(host_rgba)
+    def frame(self, host_rgba=None):
+        """One sharded frame, pipelined inside the library (vct_frame_sharded): rows of every rank land in rank 0's
+        frame ring; rank 0 receives the frame in `host_rgba`.  Asynchronous: call wait() before reading."""
+        self.ctx.frame_sharded(host_rgba)
+
+    def wait(self):
+        self.ctx.frame_sharded_wait()
 
     def frame_voxels(self, tri_begin, tri_end):
-        """One sharded voxelisation: voxelise this rank's triangle range and multicast what it touched, barrier, merge /
-        resolve + mip the local copy.  (The inbox is double buffered by frame parity, so one barrier per frame is
-        enough; the in-switch reduction needs a second one before the next frame may add into the accumulator.)"""
+        """One sharded voxelisation, serial form: voxelise this rank's triangle range and multicast what it touched,
+        barrier, merge / resolve + mip the local copy.  (The inbox is double buffered by frame parity, so one barrier
+        per frame is enough; the in-switch reduction needs a second one before the next frame may add into the
+        accumulator.)"""
         self.ctx.voxelize_shared(tri_begin, tri_end)
         self.barrier()
         self.ctx.resolve_shared()
         if self.reduce:
             self.barrier()
+
+    def close(self):
+        self.ctx.comm_destroy()
