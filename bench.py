@@ -413,6 +413,10 @@ def bench_config(env, args):
     # (2) per-pass breakdown and the dominant kernel's average duration: same steps again with pass events on,
     # one frame at a time (no overlap between frames: these are the serial per-pass costs)
     ctx.set_i("Profile", 1)
+    if not sharded:
+        # one stream: with the visibility pass on its own stream beside the voxel stages (the default), the event
+        # pairs of concurrent passes include each other's kernels (round 1 reported 166 us for a 95 us pass that way)
+        ctx.set_i("OverlapVisibility", 0)
     pass_names = ["vox_clear", "vox_cover", "vox_shade", "resolve", "mip", "visibility", "cone"]
     if sharded:
         pass_names[3:3] = ["exchange_push"] + (["exchange_merge"] if args.exchange == "inbox" else [])
@@ -434,7 +438,7 @@ def bench_config(env, args):
         samples_sum += ctx.cone_samples()
         fragments = ctx.fragment_count()
     occupied = ctx.occupied_voxels()
-    ctx.set_i("Profile", 0)
+    ctx.set_i("Profile", 0); ctx.set_i("OverlapVisibility", 1)
     env.barrier()
     passes = {p: pass_sum[p] / n_prof for p in pass_names}
     passes_max = None

@@ -941,3 +941,28 @@ def test_specular_fetch_ahead_depth_does_not_change_results(gpu_ctx):
         out[su] = (c.read_frame(), c.cone_samples())
     assert np.array_equal(out[1][0], out[2][0]) and np.array_equal(out[1][0], out[4][0])
     assert out[1][1] == out[2][1] == out[4][1]
+
+
+@pytest.mark.parametrize("cones,variants", [("6+1", (1, 2, 3, 4, 5, 8)), ("9+1", (1, 3, 4))])
+def test_cone_trace_variants_are_bit_identical(gpu_ctx, oracle, cones, variants):
+    """cone_trace's tuning variants (block size, register budget, specular fetch-ahead depth; DebugConeVariant) run the same
+    arithmetic per pixel: identical frames and identical sample counts -- and the frame they agree on is the oracle's.
+    (Guards against a code-generation problem seen with nvcc 12.9: an array of predicates carried across the texture
+    fetches of the lockstep march gave wrong pixels in SOME register allocations.)"""
+    sc = scenes.atrium(detail=0.3, tex_size=64)
+    u = uniforms.scene_uniforms(sc, V=128, width=640, height=360, shadow_map_size=2048, coverage="conservative", cones=cones)
+    c = gpu_ctx
+    run_gpu(c, sc, u)
+    run_oracle(oracle, sc, u)
+    ref, n_ref = c.read_frame(), c.cone_samples()
+    assert_frame_close(ref, oracle.frame(), f"default cone_trace, {cones}", FRAC_MIN_SMALL)
+    for su in (1, 2):
+        c.set_i("DebugSpecAhead", su)
+        c.render(); c.sync()
+        assert np.array_equal(c.read_frame(), ref) and c.cone_samples() == n_ref, f"spec-ahead {su}"
+    c.set_i("DebugSpecAhead", 4)
+    for v in variants:
+        c.set_i("DebugConeVariant", v)
+        c.render(); c.sync()
+        assert np.array_equal(c.read_frame(), ref), f"variant {v}"
+        assert c.cone_samples() == n_ref, f"variant {v}"

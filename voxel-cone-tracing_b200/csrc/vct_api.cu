@@ -143,13 +143,19 @@ int ensure_shadow(vct_context* c) {
   if (c->depth_S == c->P.S && c->d_depth) return VCT_OK;
   cudaFree(c->d_depth); c->d_depth = nullptr; c->depth_valid = false;
   if (c->depth_tex) { cudaDestroyTextureObject(c->depth_tex); c->depth_tex = 0; }
+  if (c->depth_surf) { cudaDestroySurfaceObject(c->depth_surf); c->depth_surf = 0; }
   if (c->depth_array) { cudaFreeArray(c->depth_array); c->depth_array = nullptr; }
   VCT_CUDA(c, cudaMalloc(&c->d_depth, (size_t)c->P.S * c->P.S * 4));
   cudaChannelFormatDesc dd = cudaCreateChannelDesc<unsigned int>();
-  VCT_CUDA(c, cudaMallocArray(&c->depth_array, &dd, c->P.S, c->P.S, cudaArrayTextureGather));
+  if (cudaMallocArray(&c->depth_array, &dd, c->P.S, c->P.S, cudaArrayTextureGather | cudaArraySurfaceLoadStore) != cudaSuccess) {
+    cudaGetLastError();                                   // gather-only array: the copy falls back to cudaMemcpy2DToArray
+    c->depth_array = nullptr;
+    VCT_CUDA(c, cudaMallocArray(&c->depth_array, &dd, c->P.S, c->P.S, cudaArrayTextureGather));
+  }
   cudaResourceDesc rd{};
   rd.resType = cudaResourceTypeArray;
   rd.res.array.array = c->depth_array;
+  if (cudaCreateSurfaceObject(&c->depth_surf, &rd) != cudaSuccess) { cudaGetLastError(); c->depth_surf = 0; }
   cudaTextureDesc td{};
   td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;    // GL_CLAMP_TO_EDGE, Voxel_Cone_Tracing.h:95-96
   td.filterMode = cudaFilterModePoint;
@@ -499,6 +505,7 @@ int vct_destroy(vct_handle c) {
   if (c->white_arr) cudaFreeMipmappedArray(c->white_arr);
   cudaFree(c->d_verts); cudaFree(c->d_idx); cudaFree(c->d_trimat); cudaFree(c->d_materials);
   if (c->depth_tex) cudaDestroyTextureObject(c->depth_tex);
+  if (c->depth_surf) cudaDestroySurfaceObject(c->depth_surf);
   if (c->depth_array) cudaFreeArray(c->depth_array);
   cudaFree(c->mask_prev[0]); cudaFree(c->mask_prev[1]); cudaFree(c->d_push_list); cudaFree(c->d_push_count);
   cudaFree(c->d_voxrec); cudaFree(c->d_depth); cudaFree(c->d_frags); cudaFree(c->d_items); cudaFree(c->d_counters);
@@ -552,6 +559,7 @@ int vct_set_i(vct_handle c, const char* name, int v) {
   else if (k == "MaxExchangeVoxels") { if (v < 1024) return set_error(c, VCT_ERR_INVALID, "MaxExchangeVoxels too small"); c->exchange_cap_user = (size_t)v; }
   else if (k == "PipelineFrames") c->pipeline_frames = v != 0;
   else if (k == "DebugSpecAhead") c->debug_spec_ahead = v;
+  else if (k == "DebugConeVariant") c->debug_cone_variant = v;
   else if (k == "DenseResolve") c->dense_resolve = v != 0;
   else if (k == "Profile") c->profile = v != 0;
   else if (k == "ShadowMap" || k == "VoxelTexture") { /* texture unit numbers: meaningless here */ }

@@ -137,6 +137,7 @@ struct VisibilityPass {
   unsigned long long* vis;
 
   static constexpr bool kAppends = false;
+  static constexpr bool kWarpMedium = true;
   struct Setup { HTri t; };
 
   __device__ __forceinline__ bool setup(uint32_t tri, Setup& s, int& i0, int& i1, int& j0, int& j1) const {
@@ -322,9 +323,9 @@ __device__ __forceinline__ void march_pixel(cudaTextureObject_t grid, const Para
 #pragma unroll
       for (int q = 0; q < SU; ++q) {
         sdiam[q] = fmaxf(k.vws, s2t * dk);
-        if (dk < max_dist)
-          ss[q] = tex3DLod<float4>(grid, __fmaf_rn(dk, su, u0), __fmaf_rn(dk, sv, v0), __fmaf_rn(dk, sw, w0),
-                                   __log2f(sdiam[q] * k.inv_vws));
+        // unconditional: a fetch past MAX_DISTANCE wraps like any other (GL_REPEAT) and is discarded below
+        ss[q] = tex3DLod<float4>(grid, __fmaf_rn(dk, su, u0), __fmaf_rn(dk, sv, v0), __fmaf_rn(dk, sw, w0),
+                                 __log2f(sdiam[q] * k.inv_vws));
         dk = __fmaf_rn(sdiam[q], step_mult, dk);
       }
     }
@@ -333,12 +334,13 @@ __device__ __forceinline__ void march_pixel(cudaTextureObject_t grid, const Para
       const float lod = __log2f(diam * k.inv_vws);
       const float rocc = __frcp_rn(__fmaf_rn(0.03f, diam, 1.0f));
       float4 s[NC];
-      bool on[NC];
       bool any = false;
+      // (no array of predicates between the two loops: nvcc 12.9 miscompiled `bool on[NC]` carried across the texture
+      // fetches in some register allocations -- wrong pixels with NC = 9 / SU = 2 -- so the condition is recomputed;
+      // alpha[c] does not change in between)
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        on[c] = (c < n) && (alpha[c] < max_alpha);
-        if (on[c]) {
+        if ((c < n) && (alpha[c] < max_alpha)) {
           const float du = sdir[(0 * NC + c) * stride], dv = sdir[(1 * NC + c) * stride], dw = sdir[(2 * NC + c) * stride];
           s[c] = tex3DLod<float4>(grid, __fmaf_rn(ddist, du, u0), __fmaf_rn(ddist, dv, v0), __fmaf_rn(ddist, dw, w0), lod);
           ++samples;
@@ -346,7 +348,7 @@ __device__ __forceinline__ void march_pixel(cudaTextureObject_t grid, const Para
       }
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        if (on[c]) {
+        if ((c < n) && (alpha[c] < max_alpha)) {
           const float t = P.cone_w[c] * (1.0f - alpha[c]);
           dr = __fmaf_rn(t, s[c].x, dr); dg = __fmaf_rn(t, s[c].y, dg); db = __fmaf_rn(t, s[c].z, db);
           docc = __fmaf_rn(t * s[c].w, rocc, docc);
@@ -384,8 +386,8 @@ __device__ __forceinline__ unsigned char to_unorm8(float x) {
 
 // one warp = 8x4 pixels; block = 2 warps = 8x8 pixels (small blocks: the specular chain length varies a lot
 // between warps and a block holds its registers until its slowest warp is done)
-template <int NC, int SU>
-__global__ void __launch_bounds__(64, 8) cone_trace(Params P, VertexCache vc,
+template <int NC, int SU, int BT, int MINB>
+__global__ void __launch_bounds__(BT, MINB) cone_trace(Params P, VertexCache vc,
                                                   const uint32_t* __restrict__ idx,
                                                   const uint16_t* __restrict__ trimat,
                                                   const MaterialDev* __restrict__ mats,
@@ -397,7 +399,7 @@ __global__ void __launch_bounds__(64, 8) cone_trace(Params P, VertexCache vc,
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lx = lane & 7, ly = lane >> 3;    // 8x4 pixel tile per warp (a 2x2-quad lane order measured the same)
   const int i = blockIdx.x * 8 + lx;
-  const int j = y_begin + blockIdx.y * 8 + warp * 4 + ly;
+  const int j = y_begin + blockIdx.y * (BT / 8) + warp * 4 + ly;
   unsigned samples = 0;
   if (i < P.W && j < y_end) {
     const unsigned long long key = vis[(size_t)j * P.W + i];
@@ -529,15 +531,41 @@ int launch_cone(vct_context* c) {
   VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->cone_samples, 0, sizeof(unsigned long long), c->stream));
   const int y0 = c->P.row_begin, y1 = (c->P.row_end > 0 && c->P.row_end < c->P.H) ? c->P.row_end : c->P.H;
   if (y0 >= y1) return VCT_OK;
-  dim3 b(64), g((c->P.W + 7) / 8, (y1 - y0 + 7) / 8);
-#define VCT_LAUNCH_CONE(NC, SU)                                                                                   \
-  cone_trace<NC, SU><<<g, b, 3 * NC * 64 * sizeof(float), c->stream>>>(c->P, c->vcache2[c->cur], c->d_idx, c->d_trimat, \
-      c->d_materials, c->d_depth, c->d_vis2[c->cur], c->grid[c->cur].tex, c->d_frame, c->d_counters, y0, y1)
+  // NC = 6 (the reference's table) has tuning variants selected by DebugConeVariant: specular fetch-ahead depth SU,
+  // block size BT (one or two 8x4 warp tiles), register budget via MINB blocks per SM.  All variants execute the same
+  // arithmetic per pixel: frames are bit-identical (test_cone_trace_variants_are_bit_identical).
+#define VCT_LAUNCH_CONE(NC, SU, BT, MINB)                                                                              \
+  do {                                                                                                                 \
+    dim3 b(BT), g((c->P.W + 7) / 8, (y1 - y0 + (BT / 8) - 1) / (BT / 8));                                               \
+    cone_trace<NC, SU, BT, MINB><<<g, b, 3 * NC * BT * sizeof(float), c->stream>>>(c->P, c->vcache2[c->cur], c->d_idx,  \
+        c->d_trimat, c->d_materials, c->d_depth, c->d_vis2[c->cur], c->grid[c->cur].tex, c->d_frame, c->d_counters, y0, y1); \
+  } while (0)
   const int su = c->debug_spec_ahead;
   if (c->P.n_cones <= 6) {
-    if (su == 1) VCT_LAUNCH_CONE(6, 1); else if (su == 2) VCT_LAUNCH_CONE(6, 2); else VCT_LAUNCH_CONE(6, 4);
+    switch (c->debug_cone_variant) {
+      case 1: VCT_LAUNCH_CONE(6, 4, 64, 8); break;        // round-1 shape: 128 registers, 8 blocks / SM
+      case 2: VCT_LAUNCH_CONE(6, 2, 64, 10); break;
+      case 3: VCT_LAUNCH_CONE(6, 4, 32, 16); break;
+      case 4: VCT_LAUNCH_CONE(6, 4, 32, 20); break;
+      case 5: VCT_LAUNCH_CONE(6, 2, 32, 20); break;
+      case 8: VCT_LAUNCH_CONE(6, 4, 128, 4); break;
+      default:                                            // 96 registers, 10 blocks / SM: +2.4 % on config 2 (profiles/r02_cone_variants.txt)
+        if (su == 1) VCT_LAUNCH_CONE(6, 1, 64, 8); else if (su == 2) VCT_LAUNCH_CONE(6, 2, 64, 8); else VCT_LAUNCH_CONE(6, 4, 64, 10);
+    }
+  } else if (c->P.n_cones <= 9) {                         // BASELINE config 3: 9 diffuse cones + specular
+    switch (c->debug_cone_variant) {
+      case 1: VCT_LAUNCH_CONE(16, 2, 64, 8); break;       // round-1 shape (16-cone template)
+      case 3: VCT_LAUNCH_CONE(9, 2, 64, 10); break;
+      case 4: VCT_LAUNCH_CONE(9, 4, 32, 16); break;
+      // NOT offered: <9, 2, 64, 8> and <9, 2, 32, 16>.  nvcc 12.9.86 generates code for these two instantiations (128
+      // registers, no spills) that drops ~0.4 % of the march steps -- same source, same inputs; <9, 2, 64, 10>, <9, 4, ..>,
+      // <9, 1, ..> and <16, 2, ..> agree with each other and with the oracle (tools/variant_diff.py,
+      // profiles/r02_cone_variants.txt).  test_cone_trace_variants_are_bit_identical pins every variant that IS offered.
+      default:                                            // 9-cone template + 4 specular steps ahead: -10 % vs the 16-cone template
+        if (su == 1) VCT_LAUNCH_CONE(9, 1, 64, 8); else if (su == 2) VCT_LAUNCH_CONE(9, 2, 64, 10); else VCT_LAUNCH_CONE(9, 4, 64, 8);
+    }
   } else {
-    if (su == 1) VCT_LAUNCH_CONE(16, 1); else VCT_LAUNCH_CONE(16, 2);
+    if (su == 1) VCT_LAUNCH_CONE(16, 1, 64, 8); else VCT_LAUNCH_CONE(16, 2, 64, 8);
   }
 #undef VCT_LAUNCH_CONE
   c->launches += 1;

@@ -91,6 +91,7 @@ struct vct_context {
   int dense_resolve = 0;
   int grid_format = 0;
   int debug_spec_ahead = 4;   // specular steps fetched ahead per iteration (1, 2, 4)
+  int debug_cone_variant = 0; // cone_trace tuning variant (block size / register budget / fetch-ahead), see launch_cone
   size_t max_fragments = 16u << 20;
   size_t max_items = 4u << 20;
 
@@ -116,6 +117,7 @@ struct vct_context {
   // shadow map (u32 d24, linear)
   uint32_t* d_depth = nullptr; int depth_S = 0; bool depth_valid = false;
   cudaArray_t depth_array = nullptr; cudaTextureObject_t depth_tex = 0;   // same texels as a 2D array for tex2Dgather
+  cudaSurfaceObject_t depth_surf = 0;                                     // ... written by depth_to_array (0: memcpy fallback)
 
   // voxel grid
   int grid_V = 0; int grid_fmt_alloc = -1;       // format the slots were allocated with (0 RGBA8, 1 RGBA16F)

@@ -13,6 +13,8 @@
 //                   unsigned small(Setup&, tri, i0,i1,j0,j1)    (thread-serial path)
 //                   void pixel(Setup&, tri, i, j, bool in_bbox) (warp path, called by all 32 lanes)
 //                   static constexpr bool kAppends; if true also covered(), reserve(n), emit(tri,i,j,pos)
+//                   static constexpr bool kWarpMedium: boxes up to 8x8 pixels are rasterised by the whole warp inside
+//                   raster_small through pixel() (passes whose pixel() has no warp-collective operation)
 #pragma once
 
 #include "vct_internal.h"
@@ -22,6 +24,18 @@ namespace vct {
 constexpr int SMALL_AREA = 16;
 constexpr int TILE = 8;
 constexpr int ITEM_TILES = 16;
+
+// Every lane receives lane `src`'s copy of a POD (word by word; fully unrolled, stays in registers)
+template <class T>
+__device__ __forceinline__ T warp_broadcast(const T& v, int src) {
+  static_assert(sizeof(T) % 4 == 0, "POD of 32-bit words");
+  T out;
+  const uint32_t* a = reinterpret_cast<const uint32_t*>(&v);
+  uint32_t* b = reinterpret_cast<uint32_t*>(&out);
+#pragma unroll
+  for (int k = 0; k < (int)(sizeof(T) / 4); ++k) b[k] = __shfl_sync(0xffffffffu, a[k], src);
+  return out;
+}
 
 template <class Pass>
 __global__ void __launch_bounds__(128, 5) raster_small(Pass pass, uint32_t tri_begin, uint32_t tri_end,
@@ -39,6 +53,30 @@ __global__ void __launch_bounds__(128, 5) raster_small(Pass pass, uint32_t tri_b
   bool small_tri = live && (w * h <= SMALL_AREA);
   // every lane of the warp calls small(): passes that append to a queue aggregate across the warp
   pass.small(s, tri, small_tri, i0, i1, j0, j1);
+  if constexpr (Pass::kWarpMedium) {
+    // Medium triangles (bounding box up to 8x8 pixels, too many pixels for one lane): the warp takes them one at a
+    // time, the owner lane broadcasts its set-up and 32 lanes test an 8x4 block of the box per step.  No queue entry,
+    // no second set-up in raster_tiles, no walk over the up to four 8x8 screen tiles such a box straddles -- meshes of
+    // ~1-pixel triangles (BASELINE config 4) are almost entirely of this kind in the shadow and visibility passes.
+    const bool medium = live && !small_tri && w <= 8 && h <= 8;
+    unsigned todo = __ballot_sync(0xffffffffu, medium);
+    const int lane = (int)(threadIdx.x & 31);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const typename Pass::Setup bs = warp_broadcast(s, src);
+      const int bi0 = __shfl_sync(0xffffffffu, i0, src), bi1 = __shfl_sync(0xffffffffu, i1, src);
+      const int bj0 = __shfl_sync(0xffffffffu, j0, src), bj1 = __shfl_sync(0xffffffffu, j1, src);
+      const uint32_t btri = __shfl_sync(0xffffffffu, tri, src);
+      const int i = bi0 + (lane & 7);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int j = bj0 + half * 4 + (lane >> 3);
+        if (bj0 + half * 4 <= bj1) pass.pixel(bs, btri, i, j, i <= bi1 && j <= bj1);
+      }
+    }
+    if (medium) live = false;
+  }
   if (live && !small_tri) {
     int tx0 = i0 / TILE, tx1 = i1 / TILE, ty0 = j0 / TILE, ty1 = j1 / TILE;
     uint32_t ntiles = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);

@@ -12,6 +12,7 @@ struct ShadowPass {
   uint32_t* depth;
 
   static constexpr bool kAppends = false;
+  static constexpr bool kWarpMedium = true;
   struct Setup { RasterTri t; float z0, z1, z2; };
 
   __device__ __forceinline__ bool setup(uint32_t tri, Setup& s, int& i0, int& i1, int& j0, int& j1) const {
@@ -67,6 +68,19 @@ __global__ void fill_u32(uint32_t* p, size_t n, uint32_t v) {
   for (; i < n; i += stride) p[i] = v;
 }
 
+// The D24 map as a 2D array for tex2Dgather (voxel shading): four texels per thread, 16-byte surface stores.
+// (cudaMemcpy2DToArrayAsync of the 64 MiB map took ~270 us per call -- more than rasterising it.)
+__global__ void depth_to_array(const uint32_t* __restrict__ depth, cudaSurfaceObject_t surf, int S) {
+  const int x4 = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x4 * 4 >= S || y >= S) return;
+  if (x4 * 4 + 3 < S && (S & 3) == 0) {
+    const uint4 v = *reinterpret_cast<const uint4*>(depth + (size_t)y * S + x4 * 4);
+    surf2Dwrite(v, surf, x4 * 16, y);
+  } else {
+    for (int x = x4 * 4; x < min(x4 * 4 + 4, S); ++x) surf2Dwrite(depth[(size_t)y * S + x], surf, x * 4, y);
+  }
+}
+
 int launch_shadow(vct_context* c) {
   if (!c->nt) return set_error(c, VCT_ERR_STATE, "vct_draw_depth: no mesh uploaded");
   int rc = ensure_shadow(c); if (rc) return rc;
@@ -83,8 +97,15 @@ int launch_shadow(vct_context* c) {
   c->launches += 3;
   VCT_CUDA(c, cudaGetLastError());
   // array copy for tex2Dgather (voxel shading)
-  VCT_CUDA(c, cudaMemcpy2DToArrayAsync(c->depth_array, 0, 0, c->d_depth, (size_t)c->P.S * 4, (size_t)c->P.S * 4, c->P.S,
-                                       cudaMemcpyDeviceToDevice, c->stream));
+  if (c->depth_surf) {
+    dim3 b(32, 8), g((c->P.S / 4 + 32) / 32, (c->P.S + 7) / 8);
+    depth_to_array<<<g, b, 0, c->stream>>>(c->d_depth, c->depth_surf, c->P.S);
+    c->launches += 1;
+    VCT_CUDA(c, cudaGetLastError());
+  } else {
+    VCT_CUDA(c, cudaMemcpy2DToArrayAsync(c->depth_array, 0, 0, c->d_depth, (size_t)c->P.S * 4, (size_t)c->P.S * 4, c->P.S,
+                                         cudaMemcpyDeviceToDevice, c->stream));
+  }
   c->depth_valid = true;
   return VCT_OK;
 }

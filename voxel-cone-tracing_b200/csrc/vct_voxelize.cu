@@ -185,6 +185,7 @@ struct VoxCoverPass {
 
   // warp path (raster_tiles, kAppends protocol)
   static constexpr bool kAppends = true;
+  static constexpr bool kWarpMedium = false;    // fragments are appended with warp-wide reservations: thread / tile paths only
   __device__ __forceinline__ bool covered(const Setup& s, int i, int j) const { return s.v.t.covered(i, j, P.coverage); }
   __device__ __forceinline__ uint32_t reserve(uint32_t n) const { return atomicAdd(&ctr->n_fragments, n); }
   __device__ __forceinline__ void emit(uint32_t tri, int i, int j, uint32_t pos) const {
