@@ -507,6 +507,21 @@ def test_cpp_facade_with_the_reference_class_surface_runs(gpu_ctx, oracle, tmp_p
         assert_frame_close(want, oracle.frame(), f"facade frame {f} vs oracle")
 
 
+def test_cpp_facade_renders_sharded_frames_over_two_ranks():
+    """host/Voxel_Cone_Tracing.h: Voxel_Cone_Tracing_Sharded (vct_comm_init_multi / vct_frame_sharded_multi behind the
+    reference's class surface) -- two ranks from one C++ host thread, frames byte-identical to the single-GPU ones."""
+    import subprocess
+    import tempfile
+    import torch
+    root = os.path.dirname(HERE)
+    exe = os.path.join(root, "voxel-cone-tracing_b200", "lib", "facade_demo")
+    second = 1 if torch.cuda.device_count() >= 2 else 0
+    with tempfile.TemporaryDirectory() as d:
+        out = subprocess.run([exe, d, "sharded", str(second)], capture_output=True, text=True, timeout=180)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("identical") == 3 and "DIFFERENT" not in out.stdout, out.stdout
+
+
 def test_tile_item_queue_overflow_is_detected_and_harmless(gpu_ctx):
     """MaxTileItems too small for the scene's large triangles: the pass must report VCT_ERR_OVERFLOW (not fault on the
     stale part of the queue) and the context must keep working once the queue is large enough."""

@@ -94,7 +94,11 @@ static int check_cu(vct_context* c, CUresult r, const char* what) {
 constexpr size_t COMM_PADS = 4096;               // signal pads: [channel][16 ranks] x u32 at 256-byte channel stride; [2048] = fail flag
 constexpr int COMM_CHANNELS = 4;
 
+// one process, several devices: the members of a group share ONE multicast handle; the last one out releases it
+struct InProcGroup { CUmemGenericAllocationHandle mc = 0; int refs = 0; };
+
 struct Comm {
+  InProcGroup* group = nullptr;
   int rank = 0, world = 1;
   bool multicast = false, in_process = false;
   size_t seg = 0;                                // bytes per rank segment (granularity aligned)
@@ -293,9 +297,14 @@ static void comm_release(vct_context* c) {
       g_drv.MemAddressFree(m->va, m->seg * m->world);
     }
     if (m->mc) {
-      if (m->local) g_drv.MulticastUnbind(m->mc, m->cu_dev, 0, m->seg);
-      if (!m->in_process || m->rank == 0) g_drv.MemRelease(m->mc);
+      if (m->local && m->multicast) g_drv.MulticastUnbind(m->mc, m->cu_dev, 0, m->seg);
+      if (!m->in_process) g_drv.MemRelease(m->mc);
     }
+    if (m->group && --m->group->refs == 0) {
+      if (m->group->mc) g_drv.MemRelease(m->group->mc);
+      delete m->group;
+    }
+    m->group = nullptr;
     for (int r = 0; r < (int)m->peers.size(); ++r)
       if (m->peers[r] && (r != m->rank) && !m->in_process) g_drv.MemRelease(m->peers[r]);
     if (m->local) g_drv.MemRelease(m->local);
@@ -446,11 +455,14 @@ static int comm_init_in_process(vct_context** cs, int n, int flags) {
   int rc = load_driver(c0); if (rc) return rc;
   std::vector<Comm*> ms(n, nullptr);
   int mc_all = 1;
+  for (int r = 0; r < n; ++r) { cudaSetDevice(cs[r]->device); if (cs[r]->comm) comm_release(cs[r]); }
+  InProcGroup* group = new InProcGroup();
+  group->refs = n;
   for (int r = 0; r < n; ++r) {
     vct_context* c = cs[r];
     cudaSetDevice(c->device);
-    if (c->comm) comm_release(c);
     Comm* m = new Comm();
+    m->group = group;
     c->comm = m; ms[r] = m;
     m->rank = r; m->world = n; m->in_process = true;
     c->shared_world = n; c->shared_rank = r;
@@ -474,6 +486,7 @@ static int comm_init_in_process(vct_context** cs, int n, int flags) {
     CUmulticastObjectProp mp = {};
     mp.numDevices = (unsigned)n; mp.size = seg; mp.handleTypes = 0;
     if ((rc = check_cu(c0, g_drv.MulticastCreate(&mc, &mp), "cuMulticastCreate"))) return rc;
+    group->mc = mc;
     for (int r = 0; r < n; ++r)
       if ((rc = check_cu(c0, g_drv.MulticastAddDevice(mc, ms[r]->cu_dev), "cuMulticastAddDevice"))) return rc;
   }

@@ -13,7 +13,7 @@
 //                   unsigned small(Setup&, tri, i0,i1,j0,j1)    (thread-serial path)
 //                   void pixel(Setup&, tri, i, j, bool in_bbox) (warp path, called by all 32 lanes)
 //                   static constexpr bool kAppends; if true also covered(), reserve(n), emit(tri,i,j,pos)
-//                   static constexpr bool kWarpMedium: boxes up to 8x8 pixels are rasterised by the whole warp inside
+//                   static constexpr bool kWarpMedium: boxes up to MEDIUM_MAX^2 pixels are rasterised by the whole warp inside
 //                   raster_small through pixel() (passes whose pixel() has no warp-collective operation)
 #pragma once
 
@@ -22,6 +22,7 @@
 namespace vct {
 
 constexpr int SMALL_AREA = 16;
+constexpr int MEDIUM_MAX = 16;
 constexpr int TILE = 8;
 constexpr int ITEM_TILES = 16;
 
@@ -54,11 +55,11 @@ __global__ void __launch_bounds__(128, 5) raster_small(Pass pass, uint32_t tri_b
   // every lane of the warp calls small(): passes that append to a queue aggregate across the warp
   pass.small(s, tri, small_tri, i0, i1, j0, j1);
   if constexpr (Pass::kWarpMedium) {
-    // Medium triangles (bounding box up to 8x8 pixels, too many pixels for one lane): the warp takes them one at a
-    // time, the owner lane broadcasts its set-up and 32 lanes test an 8x4 block of the box per step.  No queue entry,
+    // Medium triangles (bounding box up to MEDIUM_MAX pixels a side, too many pixels for one lane): the warp takes them
+    // one at a time, the owner lane broadcasts its set-up and 32 lanes test an 8x4 block of the box per step.  No queue entry,
     // no second set-up in raster_tiles, no walk over the up to four 8x8 screen tiles such a box straddles -- meshes of
     // ~1-pixel triangles (BASELINE config 4) are almost entirely of this kind in the shadow and visibility passes.
-    const bool medium = live && !small_tri && w <= 8 && h <= 8;
+    const bool medium = live && !small_tri && w <= MEDIUM_MAX && h <= MEDIUM_MAX;
     unsigned todo = __ballot_sync(0xffffffffu, medium);
     const int lane = (int)(threadIdx.x & 31);
     while (todo) {
@@ -68,12 +69,11 @@ __global__ void __launch_bounds__(128, 5) raster_small(Pass pass, uint32_t tri_b
       const int bi0 = __shfl_sync(0xffffffffu, i0, src), bi1 = __shfl_sync(0xffffffffu, i1, src);
       const int bj0 = __shfl_sync(0xffffffffu, j0, src), bj1 = __shfl_sync(0xffffffffu, j1, src);
       const uint32_t btri = __shfl_sync(0xffffffffu, tri, src);
-      const int i = bi0 + (lane & 7);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int j = bj0 + half * 4 + (lane >> 3);
-        if (bj0 + half * 4 <= bj1) pass.pixel(bs, btri, i, j, i <= bi1 && j <= bj1);
-      }
+      for (int by = bj0; by <= bj1; by += 4)            // warp-uniform loops over the 8x4 blocks of the box
+        for (int bx = bi0; bx <= bi1; bx += 8) {
+          const int i = bx + (lane & 7), j = by + (lane >> 3);
+          pass.pixel(bs, btri, i, j, i <= bi1 && j <= bj1);
+        }
     }
     if (medium) live = false;
   }

@@ -120,6 +120,12 @@ struct Voxel_Cone_Tracing {
 
   // host_rgba: optional H*W*4 buffer that receives the frame (the reference presents it with glfwSwapBuffers)
   void Render(uint8_t* host_rgba = nullptr) {
+    SetRenderUniforms();
+    check(vct_render(device, host_rgba));      // model.Draw(VoxelConeTracingShader)
+  }
+
+  // the uniform block of Render() (Voxel_Cone_Tracing.h:161-187), separated so that a sharded frame can set it too
+  void SetRenderUniforms() {
     mat4 vMat = camera.GetViewMatrix();
     mat4 pMat = vctm::perspective(vctm::radians(camera.Zoom), (float)screen_width / (float)screen_height, 0.1f, 1000.0f);
     vec3 camera_Position = camera.position;
@@ -138,7 +144,6 @@ struct Voxel_Cone_Tracing {
     check(vct_set_mat4(device, "ModelViewMatrix", (vMat * mMat).data()));
     check(vct_set_mat4(device, "ProjectionMatrix", pMat.data()));
     check(vct_set_mat4(device, "DepthModelViewProjectionMatrix", (DepthViewProjectionMatrix * mMat).data()));
-    check(vct_render(device, host_rgba));      // model.Draw(VoxelConeTracingShader)
   }
 
   void DrawDepthTexture() {
@@ -160,6 +165,39 @@ struct Voxel_Cone_Tracing {
     check(vct_set_i(device, "ShadowMapSize", (int)ShadowMapSize));
     check(vct_set_i(device, "CoveragePolicy", CoveragePolicy));
     check(vct_draw_voxels(device));            // model.Draw(VoxelizeShader) + glGenerateMipmap(GL_TEXTURE_3D)
+  }
+};
+
+// Several GPUs, one host thread: one Voxel_Cone_Tracing per device, joined by the library's own multi-GPU layer
+// (vct_comm_init_multi: symmetric segments + NVSwitch multicast + device-side barriers).  Render() produces ONE frame:
+// every device voxelises its share of the triangles, exchanges the voxels it touched, traces its band of rows and
+// writes it into device 0's frame; the assembled frame arrives in host_rgba.  Unlike the single-GPU Render(), the
+// sharded frame re-voxelises every time (it is the reference's whole loop body, main.cpp:81-92, for dynamic scenes).
+struct Voxel_Cone_Tracing_Sharded {
+  std::vector<Voxel_Cone_Tracing*> ranks;
+  std::vector<vct_handle> handles;
+
+  Voxel_Cone_Tracing_Sharded(int screen_width, int screen_height, const std::vector<int>& cuda_devices) {
+    for (int d : cuda_devices) ranks.push_back(new Voxel_Cone_Tracing(screen_width, screen_height, nullptr, d));
+    for (auto* r : ranks) handles.push_back(r->device);
+  }
+  ~Voxel_Cone_Tracing_Sharded() { for (auto* r : ranks) delete r; }
+  Voxel_Cone_Tracing_Sharded(const Voxel_Cone_Tracing_Sharded&) = delete;
+  Voxel_Cone_Tracing_Sharded& operator=(const Voxel_Cone_Tracing_Sharded&) = delete;
+
+  void init_voxel_cone_tracing(const Model& m, int VoxelDimensions) {
+    for (auto* r : ranks) {
+      r->VoxelDimensions = VoxelDimensions;
+      r->init_voxel_cone_tracing(m);
+      r->SetRenderUniforms();            // the segment is sized from VoxelDimensions and the screen size
+    }
+    if (vct_comm_init_multi(handles.data(), (int)handles.size(), 0) != VCT_OK) ranks[0]->check(VCT_ERR_STATE);
+  }
+
+  void Render(uint8_t* host_rgba) {
+    for (auto* r : ranks) r->SetRenderUniforms();
+    if (vct_frame_sharded_multi(handles.data(), (int)handles.size(), host_rgba) != VCT_OK) ranks[0]->check(VCT_ERR_STATE);
+    for (auto* r : ranks) r->check(vct_frame_sharded_wait(r->device));
   }
 };
 

@@ -4,7 +4,9 @@
 //   facade_demo [dump_dir]   with a directory: also writes the flattened scene (verts.f32, idx.u32, trimat.u16), the
 //   uniforms of every frame (uniforms_<f>.f32: ModelView, Projection, DepthMVP, ProjX, ProjY, ProjZ, camera) and the
 //   frames (frame_<f>.rgba), so that a test can replay the same inputs through another binding and compare bytes.
+//   facade_demo <dump_dir> sharded [second_device]   also renders the views as sharded frames over two ranks.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -77,6 +79,22 @@ int main(int argc, char** argv) {
         u.push_back(camera.position.x); u.push_back(camera.position.y); u.push_back(camera.position.z);
         dump(dir + "uniforms_" + std::to_string(f) + ".f32", u.data(), u.size() * sizeof(float));
         dump(dir + "frame_" + std::to_string(f) + ".rgba", frame.data(), frame.size());
+      }
+    }
+    // The same three views as ONE sharded frame stream over two ranks (two GPUs if the machine has them, else two
+    // handles on GPU 0): the frames must equal the single-GPU ones byte for byte.
+    if (argc > 2 && std::string(argv[2]) == "sharded") {
+      const int second = std::atoi(argc > 3 ? argv[3] : "0");
+      Voxel_Cone_Tracing_Sharded sharded(256, 256, {0, second});
+      sharded.init_voxel_cone_tracing(m, 64);
+      std::vector<uint8_t> single(256 * 256 * 4), both(256 * 256 * 4);
+      for (int f = 0; f < 3; ++f) {
+        camera.Yaw = -90.0f + 2.0f * f;
+        voxel_cone_tracing.Render(single.data());
+        sharded.Render(both.data());
+        const bool same = std::memcmp(single.data(), both.data(), single.size()) == 0;
+        std::printf("sharded frame %d over devices {0,%d}: %s\n", f, second, same ? "identical" : "DIFFERENT");
+        if (!same) return 2;
       }
     }
   } catch (const std::exception& e) {
