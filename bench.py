@@ -68,6 +68,7 @@ def parse(argv=None):
                     "and gather with NCCL instead of the pipelined vct_frame_sharded")
     ap.add_argument("--contiguous", action="store_true", help="triangle sharding by contiguous ranges instead of interleaved blocks")
     ap.add_argument("--no-multicast", action="store_true", help="--mode shard: exchange by peer stores instead of multimem.st")
+    ap.add_argument("--row-bands", action="store_true", help="--mode shard: contiguous row bands instead of interleaved strips of 8 rows")
     ap.add_argument("--exchange", default="inbox", choices=["inbox", "reduce"],
                     help="--mode shard: inbox = touched voxels multicast as records (multimem.st) and merged locally; reduce = "
                          "multimem.red into a dense symmetric accumulator (reduced in the switch; serial form only)")
@@ -77,8 +78,9 @@ def parse(argv=None):
                          "5 = light-probe bake: 64 views at 1024^2 from one 3-bounce voxelisation")
     ap.add_argument("--detail", type=float, default=1.0, help="scene tessellation scale (1.0 = config 2)")
     ap.add_argument("--grid", type=int, default=256)
-    ap.add_argument("--width", type=int, default=1920)
-    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--width", type=int, default=0, help="override the config's frame width")
+    ap.add_argument("--height", type=int, default=0, help="override the config's frame height")
+    ap.add_argument("--tune", default="", help="comma-separated library tuning knobs, e.g. ChainBlockThreads=64,ConeSmemPad=8192")
     ap.add_argument("--coverage", default=None)
     ap.add_argument("--cones", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -88,17 +90,20 @@ def parse(argv=None):
                     "default: no flush -- the per-frame working set (~220 MB, two alternating frame slots) exceeds the 126 MB L2")
     a = ap.parse_args(argv)
     a.shadow = 4096
+    w0, h0 = 1920, 1080
     if a.config == 1:
-        a.grid, a.width, a.height, a.shadow = 64, 256, 256, 1024
+        a.grid, w0, h0, a.shadow = 64, 256, 256, 1024
         a.coverage = a.coverage or "msaa4"
     elif a.config == 3:
-        a.grid, a.width, a.height = 512, 3840, 2160
+        a.grid, w0, h0 = 512, 3840, 2160
         a.cones = a.cones or "9+1"
         a.mode = a.mode or ("shard" if a.gpus > 1 else "views")
     elif a.config == 4:
         a.mode = a.mode or ("shard" if a.gpus > 1 else "views")
     elif a.config == 5:
-        a.width, a.height, a.mode = 1024, 1024, "probes"
+        w0, h0, a.mode = 1024, 1024, "probes"
+    a.nominal_size = not (a.width or a.height)
+    a.width, a.height = a.width or w0, a.height or h0
     a.coverage = a.coverage or "conservative"
     a.cones = a.cones or "6+1"
     a.mode = a.mode or "views"
@@ -149,7 +154,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -261,6 +266,9 @@ def bench_config(env, args):
     ctx = vct_b200.Context(local)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_uniforms(u)
+    for kv in filter(None, args.tune.split(",")):
+        k, v = kv.split("=")
+        ctx.set_i(k, int(v))
     ctx.load_scene(sc)
     H, W = args.height, args.width
     ctx.draw_depth()                                # static light: once, like the reference's init
@@ -272,7 +280,7 @@ def bench_config(env, args):
     tri_rng = None
     shared = None
     if sharded:
-        flags = capi.COMM_NO_MULTICAST if args.no_multicast else 0
+        flags = (capi.COMM_NO_MULTICAST if args.no_multicast else 0) | (capi.COMM_ROW_BANDS if args.row_bands else 0)
         shared = parallel.SharedAccumulator(ctx, rank=rank, world=world, session=session_name(f"c{args.config}"),
                                             exchange=args.exchange, flags=flags)      # deals triangles + row bands
         if args.contiguous:
@@ -373,6 +381,9 @@ def bench_config(env, args):
     if pipelined_shard:
         shard_check = verify_sharded(env, ctx, shared, sc, prepare)
 
+    # nvidia-smi sampling starts before the warm-up and runs until the end-to-end loop has finished: the timed region of
+    # a 20-step run lasts ~20 ms, less than one sampling period of the tool
+    sampler = ClockSampler(local); sampler.start()
     for i in range(max(args.warmup, 3)):
         step(i)
     drain()
@@ -383,7 +394,6 @@ def bench_config(env, args):
     ctx.set_i("Profile", 0)
     ctx.set_i("PipelineFrames", 0 if args.flush else 1)
     launches0 = ctx.kernel_launches()
-    sampler = ClockSampler(local); sampler.start()
     env.barrier()
     if flush is None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -404,7 +414,6 @@ def bench_config(env, args):
         drain()
         env.barrier()
         total_ms = sum(a.elapsed_time(b) for a, b in ev)
-    clocks = sampler.stop()
     launches = ctx.kernel_launches() - launches0
     total_ms = env.max_over_ranks([total_ms])[0]
     frames = args.steps * (world if args.mode == "views" else 64 if args.mode == "probes" else 1)
@@ -480,6 +489,8 @@ def bench_config(env, args):
     drain()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    clocks["window"] = "warm-up + timed region + per-pass loop + end-to-end loop"
     if os.environ.get("VCT_BENCH_DEBUG"):
         print(f"[rank {rank}] device loop {total_ms / args.steps:.4f} ms/step (max over ranks), e2e loop {e2e_s / args.steps * 1e3:.4f} ms/step", file=sys.stderr, flush=True)
     e2e_value = frames / env.max_over_ranks([e2e_s])[0]
@@ -524,7 +535,7 @@ def bench_config(env, args):
         "ms_per_step": round(total_ms / K, 4), "higher_is_better": True,
         "scaling": "weak" if args.mode == "views" else "strong",     # probes / tiles / shards: total work fixed
         "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.config] if (args.detail == 1.0) else f"config{args.config}: {sc.name} {sc.n_tris} tris, V={args.grid} {fmt_name}, {W}x{H}, cones {args.cones}",
+        "config": {"workload": WORKLOADS[args.config] if (args.detail == 1.0 and args.nominal_size and not args.tune) else f"config{args.config}: {sc.name} {sc.n_tris} tris, V={args.grid} {fmt_name}, {W}x{H}, cones {args.cones}",
                    "mode": args.mode + ("/" + args.exchange if sharded else "") + ("/serial" if sharded and not pipelined_shard else ""),
                    "l2": ("flushed between steps by an untimed 256 MiB write; frames not pipelined" if args.flush else "no flush: per-frame working set ~220 MB (64 MiB level 0 + mips, shadow texels, accumulator lines, queues, vertex cache, visibility) in two alternating frame slots exceeds the 126 MB L2"),
                    "timing": "one CUDA-event pair around the K steps on the launching stream, barrier+synchronize both sides; max over ranks",
@@ -623,14 +634,16 @@ def verify_sharded(env, ctx, shared, sc, prepare):
     torch = env.torch
     levels = ctx.get_i("MipLevels")
     H, W = ctx.get_i("screen_height"), ctx.get_i("screen_width")
-    rb, re_ = ctx.get_i("RowBegin"), ctx.get_i("RowEnd")
+    rb, re_, ril, rph = ctx.get_i("RowBegin"), ctx.get_i("RowEnd"), ctx.get_i("RowInterleave"), ctx.get_i("RowPhase")
     interleave = env.world
-    ctx.set_i("RowBegin", 0); ctx.set_i("RowEnd", 0); ctx.set_i("TriangleInterleave", 1); ctx.set_i("TrianglePhase", 0)
+    ctx.set_i("RowBegin", 0); ctx.set_i("RowEnd", 0); ctx.set_i("RowInterleave", 0); ctx.set_i("RowPhase", 0)
+    ctx.set_i("TriangleInterleave", 1); ctx.set_i("TrianglePhase", 0)
     prepare(0)
     ctx.frame(); ctx.sync()
     ref_crc = grid_checksums(ctx, levels)
     ref_frame = ctx.read_frame()
-    ctx.set_i("RowBegin", rb); ctx.set_i("RowEnd", re_); ctx.set_i("TriangleInterleave", interleave); ctx.set_i("TrianglePhase", env.rank)
+    ctx.set_i("RowBegin", rb); ctx.set_i("RowEnd", re_); ctx.set_i("RowInterleave", ril); ctx.set_i("RowPhase", rph)
+    ctx.set_i("TriangleInterleave", interleave); ctx.set_i("TrianglePhase", env.rank)
     host = torch.zeros((H, W, 4), dtype=torch.uint8).pin_memory()
     ok = True
     for _ in range(3):                 # both frame slots and both inbox parities
@@ -736,7 +749,7 @@ def strong_config3(env, steps, warmup):
             "d2h_bytes_per_step": W * H * 4,
             "passes_us_max_over_ranks": passes_max, "shard_check": check,
             "note": "one frame stream; triangles dealt in blocks of 128, touched voxels exchanged as 16-byte records with multimem.st, "
-                    "equal row bands written by cone_trace into rank 0's frame ring over NVLink, two device-side barriers per frame; "
+                    "rows dealt in strips of 8 and written by cone_trace into rank 0's frame ring over NVLink, two device-side barriers per frame; "
                     "no NCCL call in the timed region.  n1_* = the same frames rendered by one GPU alone (pipelined vct_frame) in this run."}
 
 

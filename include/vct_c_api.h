@@ -60,6 +60,8 @@ const char* vct_version(void);
  *   int   : VoxelDimensions ShadowMapSize screen_width screen_height PcfRadius CoveragePolicy
  *           Bounces NumDiffuseCones GridFormat MaxFragments MaxTileItems DenseResolve Profile
  *           RowBegin RowEnd (rows [RowBegin, RowEnd) of the frame are rendered; RowEnd 0 = all: row-band sharding)
+ *           RowInterleave RowPhase (instead: the frame is cut into strips of 8 rows and this context renders every
+ *             RowInterleave-th strip, starting at strip RowPhase -- balanced row sharding, one phase per rank)
  *           TriangleInterleave TrianglePhase (voxelisation takes every TriangleInterleave-th block of 128 triangles of
  *             the requested range, starting at block TrianglePhase: balanced triangle sharding, one phase per rank)
  *           SharedExchange SharedWorld SharedRank MaxExchangeVoxels (fused sharded voxelisation, see below)
@@ -162,10 +164,12 @@ int vct_frame_shared_end(vct_handle h, uint8_t* host_rgba_or_null);
  *
  * vct_comm_init sizes the segment from the CURRENT VoxelDimensions / screen size / MaxExchangeVoxels (call it again after
  * changing them) and, unless VCT_COMM_KEEP_SHARES is given, deals the work: triangles in blocks of 128 round-robin
- * (TriangleInterleave / TrianglePhase) and equal row bands (RowBegin / RowEnd).  All ranks must call it with the same
+ * (TriangleInterleave / TrianglePhase) and rows in strips of 8 round-robin (RowInterleave / RowPhase; contiguous bands
+ * RowBegin / RowEnd with VCT_COMM_ROW_BANDS).  All ranks must call it with the same
  * world, session and settings; it blocks until every rank has joined (120 s limit). */
 #define VCT_COMM_NO_MULTICAST 1   /* do not create a multicast object: exchange by one peer store per rank */
-#define VCT_COMM_KEEP_SHARES  2   /* leave TriangleInterleave / TrianglePhase / RowBegin / RowEnd as the caller set them */
+#define VCT_COMM_KEEP_SHARES  2   /* leave TriangleInterleave / TrianglePhase / RowInterleave / RowPhase / RowBegin / RowEnd as the caller set them */
+#define VCT_COMM_ROW_BANDS    4   /* contiguous row bands (RowBegin / RowEnd) instead of interleaved strips of 8 rows */
 int vct_comm_init(vct_handle h, int rank, int world, const char* session, int flags);
 int vct_comm_destroy(vct_handle h);
 int vct_comm_info(vct_handle h, int* rank, int* world, int* multicast, size_t* segment_bytes);
@@ -219,6 +223,9 @@ int vct_use_own_stream(vct_handle h);
 int vct_sync(vct_handle h);
 int vct_pass_time_us(vct_handle h, int pass, float* us);   /* CUDA-event time of the last run of a pass */
 int vct_kernel_launches(vct_handle h, uint64_t* n);        /* kernels launched by this context so far */
+/* begin / end of `pass` in the frame `frames_back` frames ago (0 = latest, at most 3), in microseconds since Profile was
+ * last switched on: the passes of consecutive frames on one time axis, i.e. how the three streams overlap */
+int vct_pass_timeline(vct_handle h, int frames_back, int pass, float* begin_us, float* end_us);
 
 /* ---- micro-benchmarks used for the roofline denominators (DESIGN.md "Rooflines") */
 /* trilinear+mip-linear tex3DLod throughput on a V^3 RGBA8 pyramid: n_samples per launch, pattern 0 =

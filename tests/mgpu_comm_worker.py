@@ -20,7 +20,7 @@ from vct_b200 import capi, parallel, scenes, uniforms  # noqa: E402
 
 def main():
     rank, world, session, device = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], int(sys.argv[4])
-    flags = capi.COMM_NO_MULTICAST if "nomc" in sys.argv[5:] else 0
+    flags = (capi.COMM_NO_MULTICAST if "nomc" in sys.argv[5:] else 0) | (capi.COMM_ROW_BANDS if "bands" in sys.argv[5:] else 0)
     reduce = "reduce" in sys.argv[5:]
     sc = scenes.atrium(detail=0.3, tex_size=64)
     H, W, V = 360, 640, 128

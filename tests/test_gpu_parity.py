@@ -854,9 +854,10 @@ def test_library_comm_two_processes_one_gpu():
     rank 0, asynchronous host ring) with two PROCESSES acting as two ranks on device 0: no multicast object (one device
     cannot join a team twice), so the records travel as peer stores (vox_push_inbox<2>)."""
     _run_ranks(2, [0, 0], extra=("nomc",))
+    _run_ranks(2, [0, 0], extra=("nomc", "bands"))
 
 
-@pytest.mark.parametrize("extra", [(), ("nomc",), ("reduce",)])
+@pytest.mark.parametrize("extra", [(), ("nomc",), ("reduce",), ("bands",)])
 def test_library_comm_two_gpus(extra):
     """Two processes on two GPUs: multimem.st inbox through the library's multicast mapping, the same without a multicast
     object, and the multimem.red flavour.  Needs two GPUs on the box (skipped otherwise)."""
@@ -893,7 +894,7 @@ def test_one_process_driving_several_devices(gpu_ctx):
         c.set_uniforms(u); c.load_scene(sc); c.draw_depth()
     m.comm_init()
     assert m.ctx[0].comm_info()["multicast"] == (devices[0] != devices[1])
-    assert m.ctx[1].get_i("RowBegin") == H // 2 and m.ctx[0].get_i("RowEnd") == H // 2
+    assert m.ctx[1].get_i("RowInterleave") == 2 and m.ctx[1].get_i("RowPhase") == 1      # rows dealt in strips of 8
     hosts = [np.zeros((H, W, 4), np.uint8) for _ in range(4)]
     for i in range(4):
         for c in m.ctx:

@@ -23,12 +23,12 @@ SYMBOLS = [
     "vct_readback_sums", "vct_readback_grid", "vct_upload_grid_level0", "vct_build_mips", "vct_readback_visibility",
     "vct_readback_frame", "vct_frame_buffer", "vct_cone_samples", "vct_fragment_count", "vct_occupied_voxels", "vct_debug_counter",
     "vct_trace_cones", "vct_sample_voxels", "vct_set_stream", "vct_use_own_stream", "vct_sync", "vct_pass_time_us", "vct_kernel_launches", "vct_bench_tex3d",
-    "vct_bench_tex3d_format", "vct_bench_atomics",
+    "vct_bench_tex3d_format", "vct_bench_atomics", "vct_pass_timeline",
     "vct_comm_init", "vct_comm_destroy", "vct_comm_info", "vct_comm_barrier", "vct_frame_sharded", "vct_frame_sharded_wait",
     "vct_comm_frame_buffer", "vct_create_multi", "vct_comm_init_multi", "vct_frame_sharded_multi",
 ]
 
-COMM_NO_MULTICAST, COMM_KEEP_SHARES = 1, 2
+COMM_NO_MULTICAST, COMM_KEEP_SHARES, COMM_ROW_BANDS = 1, 2, 4
 
 
 class VctError(RuntimeError):
@@ -77,6 +77,7 @@ def load_library(path=None):
         "vct_bench_tex3d": [vp, i, C.c_uint64, i, f, i, C.POINTER(f)],
         "vct_bench_tex3d_format": [vp, i, i, C.c_uint64, i, f, i, C.POINTER(f)],
         "vct_bench_atomics": [vp, C.c_uint64, i, C.POINTER(f)],
+        "vct_pass_timeline": [vp, i, i, C.POINTER(f), C.POINTER(f)],
         "vct_comm_init": [vp, i, i, cp, i], "vct_comm_destroy": [vp],
         "vct_comm_info": [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(sz)], "vct_comm_barrier": [vp],
         "vct_frame_sharded": [vp, vp], "vct_frame_sharded_wait": [vp],
@@ -158,7 +159,8 @@ class Context:
         self._ck(self.L.vct_set_cones(self.h, d.shape[0], _ptr(d), _ptr(w)))
 
     _INT = {"VoxelDimensions", "ShadowMapSize", "screen_width", "screen_height", "PcfRadius", "CoveragePolicy",
-            "Bounces", "GridFormat", "MaxFragments", "MaxTileItems", "DenseResolve", "Profile", "RowBegin", "RowEnd"}
+            "Bounces", "GridFormat", "MaxFragments", "MaxTileItems", "DenseResolve", "Profile", "RowBegin", "RowEnd",
+            "RowInterleave", "RowPhase"}
     _VEC3 = {"CameraPosition", "LightDirection"}
     _MAT4 = {"ModelMatrix", "ModelViewMatrix", "ProjectionMatrix", "DepthModelViewProjectionMatrix", "ProjX",
              "ProjY", "ProjZ"}
@@ -397,6 +399,11 @@ class Context:
         v = C.c_float()
         self._ck(self.L.vct_pass_time_us(self.h, PASSES[name] if isinstance(name, str) else int(name), C.byref(v)))
         return v.value
+
+    def pass_timeline(self, frames_back, name):
+        a, b = C.c_float(), C.c_float()
+        self._ck(self.L.vct_pass_timeline(self.h, int(frames_back), PASSES[name], C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def bench_tex3d(self, V=256, n_samples=1 << 28, pattern=0, lod=0.5, iters=5, grid_format=0):
         v = C.c_float()

@@ -394,6 +394,12 @@ int ensure_vertex_cache(vct_context* c) {
   return check_cuda(c, cudaGetLastError(), "vertex_pass");
 }
 
+void next_event_generation(vct_context* c) {
+  c->ev_gen = (c->ev_gen + 1) % VCT_EVENT_GENS;
+  for (int p = 0; p < VCT_PASS_COUNT; ++p)
+    if (p != VCT_PASS_DEPTH) c->ev_recorded[c->ev_gen][p] = false;
+}
+
 // ---- frame slots
 void mark_slot_read(vct_context* c) {
   if (!c->slot_read_done[0]) {
@@ -484,8 +490,7 @@ int vct_create(int device, vct_handle* out) {
   if (int rc = check_cuda(c, cudaSetDevice(device), "cudaSetDevice")) return fail(rc);
   if (int rc = check_cuda(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return fail(rc);
   for (int p = 0; p < VCT_PASS_COUNT; ++p) {
-    cudaEventCreate(&c->ev_begin[p]);
-    cudaEventCreate(&c->ev_end[p]);
+    for (int g = 0; g < VCT_EVENT_GENS; ++g) { cudaEventCreate(&c->ev_begin[g][p]); cudaEventCreate(&c->ev_end[g][p]); }
   }
   if (int rc = check_cuda(c, cudaMalloc(&c->d_counters, sizeof(Counters)), "cudaMalloc counters")) return fail(rc);
   cudaMemset(c->d_counters, 0, sizeof(Counters));
@@ -517,7 +522,9 @@ int vct_destroy(vct_handle c) {
   if (c->h_overflow) cudaFreeHost(c->h_overflow);
   if (c->stream2) { cudaStreamDestroy(c->stream2); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
   cudaFree(c->d_items_vis); cudaFree(c->d_counters_vis);
-  for (int p = 0; p < VCT_PASS_COUNT; ++p) { cudaEventDestroy(c->ev_begin[p]); cudaEventDestroy(c->ev_end[p]); }
+  for (int p = 0; p < VCT_PASS_COUNT; ++p)
+    for (int g = 0; g < VCT_EVENT_GENS; ++g) { cudaEventDestroy(c->ev_begin[g][p]); cudaEventDestroy(c->ev_end[g][p]); }
+  if (c->ev_ref) cudaEventDestroy(c->ev_ref);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return VCT_OK;
@@ -550,6 +557,8 @@ int vct_set_i(vct_handle c, const char* name, int v) {
   else if (k == "MaxTileItems") { if (v < 1024) return set_error(c, VCT_ERR_INVALID, "MaxTileItems too small"); c->max_items = (size_t)v; }
   else if (k == "RowBegin") { if (v < 0) return set_error(c, VCT_ERR_INVALID, "RowBegin < 0"); P.row_begin = v; }
   else if (k == "RowEnd") { if (v < 0) return set_error(c, VCT_ERR_INVALID, "RowEnd < 0"); P.row_end = v; }
+  else if (k == "RowInterleave") { if (v < 0 || v > 64) return set_error(c, VCT_ERR_INVALID, "RowInterleave out of range"); P.row_il = v; }
+  else if (k == "RowPhase") { if (v < 0 || v > 63) return set_error(c, VCT_ERR_INVALID, "RowPhase out of range"); P.row_ph = v; }
   else if (k == "OverlapVisibility") c->overlap_visibility = v != 0;
   else if (k == "SharedExchange") { if (v != 0 && v != 1) return set_error(c, VCT_ERR_INVALID, "SharedExchange: 0 inbox, 1 in-switch reduction"); c->shared_exchange = v; }
   else if (k == "TriangleInterleave") { if (v < 1) return set_error(c, VCT_ERR_INVALID, "TriangleInterleave < 1"); c->tri_interleave = v; c->scene_epoch++; }
@@ -560,8 +569,18 @@ int vct_set_i(vct_handle c, const char* name, int v) {
   else if (k == "PipelineFrames") c->pipeline_frames = v != 0;
   else if (k == "DebugSpecAhead") c->debug_spec_ahead = v;
   else if (k == "DebugConeVariant") c->debug_cone_variant = v;
+  else if (k == "ChainBlockThreads") { if (v != 32 && v != 64 && v != 128 && v != 256) return set_error(c, VCT_ERR_INVALID, "ChainBlockThreads: 32, 64, 128 or 256"); c->chain_block = v; }
+  else if (k == "RasterBlockThreads") { if (v != 32 && v != 64 && v != 128) return set_error(c, VCT_ERR_INVALID, "RasterBlockThreads: 32, 64 or 128"); c->raster_block = v; c->scene_epoch++; }
+  else if (k == "ConeSmemPad") { if (v < 0 || v > 40960) return set_error(c, VCT_ERR_INVALID, "ConeSmemPad: 0..40960 bytes"); c->cone_smem_pad = v; }
   else if (k == "DenseResolve") c->dense_resolve = v != 0;
-  else if (k == "Profile") c->profile = v != 0;
+  else if (k == "Profile") {
+    c->profile = v != 0;
+    if (c->profile) {                       // time zero of vct_pass_timeline
+      if (!c->ev_ref) cudaEventCreate(&c->ev_ref);
+      cudaEventRecord(c->ev_ref, c->stream);
+      for (auto& gen : c->ev_recorded) for (bool& r : gen) r = false;
+    }
+  }
   else if (k == "ShadowMap" || k == "VoxelTexture") { /* texture unit numbers: meaningless here */ }
   else return set_error(c, VCT_ERR_INVALID, "unknown int uniform '" + k + "'");
   return VCT_OK;
@@ -579,6 +598,7 @@ int vct_get_i(vct_handle c, const char* name, int* v) {
   else if (k == "GridFormat") *v = c->grid_format; else if (k == "MipLevels") *v = P.levels;
   else if (k == "MaxFragments") *v = (int)c->max_fragments; else if (k == "MaxTileItems") *v = (int)c->max_items;
   else if (k == "RowBegin") *v = P.row_begin; else if (k == "RowEnd") *v = P.row_end;
+  else if (k == "RowInterleave") *v = P.row_il; else if (k == "RowPhase") *v = P.row_ph;
   else if (k == "DenseResolve") *v = c->dense_resolve; else if (k == "Profile") *v = c->profile;
   else return set_error(c, VCT_ERR_INVALID, "unknown int uniform '" + k + "'");
   return VCT_OK;
@@ -830,6 +850,7 @@ int vct_frame_shared_begin(vct_handle c, size_t tb, size_t te) {
   rc = sync_materials(c); if (rc) return rc;
   rc = ensure_overlap(c); if (rc) return rc;
   const bool ordered = !c->pipeline_frames || c->scene_epoch != c->frame_epoch;
+  next_event_generation(c);
   cudaStream_t main_stream = c->stream; TileItem* main_items = c->d_items; Counters* main_ctr = c->d_counters;
   if (ordered) VCT_CUDA(c, cudaEventRecord(c->ev_fork, main_stream));
   c->stream = c->stream_vox;
@@ -943,7 +964,9 @@ static int ensure_overlap(vct_context* c) {
 
 int vct_frame(vct_handle c, uint8_t* host_rgba) {
   NEED(c);
-  if (c->profile) cudaEventRecord(c->ev_begin[VCT_PASS_FRAME], c->stream);
+  next_event_generation(c);
+  const int frame_gen = c->ev_gen;
+  if (c->profile) cudaEventRecord(c->ev_begin[frame_gen][VCT_PASS_FRAME], c->stream);
   int rc = ensure_grid(c); if (rc) return rc;
   if (c->overlap_visibility) {
     // Three streams.  voxel stream: vertex pass -> clear -> voxelise -> resolve -> mip into the slot that the
@@ -986,7 +1009,7 @@ int vct_frame(vct_handle c, uint8_t* host_rgba) {
     rc = launch_visibility(c); if (rc) return rc;
   }
   rc = launch_cone(c); if (rc) return rc;
-  if (c->profile) { cudaEventRecord(c->ev_end[VCT_PASS_FRAME], c->stream); c->ev_recorded[VCT_PASS_FRAME] = true; }
+  if (c->profile) { cudaEventRecord(c->ev_end[frame_gen][VCT_PASS_FRAME], c->stream); c->ev_recorded[frame_gen][VCT_PASS_FRAME] = true; }
   if (host_rgba) {
     VCT_CUDA(c, cudaMemcpyAsync(host_rgba, c->d_frame, (size_t)c->P.W * c->P.H * 4, cudaMemcpyDeviceToHost, c->stream));
     VCT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1236,11 +1259,32 @@ int vct_sync(vct_handle c) {
 int vct_pass_time_us(vct_handle c, int pass, float* us) {
   NEED(c);
   if (pass < 0 || pass >= VCT_PASS_COUNT || !us) return VCT_ERR_INVALID;
-  if (!c->ev_recorded[pass]) return set_error(c, VCT_ERR_STATE, "pass has not run (or Profile = 0)");
-  VCT_CUDA(c, cudaEventSynchronize(c->ev_end[pass]));
+  int g = -1;
+  if (pass == VCT_PASS_DEPTH && c->ev_recorded[0][pass]) g = 0;
+  for (int k = 0; k < VCT_EVENT_GENS && g < 0; ++k) {            // the most recent generation in which the pass ran
+    const int q = (c->ev_gen - k + VCT_EVENT_GENS) % VCT_EVENT_GENS;
+    if (c->ev_recorded[q][pass]) g = q;
+  }
+  if (g < 0) return set_error(c, VCT_ERR_STATE, "pass has not run (or Profile = 0)");
+  VCT_CUDA(c, cudaEventSynchronize(c->ev_end[g][pass]));
   float ms = 0.0f;
-  VCT_CUDA(c, cudaEventElapsedTime(&ms, c->ev_begin[pass], c->ev_end[pass]));
+  VCT_CUDA(c, cudaEventElapsedTime(&ms, c->ev_begin[g][pass], c->ev_end[g][pass]));
   *us = ms * 1000.0f;
+  return VCT_OK;
+}
+
+// begin / end of a pass of the frame `frames_back` frames ago (0 = the latest; < VCT_EVENT_GENS), in microseconds
+// since Profile was switched on: all streams of all recent frames on one time axis
+int vct_pass_timeline(vct_handle c, int frames_back, int pass, float* begin_us, float* end_us) {
+  NEED(c);
+  if (pass < 0 || pass >= VCT_PASS_COUNT || frames_back < 0 || frames_back >= VCT_EVENT_GENS || !begin_us || !end_us) return VCT_ERR_INVALID;
+  const int g = (c->ev_gen - frames_back + VCT_EVENT_GENS) % VCT_EVENT_GENS;
+  if (!c->ev_ref || !c->ev_recorded[g][pass]) return set_error(c, VCT_ERR_STATE, "vct_pass_timeline: pass not recorded in that frame");
+  VCT_CUDA(c, cudaEventSynchronize(c->ev_end[g][pass]));
+  float a = 0.0f, b = 0.0f;
+  VCT_CUDA(c, cudaEventElapsedTime(&a, c->ev_ref, c->ev_begin[g][pass]));
+  VCT_CUDA(c, cudaEventElapsedTime(&b, c->ev_ref, c->ev_end[g][pass]));
+  *begin_us = a * 1000.0f; *end_us = b * 1000.0f;
   return VCT_OK;
 }
 

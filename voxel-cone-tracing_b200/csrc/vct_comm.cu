@@ -553,13 +553,18 @@ uchar4* comm_frame_slot(vct_context* c, int rank, int slot) {
   return (uchar4*)(m->va + (size_t)rank * m->seg + m->off_frames + (size_t)slot * m->frame_bytes);
 }
 
-static void default_shares(vct_context* c, int rank, int world) {
-  // triangles dealt in blocks of 128 round-robin, equal row bands (multiples of 8 rows: cone_trace's tile height)
+static void default_shares(vct_context* c, int rank, int world, int flags) {
+  // triangles dealt in blocks of 128 round-robin; rows dealt in strips of 8 (cone_trace's block height) round-robin,
+  // or -- VCT_COMM_ROW_BANDS -- as equal contiguous bands (multiples of 8 rows)
   c->tri_interleave = world; c->tri_phase = rank;
-  const int blocks = (c->P.H + 7) / 8, per = ((blocks + world - 1) / world) * 8;
-  c->P.row_begin = rank * per < c->P.H ? rank * per : c->P.H;
-  c->P.row_end = (rank + 1) * per < c->P.H ? (rank + 1) * per : c->P.H;
-  if (world == 1) { c->P.row_begin = 0; c->P.row_end = 0; }
+  c->P.row_begin = 0; c->P.row_end = 0; c->P.row_il = 0; c->P.row_ph = 0;
+  if (world > 1 && (flags & VCT_COMM_ROW_BANDS)) {
+    const int blocks = (c->P.H + 7) / 8, per = ((blocks + world - 1) / world) * 8;
+    c->P.row_begin = rank * per < c->P.H ? rank * per : c->P.H;
+    c->P.row_end = (rank + 1) * per < c->P.H ? (rank + 1) * per : c->P.H;
+  } else if (world > 1) {
+    c->P.row_il = world; c->P.row_ph = rank;
+  }
   c->scene_epoch++;
 }
 
@@ -577,7 +582,7 @@ int vct_comm_init(vct_handle c, int rank, int world, const char* session, int fl
   if (c->shared_frame_open) return set_error(c, VCT_ERR_STATE, "vct_comm_init: a shared frame is open");
   int rc = sync_all_streams(c); if (rc) return rc;
   rc = comm_init_process(c, rank, world, session, flags); if (rc) return rc;
-  if (!(flags & VCT_COMM_KEEP_SHARES)) default_shares(c, rank, world);
+  if (!(flags & VCT_COMM_KEEP_SHARES)) default_shares(c, rank, world, flags);
   return VCT_OK;
 }
 
@@ -683,7 +688,7 @@ int vct_comm_init_multi(vct_handle* hs, int n, int flags) {
     for (int r = 0; r < n; ++r) { cudaSetDevice(hs[r]->device); comm_release(hs[r]); hs[r]->err = msg; }
     return rc;
   }
-  if (!(flags & VCT_COMM_KEEP_SHARES)) for (int r = 0; r < n; ++r) default_shares(hs[r], r, n);
+  if (!(flags & VCT_COMM_KEEP_SHARES)) for (int r = 0; r < n; ++r) default_shares(hs[r], r, n, flags);
   return VCT_OK;
 }
 

@@ -84,7 +84,8 @@ __device__ __forceinline__ bool setup_htri(const Params& P, const VertexCache& v
   }
   if (!(minx <= maxx)) return false;
   float fx0 = fmaxf(floorf(minx) - 1.0f, 0.0f), fx1 = fminf(ceilf(maxx) + 1.0f, W - 1.0f);
-  const float rb = (float)P.row_begin, re = (float)((P.row_end > 0 && P.row_end < P.H) ? P.row_end : P.H);
+  const bool strips = P.row_il > 1;      // interleaved strips: the box spans the frame, ownership is tested per row / tile
+  const float rb = strips ? 0.0f : (float)P.row_begin, re = (float)((!strips && P.row_end > 0 && P.row_end < P.H) ? P.row_end : P.H);
   float fy0 = fmaxf(floorf(miny) - 1.0f, rb), fy1 = fminf(ceilf(maxy) + 1.0f, re - 1.0f);
   if (!(fx0 <= fx1) || !(fy0 <= fy1)) return false;
   i0 = (int)fx0; i1 = (int)fx1; j0 = (int)fy0; j1 = (int)fy1;
@@ -149,7 +150,15 @@ struct VisibilityPass {
   __device__ __forceinline__ bool setup_full(uint32_t tri, Setup& s, int& i0, int& i1, int& j0, int& j1) const {
     return setup(tri, s, i0, i1, j0, j1);
   }
+  // interleaved strips: 8x8 tiles are aligned with the 8-row strips, so only every row_il-th tile row is walked
+  __device__ __forceinline__ void tile_rows(int& ty0, int& ty1, int& step) const {
+    if (P.row_il <= 1) return;
+    step = P.row_il;
+    ty0 += ((P.row_ph - ty0) % step + step) % step;          // first owned tile row >= ty0
+    if (ty0 <= ty1) ty1 = ty0 + ((ty1 - ty0) / step) * step;  // last owned tile row <= ty1
+  }
   __device__ __forceinline__ bool tile_may_cover(const Setup& s, int x0, int y0, int x1, int y1) const {
+    if (P.row_il > 1 && !row_owned(P, y0)) return false;     // (cannot happen after tile_rows; kept as a guard)
     const float xa = (float)x0 + 0.5f, xb = (float)(x1 - 1) + 0.5f, ya = (float)y0 + 0.5f, yb = (float)(y1 - 1) + 0.5f;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -184,11 +193,13 @@ struct VisibilityPass {
   }
   __device__ __forceinline__ void small(const Setup& s, uint32_t tri, bool active, int i0, int i1, int j0, int j1) const {
     if (!active) return;
-    for (int j = j0; j <= j1; ++j)
+    for (int j = j0; j <= j1; ++j) {
+      if (P.row_il > 1 && !row_owned(P, j)) continue;
       for (int i = i0; i <= i1; ++i) shade(s, tri, i, j);
+    }
   }
   __device__ __forceinline__ void pixel(const Setup& s, uint32_t tri, int i, int j, bool in_bbox) const {
-    if (in_bbox) shade(s, tri, i, j);
+    if (in_bbox && (P.row_il <= 1 || row_owned(P, j))) shade(s, tri, i, j);
   }
 };
 
@@ -206,13 +217,13 @@ int launch_visibility(vct_context* c) {
   rc = ensure_vertex_cache(c); if (rc) return rc;
   PassTimer timer(c, VCT_PASS_VISIBILITY);
   const size_t n = (size_t)c->P.W * c->P.H;
-  fill_u64<<<148 * 4, 256, 0, c->stream>>>(c->d_vis2[c->cur], n, ~0ull);
+  fill_u64<<<VCT_CHAIN(c, 4), 0, c->stream>>>(c->d_vis2[c->cur], n, ~0ull);
   VCT_CUDA(c, reset_item_queue(c));
   VisibilityPass pass{c->P, c->vcache2[c->cur], c->d_idx, c->d_trimat, c->d_materials, c->d_vis2[c->cur]};
   const uint32_t nt = (uint32_t)c->nt;
-  raster_small<VisibilityPass><<<(nt + 127) / 128, 128, 0, c->stream>>>(pass, 0, nt, c->d_items,
+  raster_small<VisibilityPass><<<(nt + c->raster_block - 1) / c->raster_block, c->raster_block, 0, c->stream>>>(pass, 0, nt, c->d_items,
                                                                         (uint32_t)c->items_cap, c->d_counters);
-  raster_tiles<VisibilityPass><<<148 * 4, 256, 0, c->stream>>>(pass, c->d_items, (uint32_t)c->items_cap, c->d_counters);
+  raster_tiles<VisibilityPass><<<VCT_CHAIN(c, 4), 0, c->stream>>>(pass, c->d_items, (uint32_t)c->items_cap, c->d_counters);
   c->launches += 3;
   VCT_CUDA(c, cudaGetLastError());
   return VCT_OK;
@@ -399,7 +410,9 @@ __global__ void __launch_bounds__(BT, MINB) cone_trace(Params P, VertexCache vc,
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lx = lane & 7, ly = lane >> 3;    // 8x4 pixel tile per warp (a 2x2-quad lane order measured the same)
   const int i = blockIdx.x * 8 + lx;
-  const int j = y_begin + blockIdx.y * (BT / 8) + warp * 4 + ly;
+  // rows of this block: contiguous from y_begin, or (interleaved strips) the blockIdx.y-th owned group of 8 rows
+  const int j = P.row_il > 1 ? (((int)blockIdx.y / (64 / BT)) * P.row_il + P.row_ph) * 8 + ((int)blockIdx.y % (64 / BT)) * (BT / 8) + warp * 4 + ly
+                             : y_begin + (int)blockIdx.y * (BT / 8) + warp * 4 + ly;
   unsigned samples = 0;
   if (i < P.W && j < y_end) {
     const unsigned long long key = vis[(size_t)j * P.W + i];
@@ -529,20 +542,28 @@ int launch_cone(vct_context* c) {
   rc = ensure_vertex_cache(c); if (rc) return rc;
   PassTimer timer(c, VCT_PASS_CONE);
   VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->cone_samples, 0, sizeof(unsigned long long), c->stream));
-  const int y0 = c->P.row_begin, y1 = (c->P.row_end > 0 && c->P.row_end < c->P.H) ? c->P.row_end : c->P.H;
+  int y0 = c->P.row_begin, y1 = (c->P.row_end > 0 && c->P.row_end < c->P.H) ? c->P.row_end : c->P.H;
+  const bool strips = c->P.row_il > 1;
+  int own_groups = 0;                              // interleaved strips: how many groups of 8 rows this context owns
+  if (strips) {
+    const int groups = (c->P.H + 7) / 8;
+    own_groups = groups > c->P.row_ph ? (groups - c->P.row_ph + c->P.row_il - 1) / c->P.row_il : 0;
+    y0 = 0; y1 = c->P.H;
+    if (!own_groups) return VCT_OK;
+  }
   if (y0 >= y1) return VCT_OK;
   // NC = 6 (the reference's table) has tuning variants selected by DebugConeVariant: specular fetch-ahead depth SU,
   // block size BT (one or two 8x4 warp tiles), register budget via MINB blocks per SM.  All variants execute the same
   // arithmetic per pixel: frames are bit-identical (test_cone_trace_variants_are_bit_identical).
 #define VCT_LAUNCH_CONE(NC, SU, BT, MINB)                                                                              \
   do {                                                                                                                 \
-    dim3 b(BT), g((c->P.W + 7) / 8, (y1 - y0 + (BT / 8) - 1) / (BT / 8));                                               \
-    cone_trace<NC, SU, BT, MINB><<<g, b, 3 * NC * BT * sizeof(float), c->stream>>>(c->P, c->vcache2[c->cur], c->d_idx,  \
+    dim3 b(BT), g((c->P.W + 7) / 8, strips ? own_groups * (64 / BT) : (y1 - y0 + (BT / 8) - 1) / (BT / 8));            \
+    cone_trace<NC, SU, BT, MINB><<<g, b, 3 * NC * BT * sizeof(float) + (size_t)c->cone_smem_pad, c->stream>>>(c->P, c->vcache2[c->cur], c->d_idx,  \
         c->d_trimat, c->d_materials, c->d_depth, c->d_vis2[c->cur], c->grid[c->cur].tex, c->d_frame, c->d_counters, y0, y1); \
   } while (0)
   const int su = c->debug_spec_ahead;
   if (c->P.n_cones <= 6) {
-    switch (c->debug_cone_variant) {
+    switch (strips && c->debug_cone_variant == 8 ? 0 : c->debug_cone_variant) {   // (128-thread blocks span two strips)
       case 1: VCT_LAUNCH_CONE(6, 4, 64, 8); break;        // round-1 shape: 128 registers, 8 blocks / SM
       case 2: VCT_LAUNCH_CONE(6, 2, 64, 10); break;
       case 3: VCT_LAUNCH_CONE(6, 4, 32, 16); break;

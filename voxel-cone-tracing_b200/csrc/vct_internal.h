@@ -13,6 +13,7 @@
 #include "../../include/vct_c_api.h"
 
 #define VCT_MAX_CONES 16
+#define VCT_EVENT_GENS 4
 
 namespace vct {
 
@@ -35,6 +36,10 @@ struct Params {
   int coverage;          // 0 CENTER, 1 MSAA4_ANY, 2 CONSERVATIVE
   int bounces;
   int row_begin, row_end;   // rows of the frame this context renders (row-band sharding); row_end 0 = H
+  // row sharding by INTERLEAVED strips of 8 rows (one cone_trace block row): this context renders the strips g with
+  // g % row_il == row_ph.  Costs vary smoothly over the image (ceiling vs floor), so dealing thin strips round-robin
+  // balances the ranks to a few per cent where contiguous bands differ by ~15 %.  row_il <= 1: off (bands apply).
+  int row_il, row_ph;
 };
 
 struct MaterialDev {
@@ -92,6 +97,11 @@ struct vct_context {
   int grid_format = 0;
   int debug_spec_ahead = 4;   // specular steps fetched ahead per iteration (1, 2, 4)
   int debug_cone_variant = 0; // cone_trace tuning variant (block size / register budget / fetch-ahead), see launch_cone
+  // Overlap tuning (frames pipeline: the voxel chain of frame i+1 runs beside cone_trace of frame i, which fills the
+  // register file with its own blocks).  chain_block: threads per block of the grid-stride kernels of the voxel chain
+  // (small blocks slot into the registers a retiring cone_trace block frees); raster_block: the same for raster_small;
+  // cone_smem_pad: extra dynamic shared memory per cone_trace block, i.e. a cap on its blocks per SM that leaves room.
+  int chain_block = 256, raster_block = 128, cone_smem_pad = 0;
   size_t max_fragments = 16u << 20;
   size_t max_items = 4u << 20;
 
@@ -178,8 +188,13 @@ struct vct_context {
   uint8_t* h_frame_pinned = nullptr; size_t h_frame_bytes = 0;
 
   // timing
-  cudaEvent_t ev_begin[VCT_PASS_COUNT]{}, ev_end[VCT_PASS_COUNT]{};
-  bool ev_recorded[VCT_PASS_COUNT]{};
+  // pass events, VCT_EVENT_GENS generations deep: every frame call (vct_frame, vct_frame_shared_begin) moves to the
+  // next generation, so that the passes of the last few frames can be placed on ONE time axis (vct_pass_timeline) --
+  // how the streams of consecutive frames overlap is otherwise invisible without a system profiler
+  cudaEvent_t ev_begin[4][VCT_PASS_COUNT]{}, ev_end[4][VCT_PASS_COUNT]{};
+  bool ev_recorded[4][VCT_PASS_COUNT]{};
+  int ev_gen = 0;
+  cudaEvent_t ev_ref = nullptr;   // time zero of vct_pass_timeline (recorded when Profile is switched on)
   uint64_t launches = 0;
 
   std::string err;
@@ -196,12 +211,13 @@ int check_cuda(vct_context* c, cudaError_t e, const char* what);
   } while (0)
 
 struct PassTimer {
-  vct_context* c; int pass;
-  PassTimer(vct_context* c_, int p) : c(c_), pass(p) {
-    if (c->profile) { cudaEventRecord(c->ev_begin[p], c->stream); }
+  vct_context* c; int pass, gen;
+  // the shadow map is not part of a frame: its events live in generation 0 and survive the generation changes
+  PassTimer(vct_context* c_, int p) : c(c_), pass(p), gen(p == VCT_PASS_DEPTH ? 0 : c_->ev_gen) {
+    if (c->profile) { cudaEventRecord(c->ev_begin[gen][p], c->stream); }
   }
   ~PassTimer() {
-    if (c->profile) { cudaEventRecord(c->ev_end[pass], c->stream); c->ev_recorded[pass] = true; }
+    if (c->profile) { cudaEventRecord(c->ev_end[gen][pass], c->stream); c->ev_recorded[gen][pass] = true; }
   }
 };
 
@@ -215,7 +231,8 @@ int ensure_vertex_cache(vct_context* c);
 int launch_shadow(vct_context* c);
 int launch_voxel_clear(vct_context* c);
 int begin_voxel_slot(vct_context* c);     // flips c->cur to the other slot (after making it safe to overwrite)
-void mark_slot_read(vct_context* c);       // records slot_read_done[c->cur] on the main stream
+void mark_slot_read(vct_context* c);
+void next_event_generation(vct_context* c);   // pass events of the next frame go to the next generation       // records slot_read_done[c->cur] on the main stream
 int launch_voxelize(vct_context* c, size_t tb, size_t te);
 int launch_resolve(vct_context* c, bool dense);
 int launch_voxelize_shared(vct_context* c, size_t tb, size_t te);
@@ -230,6 +247,8 @@ int comm_barrier(vct_context* c, int channel, cudaStream_t stream);   // device-
 int comm_check(vct_context* c);                                        // barrier time-outs -> VCT_ERR_STATE
 void comm_release_for_destroy(vct_context* c);
 int sync_all_streams(vct_context* c);      // main + voxel + visibility + copy streams idle (before freeing what frames in flight read)
+// launch shape of a grid-stride kernel of the voxel chain: `mult` x 256 threads per SM in blocks of chain_block threads
+#define VCT_CHAIN(c, mult) (unsigned)(148 * (mult) * 256 / (c)->chain_block), (unsigned)(c)->chain_block
 inline cudaError_t reset_item_queue(vct_context* c) { return cudaMemsetAsync(&c->d_counters->n_items, 0, 3 * sizeof(unsigned int), c->stream); }
 
 // ------------------------------------------------------------------------------------ device helpers
@@ -245,6 +264,12 @@ __device__ __forceinline__ F4 mul_mat_vec(const float* __restrict__ m, float x, 
   r.z = ((m[2] * x + m[6] * y) + m[10] * z) + m[14] * w;
   r.w = ((m[3] * x + m[7] * y) + m[11] * z) + m[15] * w;
   return r;
+}
+
+// does this context render frame row j?  (row-band or interleaved-strip sharding of visibility and cone_trace)
+__device__ __forceinline__ bool row_owned(const Params& P, int j) {
+  if (P.row_il > 1) return ((j >> 3) % P.row_il) == P.row_ph;
+  return j >= P.row_begin && j < ((P.row_end > 0 && P.row_end < P.H) ? P.row_end : P.H);
 }
 
 // index of the 32x8x8 level-0 brick holding voxel (x, y, z)

@@ -28,16 +28,21 @@ __device__ __forceinline__ uint32_t finish_px(uint32_t even, uint32_t odd) {
 __global__ void __launch_bounds__(128) mip_fused3(cudaSurfaceObject_t src, cudaSurfaceObject_t d1,
                                                   cudaSurfaceObject_t d2, cudaSurfaceObject_t d3,
                                                   const unsigned char* __restrict__ dirty,
-                                                  const unsigned char* __restrict__ dirty_prev) {
+                                                  const unsigned char* __restrict__ dirty_prev, int bricks_x, int n_bricks_x) {
   __shared__ uint32_t s1[4][4][16];
   __shared__ uint32_t s2[2][2][8];
-  // sparse build (level 0 only): this block's 32x8x8 source brick did not change since the pyramid was last built
-  if (dirty) {
-    const uint32_t brick = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    if (!(dirty[brick] | dirty_prev[brick])) return;
-  }
   const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
-  const int bx = blockIdx.x * 32, by = blockIdx.y * 8, bz = blockIdx.z * 8;
+  // a block walks `bricks_x` consecutive 32x8x8 source bricks along x.  Sparse build (level 0 only): bricks that did not
+  // change since the pyramid was last built are skipped -- one block per brick meant tens of thousands of blocks that
+  // exit at once, and their launch overhead WAS the kernel time at 512^3.
+  for (int kb = 0; kb < bricks_x; ++kb) {
+  const int brick_x = blockIdx.x * bricks_x + kb;
+  if (brick_x >= n_bricks_x) break;
+  if (dirty) {
+    const uint32_t brick = (blockIdx.z * gridDim.y + blockIdx.y) * n_bricks_x + brick_x;
+    if (!(dirty[brick] | dirty_prev[brick])) continue;
+  }
+  const int bx = brick_x * 32, by = blockIdx.y * 8, bz = blockIdx.z * 8;
   uint32_t e0 = 0, o0 = 0, e1 = 0, o1 = 0;
 #pragma unroll
   for (int dz = 0; dz < 2; ++dz)
@@ -79,6 +84,8 @@ __global__ void __launch_bounds__(128) mip_fused3(cudaSurfaceObject_t src, cudaS
         acc_px(s2[dz][dy][t * 2 + 1], e, o);
       }
     surf3Dwrite(finish_px(e, o), d3, ((bx >> 3) + t) * 4, by >> 3, bz >> 3);
+  }
+  __syncthreads();     // the staging buffers are reused by the next brick
   }
 }
 
@@ -168,6 +175,84 @@ __global__ void mip_level_f16(cudaSurfaceObject_t src, cudaSurfaceObject_t dst, 
   surf3Dwrite(make_uint2((unsigned)o[0] | ((unsigned)o[1] << 16), (unsigned)o[2] | ((unsigned)o[3] << 16)), dst, x * 8, y, z);
 }
 
+// RGBA16F, three levels per launch: a block of (16,4,4) threads reads a 32x8x8 brick of `src` once (16-byte surface
+// loads: two texels) and writes its 16x4x4, 8x2x2 and 4x1x1 children, staging the intermediate levels in shared
+// memory AS HALVES -- every level is computed from the rounded texels of the level above, in the order
+// ((a00 + a10) + a01) + a11 of mip_level_f16, so the result is bit-identical to the level-by-level build.
+__device__ __forceinline__ void f16_acc(const uint2 t, float acc[4], bool first) {
+  const unsigned w[4] = {t.x & 0xFFFFu, t.x >> 16, t.y & 0xFFFFu, t.y >> 16};
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    const float a = __half2float(__ushort_as_half((unsigned short)w[ch]));
+    acc[ch] = first ? a : acc[ch] + a;
+  }
+}
+__device__ __forceinline__ uint2 f16_pack(const float acc[4]) {
+  unsigned short o[4];
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) o[ch] = __half_as_ushort(__float2half_rn(acc[ch] * 0.125f));
+  return make_uint2((unsigned)o[0] | ((unsigned)o[1] << 16), (unsigned)o[2] | ((unsigned)o[3] << 16));
+}
+// the 2x2x2 parents of child (x, y, z) in a staged level: x pair first, then rows, then slices
+template <int NX, int NY>
+__device__ __forceinline__ uint2 f16_reduce_staged(const uint2* s, int x, int y, int z) {
+  float acc[4], pair[4];
+#pragma unroll
+  for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const uint2* row = s + ((2 * z + dz) * NY + (2 * y + dy)) * NX + 2 * x;
+      f16_acc(row[0], pair, true);
+      f16_acc(row[1], pair, false);
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) acc[ch] = (dz == 0 && dy == 0) ? pair[ch] : acc[ch] + pair[ch];
+    }
+  return f16_pack(acc);
+}
+
+__global__ void __launch_bounds__(256) mip_fused3_f16(cudaSurfaceObject_t src, cudaSurfaceObject_t d1, cudaSurfaceObject_t d2,
+                                                      cudaSurfaceObject_t d3, const unsigned char* __restrict__ dirty,
+                                                      const unsigned char* __restrict__ dirty_prev, int bricks_x, int n_bricks_x) {
+  __shared__ uint2 s1[4 * 4 * 16];
+  __shared__ uint2 s2[2 * 2 * 8];
+  const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
+  for (int kb = 0; kb < bricks_x; ++kb) {      // see mip_fused3: a block walks several bricks along x
+  const int brick_x = blockIdx.x * bricks_x + kb;
+  if (brick_x >= n_bricks_x) break;
+  if (dirty) {    // sparse build (level 0 only): this brick did not change since the pyramid was last built
+    const uint32_t brick = (blockIdx.z * gridDim.y + blockIdx.y) * n_bricks_x + brick_x;
+    if (!(dirty[brick] | dirty_prev[brick])) continue;
+  }
+  const int bx = brick_x * 32, by = blockIdx.y * 8, bz = blockIdx.z * 8;
+  float acc[4], pair[4];
+#pragma unroll
+  for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const uint4 q = surf3Dread<uint4>(src, (bx + tx * 2) * 8, by + ty * 2 + dy, bz + tz * 2 + dz);   // two texels
+      f16_acc(make_uint2(q.x, q.y), pair, true);
+      f16_acc(make_uint2(q.z, q.w), pair, false);
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) acc[ch] = (dz == 0 && dy == 0) ? pair[ch] : acc[ch] + pair[ch];
+    }
+  const uint2 c1 = f16_pack(acc);
+  surf3Dwrite(c1, d1, ((bx >> 1) + tx) * 8, (by >> 1) + ty, (bz >> 1) + tz);
+  s1[(tz * 4 + ty) * 16 + tx] = c1;
+  __syncthreads();
+  const int t = (tz * 4 + ty) * 16 + tx;
+  if (t < 32) {   // level +2: 8x2x2
+    const int x = t & 7, y = (t >> 3) & 1, z = t >> 4;
+    const uint2 c2 = f16_reduce_staged<16, 4>(s1, x, y, z);
+    surf3Dwrite(c2, d2, ((bx >> 2) + x) * 8, (by >> 2) + y, (bz >> 2) + z);
+    s2[(z * 2 + y) * 8 + x] = c2;
+  }
+  __syncthreads();
+  if (t < 4)      // level +3: 4x1x1
+    surf3Dwrite(f16_reduce_staged<8, 2>(s2, t, 0, 0), d3, ((bx >> 3) + t) * 8, by >> 3, bz >> 3);
+  __syncthreads();     // the staging buffers are reused by the next brick
+  }
+}
+
 int launch_mip(vct_context* c) {
   int rc = ensure_grid(c); if (rc) return rc;
   PassTimer timer(c, VCT_PASS_MIP);
@@ -176,7 +261,15 @@ int launch_mip(vct_context* c) {
   const unsigned char* dirty = (gb.dirty_valid && c->P.V >= 32 && !c->dense_resolve) ? gb.dirty_now : nullptr;
   gb.mips_current = true;
   if (c->grid_format == 1) {
-    for (int l = 0, n = c->P.V; l + 1 < levels; ++l, n >>= 1) {
+    int l = 0, n = c->P.V;
+    while (n >= 32 && l + 3 < levels) {      // three levels per launch while the source level has whole 32x8x8 bricks
+      const int nbx = n / 32, per = (l == 0 && dirty && nbx >= 8) ? 8 : 1;
+      dim3 b(16, 4, 4), g((nbx + per - 1) / per, n / 8, n / 8);
+      mip_fused3_f16<<<g, b, 0, c->stream>>>(gb.surf[l], gb.surf[l + 1], gb.surf[l + 2], gb.surf[l + 3], l == 0 ? dirty : nullptr, gb.dirty_prev, per, nbx);
+      c->launches += 1;
+      l += 3; n >>= 3;
+    }
+    for (; l + 1 < levels; ++l, n >>= 1) {
       const int h = n >> 1;
       dim3 b(32, 4), g((h + 31) / 32, (h + 3) / 4, h);
       mip_level_f16<<<g, b, 0, c->stream>>>(gb.surf[l], gb.surf[l + 1], h, l + 1 <= 3 ? dirty : nullptr, gb.dirty_prev, l + 1, c->P.V);
@@ -187,8 +280,9 @@ int launch_mip(vct_context* c) {
   }
   int l = 0, n = c->P.V;
   while (n >= 32 && l + 3 < levels) {
-    dim3 b(8, 4, 4), g(n / 32, n / 8, n / 8);
-    mip_fused3<<<g, b, 0, c->stream>>>(gb.surf[l], gb.surf[l + 1], gb.surf[l + 2], gb.surf[l + 3], l == 0 ? dirty : nullptr, gb.dirty_prev);
+    const int nbx = n / 32, per = (l == 0 && dirty && nbx >= 8) ? 8 : 1;
+    dim3 b(8, 4, 4), g((nbx + per - 1) / per, n / 8, n / 8);
+    mip_fused3<<<g, b, 0, c->stream>>>(gb.surf[l], gb.surf[l + 1], gb.surf[l + 2], gb.surf[l + 3], l == 0 ? dirty : nullptr, gb.dirty_prev, per, nbx);
     c->launches += 1;
     l += 3; n >>= 3;
   }

@@ -12,6 +12,7 @@
 //                   bool tile_may_cover(Setup&, x0,y0,x1,y1)   (exact or conservative reject)
 //                   unsigned small(Setup&, tri, i0,i1,j0,j1)    (thread-serial path)
 //                   void pixel(Setup&, tri, i, j, bool in_bbox) (warp path, called by all 32 lanes)
+//                   void tile_rows(int& ty0, int& ty1, int& step)  (which 8-pixel tile rows of [ty0, ty1] to walk; default all)
 //                   static constexpr bool kAppends; if true also covered(), reserve(n), emit(tri,i,j,pos)
 //                   static constexpr bool kWarpMedium: boxes up to MEDIUM_MAX^2 pixels are rasterised by the whole warp inside
 //                   raster_small through pixel() (passes whose pixel() has no warp-collective operation)
@@ -79,9 +80,11 @@ __global__ void __launch_bounds__(128, 5) raster_small(Pass pass, uint32_t tri_b
   }
   if (live && !small_tri) {
     int tx0 = i0 / TILE, tx1 = i1 / TILE, ty0 = j0 / TILE, ty1 = j1 / TILE;
-    uint32_t ntiles = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
+    int ty_step = 1;
+    pass.tile_rows(ty0, ty1, ty_step);           // the tile rows this pass wants of [ty0, ty1]: first, last, stride
+    uint32_t ntiles = ty0 <= ty1 ? (uint32_t)(tx1 - tx0 + 1) * (uint32_t)((ty1 - ty0) / ty_step + 1) : 0u;
     uint32_t nitems = (ntiles + ITEM_TILES - 1) / ITEM_TILES;
-    uint32_t base = atomicAdd(&ctr->n_items, nitems);
+    uint32_t base = nitems ? atomicAdd(&ctr->n_items, nitems) : 0u;
     if (base + nitems > items_cap) {
       // Nothing of this triangle is queued and n_items now overstates what was written: raster_tiles must not
       // touch the queue at all (slots past the last complete write hold stale or uninitialised items).
@@ -115,15 +118,18 @@ __global__ void __launch_bounds__(256) raster_tiles(Pass pass, const TileItem* _
     int i0, i1, j0, j1;
     if (!pass.setup(item.tri, s, i0, i1, j0, j1)) continue;   // warp-uniform
     int tx0 = i0 / TILE, tx1 = i1 / TILE, ty0 = j0 / TILE, ty1 = j1 / TILE;
+    int ty_step = 1;
+    pass.tile_rows(ty0, ty1, ty_step);
+    if (ty0 > ty1) continue;
     uint32_t tw = (uint32_t)(tx1 - tx0 + 1);
-    uint32_t ntiles = tw * (uint32_t)(ty1 - ty0 + 1);
+    uint32_t ntiles = tw * (uint32_t)((ty1 - ty0) / ty_step + 1);
     uint32_t t_end = min(item.origin + (uint32_t)ITEM_TILES, ntiles);
     if constexpr (Pass::kAppends) {
       // Passes that append to a queue: count the item's fragments first (ballots only), reserve the whole
       // range with ONE atomic per item, then write.  The fragment order inside the item stays tile by tile.
       uint32_t total = 0;
       for (uint32_t t = item.origin; t < t_end; ++t) {
-        int px0 = (tx0 + (int)(t % tw)) * TILE, py0 = (ty0 + (int)(t / tw)) * TILE;
+        int px0 = (tx0 + (int)(t % tw)) * TILE, py0 = (ty0 + (int)(t / tw) * ty_step) * TILE;
         if (!pass.tile_may_cover(s, px0, py0, px0 + TILE, py0 + TILE)) continue;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -137,7 +143,7 @@ __global__ void __launch_bounds__(256) raster_tiles(Pass pass, const TileItem* _
       if (lane == 0) base = pass.reserve(total);
       base = __shfl_sync(0xffffffffu, base, 0);
       for (uint32_t t = item.origin; t < t_end; ++t) {
-        int px0 = (tx0 + (int)(t % tw)) * TILE, py0 = (ty0 + (int)(t / tw)) * TILE;
+        int px0 = (tx0 + (int)(t % tw)) * TILE, py0 = (ty0 + (int)(t / tw) * ty_step) * TILE;
         if (!pass.tile_may_cover(s, px0, py0, px0 + TILE, py0 + TILE)) continue;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -150,7 +156,7 @@ __global__ void __launch_bounds__(256) raster_tiles(Pass pass, const TileItem* _
       }
     } else {
       for (uint32_t t = item.origin; t < t_end; ++t) {
-        int tx = tx0 + (int)(t % tw), ty = ty0 + (int)(t / tw);
+        int tx = tx0 + (int)(t % tw), ty = ty0 + (int)(t / tw) * ty_step;
         int px0 = tx * TILE, py0 = ty * TILE;
         if (!pass.tile_may_cover(s, px0, py0, px0 + TILE, py0 + TILE)) continue;  // warp-uniform
 #pragma unroll

@@ -49,6 +49,7 @@ struct ShadowPass {
   __device__ __forceinline__ bool tile_may_cover(const Setup& s, int x0, int y0, int x1, int y1) const {
     return tile_may_cover_exact(s.t, x0, y0, x1, y1);
   }
+  __device__ __forceinline__ void tile_rows(int&, int&, int&) const {}      // every tile row of the box
 
   __device__ __forceinline__ void small(const Setup& s, uint32_t, bool active, int i0, int i1, int j0, int j1) const {
     if (!active) return;

@@ -148,6 +148,7 @@ struct VoxCoverPass {
   __device__ __forceinline__ bool tile_may_cover(const Setup& s, int x0, int y0, int x1, int y1) const {
     return tile_may_cover_exact(s.v.t, x0, y0, x1, y1);
   }
+  __device__ __forceinline__ void tile_rows(int&, int&, int&) const {}      // every tile row of the box
 
   // thread-serial path: <= 16 pixels -> 16-bit coverage mask, one warp-wide reservation
   __device__ __forceinline__ void small(const Setup& s, uint32_t tri, bool active, int i0, int i1, int j0, int j1) const {
@@ -446,7 +447,7 @@ int launch_voxel_clear(vct_context* c) {
   }
   if (accum_sparse || g.list_valid) {
     const vct_context::GridBuf* a = accum_sparse ? &c->grid[c->accum_list_slot] : nullptr;
-    vox_clear_sparse<<<148 * 8, 256, 0, c->stream>>>(c->d_accum, a ? a->touched : nullptr, a ? a->n_touched : nullptr,
+    vox_clear_sparse<<<VCT_CHAIN(c, 8), 0, c->stream>>>(c->d_accum, a ? a->touched : nullptr, a ? a->n_touched : nullptr,
                                                      g.surf[0], g.list_valid ? g.touched : nullptr, g.n_touched, V, c->grid_format);
     c->launches += 1;
   }
@@ -479,19 +480,20 @@ static int voxelize_impl(vct_context* c, size_t tb, size_t te, int shared) {
     VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->n_fragments, 0, sizeof(unsigned int), c->stream));
     VoxCoverPass pass{c->P, c->vcache2[c->cur], c->d_idx, c->d_trimat, c->d_materials, (VoxRecord*)c->d_voxrec, c->d_frags, (uint32_t)c->frags_cap, c->d_counters};
     const uint32_t n = (uint32_t)(te - tb);
-    const uint32_t n_blocks = (n + 127) / 128, il = (uint32_t)c->tri_interleave, ph = (uint32_t)c->tri_phase % il;
+    const uint32_t rb = (uint32_t)c->raster_block;
+    const uint32_t n_blocks = (n + rb - 1) / rb, il = (uint32_t)c->tri_interleave, ph = (uint32_t)c->tri_phase % il;
     const uint32_t own_blocks = n_blocks > ph ? (n_blocks - ph + il - 1) / il : 0;
     if (own_blocks)
-      raster_small<VoxCoverPass><<<own_blocks, 128, 0, c->stream>>>(pass, (uint32_t)tb, (uint32_t)te, c->d_items,
+      raster_small<VoxCoverPass><<<own_blocks, rb, 0, c->stream>>>(pass, (uint32_t)tb, (uint32_t)te, c->d_items,
                                                                     (uint32_t)c->items_cap, c->d_counters, il, ph);
-    raster_tiles<VoxCoverPass><<<148 * 4, 256, 0, c->stream>>>(pass, c->d_items, (uint32_t)c->items_cap, c->d_counters);
+    raster_tiles<VoxCoverPass><<<VCT_CHAIN(c, 4), 0, c->stream>>>(pass, c->d_items, (uint32_t)c->items_cap, c->d_counters);
     c->launches += 2;
   }
   {
     PassTimer timer(c, VCT_PASS_VOX_SHADE);
     uint32_t* list = shared ? c->d_push_list : c->grid[c->cur].touched;
     unsigned int* n_list = shared ? c->d_push_count : c->grid[c->cur].n_touched;
-    vox_shade<<<148 * 8, 256, 0, c->stream>>>(c->P, (const VoxRecord*)c->d_voxrec, c->d_materials, c->d_depth,
+    vox_shade<<<VCT_CHAIN(c, 8), 0, c->stream>>>(c->P, (const VoxRecord*)c->d_voxrec, c->d_materials, c->d_depth,
                                               c->depth_tex, c->d_frags, (uint32_t)c->frags_cap, c->d_accum, list, n_list,
                                               c->d_counters);
     c->launches += 1;
@@ -628,9 +630,9 @@ int launch_voxelize_shared(vct_context* c, size_t tb, size_t te) {
   {
     PassTimer timer(c, VCT_PASS_EXCHANGE_PUSH);
     if (c->shared_mc)
-      vox_push_shared<true><<<148 * 8, 256, 0, c->stream>>>(c->d_accum, c->d_push_list, c->d_push_count, (float4*)c->shared_mc, c->P.V);
+      vox_push_shared<true><<<VCT_CHAIN(c, 8), 0, c->stream>>>(c->d_accum, c->d_push_list, c->d_push_count, (float4*)c->shared_mc, c->P.V);
     else
-      vox_push_shared<false><<<148 * 8, 256, 0, c->stream>>>(c->d_accum, c->d_push_list, c->d_push_count, (float4*)c->shared_local, c->P.V);
+      vox_push_shared<false><<<VCT_CHAIN(c, 8), 0, c->stream>>>(c->d_accum, c->d_push_list, c->d_push_count, (float4*)c->shared_local, c->P.V);
     c->launches += 1;
   }
   VCT_CUDA(c, cudaGetLastError());
@@ -699,7 +701,7 @@ int launch_resolve_shared(vct_context* c) {
     c->launches += 1;
   }
   uint32_t* mask = reinterpret_cast<uint32_t*>(c->shared_local + 2 * (size_t)V * V * V);
-  vox_resolve_shared<<<148 * 8, 256, 0, c->stream>>>(c->shared_local, mask, c->mask_prev[c->cur], g.surf[0], V, c->grid_format);
+  vox_resolve_shared<<<VCT_CHAIN(c, 8), 0, c->stream>>>(c->shared_local, mask, c->mask_prev[c->cur], g.surf[0], V, c->grid_format);
   c->launches += 1;
   // the slot is now described by mask_prev, not by a touched list: a later private-accumulator voxelisation into
   // this slot must start from a dense zero, and mask_prev stays exact as long as only this path writes the slot
@@ -722,13 +724,13 @@ static int voxelize_inbox(vct_context* c, size_t tb, size_t te, bool slot_ready)
   const uint32_t cap = (uint32_t)c->exchange_cap;
   PassTimer timer(c, VCT_PASS_EXCHANGE_PUSH);
   if (c->shared_mc)
-    vox_push_inbox<1><<<148 * 4, 256, 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, (unsigned char*)c->shared_mc, 0,
+    vox_push_inbox<1><<<VCT_CHAIN(c, 4), 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, (unsigned char*)c->shared_mc, 0,
                                                       c->exchange_parity, c->shared_world, c->shared_rank, cap, c->d_counters);
   else if (c->shared_peers && c->shared_world > 1)
-    vox_push_inbox<2><<<148 * 4, 256, 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, c->shared_peers, c->shared_seg,
+    vox_push_inbox<2><<<VCT_CHAIN(c, 4), 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, c->shared_peers, c->shared_seg,
                                                       c->exchange_parity, c->shared_world, c->shared_rank, cap, c->d_counters);
   else
-    vox_push_inbox<0><<<148 * 4, 256, 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, (unsigned char*)c->shared_local, 0,
+    vox_push_inbox<0><<<VCT_CHAIN(c, 4), 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, (unsigned char*)c->shared_local, 0,
                                                       c->exchange_parity, c->shared_world, c->shared_rank, cap, c->d_counters);
   // own record count, needed by the merge for the overflow check (the list keeps growing during the merge)
   if (!c->d_push_count) VCT_CUDA(c, cudaMalloc(&c->d_push_count, 128));
@@ -744,7 +746,7 @@ static int resolve_inbox(vct_context* c) {
     PassTimer timer(c, VCT_PASS_EXCHANGE_MERGE);
     for (int r = 0; r < c->shared_world; ++r) {
       if (r == c->shared_rank) continue;
-      vox_merge_inbox<<<148 * 4, 256, 0, c->stream>>>(c->d_accum, (const unsigned char*)c->shared_local, c->exchange_parity,
+      vox_merge_inbox<<<VCT_CHAIN(c, 4), 0, c->stream>>>(c->d_accum, (const unsigned char*)c->shared_local, c->exchange_parity,
                                                       c->shared_world, r, (uint32_t)c->exchange_cap, g.touched, g.n_touched,
                                                       c->d_counters, c->d_push_count);
       c->launches += 1;
@@ -769,7 +771,7 @@ int launch_resolve(vct_context* c, bool dense) {
     c->mask_valid[c->cur] = false;
     c->accum_list_slot = -1;
   } else {
-    vox_resolve_sparse<<<148 * 8, 256, 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, g.surf[0], V, c->grid_format, g.dirty_now);
+    vox_resolve_sparse<<<VCT_CHAIN(c, 8), 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, g.surf[0], V, c->grid_format, g.dirty_now);
     g.occ_valid = g.list_valid;
   }
   g.mips_current = false;
