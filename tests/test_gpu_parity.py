@@ -849,6 +849,38 @@ def _run_ranks(world, devices, extra=(), timeout=600):
     return outs
 
 
+def test_accumulator_consumed_by_the_resolve(gpu_ctx):
+    """KeepAccumulator = 0: the sparse resolve zeroes each accumulator cell it reads, so the next frame's clear has no
+    accumulator part.  Grids and frames must not change (moving mesh, both frame slots), read-back of counts must say so."""
+    sc = scenes.dynamic_knot(nu=192, nv=96)
+    u = uniforms.scene_uniforms(sc, V=64, width=256, height=144, shadow_map_size=1024, coverage="conservative")
+    c = gpu_ctx
+    c.set_uniforms(u); c.load_scene(sc)
+
+    def run(keep):
+        c.set_i("KeepAccumulator", keep)
+        out = []
+        for i in range(5):
+            P = scenes.torus_knot_positions(192, 96, t=0.3 * i).reshape(-1, 3) * 20.0
+            c.update_positions(P.astype(np.float32)); c.draw_depth()
+            c.frame(); c.sync()
+            out.append((c.grid(0), c.grid(3), c.read_frame()))
+        return out
+    a, b = run(1), run(0)
+    for i, (x, y) in enumerate(zip(a, b)):
+        assert all(np.array_equal(p, q) for p, q in zip(x, y)), i
+    with pytest.raises(capi.VctError):
+        c.counts()
+    c.set_i("KeepAccumulator", 1)
+    c.frame(); c.sync()
+    assert c.counts().sum() == c.fragment_count()
+
+
+def test_library_comm_three_ranks_one_gpu():
+    """Three processes on device 0: more than one remote rank, i.e. the single-launch atomic merge (vox_merge_inbox_all)."""
+    _run_ranks(3, [0, 0, 0], extra=("nomc",))
+
+
 def test_library_comm_two_processes_one_gpu():
     """The library's own bootstrap (handle exchange over a unix socket, peer mapping, device barrier, frame gather into
     rank 0, asynchronous host ring) with two PROCESSES acting as two ranks on device 0: no multicast object (one device

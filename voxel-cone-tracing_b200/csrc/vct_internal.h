@@ -94,6 +94,8 @@ struct vct_context {
   vct::Params P{};
   bool profile = true;
   int dense_resolve = 0;
+  int keep_accum = 1;           // 0: the sparse resolve zeroes every accumulator cell it consumes (no separate clear of the
+                                // accumulator next frame); vct_readback_counts / _sums then have nothing to read
   int grid_format = 0;
   int debug_spec_ahead = 4;   // specular steps fetched ahead per iteration (1, 2, 4)
   int debug_cone_variant = 0; // cone_trace tuning variant (block size / register budget / fetch-ahead), see launch_cone

@@ -253,6 +253,17 @@ __global__ void __launch_bounds__(256) mip_fused3_f16(cudaSurfaceObject_t src, c
   }
 }
 
+// Sparse build: bricks per block such that the launch has ~8 K blocks.  With one brick per block a 512^3 level has
+// 65 536 blocks, most of which exit at once -- their launch overhead was the kernel time (82 -> 67 us); at 256^3 there
+// are 8 192 bricks and walking several per block only serialises the dirty ones (22 -> 32 us), so it stays at one.
+static int sparse_bricks_per_block(bool sparse, int n) {
+  if (!sparse) return 1;
+  const long long bricks = (long long)(n / 32) * (n / 8) * (n / 8);
+  int per = 1;
+  while (per < 8 && bricks / per > 8192 && (n / 32) % (per * 2) == 0) per *= 2;
+  return per;
+}
+
 int launch_mip(vct_context* c) {
   int rc = ensure_grid(c); if (rc) return rc;
   PassTimer timer(c, VCT_PASS_MIP);
@@ -263,7 +274,7 @@ int launch_mip(vct_context* c) {
   if (c->grid_format == 1) {
     int l = 0, n = c->P.V;
     while (n >= 32 && l + 3 < levels) {      // three levels per launch while the source level has whole 32x8x8 bricks
-      const int nbx = n / 32, per = (l == 0 && dirty && nbx >= 8) ? 8 : 1;
+      const int nbx = n / 32, per = sparse_bricks_per_block(l == 0 && dirty, n);
       dim3 b(16, 4, 4), g((nbx + per - 1) / per, n / 8, n / 8);
       mip_fused3_f16<<<g, b, 0, c->stream>>>(gb.surf[l], gb.surf[l + 1], gb.surf[l + 2], gb.surf[l + 3], l == 0 ? dirty : nullptr, gb.dirty_prev, per, nbx);
       c->launches += 1;
@@ -280,7 +291,7 @@ int launch_mip(vct_context* c) {
   }
   int l = 0, n = c->P.V;
   while (n >= 32 && l + 3 < levels) {
-    const int nbx = n / 32, per = (l == 0 && dirty && nbx >= 8) ? 8 : 1;
+    const int nbx = n / 32, per = sparse_bricks_per_block(l == 0 && dirty, n);
     dim3 b(8, 4, 4), g((nbx + per - 1) / per, n / 8, n / 8);
     mip_fused3<<<g, b, 0, c->stream>>>(gb.surf[l], gb.surf[l + 1], gb.surf[l + 2], gb.surf[l + 3], l == 0 ? dirty : nullptr, gb.dirty_prev, per, nbx);
     c->launches += 1;

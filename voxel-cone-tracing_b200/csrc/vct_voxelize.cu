@@ -345,8 +345,7 @@ __global__ void vox_clear_sparse(unsigned long long* __restrict__ accum, const u
     const uint32_t n = *nA;
     for (uint32_t k = t0; k < n; k += stride) {
       uint32_t v = listA[k];
-      accum[2 * (size_t)v] = 0ull;
-      accum[2 * (size_t)v + 1] = 0ull;
+      *reinterpret_cast<ulonglong2*>(&accum[2 * (size_t)v]) = make_ulonglong2(0ull, 0ull);     // one 16-byte store per cell
     }
   }
   if (listB) {
@@ -387,13 +386,15 @@ __device__ __forceinline__ uint2 resolve_cell16(unsigned long long rg, unsigned 
                     (unsigned)__half_as_ushort(b) | ((unsigned)__half_as_ushort(a) << 16));
 }
 
-__global__ void vox_resolve_sparse(const unsigned long long* __restrict__ accum,
+__global__ void vox_resolve_sparse(unsigned long long* __restrict__ accum,
                                    const uint32_t* __restrict__ touched, const unsigned int* __restrict__ n_touched,
-                                   cudaSurfaceObject_t level0, int V, int f16, unsigned char* __restrict__ dirty) {
+                                   cudaSurfaceObject_t level0, int V, int f16, unsigned char* __restrict__ dirty, int zero_after) {
   const uint32_t n = *n_touched;
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     uint32_t v = touched[k];
     const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(&accum[2 * (size_t)v]);
+    // the cell is consumed here; zeroing it while its sector is at hand replaces next frame's scattered clear
+    if (zero_after) *reinterpret_cast<ulonglong2*>(&accum[2 * (size_t)v]) = make_ulonglong2(0ull, 0ull);
     int x = v % V, y = (v / V) % V, z = v / (V * V);
     if (f16) surf3Dwrite(resolve_cell16(a.x, a.y), level0, x * 8, y, z);
     else surf3Dwrite(resolve_cell(a.x, a.y), level0, x * 4, y, z);
@@ -426,8 +427,11 @@ int launch_voxel_clear(vct_context* c) {
   PassTimer timer(c, VCT_PASS_VOX_CLEAR);
   const int V = c->P.V;
   vct_context::GridBuf& g = c->grid[c->cur];
+  // accumulator: all zero already (the last sparse resolve zeroed what it consumed, KeepAccumulator = 0), or described by
+  // a slot's touched list (sparse clear), or unknown (dense memset)
+  const bool accum_clean = c->accum_list_slot == -2 && !c->dense_resolve;
   const bool accum_sparse = c->accum_list_slot >= 0 && !c->dense_resolve;
-  if (!accum_sparse) VCT_CUDA(c, cudaMemsetAsync(c->d_accum, 0, (size_t)V * V * V * 16, c->stream));
+  if (!accum_sparse && !accum_clean) VCT_CUDA(c, cudaMemsetAsync(c->d_accum, 0, (size_t)V * V * V * 16, c->stream));
   if (g.list_valid && g.occ_valid && g.mips_current) {
     // a new tracking period for the sparse mip build: the bricks of the content about to be zeroed become "prev"
     std::swap(g.dirty_now, g.dirty_prev);
@@ -606,6 +610,25 @@ __global__ void vox_merge_inbox(unsigned long long* __restrict__ accum, const un
   }
 }
 
+// All remote ranks in ONE launch (blockIdx.y = remote rank): different ranks may name the same voxel at the same time,
+// so the two 64-bit adds are atomic (as in vox_shade); the returned old count still tells who touched the voxel first.
+__global__ void vox_merge_inbox_all(unsigned long long* __restrict__ accum, const unsigned char* __restrict__ inbox, int parity,
+                                    int world, int own_rank, uint32_t cap, uint32_t* __restrict__ touched,
+                                    unsigned int* __restrict__ n_touched, Counters* __restrict__ ctr, const unsigned int* own_n) {
+  const uint32_t* counts = reinterpret_cast<const uint32_t*>(inbox) + parity * 16;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && *own_n > cap) ctr->overflow = 1;
+  const int src_rank = (int)blockIdx.y + ((int)blockIdx.y >= own_rank ? 1 : 0);
+  const uint32_t n = min(counts[src_rank], cap);
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const uint4 q = *reinterpret_cast<const uint4*>(inbox + exch_record_offset(parity, world, src_rank, cap, k));
+    const uint32_t v = q.w, n_frag = (q.x >> 24) | ((q.y >> 24) << 8) | ((q.z >> 24) << 16);
+    atomicAdd(&accum[2 * (size_t)v], ((unsigned long long)(q.x & 0xFFFFFFu) << 32) | (q.y & 0xFFFFFFu));
+    const unsigned long long old = atomicAdd(&accum[2 * (size_t)v + 1], ((unsigned long long)(q.z & 0xFFFFFFu) << 32) | n_frag);
+    bool pending = true;
+    append_first_touch(pending, old, v, touched, n_touched);
+  }
+}
+
 static int voxelize_inbox(vct_context* c, size_t tb, size_t te, bool slot_ready);
 static int resolve_inbox(vct_context* c);
 
@@ -744,12 +767,20 @@ static int resolve_inbox(vct_context* c) {
   vct_context::GridBuf& g = c->grid[c->cur];
   {
     PassTimer timer(c, VCT_PASS_EXCHANGE_MERGE);
-    for (int r = 0; r < c->shared_world; ++r) {
-      if (r == c->shared_rank) continue;
-      vox_merge_inbox<<<VCT_CHAIN(c, 4), 0, c->stream>>>(c->d_accum, (const unsigned char*)c->shared_local, c->exchange_parity,
-                                                      c->shared_world, r, (uint32_t)c->exchange_cap, g.touched, g.n_touched,
-                                                      c->d_counters, c->d_push_count);
+    if (c->shared_world > 2) {          // every remote rank in one launch (atomic adds)
+      dim3 grid(148 * 2, (unsigned)(c->shared_world - 1));
+      vox_merge_inbox_all<<<grid, 256, 0, c->stream>>>(c->d_accum, (const unsigned char*)c->shared_local, c->exchange_parity,
+                                                       c->shared_world, c->shared_rank, (uint32_t)c->exchange_cap, g.touched,
+                                                       g.n_touched, c->d_counters, c->d_push_count);
       c->launches += 1;
+    } else {
+      for (int r = 0; r < c->shared_world; ++r) {   // one remote rank: its records name distinct voxels, plain read-modify-write
+        if (r == c->shared_rank) continue;
+        vox_merge_inbox<<<VCT_CHAIN(c, 4), 0, c->stream>>>(c->d_accum, (const unsigned char*)c->shared_local, c->exchange_parity,
+                                                        c->shared_world, r, (uint32_t)c->exchange_cap, g.touched, g.n_touched,
+                                                        c->d_counters, c->d_push_count);
+        c->launches += 1;
+      }
     }
   }
   c->exchange_parity ^= 1;
@@ -771,8 +802,10 @@ int launch_resolve(vct_context* c, bool dense) {
     c->mask_valid[c->cur] = false;
     c->accum_list_slot = -1;
   } else {
-    vox_resolve_sparse<<<VCT_CHAIN(c, 8), 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, g.surf[0], V, c->grid_format, g.dirty_now);
+    const int zero_after = c->keep_accum ? 0 : 1;
+    vox_resolve_sparse<<<VCT_CHAIN(c, 8), 0, c->stream>>>(c->d_accum, g.touched, g.n_touched, g.surf[0], V, c->grid_format, g.dirty_now, zero_after);
     g.occ_valid = g.list_valid;
+    if (zero_after && c->accum_list_slot == c->cur) c->accum_list_slot = -2;     // every non-zero cell was on this list
   }
   g.mips_current = false;
   c->launches += 1;
@@ -782,6 +815,7 @@ int launch_resolve(vct_context* c, bool dense) {
 
 int readback_accum(vct_context* c, uint32_t* counts, uint32_t* sums) {
   int rc = ensure_grid(c); if (rc) return rc;
+  if (!c->keep_accum) return set_error(c, VCT_ERR_STATE, "the accumulator is consumed by the resolve (KeepAccumulator = 0): nothing to read back");
   const size_t n = (size_t)c->P.V * c->P.V * c->P.V;
   uint32_t *dc = nullptr, *ds = nullptr;
   if (counts) VCT_CUDA(c, cudaMalloc(&dc, n * 4));
