@@ -207,7 +207,7 @@ class Env:
         self.dev = torch.device("cuda", self.local)
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
-        self.stream = torch.cuda.Stream(device=self.dev)
+        self.stream = torch.cuda.Stream(device=self.dev, priority=int(os.environ.get("VCT_MAIN_STREAM_PRIORITY", "0")))
         torch.cuda.set_stream(self.stream)
 
     def barrier(self):

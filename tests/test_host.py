@@ -125,3 +125,18 @@ def test_equal_row_bands_tile_the_frame():
                 rows += list(range(b0, b1)); per_all.add(per)
             assert rows == list(range(H)) and len(per_all) == 1
             assert per_all.pop() * world >= H
+
+
+@pytest.mark.parametrize("height,world", [(1080, 2), (1080, 8), (2160, 8), (360, 3), (7, 4), (256, 1)])
+def test_interleaved_row_strips_partition_the_frame(height, world):
+    """RowInterleave / RowPhase: every row belongs to exactly one rank, strips are 8 rows, shares differ by at most one strip."""
+    owner = np.full(height, -1)
+    counts = []
+    for r in range(world):
+        strips = parallel.row_strips_for_rank(height, r, world)
+        counts.append(len(strips))
+        for b, e in strips:
+            assert b % 8 == 0 and 0 < e - b <= 8 and (owner[b:e] == -1).all()
+            owner[b:e] = r
+            assert (b // 8) % world == r
+    assert (owner >= 0).all() and max(counts) - min(counts) <= 1

@@ -571,6 +571,7 @@ int vct_set_i(vct_handle c, const char* name, int v) {
   else if (k == "DebugConeVariant") c->debug_cone_variant = v;
   else if (k == "ChainBlockThreads") { if (v != 32 && v != 64 && v != 128 && v != 256) return set_error(c, VCT_ERR_INVALID, "ChainBlockThreads: 32, 64, 128 or 256"); c->chain_block = v; }
   else if (k == "RasterBlockThreads") { if (v != 32 && v != 64 && v != 128) return set_error(c, VCT_ERR_INVALID, "RasterBlockThreads: 32, 64 or 128"); c->raster_block = v; c->scene_epoch++; }
+  else if (k == "SideStreamsLowPriority") { if (c->stream2) return set_error(c, VCT_ERR_STATE, "SideStreamsLowPriority: set it before the first frame"); c->side_streams_low = v != 0; }
   else if (k == "ConeSmemPad") { if (v < 0 || v > 40960) return set_error(c, VCT_ERR_INVALID, "ConeSmemPad: 0..40960 bytes"); c->cone_smem_pad = v; }
   else if (k == "DenseResolve") c->dense_resolve = v != 0;
   else if (k == "KeepAccumulator") { c->keep_accum = v != 0; c->scene_epoch++; }
@@ -947,6 +948,7 @@ static int ensure_overlap(vct_context* c) {
     // scheduler only hands SM slots to another grid ahead of them if that grid's stream has priority
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (c->side_streams_low) prio_hi = prio_lo;
     VCT_CUDA(c, cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_hi));
     VCT_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     VCT_CUDA(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));

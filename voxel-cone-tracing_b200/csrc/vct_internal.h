@@ -104,6 +104,7 @@ struct vct_context {
   // (small blocks slot into the registers a retiring cone_trace block frees); raster_block: the same for raster_small;
   // cone_smem_pad: extra dynamic shared memory per cone_trace block, i.e. a cap on its blocks per SM that leaves room.
   int chain_block = 256, raster_block = 128, cone_smem_pad = 0;
+  int side_streams_low = 0;   // 1: the voxel / visibility streams get the LOWEST priority (set before the first frame)
   size_t max_fragments = 16u << 20;
   size_t max_items = 4u << 20;
 

@@ -45,6 +45,18 @@ def row_band_equal(height: int, rank: int, world: int, align: int = 8):
     return min(rank * per, height), min((rank + 1) * per, height), per
 
 
+def row_strips_for_rank(height: int, rank: int, world: int, strip: int = 8):
+    """Interleaved row sharding (RowInterleave / RowPhase; what vct_comm_init deals by default): the frame is cut into
+    strips of `strip` rows -- cone_trace's block height -- and rank r renders strips r, r + world, ...  Returns the
+    [begin, end) row ranges of `rank`.  Mirrors row_owned() / launch_cone() in csrc/vct_cone.cu."""
+    out = []
+    g = rank
+    while g * strip < height:
+        out.append((g * strip, min((g + 1) * strip, height)))
+        g += world
+    return out
+
+
 def views_for_rank(n_views: int, rank: int, world: int):
     """Round-robin view assignment (light-probe bake, BASELINE config 5)."""
     return list(range(rank, n_views, world))
