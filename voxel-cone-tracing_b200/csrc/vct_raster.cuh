@@ -128,8 +128,9 @@ __global__ void __launch_bounds__(256) raster_tiles(Pass pass, const TileItem* _
       // Passes that append to a queue: count the item's fragments first (ballots only), reserve the whole
       // range with ONE atomic per item, then write.  The fragment order inside the item stays tile by tile.
       uint32_t total = 0;
-      for (uint32_t t = item.origin; t < t_end; ++t) {
-        int px0 = (tx0 + (int)(t % tw)) * TILE, py0 = (ty0 + (int)(t / tw) * ty_step) * TILE;
+      for (uint32_t t = item.origin, tcol = item.origin % tw, trow = item.origin / tw; t < t_end;
+           ++t, trow += (tcol + 1 == tw), tcol = (tcol + 1 == tw) ? 0u : tcol + 1) {     // one division per item, not per tile
+        int px0 = (tx0 + (int)tcol) * TILE, py0 = (ty0 + (int)trow * ty_step) * TILE;
         if (!pass.tile_may_cover(s, px0, py0, px0 + TILE, py0 + TILE)) continue;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -142,8 +143,9 @@ __global__ void __launch_bounds__(256) raster_tiles(Pass pass, const TileItem* _
       uint32_t base = 0;
       if (lane == 0) base = pass.reserve(total);
       base = __shfl_sync(0xffffffffu, base, 0);
-      for (uint32_t t = item.origin; t < t_end; ++t) {
-        int px0 = (tx0 + (int)(t % tw)) * TILE, py0 = (ty0 + (int)(t / tw) * ty_step) * TILE;
+      for (uint32_t t = item.origin, tcol = item.origin % tw, trow = item.origin / tw; t < t_end;
+           ++t, trow += (tcol + 1 == tw), tcol = (tcol + 1 == tw) ? 0u : tcol + 1) {     // one division per item, not per tile
+        int px0 = (tx0 + (int)tcol) * TILE, py0 = (ty0 + (int)trow * ty_step) * TILE;
         if (!pass.tile_may_cover(s, px0, py0, px0 + TILE, py0 + TILE)) continue;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -155,8 +157,9 @@ __global__ void __launch_bounds__(256) raster_tiles(Pass pass, const TileItem* _
         }
       }
     } else {
-      for (uint32_t t = item.origin; t < t_end; ++t) {
-        int tx = tx0 + (int)(t % tw), ty = ty0 + (int)(t / tw) * ty_step;
+      for (uint32_t t = item.origin, tcol = item.origin % tw, trow = item.origin / tw; t < t_end;
+           ++t, trow += (tcol + 1 == tw), tcol = (tcol + 1 == tw) ? 0u : tcol + 1) {
+        int tx = tx0 + (int)tcol, ty = ty0 + (int)trow * ty_step;
         int px0 = tx * TILE, py0 = ty * TILE;
         if (!pass.tile_may_cover(s, px0, py0, px0 + TILE, py0 + TILE)) continue;  // warp-uniform
 #pragma unroll
