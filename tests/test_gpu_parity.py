@@ -59,8 +59,10 @@ def assert_radiance_close(a, b, what):
 
 
 def assert_frame_close(fg, fo, what, frac_min=FRAC_MIN):
-    assert psnr(fg[..., :3], fo[..., :3]) >= PSNR_MIN, f"{what}: psnr {psnr(fg[..., :3], fo[..., :3]):.2f}"
-    assert frac_within(fg, fo, LSB_TOL) >= frac_min, f"{what}: {frac_within(fg, fo, LSB_TOL):.5f}"
+    p, f = psnr(fg[..., :3], fo[..., :3]), frac_within(fg, fo, LSB_TOL)
+    print(f"[parity] {what}: psnr {p:.2f} dB, {100 * f:.4f} % of pixels within {LSB_TOL}/255 (bar {100 * frac_min:.1f} %)")
+    assert p >= PSNR_MIN, f"{what}: psnr {p:.2f}"
+    assert f >= frac_min, f"{what}: {f:.5f}"
 
 
 # ------------------------------------------------------------------------------------------ golden fixtures

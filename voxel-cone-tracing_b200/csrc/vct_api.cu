@@ -146,16 +146,12 @@ int ensure_shadow(vct_context* c) {
   if (c->depth_surf) { cudaDestroySurfaceObject(c->depth_surf); c->depth_surf = 0; }
   if (c->depth_array) { cudaFreeArray(c->depth_array); c->depth_array = nullptr; }
   VCT_CUDA(c, cudaMalloc(&c->d_depth, (size_t)c->P.S * c->P.S * 4));
-  cudaChannelFormatDesc dd = cudaCreateChannelDesc<unsigned int>();
-  if (cudaMallocArray(&c->depth_array, &dd, c->P.S, c->P.S, cudaArrayTextureGather | cudaArraySurfaceLoadStore) != cudaSuccess) {
-    cudaGetLastError();                                   // gather-only array: the copy falls back to cudaMemcpy2DToArray
-    c->depth_array = nullptr;
-    VCT_CUDA(c, cudaMallocArray(&c->depth_array, &dd, c->P.S, c->P.S, cudaArrayTextureGather));
-  }
+  cudaChannelFormatDesc dd = cudaCreateChannelDesc<float>();
+  VCT_CUDA(c, cudaMallocArray(&c->depth_array, &dd, c->P.S, c->P.S, cudaArrayTextureGather | cudaArraySurfaceLoadStore));
   cudaResourceDesc rd{};
   rd.resType = cudaResourceTypeArray;
   rd.res.array.array = c->depth_array;
-  if (cudaCreateSurfaceObject(&c->depth_surf, &rd) != cudaSuccess) { cudaGetLastError(); c->depth_surf = 0; }
+  VCT_CUDA(c, cudaCreateSurfaceObject(&c->depth_surf, &rd));
   cudaTextureDesc td{};
   td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;    // GL_CLAMP_TO_EDGE, Voxel_Cone_Tracing.h:95-96
   td.filterMode = cudaFilterModePoint;

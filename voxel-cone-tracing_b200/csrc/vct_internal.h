@@ -130,7 +130,7 @@ struct vct_context {
   // shadow map (u32 d24, linear)
   uint32_t* d_depth = nullptr; int depth_S = 0; bool depth_valid = false;
   cudaArray_t depth_array = nullptr; cudaTextureObject_t depth_tex = 0;   // same texels as a 2D array for tex2Dgather
-  cudaSurfaceObject_t depth_surf = 0;                                     // ... written by depth_to_array (0: memcpy fallback)
+  cudaSurfaceObject_t depth_surf = 0;                                     // ... written by depth_to_array, as floats
 
   // voxel grid
   int grid_V = 0; int grid_fmt_alloc = -1;       // format the slots were allocated with (0 RGBA8, 1 RGBA16F)
@@ -511,11 +511,11 @@ __device__ __forceinline__ float pcf_lit_taps_gather(cudaTextureObject_t dtex, c
 #pragma unroll
     for (int gx = 0; gx < 3; ++gx) {
       // footprint texels (ix0+2gx .. +1, iy0+2gy .. +1); gather order: .w=(x,y) .z=(x+1,y) .x=(x,y+1) .y=(x+1,y+1)
-      const uint4 g = tex2Dgather<uint4>(dtex, (float)(ix0 + 2 * gx + 1), (float)(iy0 + 2 * gy + 1), 0);
-      t[2 * gy][2 * gx] = (float)g.w * (1.0f / 16777215.0f);
-      t[2 * gy][2 * gx + 1] = (float)g.z * (1.0f / 16777215.0f);
-      t[2 * gy + 1][2 * gx] = (float)g.x * (1.0f / 16777215.0f);
-      t[2 * gy + 1][2 * gx + 1] = (float)g.y * (1.0f / 16777215.0f);
+      const float4 g = tex2Dgather<float4>(dtex, (float)(ix0 + 2 * gx + 1), (float)(iy0 + 2 * gy + 1), 0);
+      t[2 * gy][2 * gx] = g.w;              // the array already holds float(d24) * (1/16777215) (depth_to_array)
+      t[2 * gy][2 * gx + 1] = g.z;
+      t[2 * gy + 1][2 * gx] = g.x;
+      t[2 * gy + 1][2 * gx + 1] = g.y;
     }
   float lit = 0.0f;
   float hprev[T];

@@ -69,16 +69,21 @@ __global__ void fill_u32(uint32_t* p, size_t n, uint32_t v) {
   for (; i < n; i += stride) p[i] = v;
 }
 
-// The D24 map as a 2D array for tex2Dgather (voxel shading): four texels per thread, 16-byte surface stores.
+// The D24 map as a 2D float array for tex2Dgather (voxel shading): four texels per thread, 16-byte surface stores.
 // (cudaMemcpy2DToArrayAsync of the 64 MiB map took ~270 us per call -- more than rasterising it.)
 __global__ void depth_to_array(const uint32_t* __restrict__ depth, cudaSurfaceObject_t surf, int S) {
   const int x4 = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x4 * 4 >= S || y >= S) return;
+  // the array holds the texels as the floats every PCF tap would otherwise derive from the D24 integers
+  // (`float(d24) * (1/16777215)`, the same expression, evaluated once per texel instead of 36 times per fragment)
   if (x4 * 4 + 3 < S && (S & 3) == 0) {
     const uint4 v = *reinterpret_cast<const uint4*>(depth + (size_t)y * S + x4 * 4);
-    surf2Dwrite(v, surf, x4 * 16, y);
+    const float4 f = make_float4((float)v.x * (1.0f / 16777215.0f), (float)v.y * (1.0f / 16777215.0f),
+                                 (float)v.z * (1.0f / 16777215.0f), (float)v.w * (1.0f / 16777215.0f));
+    surf2Dwrite(f, surf, x4 * 16, y);
   } else {
-    for (int x = x4 * 4; x < min(x4 * 4 + 4, S); ++x) surf2Dwrite(depth[(size_t)y * S + x], surf, x * 4, y);
+    for (int x = x4 * 4; x < min(x4 * 4 + 4, S); ++x)
+      surf2Dwrite((float)depth[(size_t)y * S + x] * (1.0f / 16777215.0f), surf, x * 4, y);
   }
 }
 
@@ -104,8 +109,7 @@ int launch_shadow(vct_context* c) {
     c->launches += 1;
     VCT_CUDA(c, cudaGetLastError());
   } else {
-    VCT_CUDA(c, cudaMemcpy2DToArrayAsync(c->depth_array, 0, 0, c->d_depth, (size_t)c->P.S * 4, (size_t)c->P.S * 4, c->P.S,
-                                         cudaMemcpyDeviceToDevice, c->stream));
+    return set_error(c, VCT_ERR_CUDA, "the shadow-map gather array has no surface object");
   }
   c->depth_valid = true;
   return VCT_OK;
