@@ -851,6 +851,42 @@ def _run_ranks(world, devices, extra=(), timeout=600):
     return outs
 
 
+def test_loaded_obj_asset_vs_oracle(gpu_ctx, oracle, tmp_path):
+    """The real-asset path: an OBJ + MTL + PNG / TGA textures on disk -> objloader (assimp's
+    post-processing restated, textures decoded by images.py) -> the device, against the oracle on the same loaded scene.
+    The asset has a noise albedo, a height map, a cut-out (alpha) quad in front of a wall and a quad without normals."""
+    from vct_b200 import images, objloader
+    rng = np.random.default_rng(11)
+    d = str(tmp_path)
+    images.save_png(rng.integers(60, 230, (64, 64, 3), dtype=np.uint8), os.path.join(d, "albedo.png"))
+    images.save_png((scenes.value_noise(64, 4, rng) * 255).astype(np.uint8), os.path.join(d, "height.png"))
+    cut = np.zeros((32, 32, 4), np.uint8); cut[..., :3] = (40, 200, 60); cut[8:24, 8:24, 3] = 255     # opaque square in the middle
+    images.save_png(cut, os.path.join(d, "cutout.png"))
+    open(os.path.join(d, "room.mtl"), "w").write(
+        "newmtl wall\nKd 0.7 0.7 0.7\nKs 0.2 0.2 0.2\nmap_Kd albedo.png\nmap_Ka height.png\n"
+        "newmtl leaf\nKd 0.2 0.8 0.3\nKs 0 0 0\nmap_Kd cutout.png\nnewmtl plain\nKd 0.8 0.3 0.2\nKs 0.4 0.4 0.4\n")
+    S = 1100.0      # model units (ModelMatrix = scale(0.05): +-55 world)
+    v = [(-S, -S, -S), (S, -S, -S), (S, S, -S), (-S, S, -S), (-S, -S, S), (S, -S, S), (S, S, S), (-S, S, S),
+         (-400, -400, -300), (400, -400, -300), (400, 400, -300), (-400, 400, -300)]
+    with open(os.path.join(d, "room.obj"), "w") as f:
+        f.write("mtllib room.mtl\n" + "".join("v %g %g %g\n" % p for p in v) + "vt 0 0\nvt 3 0\nvt 3 3\nvt 0 3\nvt 1 0\nvt 1 1\nvt 0 1\n")
+        f.write("usemtl wall\nf 1/1 2/2 3/3 4/4\nf 1/1 5/2 6/3 2/4\nf 1/1 4/2 8/3 5/4\nf 2/1 6/2 7/3 3/4\n")       # back, floor, left, right
+        f.write("usemtl plain\nf 4/1 3/2 7/3 8/4\n")                                                                 # ceiling
+        f.write("usemtl leaf\nf 9/1 10/5 11/6 12/7\n")                                                               # cut-out card
+    sc = objloader.load_obj(os.path.join(d, "room.obj"))
+    assert sc.n_tris == 12 and sc.textures[sc.materials[2][0]].shape == (32, 32, 4)     # wall, plain, leaf
+    u = uniforms.reference_uniforms(V=64, width=320, height=240, shadow_map_size=1024, camera_pos=(0.0, 0.0, 52.0), coverage="msaa4")
+    run_gpu(gpu_ctx, sc, u)
+    run_oracle(oracle, sc, u)
+    assert np.array_equal(gpu_ctx.depth(), oracle.depth())
+    assert np.array_equal(gpu_ctx.counts(), oracle.counts()) and gpu_ctx.counts().sum() > 5000
+    vg, vo = gpu_ctx.visibility(), oracle.visibility()
+    assert (vg != vo).mean() <= 1e-3
+    card = np.isin(vo, [10, 11])
+    assert card.any() and (vo[120, 160] in (10, 11)) and not np.isin(vo[120, 60], [10, 11])      # alpha discard: only the middle of the card
+    assert_frame_close(gpu_ctx.read_frame(), oracle.frame(), "loaded OBJ asset", FRAC_MIN_SMALL)
+
+
 def test_accumulator_consumed_by_the_resolve(gpu_ctx):
     """KeepAccumulator = 0: the sparse resolve zeroes each accumulator cell it reads, so the next frame's clear has no
     accumulator part.  Grids and frames must not change (moving mesh, both frame slots), read-back of counts must say so."""

@@ -62,3 +62,56 @@ def test_obj_scene_runs_through_the_oracle(tmp_path, oracle):
     assert (f[..., :3] != 128).any()                                          # the cube is visible
     objloader.save_frame_png(f, str(tmp_path / "frame.png"))
     assert os.path.getsize(tmp_path / "frame.png") > 100
+
+
+def test_builtin_decoders_against_pillow_and_round_trip(tmp_path):
+    """images.py (the stb_image stand-in): PNG with every filter type / colour type, PPM, TGA (raw and RLE, both origins)."""
+    import zlib, struct
+    from PIL import Image
+    from vct_b200 import images
+    rng = np.random.default_rng(3)
+    smooth = (np.add.outer(np.arange(37), np.arange(53))[..., None] * np.array([3, 5, 7, 2]) % 256).astype(np.uint8)
+    noisy = rng.integers(0, 256, (37, 53, 4), dtype=np.uint8)
+    for arr in (smooth, noisy):
+        for mode, a in (("L", arr[..., 0]), ("RGB", arr[..., :3]), ("RGBA", arr), ("LA", arr[..., :2])):
+            p = str(tmp_path / f"t_{mode}.png")
+            Image.fromarray(a, mode).save(p, optimize=True)          # Pillow picks filters per row (all five occur)
+            got = images.load_image(p)
+            want = np.asarray(Image.open(p).convert("RGBA" if mode == "LA" else mode))
+            assert np.array_equal(got.reshape(want.shape), want), mode
+    pal = Image.fromarray(noisy[..., :3], "RGB").quantize(16)
+    pal.save(str(tmp_path / "pal.png"))
+    assert np.array_equal(images.load_image(str(tmp_path / "pal.png")), np.asarray(pal.convert("RGB")))
+    # every filter type explicitly, written by hand
+    img = noisy[:5, :11, :3]
+    def filt(ft, row, prev):
+        row, prev = row.astype(int).reshape(-1), prev.astype(int).reshape(-1)
+        out = np.zeros_like(row)
+        for x in range(len(row)):
+            a = row[x - 3] if x >= 3 else 0; b = prev[x]; c = prev[x - 3] if x >= 3 else 0
+            pa, pb, pc = abs(b - c), abs(a - c), abs(a + b - 2 * c)
+            paeth = a if (pa <= pb and pa <= pc) else b if pb <= pc else c
+            out[x] = (row[x] - [0, a, b, (a + b) // 2, paeth][ft]) % 256
+        return bytes([ft]) + bytes(out.astype(np.uint8))
+    raw = b"".join(filt(y % 5, img[y], img[y - 1] if y else np.zeros_like(img[0])) for y in range(5))
+    ck = lambda k, b: struct.pack(">I", len(b)) + k + b + struct.pack(">I", zlib.crc32(k + b))
+    png = b"\x89PNG\r\n\x1a\n" + ck(b"IHDR", struct.pack(">IIBBBBB", 11, 5, 8, 2, 0, 0, 0)) + ck(b"IDAT", zlib.compress(raw)) + ck(b"IEND", b"")
+    assert np.array_equal(images.decode_png(png), img)
+    # own encoder <-> own decoder <-> Pillow
+    for a in (noisy[..., 0], noisy[..., :3], noisy):
+        b = images.encode_png(a)
+        assert np.array_equal(images.decode_png(b).reshape(a.shape), a)
+        open(tmp_path / "e.png", "wb").write(b)
+        assert np.array_equal(np.asarray(Image.open(tmp_path / "e.png")).reshape(a.shape), a)
+    # PPM / PGM
+    Image.fromarray(noisy[..., :3], "RGB").save(str(tmp_path / "t.ppm"))
+    assert np.array_equal(images.load_image(str(tmp_path / "t.ppm")), noisy[..., :3])
+    # TGA: raw + RLE, bottom-left and top-left origin
+    for rle in (False, True):
+        for mode, a in (("RGB", smooth[..., :3]), ("RGBA", smooth), ("L", smooth[..., 0])):
+            p = str(tmp_path / f"t_{mode}_{int(rle)}.tga")
+            Image.fromarray(a, mode).save(p, compression="tga_rle" if rle else None, orientation=-1 if rle else 1)
+            got = images.load_image(p)
+            assert np.array_equal(got.reshape(a.shape), a), (mode, rle)
+    with np.testing.assert_raises(images.UnsupportedImage):
+        images.load_image(__file__)

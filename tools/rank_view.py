@@ -9,7 +9,10 @@ cfg, N = sys.argv[1], int(sys.argv[2])
 frames = int(sys.argv[3]) if len(sys.argv) > 3 else 6
 a = bench.parse(["--config", cfg])
 sc, u = bench.make_scene_and_uniforms(a)
-c = vct_b200.Context(0); c.set_uniforms(u); c.load_scene(sc); c.draw_depth()
+c = vct_b200.Context(0); c.set_uniforms(u)
+for kv in filter(None, os.environ.get("VCT_TUNE", "").split(",")):
+    k, v = kv.split("="); c.set_i(k, int(v))
+c.load_scene(sc); c.draw_depth()
 c.set_i("TriangleInterleave", N); c.set_i("TrianglePhase", 1); c.set_i("RowInterleave", N); c.set_i("RowPhase", 1)
 shared = parallel.SharedAccumulator(c, rank=0, world=1, session="rv", flags=capi.COMM_KEEP_SHARES)
 c.set_i("PipelineFrames", 1); c.set_i("Profile", 1)
@@ -25,3 +28,13 @@ for back in (1, 0):
         t0 = b if t0 is None else t0
         row.append(f"{n} {b - t0:6.0f}-{e - t0:6.0f}")
     print(f"frame -{back}: " + " | ".join(row))
+
+import time
+c.set_i("Profile", 0)
+for i in range(5):
+    bench.set_camera(c, sc, i, 0); shared.frame(None)
+shared.wait(); t0 = time.perf_counter()
+for i in range(60):
+    bench.set_camera(c, sc, i, 0); shared.frame(None)
+shared.wait(); dt = (time.perf_counter() - t0) / 60
+print(f"steady-state period {dt * 1e6:.0f} us/frame  (tune: {os.environ.get('VCT_TUNE', '')})")

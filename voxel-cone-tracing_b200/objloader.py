@@ -14,7 +14,8 @@ Texture slots follow the reference's (quirky) mapping, Model.h:126-136 and Mesh.
 map_Ks -> SpecularTexture, map_Ka (aiTextureType_AMBIENT) -> HeightTexture; bump maps (aiTextureType_HEIGHT) are loaded
 by the reference but never bound, so they are ignored here.  A material without one of the three gets a 1x1 texture
 (Kd / Ks colour, flat height): the reference would otherwise inherit the previous mesh's binding (undefined, A.6 #9).
-Images are decoded with Pillow (the reference uses stb_image, Model.h:150)."""
+Images are decoded by images.py (PNG / PNM / TGA on numpy + zlib, restating the part of stb_image the asset path needs,
+Model.h:150), with Pillow as the fallback for other formats."""
 from __future__ import annotations
 
 import os
@@ -25,7 +26,12 @@ from .scenes import Scene
 
 
 def _load_image(path):
-    from PIL import Image
+    from . import images
+    try:                                  # built-in decoders (PNG / PNM / TGA: the stb_image subset the asset path needs)
+        return images.load_image(path)
+    except images.UnsupportedImage:
+        pass
+    from PIL import Image                 # anything else (JPEG, 16-bit or interlaced PNG): Pillow, if it is installed
     im = Image.open(path)
     if im.mode not in ("L", "RGB", "RGBA"):
         im = im.convert("RGBA" if "A" in im.getbands() else "RGB")
@@ -177,5 +183,5 @@ def load_obj(path, name=None):
 
 def save_frame_png(frame_rgba, path):
     """Frame as returned by vct_render (row 0 = bottom row, GL window order) -> PNG, top row first."""
-    from PIL import Image
-    Image.fromarray(np.ascontiguousarray(frame_rgba[::-1, :, :3])).save(path)
+    from . import images
+    images.save_png(np.ascontiguousarray(frame_rgba[::-1, :, :3]), path)
