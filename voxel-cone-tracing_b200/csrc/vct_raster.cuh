@@ -125,35 +125,43 @@ __global__ void __launch_bounds__(256) raster_tiles(Pass pass, const TileItem* _
     uint32_t ntiles = tw * (uint32_t)((ty1 - ty0) / ty_step + 1);
     uint32_t t_end = min(item.origin + (uint32_t)ITEM_TILES, ntiles);
     if constexpr (Pass::kAppends) {
-      // Passes that append to a queue: count the item's fragments first (ballots only), reserve the whole
-      // range with ONE atomic per item, then write.  The fragment order inside the item stays tile by tile.
-      uint32_t total = 0;
-      for (uint32_t t = item.origin, tcol = item.origin % tw, trow = item.origin / tw; t < t_end;
-           ++t, trow += (tcol + 1 == tw), tcol = (tcol + 1 == tw) ? 0u : tcol + 1) {     // one division per item, not per tile
-        int px0 = (tx0 + (int)tcol) * TILE, py0 = (ty0 + (int)trow * ty_step) * TILE;
-        if (!pass.tile_may_cover(s, px0, py0, px0 + TILE, py0 + TILE)) continue;
+      // Passes that append to a queue: evaluate the coverage of the item's (up to 16 tiles x 2 half-tiles =) 32 steps
+      // ONCE, each lane remembering its own result as one bit per step; reserve the whole range with ONE atomic per item;
+      // then replay the bits (one ballot per step instead of a second coverage test).  The fragment order inside the
+      // item stays tile by tile.
+      static_assert(ITEM_TILES * 2 <= 32, "one coverage bit per half-tile step");
+      uint32_t total = 0, mine = 0;
+      {
+        uint32_t k = 0;
+        for (uint32_t t = item.origin, tcol = item.origin % tw, trow = item.origin / tw; t < t_end;
+             ++t, k += 2, trow += (tcol + 1 == tw), tcol = (tcol + 1 == tw) ? 0u : tcol + 1) {     // one division per item, not per tile
+          int px0 = (tx0 + (int)tcol) * TILE, py0 = (ty0 + (int)trow * ty_step) * TILE;
+          if (!pass.tile_may_cover(s, px0, py0, px0 + TILE, py0 + TILE)) continue;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          int i = px0 + (int)(lane & 7), j = py0 + half * 4 + (int)(lane >> 3);
-          bool cov = i >= i0 && i <= i1 && j >= j0 && j <= j1 && pass.covered(s, i, j);
-          total += __popc(__ballot_sync(0xffffffffu, cov));
+          for (int half = 0; half < 2; ++half) {
+            int i = px0 + (int)(lane & 7), j = py0 + half * 4 + (int)(lane >> 3);
+            bool cov = i >= i0 && i <= i1 && j >= j0 && j <= j1 && pass.covered(s, i, j);
+            mine |= (cov ? 1u : 0u) << (k + half);
+            total += __popc(__ballot_sync(0xffffffffu, cov));
+          }
         }
       }
       if (!total) continue;
       uint32_t base = 0;
       if (lane == 0) base = pass.reserve(total);
       base = __shfl_sync(0xffffffffu, base, 0);
-      for (uint32_t t = item.origin, tcol = item.origin % tw, trow = item.origin / tw; t < t_end;
-           ++t, trow += (tcol + 1 == tw), tcol = (tcol + 1 == tw) ? 0u : tcol + 1) {     // one division per item, not per tile
-        int px0 = (tx0 + (int)tcol) * TILE, py0 = (ty0 + (int)trow * ty_step) * TILE;
-        if (!pass.tile_may_cover(s, px0, py0, px0 + TILE, py0 + TILE)) continue;
+      {
+        uint32_t k = 0;
+        for (uint32_t t = item.origin, tcol = item.origin % tw, trow = item.origin / tw; t < t_end;
+             ++t, k += 2, trow += (tcol + 1 == tw), tcol = (tcol + 1 == tw) ? 0u : tcol + 1) {
+          int px0 = (tx0 + (int)tcol) * TILE, py0 = (ty0 + (int)trow * ty_step) * TILE;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          int i = px0 + (int)(lane & 7), j = py0 + half * 4 + (int)(lane >> 3);
-          bool cov = i >= i0 && i <= i1 && j >= j0 && j <= j1 && pass.covered(s, i, j);
-          unsigned m = __ballot_sync(0xffffffffu, cov);
-          if (cov) pass.emit(item.tri, i, j, base + __popc(m & ((1u << lane) - 1)));
-          base += __popc(m);
+          for (int half = 0; half < 2; ++half) {
+            const bool cov = (mine >> (k + half)) & 1u;
+            const unsigned m = __ballot_sync(0xffffffffu, cov);
+            if (cov) pass.emit(item.tri, px0 + (int)(lane & 7), py0 + half * 4 + (int)(lane >> 3), base + __popc(m & ((1u << lane) - 1)));
+            base += __popc(m);
+          }
         }
       }
     } else {
