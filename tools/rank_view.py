@@ -38,3 +38,13 @@ for i in range(60):
     bench.set_camera(c, sc, i, 0); shared.frame(None)
 shared.wait(); dt = (time.perf_counter() - t0) / 60
 print(f"steady-state period {dt * 1e6:.0f} us/frame  (tune: {os.environ.get('VCT_TUNE', '')})")
+t0 = time.perf_counter()
+for i in range(60):
+    bench.set_camera(c, sc, i, 0); shared.frame(None)
+t_enq = (time.perf_counter() - t0) / 60
+shared.wait()
+t0 = time.perf_counter()
+for i in range(60):
+    bench.set_camera(c, sc, i, 0)
+t_cam = (time.perf_counter() - t0) / 60
+print(f"host enqueue time {t_enq * 1e6:.0f} us/frame (of which camera set-up in Python {t_cam * 1e6:.0f} us)")
