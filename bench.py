@@ -68,6 +68,8 @@ def parse(argv=None):
                     "and gather with NCCL instead of the pipelined vct_frame_sharded")
     ap.add_argument("--contiguous", action="store_true", help="triangle sharding by contiguous ranges instead of interleaved blocks")
     ap.add_argument("--no-multicast", action="store_true", help="--mode shard: exchange by peer stores instead of multimem.st")
+    ap.add_argument("--shard-shadow", action="store_true", help="--mode shard: triangle-sharded shadow map (every rank rasterises its "
+                    "share, depth fragments min-reduced into all ranks' images through the switch); matters for config 4, where the map is redrawn every frame")
     ap.add_argument("--row-bands", action="store_true", help="--mode shard: contiguous row bands instead of interleaved strips of 8 rows")
     ap.add_argument("--exchange", default="inbox", choices=["inbox", "reduce"],
                     help="--mode shard: inbox = touched voxels multicast as records (multimem.st) and merged locally; reduce = "
@@ -281,6 +283,8 @@ def bench_config(env, args):
     shared = None
     if sharded:
         flags = (capi.COMM_NO_MULTICAST if args.no_multicast else 0) | (capi.COMM_ROW_BANDS if args.row_bands else 0)
+        if args.shard_shadow:
+            ctx.set_i("ShardShadowMap", 1)
         shared = parallel.SharedAccumulator(ctx, rank=rank, world=world, session=session_name(f"c{args.config}"),
                                             exchange=args.exchange, flags=flags)      # deals triangles + row bands
         if args.contiguous:
@@ -539,7 +543,7 @@ def bench_config(env, args):
         "scaling": "weak" if args.mode == "views" else "strong",     # probes / tiles / shards: total work fixed
         "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
         "config": {"workload": WORKLOADS[args.config] if (args.detail == 1.0 and args.nominal_size and not args.tune) else f"config{args.config}: {sc.name} {sc.n_tris} tris, V={args.grid} {fmt_name}, {W}x{H}, cones {args.cones}",
-                   "mode": args.mode + ("/" + args.exchange if sharded else "") + ("/serial" if sharded and not pipelined_shard else ""),
+                   "mode": args.mode + ("/" + args.exchange if sharded else "") + ("/serial" if sharded and not pipelined_shard else "") + ("/sharded-shadow-map" if sharded and args.shard_shadow else ""),
                    "l2": ("flushed between steps by an untimed 256 MiB write; frames not pipelined" if args.flush else "no flush: per-frame working set ~220 MB (64 MiB level 0 + mips, shadow texels, accumulator lines, queues, vertex cache, visibility) in two alternating frame slots exceeds the 126 MB L2"),
                    "timing": "one CUDA-event pair around the K steps on the launching stream, barrier+synchronize both sides; max over ranks",
                    "step": ("one bake = clear+voxelize+resolve+mip+reinject+mip once, then visibility+cone-trace of 64 probe views (round-robin over ranks); value counts views"

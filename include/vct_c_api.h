@@ -65,6 +65,10 @@ const char* vct_version(void);
  *           TriangleInterleave TrianglePhase (voxelisation takes every TriangleInterleave-th block of 128 triangles of
  *             the requested range, starting at block TrianglePhase: balanced triangle sharding, one phase per rank)
  *           SharedExchange SharedWorld SharedRank MaxExchangeVoxels (fused sharded voxelisation, see below)
+ *           ShardShadowMap (1, set before vct_comm_init: vct_draw_depth rasterises only this rank's triangle share and
+ *             min-reduces every depth fragment into all ranks' D24 images -- multimem.red.min.u32 in the NVSwitch; the
+ *             resulting map is bit-identical to the single-GPU one.  SURVEY 8e "shadow map")
+ *           KeepAccumulator (0: the sparse resolve zeroes the cells it consumes; measured slower, default 1)
  *           ShadowMap VoxelTexture (texture-unit numbers: accepted and ignored)
  *   float : VoxelGridWorldSize ambientFactor DiffuseTanHalfAngle SpecularTanHalfAngle StepMultiplier
  *           MaxDistance MaxAlpha ShadowBias

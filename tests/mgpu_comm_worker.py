@@ -38,11 +38,24 @@ def main():
         ref.append(c.read_frame())
     ref_grid = [c.grid(l) for l in range(8)]
     ok = bool((ref_grid[0][..., 3] > 0).sum() > 10000)
+    ref_depth = c.depth()
+    shard_shadow = "shadow" in sys.argv[5:]
+    if shard_shadow:
+        c.set_i("ShardShadowMap", 1)            # before comm_init: the segment gets a D24 image
 
     shared = parallel.SharedAccumulator(c, rank=rank, world=world, session=session, flags=flags,
                                         exchange="reduce" if reduce else "inbox")
     info = shared.info
     assert info["rank"] == rank and info["world"] == world
+    if shard_shadow:
+        # triangle-sharded shadow map: every rank rasterises its share, the depth fragments are min-reduced into every
+        # rank's image (multimem.red.min.u32 / peer atomics): the map must equal the single-GPU one on EVERY rank
+        for _ in range(2):
+            c.draw_depth(); c.sync()
+            same = bool(np.array_equal(c.depth(), ref_depth))
+            if not same:
+                print(f"rank {rank}: sharded shadow map differs in {(c.depth() != ref_depth).sum()} texels", flush=True)
+            ok &= same
     if reduce:
         for it in range(3):
             shared.frame_voxels(0, sc.n_tris)

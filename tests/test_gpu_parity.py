@@ -924,10 +924,10 @@ def test_library_comm_two_processes_one_gpu():
     rank 0, asynchronous host ring) with two PROCESSES acting as two ranks on device 0: no multicast object (one device
     cannot join a team twice), so the records travel as peer stores (vox_push_inbox<2>)."""
     _run_ranks(2, [0, 0], extra=("nomc",))
-    _run_ranks(2, [0, 0], extra=("nomc", "bands"))
+    _run_ranks(2, [0, 0], extra=("nomc", "bands", "shadow"))
 
 
-@pytest.mark.parametrize("extra", [(), ("nomc",), ("reduce",), ("bands",)])
+@pytest.mark.parametrize("extra", [(), ("nomc",), ("reduce",), ("bands",), ("shadow",), ("shadow", "nomc")])
 def test_library_comm_two_gpus(extra):
     """Two processes on two GPUs: multimem.st inbox through the library's multicast mapping, the same without a multicast
     object, and the multimem.red flavour.  Needs two GPUs on the box (skipped otherwise)."""

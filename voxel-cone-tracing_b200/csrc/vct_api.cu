@@ -571,6 +571,7 @@ int vct_set_i(vct_handle c, const char* name, int v) {
   else if (k == "ConeSmemPad") { if (v < 0 || v > 40960) return set_error(c, VCT_ERR_INVALID, "ConeSmemPad: 0..40960 bytes"); c->cone_smem_pad = v; }
   else if (k == "DenseResolve") c->dense_resolve = v != 0;
   else if (k == "KeepAccumulator") { c->keep_accum = v != 0; c->scene_epoch++; }
+  else if (k == "ShardShadowMap") { c->shard_shadow = v != 0; c->depth_valid = false; c->scene_epoch++; }
   else if (k == "Profile") {
     c->profile = v != 0;
     if (c->profile) {                       // time zero of vct_pass_timeline
@@ -599,6 +600,7 @@ int vct_get_i(vct_handle c, const char* name, int* v) {
   else if (k == "RowInterleave") *v = P.row_il; else if (k == "RowPhase") *v = P.row_ph;
   else if (k == "DenseResolve") *v = c->dense_resolve; else if (k == "Profile") *v = c->profile;
   else if (k == "KeepAccumulator") *v = c->keep_accum;
+  else if (k == "ShardShadowMap") *v = c->shard_shadow;
   else return set_error(c, VCT_ERR_INVALID, "unknown int uniform '" + k + "'");
   return VCT_OK;
 }

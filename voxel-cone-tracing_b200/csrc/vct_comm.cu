@@ -102,7 +102,7 @@ struct Comm {
   int rank = 0, world = 1;
   bool multicast = false, in_process = false;
   size_t seg = 0;                                // bytes per rank segment (granularity aligned)
-  size_t off_inbox = 0, inbox_bytes = 0, off_frames = 0, frame_bytes = 0;
+  size_t off_inbox = 0, inbox_bytes = 0, off_frames = 0, frame_bytes = 0, off_depth = 0, depth_bytes = 0;
   CUmemGenericAllocationHandle local = 0, mc = 0;
   std::vector<CUmemGenericAllocationHandle> peers;      // imported handles (index = rank; own slot = local)
   CUdeviceptr va = 0, mc_va = 0;
@@ -321,7 +321,9 @@ static int segment_size(vct_context* c, Comm* m, bool want_mc, size_t* seg) {
   m->frame_bytes = align_up((size_t)c->P.W * c->P.H * 4, 4096);
   m->off_inbox = COMM_PADS;
   m->off_frames = m->off_inbox + m->inbox_bytes;
-  size_t bytes = m->off_frames + 3 * m->frame_bytes;
+  m->off_depth = m->off_frames + 3 * m->frame_bytes;
+  m->depth_bytes = c->shard_shadow ? align_up((size_t)c->P.S * c->P.S * 4, 4096) : 0;     // sharded shadow map: one D24 image per rank
+  size_t bytes = m->off_depth + m->depth_bytes;
   CUmemAllocationProp p = alloc_prop(c->device, !m->in_process);
   size_t gran = 0;
   VCT_CU(c, g_drv.MemGetAllocationGranularity(&gran, &p, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
@@ -546,6 +548,18 @@ static int comm_settings_match(vct_context* c, Comm* m) {
   if (m->V != c->P.V || m->W != c->P.W || m->H != c->P.H || m->shared_exchange != c->shared_exchange)
     return set_error(c, VCT_ERR_STATE, "VoxelDimensions / screen size changed after vct_comm_init: call vct_comm_init again");
   return VCT_OK;
+}
+
+// the symmetric D24 image of the sharded shadow map: local view, multicast view (null without a multicast object), and
+// the base + stride of the peer views
+bool comm_depth_views(vct_context* c, uint32_t** local, uint32_t** mc, uint32_t** peers, size_t* seg_words, int* world, int* rank) {
+  Comm* m = (Comm*)c->comm;
+  if (!m || !m->depth_bytes || m->depth_bytes < (size_t)c->P.S * c->P.S * 4) return false;
+  *local = (uint32_t*)(m->va + (size_t)m->rank * m->seg + m->off_depth);
+  *mc = m->multicast ? (uint32_t*)(m->mc_va + m->off_depth) : nullptr;
+  *peers = (uint32_t*)(m->va + m->off_depth);
+  *seg_words = m->seg / 4; *world = m->world; *rank = m->rank;
+  return true;
 }
 
 uchar4* comm_frame_slot(vct_context* c, int rank, int slot) {

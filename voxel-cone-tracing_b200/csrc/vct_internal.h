@@ -94,6 +94,8 @@ struct vct_context {
   vct::Params P{};
   bool profile = true;
   int dense_resolve = 0;
+  int shard_shadow = 0;         // 1 (set before vct_comm_init): vct_draw_depth rasterises this rank's triangle share and
+                                // min-reduces it into every rank's D24 image through the switch (multimem.red.min.u32)
   int keep_accum = 1;           // 0: the sparse resolve zeroes every accumulator cell it consumes (no separate clear of the
                                 // accumulator next frame); vct_readback_counts / _sums then have nothing to read
   int grid_format = 0;
@@ -248,6 +250,7 @@ int launch_reinject(vct_context* c);
 int check_overflow(vct_context* c);
 int comm_barrier(vct_context* c, int channel, cudaStream_t stream);   // device-side cross-rank barrier, in stream order
 int comm_check(vct_context* c);                                        // barrier time-outs -> VCT_ERR_STATE
+bool comm_depth_views(vct_context* c, uint32_t** local, uint32_t** mc, uint32_t** peers, size_t* seg_words, int* world, int* rank);
 void comm_release_for_destroy(vct_context* c);
 int sync_all_streams(vct_context* c);      // main + voxel + visibility + copy streams idle (before freeing what frames in flight read)
 // launch shape of a grid-stride kernel of the voxel chain: `mult` x 256 threads per SM in blocks of chain_block threads

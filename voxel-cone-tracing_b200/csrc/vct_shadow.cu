@@ -10,6 +10,10 @@ struct ShadowPass {
   Params P;                  // uniform block, by value: lives in the kernel's constant bank
   const float* verts; const uint32_t* idx;
   uint32_t* depth;
+  // sharded shadow map (triangle ranges + min-reduction of the depth image): mode 1 = every depth fragment is
+  // min-reduced into ALL ranks' images by one multimem.red.min.u32 (performed in the NVSwitch), mode 2 = one atomicMin
+  // per rank through the peer mappings; mode 0 = the private image
+  int mode; int world; size_t seg_words;
 
   static constexpr bool kAppends = false;
   static constexpr bool kWarpMedium = true;
@@ -40,7 +44,10 @@ struct ShadowPass {
     float z = interp3(s.z0, s.z1, s.z2, l1, l2);
     if (!(z >= 0.0f) || z > 1.0f) return;   // near/far clip
     uint32_t d = (uint32_t)__float2int_rn(z * 16777215.0f);
-    atomicMin(&depth[(size_t)j * P.S + i], d);
+    const size_t texel = (size_t)j * P.S + i;
+    if (mode == 1) asm volatile("multimem.red.relaxed.sys.global.min.u32 [%0], %1;" ::"l"(depth + texel), "r"(d) : "memory");
+    else if (mode == 2) { for (int p = 0; p < world; ++p) atomicMin(depth + (size_t)p * seg_words + texel, d); }
+    else atomicMin(&depth[texel], d);
   }
 
   __device__ __forceinline__ bool setup_full(uint32_t tri, Setup& s, int& i0, int& i1, int& j0, int& j1) const {
@@ -93,14 +100,32 @@ int launch_shadow(vct_context* c) {
   rc = ensure_queues(c); if (rc) return rc;
   PassTimer timer(c, VCT_PASS_DEPTH);
   const size_t n = (size_t)c->P.S * c->P.S;
-  fill_u32<<<148 * 8, 256, 0, c->stream>>>(c->d_depth, n, 0xFFFFFFu);
+  uint32_t *sym_local = nullptr, *sym_mc = nullptr, *sym_peers = nullptr; size_t seg_words = 0; int world = 1, rank = 0;
+  const bool sharded = c->shard_shadow && c->shared_world > 1 && comm_depth_views(c, &sym_local, &sym_mc, &sym_peers, &seg_words, &world, &rank);
+  if (c->shard_shadow && c->shared_world > 1 && !sharded)
+    return set_error(c, VCT_ERR_STATE, "ShardShadowMap: set it (and ShadowMapSize) before vct_comm_init");
   VCT_CUDA(c, reset_item_queue(c));
-  ShadowPass pass{c->P, c->d_verts, c->d_idx, c->d_depth};
   const uint32_t nt = (uint32_t)c->nt;
-  raster_small<ShadowPass><<<(nt + 127) / 128, 128, 0, c->stream>>>(pass, 0, nt, c->d_items,
-                                                                    (uint32_t)c->items_cap, c->d_counters);
-  raster_tiles<ShadowPass><<<148 * 4, 256, 0, c->stream>>>(pass, c->d_items, (uint32_t)c->items_cap, c->d_counters);
-  c->launches += 3;
+  if (!sharded) {
+    fill_u32<<<148 * 8, 256, 0, c->stream>>>(c->d_depth, n, 0xFFFFFFu);
+    ShadowPass pass{c->P, c->d_verts, c->d_idx, c->d_depth, 0, 1, 0};
+    raster_small<ShadowPass><<<(nt + 127) / 128, 128, 0, c->stream>>>(pass, 0, nt, c->d_items, (uint32_t)c->items_cap, c->d_counters);
+    raster_tiles<ShadowPass><<<148 * 4, 256, 0, c->stream>>>(pass, c->d_items, (uint32_t)c->items_cap, c->d_counters);
+    c->launches += 3;
+  } else {
+    // every rank clears ITS image, all wait, every rank rasterises its share of the triangles (blocks of 128 dealt
+    // round-robin) into ALL images, all wait, every rank takes a private copy for the passes that sample the map
+    fill_u32<<<148 * 8, 256, 0, c->stream>>>(sym_local, n, 0xFFFFFFu);
+    int rc2 = comm_barrier(c, 3, c->stream); if (rc2) return rc2;
+    ShadowPass pass{c->P, c->d_verts, c->d_idx, sym_mc ? sym_mc : sym_peers, sym_mc ? 1 : 2, world, seg_words};
+    const uint32_t n_blocks = (nt + 127) / 128, own = n_blocks > (uint32_t)rank ? (n_blocks - rank + world - 1) / world : 0;
+    if (own)
+      raster_small<ShadowPass><<<own, 128, 0, c->stream>>>(pass, 0, nt, c->d_items, (uint32_t)c->items_cap, c->d_counters, (uint32_t)world, (uint32_t)rank);
+    raster_tiles<ShadowPass><<<148 * 4, 256, 0, c->stream>>>(pass, c->d_items, (uint32_t)c->items_cap, c->d_counters);
+    rc2 = comm_barrier(c, 3, c->stream); if (rc2) return rc2;
+    VCT_CUDA(c, cudaMemcpyAsync(c->d_depth, sym_local, n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    c->launches += 3;
+  }
   VCT_CUDA(c, cudaGetLastError());
   // array copy for tex2Dgather (voxel shading)
   if (c->depth_surf) {
