@@ -70,6 +70,9 @@ const char* vct_version(void);
  *             resulting map is bit-identical to the single-GPU one.  SURVEY 8e "shadow map")
  *           KeepAccumulator (0: the sparse resolve zeroes the cells it consumes; measured slower, default 1)
  *           ShadowMap VoxelTexture (texture-unit numbers: accepted and ignored)
+ *           tuning / diagnostics (defaults are the measured best): DebugConeVariant DebugSpecAhead (cone_trace shapes,
+ *             all bit-identical), ChainBlockThreads RasterBlockThreads ConeSmemPad SideStreamsLowPriority PipelineFrames
+ *             OverlapVisibility (frame pipeline)
  *   float : VoxelGridWorldSize ambientFactor DiffuseTanHalfAngle SpecularTanHalfAngle StepMultiplier
  *           MaxDistance MaxAlpha ShadowBias
  *   vec3  : CameraPosition LightDirection
