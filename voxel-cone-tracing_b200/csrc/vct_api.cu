@@ -70,8 +70,8 @@ static void free_grid(vct_context* c) {
     cudaFree(g.touched); cudaFree(g.n_touched); cudaFree(g.dirty_now); cudaFree(g.dirty_prev);
     g = vct_context::GridBuf();
   }
-  cudaFree(c->d_accum);
-  c->d_accum = nullptr; c->grid_V = 0; c->accum_list_slot = -1;
+  cudaFree(c->d_accum); cudaFree(c->d_occ_mask);
+  c->d_accum = nullptr; c->d_occ_mask = nullptr; c->grid_V = 0; c->accum_list_slot = -1;
   c->mask_valid[0] = c->mask_valid[1] = false;
 }
 
@@ -84,6 +84,8 @@ int ensure_grid(vct_context* c) {
   c->grid_fmt_alloc = c->grid_format;
   const size_t n = (size_t)V * V * V;
   VCT_CUDA(c, cudaMalloc(&c->d_accum, n * 16));
+  VCT_CUDA(c, cudaMalloc(&c->d_occ_mask, (n + 31) / 32 * 4));
+  VCT_CUDA(c, cudaMemsetAsync(c->d_occ_mask, 0, (n + 31) / 32 * 4, c->stream));
   c->touched_cap = n;
   // RGBA8 is the reference's format (GL_RGBA8, Voxel_Cone_Tracing.h:119); RGBA16F is BASELINE config 3
   cudaChannelFormatDesc desc = c->grid_format == 1 ? cudaCreateChannelDescHalf4() : cudaCreateChannelDesc<uchar4>();

@@ -153,6 +153,9 @@ struct vct_context {
     bool dirty_valid = false, occ_valid = false, mips_current = false;
   } grid[2];
   size_t touched_cap = 0;
+  // first-touch bits of the voxelisation in flight (one bit per voxel, x-runs of 32 per word): vox_shade sets a bit for
+  // every voxel it touches first, vox_compact_mask turns the bits into the touched list IN MEMORY ORDER and clears them
+  uint32_t* d_occ_mask = nullptr;
   // fused sharded voxelisation: external symmetric accumulator + occupancy mask (local view and multicast view)
   unsigned long long* shared_local = nullptr; unsigned long long* shared_mc = nullptr;
   // library-owned multi-GPU state (vct_comm.cu): symmetric segments, multicast mapping, bootstrap sockets.  When the
