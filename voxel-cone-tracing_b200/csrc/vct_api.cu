@@ -1192,8 +1192,10 @@ static int read_counter(vct_context* c, const void* dptr, void* out, size_t byte
 }
 int vct_cone_samples(vct_handle c, uint64_t* n) {
   NEED(c);
+  unsigned long long parts[64 * 4];
+  int rc = read_counter(c, c->d_counters->cone_samples, parts, sizeof(parts));
   unsigned long long v = 0;
-  int rc = read_counter(c, &c->d_counters->cone_samples, &v, 8);
+  for (int k = 0; k < 64; ++k) v += parts[k * 4];
   if (n) *n = v;
   return rc;
 }

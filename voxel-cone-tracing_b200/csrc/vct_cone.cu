@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(BT, MINB) cone_trace(Params P, VertexCache vc,
   // executed textureLod calls (Gcone-samples/s numerator): one atomic per warp
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) samples += __shfl_xor_sync(0xffffffffu, samples, d);
-  if (lane == 0 && samples) atomicAdd(&ctr->cone_samples, (unsigned long long)samples);
+  if (lane == 0 && samples) atomicAdd(&ctr->cone_samples[((blockIdx.x + blockIdx.y * 7u) & 63u) * 4], (unsigned long long)samples);
 }
 
 int launch_cone(vct_context* c) {
@@ -541,7 +541,7 @@ int launch_cone(vct_context* c) {
   if (!c->depth_valid) return set_error(c, VCT_ERR_STATE, "vct_render: call vct_draw_depth first (shadow map missing)");
   rc = ensure_vertex_cache(c); if (rc) return rc;
   PassTimer timer(c, VCT_PASS_CONE);
-  VCT_CUDA(c, cudaMemsetAsync(&c->d_counters->cone_samples, 0, sizeof(unsigned long long), c->stream));
+  VCT_CUDA(c, cudaMemsetAsync(c->d_counters->cone_samples, 0, sizeof(c->d_counters->cone_samples), c->stream));
   int y0 = c->P.row_begin, y1 = (c->P.row_end > 0 && c->P.row_end < c->P.H) ? c->P.row_end : c->P.H;
   const bool strips = c->P.row_il > 1;
   int own_groups = 0;                              // interleaved strips: how many groups of 8 rows this context owns

@@ -67,7 +67,9 @@ struct Counters {
   unsigned int n_items, next_item, items_overflow; unsigned int pad1[29];
   unsigned int n_touched;     unsigned int pad2[31];
   unsigned int overflow;      unsigned int pad3[31];   // sticky until read by check_overflow
-  unsigned long long cone_samples; unsigned int pad4[30];
+  // executed textureLod calls of the last cone_trace: 64 partial counters, one 32-byte sector each (65 K warps adding
+  // into ONE address serialise in a single L2 atomic unit); vct_cone_samples sums them
+  unsigned long long cone_samples[64 * 4];
 };
 
 // Per-vertex transform cache written once per frame by vertex_pass -- the vertex-shader stage of the three

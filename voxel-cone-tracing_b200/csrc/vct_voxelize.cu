@@ -196,19 +196,6 @@ struct VoxCoverPass {
   __device__ __forceinline__ void pixel(const Setup&, uint32_t, int, int, bool) const {}
 };
 
-// first fragment of a voxel (old count == 0): append the voxel to the touched list, one counter atomic per warp-step
-__device__ __forceinline__ void append_first_touch(bool& pending, unsigned long long old, uint32_t voxel,
-                                                   uint32_t* __restrict__ touched, unsigned int* __restrict__ n_touched) {
-  if (pending && (uint32_t)old == 0u) {
-    cg::coalesced_group firsts = cg::coalesced_threads();
-    uint32_t base = 0;
-    if (firsts.thread_rank() == 0) base = atomicAdd(n_touched, (uint32_t)firsts.size());
-    base = firsts.shfl(base, 0);
-    touched[base + firsts.thread_rank()] = voxel;
-  }
-  pending = false;
-}
-
 // vox_shade: the first fragment of a voxel sets the voxel's bit; vox_compact_mask then emits the touched list in MEMORY
 // ORDER (runs of x-adjacent voxels), so that the list-driven kernels behind it -- clear, resolve, push, merge -- touch
 // the accumulator and level 0 in coalesced runs instead of at random (they are bound by scattered 32-byte DRAM
@@ -346,7 +333,7 @@ __global__ void __launch_bounds__(256) vox_shade(Params P, const VoxRecord* __re
     }
     if (same.thread_rank() == 0) {
       atomicAdd(&accum[2 * (size_t)voxel], rg);
-      // The returned old count is consumed one iteration later (append_first_touch at the loop top), so the
+      // The returned old count is consumed one iteration later (mark_first_touch at the loop top), so the
       // warp does not sit on the L2 round trip of this atomic.
       pend_old = atomicAdd(&accum[2 * (size_t)voxel + 1], bc);
       pend_voxel = voxel;
@@ -656,8 +643,8 @@ __global__ void vox_push_inbox(const unsigned long long* __restrict__ accum, con
 // accumulator between the barrier and the resolve, so each record is a plain 16-byte read-modify-write of its cell
 // (no atomics); the cell read also tells whether the voxel is new to this rank's touched list.
 __global__ void vox_merge_inbox(unsigned long long* __restrict__ accum, const unsigned char* __restrict__ inbox, int parity,
-                                int world, int src_rank, uint32_t cap, uint32_t* __restrict__ touched,
-                                unsigned int* __restrict__ n_touched, Counters* __restrict__ ctr, const unsigned int* own_n) {
+                                int world, int src_rank, uint32_t cap, uint32_t* __restrict__ occ_mask,
+                                Counters* __restrict__ ctr, const unsigned int* own_n) {
   const uint32_t* counts = reinterpret_cast<const uint32_t*>(inbox) + parity * 16;
   if (blockIdx.x == 0 && threadIdx.x == 0 && *own_n > cap) ctr->overflow = 1;   // this rank touched more voxels than fit
   const uint32_t n = min(counts[src_rank], cap);
@@ -682,7 +669,7 @@ __global__ void vox_merge_inbox(unsigned long long* __restrict__ accum, const un
       a[m].y += ((unsigned long long)(q[m].z & 0xFFFFFFu) << 32) | n_frag;
       *reinterpret_cast<ulonglong2*>(&accum[2 * (size_t)v]) = a[m];
       bool pending = true;
-      append_first_touch(pending, old, v, touched, n_touched);
+      mark_first_touch(pending, old, v, occ_mask);      // voxels new to this rank: listed by vox_compact_mask after the merges
     }
   }
 }
@@ -830,8 +817,13 @@ static int resolve_inbox(vct_context* c) {
     for (int r = 0; r < c->shared_world; ++r) {
       if (r == c->shared_rank) continue;
       vox_merge_inbox<<<VCT_CHAIN(c, 4), 0, c->stream>>>(c->d_accum, (const unsigned char*)c->shared_local, c->exchange_parity,
-                                                      c->shared_world, r, (uint32_t)c->exchange_cap, g.touched, g.n_touched,
+                                                      c->shared_world, r, (uint32_t)c->exchange_cap, c->d_occ_mask,
                                                       c->d_counters, c->d_push_count);
+      c->launches += 1;
+    }
+    if (c->shared_world > 1) {
+      const uint32_t n_words = (uint32_t)(((size_t)c->P.V * c->P.V * c->P.V + 31) / 32);
+      vox_compact_mask<<<VCT_CHAIN(c, 4), 0, c->stream>>>(c->d_occ_mask, n_words, g.touched, g.n_touched);
       c->launches += 1;
     }
   }
