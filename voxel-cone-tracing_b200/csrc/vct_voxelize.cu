@@ -206,6 +206,20 @@ __device__ __forceinline__ void mark_first_touch(bool& pending, unsigned long lo
   pending = false;
 }
 
+// The merge appends the voxels that are new to this rank directly to the list (one counter atomic per warp-step): its
+// records arrive in the SENDER's memory order, so the appended tail is memory-ordered in chunks anyway, and going through
+// the bit mask instead costs a second compaction pass (measured: merge 86 -> 104 us at eight ranks).
+__device__ __forceinline__ void append_first_touch(unsigned long long old, uint32_t voxel, uint32_t* __restrict__ touched,
+                                                   unsigned int* __restrict__ n_touched) {
+  if ((uint32_t)old == 0u) {
+    cg::coalesced_group firsts = cg::coalesced_threads();
+    uint32_t base = 0;
+    if (firsts.thread_rank() == 0) base = atomicAdd(n_touched, (uint32_t)firsts.size());
+    base = firsts.shfl(base, 0);
+    touched[base + firsts.thread_rank()] = voxel;
+  }
+}
+
 // One thread per 32-voxel mask word; a warp covers 1024 consecutive voxels and reserves its output range with one
 // atomic, so the list is a sequence of memory-ordered chunks.  The words are cleared on the way.
 __global__ void __launch_bounds__(256) vox_compact_mask(uint32_t* __restrict__ occ_mask, uint32_t n_words,
@@ -643,8 +657,8 @@ __global__ void vox_push_inbox(const unsigned long long* __restrict__ accum, con
 // accumulator between the barrier and the resolve, so each record is a plain 16-byte read-modify-write of its cell
 // (no atomics); the cell read also tells whether the voxel is new to this rank's touched list.
 __global__ void vox_merge_inbox(unsigned long long* __restrict__ accum, const unsigned char* __restrict__ inbox, int parity,
-                                int world, int src_rank, uint32_t cap, uint32_t* __restrict__ occ_mask,
-                                Counters* __restrict__ ctr, const unsigned int* own_n) {
+                                int world, int src_rank, uint32_t cap, uint32_t* __restrict__ touched,
+                                unsigned int* __restrict__ n_touched, Counters* __restrict__ ctr, const unsigned int* own_n) {
   const uint32_t* counts = reinterpret_cast<const uint32_t*>(inbox) + parity * 16;
   if (blockIdx.x == 0 && threadIdx.x == 0 && *own_n > cap) ctr->overflow = 1;   // this rank touched more voxels than fit
   const uint32_t n = min(counts[src_rank], cap);
@@ -668,8 +682,7 @@ __global__ void vox_merge_inbox(unsigned long long* __restrict__ accum, const un
       a[m].x += ((unsigned long long)(q[m].x & 0xFFFFFFu) << 32) | (q[m].y & 0xFFFFFFu);
       a[m].y += ((unsigned long long)(q[m].z & 0xFFFFFFu) << 32) | n_frag;
       *reinterpret_cast<ulonglong2*>(&accum[2 * (size_t)v]) = a[m];
-      bool pending = true;
-      mark_first_touch(pending, old, v, occ_mask);      // voxels new to this rank: listed by vox_compact_mask after the merges
+      append_first_touch(old, v, touched, n_touched);
     }
   }
 }
@@ -817,13 +830,8 @@ static int resolve_inbox(vct_context* c) {
     for (int r = 0; r < c->shared_world; ++r) {
       if (r == c->shared_rank) continue;
       vox_merge_inbox<<<VCT_CHAIN(c, 4), 0, c->stream>>>(c->d_accum, (const unsigned char*)c->shared_local, c->exchange_parity,
-                                                      c->shared_world, r, (uint32_t)c->exchange_cap, c->d_occ_mask,
+                                                      c->shared_world, r, (uint32_t)c->exchange_cap, g.touched, g.n_touched,
                                                       c->d_counters, c->d_push_count);
-      c->launches += 1;
-    }
-    if (c->shared_world > 1) {
-      const uint32_t n_words = (uint32_t)(((size_t)c->P.V * c->P.V * c->P.V + 31) / 32);
-      vox_compact_mask<<<VCT_CHAIN(c, 4), 0, c->stream>>>(c->d_occ_mask, n_words, g.touched, g.n_touched);
       c->launches += 1;
     }
   }
