@@ -110,8 +110,19 @@ def _worker_inbox(rank, world, port, out_dir):
     band[:y1 - y0] = torch.from_numpy(o.frame()[y0:y1].copy())
     full = torch.zeros((world * per, W, 4), dtype=torch.uint8)
     dist.all_gather_into_tensor(full, band)
+    # the library's default row deal (vct_comm_init): interleaved 8-row strips, every rank stores its strips straight
+    # into rank 0's frame slot.  Disjoint writes are modelled by a sum of frames that are zero outside the own strips.
+    strips = parallel.row_strips_for_rank(H, rank, world)
+    own = torch.zeros((H, W, 4), dtype=torch.int32)
+    rows = torch.zeros(H, dtype=torch.int32)
+    for a, b in strips:
+        own[a:b] = torch.from_numpy(o.frame()[a:b].astype(np.int32))
+        rows[a:b] += 1
+    dist.all_reduce(own)
+    dist.all_reduce(rows)
     np.savez(os.path.join(out_dir, f"inbox_{rank}.npz"), counts=counts, sums=sums, grid0=o.grid(0), grid3=o.grid(3),
-             frame=full.numpy()[:H], n_records=np.array([int(x) for x in ns]))
+             frame=full.numpy()[:H], n_records=np.array([int(x) for x in ns]),
+             strip_frame=own.numpy().astype(np.uint8), strip_rows=rows.numpy(), n_strips=len(strips))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -132,6 +143,9 @@ def test_inbox_exchange_model_is_bit_exact_on_every_rank(tmp_path, oracle_mod):
         assert np.array_equal(got["grid0"], o.grid(0)) and np.array_equal(got["grid3"], o.grid(3))
         assert np.array_equal(got["frame"], o.frame())
         assert 0 < got["n_records"].min() and got["n_records"].sum() >= int((o.counts() > 0).sum())
+        assert np.array_equal(got["strip_rows"], np.ones(72, dtype=np.int32))      # every row owned exactly once
+        assert np.array_equal(got["strip_frame"], o.frame())
+        assert int(got["n_strips"]) == (5 if rank == 0 else 4)                    # 72 rows = 9 strips, dealt 5 + 4
     # record format: round trip and the 24-bit limit
     c = np.zeros(8, dtype=np.uint32); s = np.zeros((8, 3), dtype=np.uint32)
     c[3], s[3] = 65793, (65793 * 255, 1, 0)
