@@ -1,11 +1,14 @@
 /*
  * vct_oracle.cpp -- CPU ORACLE: scalar restatement of the reference's three passes.
  *
- * TEST INFRASTRUCTURE ONLY (see vct_oracle.h).  PARITY UNPINNED by the reference (it has no tests,
- * cannot be built here and reads nothing back).  What pins this file instead: the hand-derived
- * known-answer tests (tests/test_oracle_kat.py), the committed golden fixtures (tests/golden/) and a
- * second, independent restatement of the same shader lines in float64 numpy / exact integers
- * (tests/test_oracle_independent.py).
+ * TEST INFRASTRUCTURE ONLY (see vct_oracle.h).  PARITY: the programmable stages are pinned against
+ * vectors produced by executing the reference's own shader files (tests/glsl_run.py,
+ * tests/golden/reference_shader_vectors.npz, tests/test_reference_glsl.py: byte-exact frames); the
+ * fixed-function stages between them are UNPINNED by the reference (it contains no code for them,
+ * has no tests, cannot be built here and reads nothing back) and follow the GL 4.3 specification.
+ * Further pins: the hand-derived known-answer tests (tests/test_oracle_kat.py), the committed golden
+ * fixtures (tests/golden/) and a second, independent restatement of the same shader lines in float64
+ * numpy / exact integers (tests/test_oracle_independent.py).
  *
  * Each function cites the reference file:line it restates; paths are relative to
  * /root/reference/Voxel_Cone_Tracing_Final/.  Where the reference leans on GL fixed function

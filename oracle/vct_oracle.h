@@ -6,10 +6,14 @@
  * cpu_baseline / --impl reference legs of bench.py may load it.  The shipped library
  * (libvct_b200.so) never links or calls anything in this directory.
  *
- * PARITY UNPINNED: the reference (AlerianEmperor/Voxel-Cone-Tracing) has no tests, golden
- * vectors or fixtures, cannot be compiled in this image (Windows-only source, glm/assimp/GL
- * absent) and never reads anything back.  The pins are the hand-derivable known-answer vectors of
- * SURVEY.md A.7 (tests/test_oracle_kat.py) and the fixtures under tests/golden/.
+ * PARITY: the reference (AlerianEmperor/Voxel-Cone-Tracing) has no tests, golden vectors or
+ * fixtures, cannot be compiled in this image (Windows-only source, glm/assimp/GL absent) and never
+ * reads anything back.  Its shader files CAN be executed: tests/glsl_run.py interprets them and
+ * tests/golden/reference_shader_vectors.npz holds their outputs (generator committed next to it);
+ * the oracle reproduces those byte for byte (tests/test_reference_glsl.py).  The fixed-function GL
+ * stages between the shaders remain UNPINNED by the reference (GL 4.3 specification restated).
+ * Further pins: the hand-derivable known-answer vectors of SURVEY.md A.7 (tests/test_oracle_kat.py),
+ * tests/test_oracle_independent.py and the fixtures under tests/golden/.
  */
 #ifndef VCT_ORACLE_H_
 #define VCT_ORACLE_H_

@@ -1,0 +1,94 @@
+"""Writes tests/golden/reference_shader_vectors.npz:  python tests/golden/make_reference_shader_vectors.py
+
+Vectors produced by EXECUTING THE REFERENCE'S SHADER FILES (/root/reference/Voxel_Cone_Tracing_Final/Shader/*.vs|.gs|.fs,
+read in place, never copied) with the GLSL interpreter in tests/glsl_run.py and the fixed-function glue in
+tests/glsl_harness.py.  This is the nearest thing to "outputs of the reference itself run here" this image allows: there
+is no GL stack and no GPU in the build container, so the C++ host cannot run, but its programmable stages can.
+
+Contents (scene: tests/glsl_harness.fixture_scene(), centre-sample coverage):
+  shadow_*   Shadow.vs over every vertex -> window depth at every shadow-map texel well inside one front-facing triangle
+  vox_*      Voxelization.vs -> .gs -> .fs over every triangle at V = 16: per voxel, the number of fragments stored and
+             the sum of the RGB bytes imageStore would write, for voxels whose fragments are all `certain`
+  frame_*    VoxelConeTracing.vs -> .fs for every covered pixel of a 48 x 40 frame at V = 32, given the shadow map, the
+             voxel grid and the triangle-per-pixel map stored next to them (the fixed-function inputs of that stage)
+  card_*     the same stage on an alpha cut-out card in front of a wall WITHOUT a triangle-per-pixel map: the fragment
+             shader runs on the covering triangles nearest first and its `discard` decides which one is seen
+The float32 run is the vector; the float64 run (and, for the voxel pass, a 1/256 px jitter) marks the entries that are
+numerically stable, i.e. whose value does not hinge on a rounding the GL specification leaves open.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+TESTS = os.path.dirname(HERE)
+ROOT = os.path.dirname(TESTS)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, TESTS)
+import vct_b200  # noqa: E402,F401
+import glsl_harness as gh  # noqa: E402
+from oracle.oracle_py import Oracle  # noqa: E402
+
+OUT = os.path.join(HERE, "reference_shader_vectors.npz")
+
+
+def fixed_function_inputs(kind):
+    """Shadow map, voxel grid and visibility for the fixture scene.  They are INPUTS of the stages under test (the
+    reference's own frame would get them from the GL pipeline); the oracle supplies them here and the tests check that
+    whatever they compare was given the same ones."""
+    sc = gh.card_scene() if kind == "card" else gh.fixture_scene()
+    u = gh.scene_uniforms(sc, kind)
+    u["FilterMode"] = 0
+    o = Oracle(); o.set_uniforms(u); o.load_scene(sc)
+    o.draw_depth(); o.draw_voxels(); o.render()
+    out = dict(depth=o.depth().copy(), grid0=o.grid(0).copy(), visibility=o.visibility().copy())
+    o.close()
+    return sc, u, out
+
+
+def generate(frame_stride=1, voxel_tris=None, card_stride=1, log=print):
+    t0 = time.time()
+    out = {}
+    sc, u, ff = fixed_function_inputs("voxel")
+    ij, z, tol = gh.shadow_reference_depths(sc, u)
+    out.update(shadow_ij=ij, shadow_z=z, shadow_tol=tol)
+    log(f"shadow: {len(ij)} texels  [{time.time() - t0:.1f} s]")
+    idx, cnt, sums, bad, nf = gh.voxel_reference_accumulator(sc, u, ff["depth"], voxel_tris)
+    out.update(vox_index=idx, vox_count=cnt, vox_sums=sums, vox_uncertain=bad, vox_fragments=np.int64(nf),
+               vox_depth_in=ff["depth"])
+    log(f"voxel: {nf} fragments, {len(idx)} certain voxels, {len(bad)} uncertain  [{time.time() - t0:.1f} s]")
+    sc, u, ff = fixed_function_inputs("frame")
+    W, H = int(u["screen_width"]), int(u["screen_height"])
+    pixels = [(i, j) for j in range(H) for i in range(W) if ff["visibility"][j, i] != 0xFFFFFFFF][::frame_stride]
+    c32 = gh.frame_reference_pixels(sc, u, ff["depth"], ff["grid0"], ff["visibility"], pixels, np.float32)
+    c64 = gh.frame_reference_pixels(sc, u, ff["depth"], ff["grid0"], ff["visibility"], pixels, np.float64)
+    stable = np.abs(np.clip(c32, 0, 1) - np.clip(c64, 0, 1)).max(1) * 255.0 < 0.25
+    out.update(frame_px=np.array(pixels, dtype=np.int32), frame_rgba=c32.astype(np.float32), frame_stable=stable,
+               frame_depth_in=ff["depth"], frame_grid0_in=ff["grid0"], frame_visibility_in=ff["visibility"])
+    log(f"frame: {len(pixels)} pixels, {int(stable.sum())} stable  [{time.time() - t0:.1f} s]")
+    # alpha cut-out: no visibility map is given, the discard in the fragment shader decides what is seen
+    sc, u, ff = fixed_function_inputs("card")
+    W, H = int(u["screen_width"]), int(u["screen_height"])
+    pixels = [(i, j) for j in range(H) for i in range(W)][::card_stride]
+    t32, c32, nd = gh.frame_reference_depth_ordered(sc, u, ff["depth"], ff["grid0"], pixels, np.float32)
+    t64, c64, _ = gh.frame_reference_depth_ordered(sc, u, ff["depth"], ff["grid0"], pixels, np.float64)
+    both_bg = np.isnan(c32[:, 0]) & np.isnan(c64[:, 0])
+    close = np.abs(np.clip(np.nan_to_num(c32), 0, 1) - np.clip(np.nan_to_num(c64), 0, 1)).max(1) * 255.0 < 0.25
+    stable = (t32 >= 0) & (t32 == t64) & (both_bg | close)
+    out.update(card_px=np.array(pixels, dtype=np.int32), card_tri=t32, card_rgba=c32.astype(np.float32), card_stable=stable,
+               card_discarded=np.int64(nd), card_depth_in=ff["depth"], card_grid0_in=ff["grid0"])
+    log(f"card: {len(pixels)} pixels, {int(stable.sum())} stable, {nd} fragments discarded  [{time.time() - t0:.1f} s]")
+    return out
+
+
+if __name__ == "__main__":
+    if not gh.reference_available():
+        sys.exit("the reference's shader files are not at " + gh.SHADER_DIR)
+    vectors = generate()
+    meta = dict(shader_sha256=gh.shader_hashes(), frame=gh.FRAME, voxel=gh.VOXEL, card=gh.CARD, edge_px=gh.EDGE_PX,
+                note="float32 execution of the reference's GLSL text by tests/glsl_run.py")
+    np.savez_compressed(OUT, meta=np.array(json.dumps(meta)), **vectors)
+    print("wrote", OUT, os.path.getsize(OUT), "bytes")

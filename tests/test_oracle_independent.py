@@ -1,7 +1,8 @@
 """Second, independent restatement of the arithmetic-heavy pieces of the path, in float64 numpy / exact Python
 integers, written from the GLSL and the GL 4.3 filtering rules rather than from the C++ oracle, and compared with
-the oracle on random inputs.  The reference has no tests of its own (parity is unpinned); these
-cross-checks, the hand-derived vectors in test_oracle_kat.py and the golden fixtures are what pins the oracle.
+the oracle on random inputs.  The reference has no tests of its own; next to the executed reference
+shaders of test_reference_glsl.py, these cross-checks, the hand-derived vectors in test_oracle_kat.py and the golden
+fixtures are what pins the oracle.
 
   * SampleVoxels / textureLod        VoxelConeTracing.fs:59-66, GL 4.3 8.14 (weighted-sum form, float64)
   * Voxel_Cone_Tracing loop          VoxelConeTracing.fs:82-107
