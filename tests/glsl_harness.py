@@ -54,7 +54,7 @@ def fixture_scene():
 
 
 def scene_uniforms(sc, kind):
-    return uniforms.scene_uniforms(sc, coverage="center", **{"frame": FRAME, "voxel": VOXEL, "card": CARD}[kind])
+    return uniforms.scene_uniforms(sc, coverage="center", **{"frame": FRAME, "voxel": VOXEL, "card": CARD, "shards": SHARDS}[kind])
 
 
 # ------------------------------------------------------------------------------- fixed function: textures
@@ -497,6 +497,28 @@ def _quad(p00, p10, p11, p01, scale=20.0):
 
 
 CARD = dict(V=32, width=40, height=30, shadow_map_size=256)
+SHARDS = dict(V=32, width=16, height=16, shadow_map_size=128)
+
+
+def shards_scene():
+    """Forty randomly oriented triangles in general position (seeded), half of them textured: every dominant axis and
+    both windings of Voxelization.gs:25-41, every voxelPos permutation of Voxelization.fs:70-86, on tilted geometry."""
+    rng = np.random.default_rng(77)
+    n = 40
+    centre = rng.uniform(-45, 45, (n, 1, 3))
+    tri = centre + rng.normal(0, 20, (n, 3, 3))                      # world units; the grid spans +-75
+    v = np.zeros((n * 3, 14), dtype=np.float32)
+    v[:, :3] = (tri * 20.0).reshape(-1, 3)                           # model units (ModelMatrix = scale(0.05))
+    nrm = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    v[:, 3:6] = np.repeat(nrm, 3, axis=0)
+    v[:, 6:8] = rng.uniform(0, 2, (n * 3, 2))
+    v[:, 8:11], v[:, 11:14] = (1, 0, 0), (0, 1, 0)
+    tex = rng.integers(30, 256, (8, 8, 3), dtype=np.uint8)
+    flat = np.array([[[200, 160, 90]]], dtype=np.uint8)
+    grey = np.array([[[128]]], dtype=np.uint8)
+    return scenes.Scene("shards", v, np.arange(n * 3, dtype=np.uint32).reshape(n, 3), (np.arange(n) % 2).astype(np.uint16),
+                        [tex, flat, grey], [(0, 2, 2, 20.0), (1, 2, 2, 20.0)])
 
 
 def card_scene():

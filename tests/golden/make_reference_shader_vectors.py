@@ -9,6 +9,7 @@ Contents (scene: tests/glsl_harness.fixture_scene(), centre-sample coverage):
   shadow_*   Shadow.vs over every vertex -> window depth at every shadow-map texel well inside one front-facing triangle
   vox_*      Voxelization.vs -> .gs -> .fs over every triangle at V = 16: per voxel, the number of fragments stored and
              the sum of the RGB bytes imageStore would write, for voxels whose fragments are all `certain`
+  shards_*   the same program over forty randomly oriented triangles (tests/glsl_harness.shards_scene())
   frame_*    VoxelConeTracing.vs -> .fs for every covered pixel of a 48 x 40 frame at V = 32, given the shadow map, the
              voxel grid and the triangle-per-pixel map stored next to them (the fixed-function inputs of that stage)
   card_*     the same stage on an alpha cut-out card in front of a wall WITHOUT a triangle-per-pixel map: the fragment
@@ -39,7 +40,7 @@ def fixed_function_inputs(kind):
     """Shadow map, voxel grid and visibility for the fixture scene.  They are INPUTS of the stages under test (the
     reference's own frame would get them from the GL pipeline); the oracle supplies them here and the tests check that
     whatever they compare was given the same ones."""
-    sc = gh.card_scene() if kind == "card" else gh.fixture_scene()
+    sc = {"card": gh.card_scene, "shards": gh.shards_scene}.get(kind, gh.fixture_scene)()
     u = gh.scene_uniforms(sc, kind)
     u["FilterMode"] = 0
     o = Oracle(); o.set_uniforms(u); o.load_scene(sc)
@@ -49,7 +50,7 @@ def fixed_function_inputs(kind):
     return sc, u, out
 
 
-def generate(frame_stride=1, voxel_tris=None, card_stride=1, log=print):
+def generate(frame_stride=1, voxel_tris=None, card_stride=1, shard_tris=None, log=print):
     t0 = time.time()
     out = {}
     sc, u, ff = fixed_function_inputs("voxel")
@@ -60,6 +61,10 @@ def generate(frame_stride=1, voxel_tris=None, card_stride=1, log=print):
     out.update(vox_index=idx, vox_count=cnt, vox_sums=sums, vox_uncertain=bad, vox_fragments=np.int64(nf),
                vox_depth_in=ff["depth"])
     log(f"voxel: {nf} fragments, {len(idx)} certain voxels, {len(bad)} uncertain  [{time.time() - t0:.1f} s]")
+    sc, u, ff = fixed_function_inputs("shards")
+    idx, cnt, sums, bad, nf = gh.voxel_reference_accumulator(sc, u, ff["depth"], shard_tris)
+    out.update(shards_index=idx, shards_count=cnt, shards_sums=sums, shards_uncertain=bad, shards_fragments=np.int64(nf))
+    log(f"shards: {nf} fragments, {len(idx)} certain voxels, {len(bad)} uncertain  [{time.time() - t0:.1f} s]")
     sc, u, ff = fixed_function_inputs("frame")
     W, H = int(u["screen_width"]), int(u["screen_height"])
     pixels = [(i, j) for j in range(H) for i in range(W) if ff["visibility"][j, i] != 0xFFFFFFFF][::frame_stride]
@@ -88,7 +93,8 @@ if __name__ == "__main__":
     if not gh.reference_available():
         sys.exit("the reference's shader files are not at " + gh.SHADER_DIR)
     vectors = generate()
-    meta = dict(shader_sha256=gh.shader_hashes(), frame=gh.FRAME, voxel=gh.VOXEL, card=gh.CARD, edge_px=gh.EDGE_PX,
+    meta = dict(shader_sha256=gh.shader_hashes(), frame=gh.FRAME, voxel=gh.VOXEL, card=gh.CARD, shards=gh.SHARDS,
+                edge_px=gh.EDGE_PX,
                 note="float32 execution of the reference's GLSL text by tests/glsl_run.py")
     np.savez_compressed(OUT, meta=np.array(json.dumps(meta)), **vectors)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
