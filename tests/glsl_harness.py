@@ -54,7 +54,9 @@ def fixture_scene():
 
 
 def scene_uniforms(sc, kind):
-    return uniforms.scene_uniforms(sc, coverage="center", **{"frame": FRAME, "voxel": VOXEL, "card": CARD, "shards": SHARDS}[kind])
+    kw = dict({"frame": FRAME, "voxel": VOXEL, "card": CARD, "shards": SHARDS, "config1": CONFIG1}[kind])
+    kw.setdefault("coverage", "center")
+    return uniforms.scene_uniforms(sc, **kw)
 
 
 # ------------------------------------------------------------------------------- fixed function: textures
@@ -125,8 +127,12 @@ class Sampler2D:
 
 
 class Sampler3D:
-    def __init__(self, levels):
-        self.levels = levels
+    """`gain` scales every fetch: the generator reruns the fragment stage with gain 1 +- 4e-6 (a few float32 ulps of
+    filter arithmetic, which GL leaves open) and drops pixels whose colour depends on it -- in practice those whose
+    cone loop ends with alpha within ~1e-6 of MAX_ALPHA."""
+
+    def __init__(self, levels, gain=1.0):
+        self.levels, self.gain = levels, gain
 
     def _level(self, level, uvw):
         n = level.shape[0]
@@ -147,7 +153,7 @@ class Sampler3D:
         a = self._level(self.levels[l0], uvw)
         if f > 0 and l0 + 1 < len(self.levels):
             a = (1 - f) * a + f * self._level(self.levels[l0 + 1], uvw)
-        return a
+        return a * self.gain
 
 
 def install_texture_hooks(prog):
@@ -348,7 +354,7 @@ class FrameStage:
 
     NAMES = ["tex", "Position_world", "Normal_world", "Tangent_world", "BiTangent_world", "CameraDirection_world", "Position_depth"]
 
-    def __init__(self, sc, u, shadow_d24, grid0, dtype):
+    def __init__(self, sc, u, shadow_d24, grid0, dtype, voxel_gain=1.0):
         self.sc, self.dtype = sc, dtype
         self.W, self.H = int(u["screen_width"]), int(u["screen_height"])
         self.vs, self.fs = load("VoxelConeTracing.vs", dtype), load("VoxelConeTracing.fs", dtype)
@@ -364,7 +370,7 @@ class FrameStage:
         fs.set_uniform("VoxelGridWorldSize", u["VoxelGridWorldSize"])
         fs.set_uniform("VoxelDimensions", int(u["VoxelDimensions"]))
         fs.globals["ShadowMap"] = shadow_sampler(shadow_d24)
-        fs.globals["VoxelTexture"] = Sampler3D(box_mips_3d(grid0))
+        fs.globals["VoxelTexture"] = Sampler3D(box_mips_3d(grid0), voxel_gain)
         self.samplers = scene_samplers(sc)
         self.cache = {}
 
@@ -445,11 +451,11 @@ class FrameStage:
         return [ti for _, ti in found]
 
 
-def frame_reference_pixels(sc, u, shadow_d24, grid0, visibility, pixels, dtype):
+def frame_reference_pixels(sc, u, shadow_d24, grid0, visibility, pixels, dtype, voxel_gain=1.0):
     """Runs VoxelConeTracing.vs on the three vertices of the triangle the visibility pass found at each pixel,
     interpolates the seven varyings perspective-correctly at the pixel centre (fixed function, float64) and runs
     VoxelConeTracing.fs.  Returns float colours [n, 4] (NaN rows for background pixels and discarded fragments)."""
-    st = FrameStage(sc, u, shadow_d24, grid0, dtype)
+    st = FrameStage(sc, u, shadow_d24, grid0, dtype, voxel_gain)
     out = np.full((len(pixels), 4), np.nan)
     for n, (i, j) in enumerate(pixels):
         ti = int(visibility[j, i])
@@ -460,12 +466,12 @@ def frame_reference_pixels(sc, u, shadow_d24, grid0, visibility, pixels, dtype):
     return out
 
 
-def frame_reference_depth_ordered(sc, u, shadow_d24, grid0, pixels, dtype):
+def frame_reference_depth_ordered(sc, u, shadow_d24, grid0, pixels, dtype, voxel_gain=1.0):
     """The same without a visibility map: per pixel the fragment shader runs on the covering front-facing triangles from
     the nearest on, and the first fragment that is not discarded is what depth test LESS leaves in the framebuffer
     (a discarded fragment writes neither colour nor depth).  Returns (triangle id [n] -- 0xFFFFFFFF background, -1 pixel
     left to the fill rule --, colours [n, 4], fragments discarded)."""
-    st = FrameStage(sc, u, shadow_d24, grid0, dtype)
+    st = FrameStage(sc, u, shadow_d24, grid0, dtype, voxel_gain)
     tri = np.full(len(pixels), -1, dtype=np.int64)
     out = np.full((len(pixels), 4), np.nan)
     discarded = 0
@@ -498,6 +504,8 @@ def _quad(p00, p10, p11, p01, scale=20.0):
 
 CARD = dict(V=32, width=40, height=30, shadow_map_size=256)
 SHARDS = dict(V=32, width=16, height=16, shadow_map_size=128)
+CONFIG1 = dict(V=64, width=256, height=256, shadow_map_size=1024, coverage="msaa4")     # BASELINE.json configs[0]
+CONFIG1_STRIDE = 13                                                                   # every 13th covered pixel
 
 
 def shards_scene():
@@ -535,6 +543,16 @@ def card_scene():
     return scenes.Scene("card", np.concatenate([cv, wv]), np.concatenate([ci, wi + 4]).astype(np.uint32),
                         np.array([0, 0, 1, 1], dtype=np.uint16), [card_tex, wall_tex, grey],
                         [(0, 2, 2, 20.0), (1, 2, 2, 8.0)], camera_pos=(6.0, 3.0, 140.0), yaw=-92.0, pitch=-1.0)
+
+
+GAINS = (1.0 + 4e-6, 1.0 - 4e-6)
+
+
+def colours_agree(a, b):
+    """rows of two float colour arrays equal to a quarter of an 8-bit step (NaN = no fragment, must match too)"""
+    na, nb = np.isnan(a[:, 0]), np.isnan(b[:, 0])
+    close = np.abs(np.clip(np.nan_to_num(a), 0, 1) - np.clip(np.nan_to_num(b), 0, 1)).max(1) * 255.0 < 0.25
+    return (na == nb) & (na | close)
 
 
 def to_unorm8(c):

@@ -12,15 +12,19 @@ Contents (scene: tests/glsl_harness.fixture_scene(), centre-sample coverage):
   shards_*   the same program over forty randomly oriented triangles (tests/glsl_harness.shards_scene())
   frame_*    VoxelConeTracing.vs -> .fs for every covered pixel of a 48 x 40 frame at V = 32, given the shadow map, the
              voxel grid and the triangle-per-pixel map stored next to them (the fixed-function inputs of that stage)
+  config1_*  the same stage at BASELINE config 1 (Cornell box, 64^3, 256 x 256, 1024^2 shadow map, 4x MSAA voxel coverage)
+             on every 13th covered pixel; the inputs are pinned by CRC-32 instead of being stored
   card_*     the same stage on an alpha cut-out card in front of a wall WITHOUT a triangle-per-pixel map: the fragment
              shader runs on the covering triangles nearest first and its `discard` decides which one is seen
-The float32 run is the vector; the float64 run (and, for the voxel pass, a 1/256 px jitter) marks the entries that are
-numerically stable, i.e. whose value does not hinge on a rounding the GL specification leaves open.
+The float32 run is the vector; a float64 run, a +-4e-6 gain on the voxel-texture fetches (frame stages) and a 1/256 px
+jitter (voxel stages) mark the entries that are numerically stable, i.e. whose value does not hinge on a rounding the GL
+specification leaves open (in practice: a cone loop ending with alpha within ~1e-6 of MAX_ALPHA).
 """
 import json
 import os
 import sys
 import time
+import zlib
 
 import numpy as np
 
@@ -31,6 +35,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, TESTS)
 import vct_b200  # noqa: E402,F401
 import glsl_harness as gh  # noqa: E402
+from vct_b200 import scenes  # noqa: E402
 from oracle.oracle_py import Oracle  # noqa: E402
 
 OUT = os.path.join(HERE, "reference_shader_vectors.npz")
@@ -40,7 +45,7 @@ def fixed_function_inputs(kind):
     """Shadow map, voxel grid and visibility for the fixture scene.  They are INPUTS of the stages under test (the
     reference's own frame would get them from the GL pipeline); the oracle supplies them here and the tests check that
     whatever they compare was given the same ones."""
-    sc = {"card": gh.card_scene, "shards": gh.shards_scene}.get(kind, gh.fixture_scene)()
+    sc = {"card": gh.card_scene, "shards": gh.shards_scene, "config1": scenes.cornell}.get(kind, gh.fixture_scene)()
     u = gh.scene_uniforms(sc, kind)
     u["FilterMode"] = 0
     o = Oracle(); o.set_uniforms(u); o.load_scene(sc)
@@ -50,7 +55,18 @@ def fixed_function_inputs(kind):
     return sc, u, out
 
 
-def generate(frame_stride=1, voxel_tris=None, card_stride=1, shard_tris=None, log=print):
+def stable_frame(sc, u, ff, pixels):
+    """float32 colours of the executed fragment stage + which of them survive float64 execution and a +-4e-6 gain on the
+    voxel fetches unchanged (to a quarter of an 8-bit step)"""
+    run = lambda dtype, gain=1.0: gh.frame_reference_pixels(sc, u, ff["depth"], ff["grid0"], ff["visibility"], pixels, dtype, gain)
+    c32 = run(np.float32)
+    stable = gh.colours_agree(c32, run(np.float64))
+    for gain in gh.GAINS:
+        stable &= gh.colours_agree(c32, run(np.float32, gain))
+    return c32, stable
+
+
+def generate(frame_stride=1, voxel_tris=None, card_stride=1, shard_tris=None, config1_stride=1, log=print):
     t0 = time.time()
     out = {}
     sc, u, ff = fixed_function_inputs("voxel")
@@ -68,9 +84,7 @@ def generate(frame_stride=1, voxel_tris=None, card_stride=1, shard_tris=None, lo
     sc, u, ff = fixed_function_inputs("frame")
     W, H = int(u["screen_width"]), int(u["screen_height"])
     pixels = [(i, j) for j in range(H) for i in range(W) if ff["visibility"][j, i] != 0xFFFFFFFF][::frame_stride]
-    c32 = gh.frame_reference_pixels(sc, u, ff["depth"], ff["grid0"], ff["visibility"], pixels, np.float32)
-    c64 = gh.frame_reference_pixels(sc, u, ff["depth"], ff["grid0"], ff["visibility"], pixels, np.float64)
-    stable = np.abs(np.clip(c32, 0, 1) - np.clip(c64, 0, 1)).max(1) * 255.0 < 0.25
+    c32, stable = stable_frame(sc, u, ff, pixels)
     out.update(frame_px=np.array(pixels, dtype=np.int32), frame_rgba=c32.astype(np.float32), frame_stable=stable,
                frame_depth_in=ff["depth"], frame_grid0_in=ff["grid0"], frame_visibility_in=ff["visibility"])
     log(f"frame: {len(pixels)} pixels, {int(stable.sum())} stable  [{time.time() - t0:.1f} s]")
@@ -80,12 +94,23 @@ def generate(frame_stride=1, voxel_tris=None, card_stride=1, shard_tris=None, lo
     pixels = [(i, j) for j in range(H) for i in range(W)][::card_stride]
     t32, c32, nd = gh.frame_reference_depth_ordered(sc, u, ff["depth"], ff["grid0"], pixels, np.float32)
     t64, c64, _ = gh.frame_reference_depth_ordered(sc, u, ff["depth"], ff["grid0"], pixels, np.float64)
-    both_bg = np.isnan(c32[:, 0]) & np.isnan(c64[:, 0])
-    close = np.abs(np.clip(np.nan_to_num(c32), 0, 1) - np.clip(np.nan_to_num(c64), 0, 1)).max(1) * 255.0 < 0.25
-    stable = (t32 >= 0) & (t32 == t64) & (both_bg | close)
+    stable = (t32 >= 0) & (t32 == t64) & gh.colours_agree(c32, c64)
+    for gain in gh.GAINS:
+        tg, cg, _ = gh.frame_reference_depth_ordered(sc, u, ff["depth"], ff["grid0"], pixels, np.float32, gain)
+        stable &= (tg == t32) & gh.colours_agree(c32, cg)
     out.update(card_px=np.array(pixels, dtype=np.int32), card_tri=t32, card_rgba=c32.astype(np.float32), card_stable=stable,
                card_discarded=np.int64(nd), card_depth_in=ff["depth"], card_grid0_in=ff["grid0"])
     log(f"card: {len(pixels)} pixels, {int(stable.sum())} stable, {nd} fragments discarded  [{time.time() - t0:.1f} s]")
+    # BASELINE config 1 (Cornell box, 64^3, 256 x 256, 1024^2 shadow map, 4x MSAA voxel coverage) at its full size
+    sc, u, ff = fixed_function_inputs("config1")
+    W, H = int(u["screen_width"]), int(u["screen_height"])
+    pixels = [(i, j) for j in range(H) for i in range(W) if ff["visibility"][j, i] != 0xFFFFFFFF][::gh.CONFIG1_STRIDE * config1_stride]
+    c32, stable = stable_frame(sc, u, ff, pixels)
+    px = np.array(pixels, dtype=np.int32)
+    out.update(config1_px=px, config1_rgba=c32.astype(np.float32), config1_stable=stable,
+               config1_tri=ff["visibility"][px[:, 1], px[:, 0]].astype(np.int64),
+               config1_depth_crc=np.uint32(zlib.crc32(ff["depth"].tobytes())), config1_grid0_crc=np.uint32(zlib.crc32(ff["grid0"].tobytes())))
+    log(f"config 1: {len(pixels)} pixels, {int(stable.sum())} stable  [{time.time() - t0:.1f} s]")
     return out
 
 
@@ -93,7 +118,7 @@ if __name__ == "__main__":
     if not gh.reference_available():
         sys.exit("the reference's shader files are not at " + gh.SHADER_DIR)
     vectors = generate()
-    meta = dict(shader_sha256=gh.shader_hashes(), frame=gh.FRAME, voxel=gh.VOXEL, card=gh.CARD, shards=gh.SHARDS,
+    meta = dict(shader_sha256=gh.shader_hashes(), frame=gh.FRAME, voxel=gh.VOXEL, card=gh.CARD, shards=gh.SHARDS, config1=gh.CONFIG1, config1_stride=gh.CONFIG1_STRIDE,
                 edge_px=gh.EDGE_PX,
                 note="float32 execution of the reference's GLSL text by tests/glsl_run.py")
     np.savez_compressed(OUT, meta=np.array(json.dumps(meta)), **vectors)
