@@ -14,8 +14,8 @@ Texture slots follow the reference's (quirky) mapping, Model.h:126-136 and Mesh.
 map_Ks -> SpecularTexture, map_Ka (aiTextureType_AMBIENT) -> HeightTexture; bump maps (aiTextureType_HEIGHT) are loaded
 by the reference but never bound, so they are ignored here.  A material without one of the three gets a 1x1 texture
 (Kd / Ks colour, flat height): the reference would otherwise inherit the previous mesh's binding (undefined, A.6 #9).
-Images are decoded by images.py (PNG / PNM / TGA on numpy + zlib, restating the part of stb_image the asset path needs,
-Model.h:150), with Pillow as the fallback for other formats."""
+Images are decoded by images.py (PNG / JPEG / TGA / BMP / PNM on numpy + zlib, byte-identical to the stb_image the
+reference calls at Model.h:152 -- tests/test_images_vs_stb.py), with Pillow as the fallback for the rest (GIF, PSD, HDR)."""
 from __future__ import annotations
 
 import os
@@ -27,11 +27,11 @@ from .scenes import Scene
 
 def _load_image(path):
     from . import images
-    try:                                  # built-in decoders (PNG / PNM / TGA: the stb_image subset the asset path needs)
+    try:                                  # built-in decoders (PNG / JPEG / TGA / BMP / PNM, stb_image's results)
         return images.load_image(path)
     except images.UnsupportedImage:
         pass
-    from PIL import Image                 # anything else (JPEG, 16-bit or interlaced PNG): Pillow, if it is installed
+    from PIL import Image                 # anything else (GIF, PSD, ...): Pillow, if it is installed
     im = Image.open(path)
     if im.mode not in ("L", "RGB", "RGBA"):
         im = im.convert("RGBA" if "A" in im.getbands() else "RGB")
