@@ -370,3 +370,23 @@ def test_load_image_dispatch_and_objloader_use(tmp_path):
         assert np.array_equal(got, ref_stb.load(str(tmp_path / name))), name
         if name != "e.jpg":
             assert np.array_equal(got, rgb), name
+
+
+def test_obj_asset_textures_are_what_the_reference_would_upload(tmp_path):
+    """An OBJ whose material maps are a JPEG (4:2:0, as Sponza's are), an RLE TGA and a palettised BMP: objloader's
+    textures equal stbi_load's bytes -- what TextureFromFile (Model.h:141-186) hands to glTexImage2D."""
+    PIL = pytest.importorskip("PIL.Image")
+    from vct_b200 import objloader
+    rgb = picture(48, 64, 3, 99)
+    PIL.fromarray(rgb).save(str(tmp_path / "albedo.jpg"), quality=85, subsampling=2)
+    (tmp_path / "spec.tga").write_bytes(make_tga(np.repeat(picture(8, 4, 3, 5), 4, 1), 2, 24, rle=True))
+    pal = np.random.default_rng(3).integers(0, 256, (16, 3))
+    (tmp_path / "height.bmp").write_bytes(make_bmp(np.random.default_rng(4).integers(0, 16, (8, 8)), 4, palette=pal))
+    (tmp_path / "m.mtl").write_text("newmtl m\nKd 1 1 1\nmap_Kd albedo.jpg\nmap_Ks spec.tga\nmap_Ka height.bmp\n")
+    (tmp_path / "m.obj").write_text("mtllib m.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 0 1\nusemtl m\nf 1/1 2/2 3/3\n")
+    sc = objloader.load_obj(str(tmp_path / "m.obj"))
+    d, s, h, _ = sc.materials[0]
+    for tex, name in ((d, "albedo.jpg"), (s, "spec.tga"), (h, "height.bmp")):
+        want = ref_stb.load(str(tmp_path / name))
+        assert np.array_equal(sc.textures[tex], want), name
+    assert sc.textures[d].shape == (48, 64, 3) and np.abs(sc.textures[d].astype(int) - rgb).mean() < 40     # lossy (noisy chroma at 4:2:0), but that picture
