@@ -53,8 +53,14 @@ def fixture_scene():
     return sc
 
 
+def atrium_scene():
+    """6126 triangles, 22 materials: 32^2 RGB albedo maps (minified at this frame size), single-channel specular and
+    height maps, alpha cut-out cards -- the scene of tests/golden/atrium_v32_conservative.npz"""
+    return scenes.atrium(detail=0.1, tex_size=32)
+
+
 def scene_uniforms(sc, kind):
-    kw = dict({"frame": FRAME, "voxel": VOXEL, "card": CARD, "shards": SHARDS, "config1": CONFIG1}[kind])
+    kw = dict({"frame": FRAME, "voxel": VOXEL, "card": CARD, "shards": SHARDS, "config1": CONFIG1, "atrium": ATRIUM}[kind])
     kw.setdefault("coverage", "center")
     return uniforms.scene_uniforms(sc, **kw)
 
@@ -505,6 +511,8 @@ def _quad(p00, p10, p11, p01, scale=20.0):
 CARD = dict(V=32, width=40, height=30, shadow_map_size=256)
 SHARDS = dict(V=32, width=16, height=16, shadow_map_size=128)
 CONFIG1 = dict(V=64, width=256, height=256, shadow_map_size=1024, coverage="msaa4")     # BASELINE.json configs[0]
+ATRIUM = dict(V=32, width=96, height=54, shadow_map_size=512, coverage="conservative")  # the golden atrium case
+ATRIUM_STRIDE = 3
 CONFIG1_STRIDE = 13                                                                   # every 13th covered pixel
 
 

@@ -14,6 +14,8 @@ Contents (scene: tests/glsl_harness.fixture_scene(), centre-sample coverage):
              voxel grid and the triangle-per-pixel map stored next to them (the fixed-function inputs of that stage)
   config1_*  the same stage at BASELINE config 1 (Cornell box, 64^3, 256 x 256, 1024^2 shadow map, 4x MSAA voxel coverage)
              on every 13th covered pixel; the inputs are pinned by CRC-32 instead of being stored
+  atrium_*   the same stage on the 6126-triangle atrium (22 materials, minified textures, cut-out cards, conservative voxel
+             coverage; the scene of atrium_v32_conservative.npz) on every 3rd covered pixel; inputs pinned by CRC-32
   card_*     the same stage on an alpha cut-out card in front of a wall WITHOUT a triangle-per-pixel map: the fragment
              shader runs on the covering triangles nearest first and its `discard` decides which one is seen
 The float32 run is the vector; a float64 run, a +-4e-6 gain on the voxel-texture fetches (frame stages) and a 1/256 px
@@ -45,7 +47,7 @@ def fixed_function_inputs(kind):
     """Shadow map, voxel grid and visibility for the fixture scene.  They are INPUTS of the stages under test (the
     reference's own frame would get them from the GL pipeline); the oracle supplies them here and the tests check that
     whatever they compare was given the same ones."""
-    sc = {"card": gh.card_scene, "shards": gh.shards_scene, "config1": scenes.cornell}.get(kind, gh.fixture_scene)()
+    sc = {"card": gh.card_scene, "shards": gh.shards_scene, "config1": scenes.cornell, "atrium": gh.atrium_scene}.get(kind, gh.fixture_scene)()
     u = gh.scene_uniforms(sc, kind)
     u["FilterMode"] = 0
     o = Oracle(); o.set_uniforms(u); o.load_scene(sc)
@@ -66,7 +68,7 @@ def stable_frame(sc, u, ff, pixels):
     return c32, stable
 
 
-def generate(frame_stride=1, voxel_tris=None, card_stride=1, shard_tris=None, config1_stride=1, log=print):
+def generate(frame_stride=1, voxel_tris=None, card_stride=1, shard_tris=None, config1_stride=1, atrium_stride=1, log=print):
     t0 = time.time()
     out = {}
     sc, u, ff = fixed_function_inputs("voxel")
@@ -111,6 +113,16 @@ def generate(frame_stride=1, voxel_tris=None, card_stride=1, shard_tris=None, co
                config1_tri=ff["visibility"][px[:, 1], px[:, 0]].astype(np.int64),
                config1_depth_crc=np.uint32(zlib.crc32(ff["depth"].tobytes())), config1_grid0_crc=np.uint32(zlib.crc32(ff["grid0"].tobytes())))
     log(f"config 1: {len(pixels)} pixels, {int(stable.sum())} stable  [{time.time() - t0:.1f} s]")
+    # the atrium: many materials, minified textures (implicit LOD), single-channel maps, cut-out cards, conservative coverage
+    sc, u, ff = fixed_function_inputs("atrium")
+    W, H = int(u["screen_width"]), int(u["screen_height"])
+    pixels = [(i, j) for j in range(H) for i in range(W) if ff["visibility"][j, i] != 0xFFFFFFFF][::gh.ATRIUM_STRIDE * atrium_stride]
+    c32, stable = stable_frame(sc, u, ff, pixels)
+    px = np.array(pixels, dtype=np.int32)
+    out.update(atrium_px=px, atrium_rgba=c32.astype(np.float32), atrium_stable=stable,
+               atrium_tri=ff["visibility"][px[:, 1], px[:, 0]].astype(np.int64),
+               atrium_depth_crc=np.uint32(zlib.crc32(ff["depth"].tobytes())), atrium_grid0_crc=np.uint32(zlib.crc32(ff["grid0"].tobytes())))
+    log(f"atrium: {len(pixels)} pixels, {int(stable.sum())} stable  [{time.time() - t0:.1f} s]")
     return out
 
 
@@ -118,7 +130,7 @@ if __name__ == "__main__":
     if not gh.reference_available():
         sys.exit("the reference's shader files are not at " + gh.SHADER_DIR)
     vectors = generate()
-    meta = dict(shader_sha256=gh.shader_hashes(), frame=gh.FRAME, voxel=gh.VOXEL, card=gh.CARD, shards=gh.SHARDS, config1=gh.CONFIG1, config1_stride=gh.CONFIG1_STRIDE,
+    meta = dict(shader_sha256=gh.shader_hashes(), frame=gh.FRAME, voxel=gh.VOXEL, card=gh.CARD, shards=gh.SHARDS, config1=gh.CONFIG1, config1_stride=gh.CONFIG1_STRIDE, atrium=gh.ATRIUM, atrium_stride=gh.ATRIUM_STRIDE,
                 edge_px=gh.EDGE_PX,
                 note="float32 execution of the reference's GLSL text by tests/glsl_run.py")
     np.savez_compressed(OUT, meta=np.array(json.dumps(meta)), **vectors)
