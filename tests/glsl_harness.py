@@ -60,6 +60,8 @@ def atrium_scene():
 
 
 def scene_uniforms(sc, kind):
+    if kind.endswith("_msaa4"):
+        return uniforms.scene_uniforms(sc, coverage="msaa4", **{"voxel_msaa4": VOXEL, "shards_msaa4": SHARDS}[kind])
     kw = dict({"frame": FRAME, "voxel": VOXEL, "card": CARD, "shards": SHARDS, "config1": CONFIG1, "atrium": ATRIUM}[kind])
     kw.setdefault("coverage", "center")
     return uniforms.scene_uniforms(sc, **kw)
@@ -231,12 +233,18 @@ def shadow_reference_depths(sc, u, dtype=np.float32):
 
 
 # ------------------------------------------------------------------------ Voxelization.vs / .gs / .fs
-def voxel_reference_fragments(sc, u, shadow_d24, dtype, tri_ids=None, jitter=False):
+MSAA4 = [(0.375, 0.125), (0.875, 0.375), (0.125, 0.625), (0.625, 0.875)]      # the standard 4x pattern (GL 4.3 14.3.1 leaves it
+                                                                              # to the implementation; D3D / NVIDIA / the oracle use this)
+
+
+def voxel_reference_fragments(sc, u, shadow_d24, dtype, tri_ids=None, jitter=False, coverage="center"):
     """Runs the voxelisation program over triangles of the scene.  Returns a list of fragments
     ([(voxel index or -1 when the store is out of bounds, rgba8 bytes stored)], certain, triangle) -- one result for the
     pixel centre and, with `jitter`, four more with the attributes evaluated 1/256 px away (the freedom GL's sub-pixel
     vertex snap leaves); `certain` is False when the pixel centre lies within EDGE_PX of a triangle edge, where the
-    fill rule, not the shaders, decides."""
+    fill rule, not the shaders, decides.  coverage = "msaa4": the reference's default framebuffer has four samples
+    (main.cpp:30), a fragment is generated when any of them is inside and -- no `centroid` qualifier in the shaders --
+    its inputs and gl_FragCoord are evaluated at the pixel centre, inside the triangle or not."""
     V = int(u["VoxelDimensions"])
     vs, gs, fs = load("Voxelization.vs", dtype), load("Voxelization.gs", dtype), load("Voxelization.fs", dtype)
     for p in (vs, gs, fs):
@@ -303,11 +311,18 @@ def voxel_reference_fragments(sc, u, shadow_d24, dtype, tri_ids=None, jitter=Fal
         for j in range(max(j0, 0), min(j1, V - 1) + 1):
             for i in range(max(i0, 0), min(i1, V - 1) + 1):
                 w = bary(i + 0.5, j + 0.5)
-                if w.min() * px_per_bary < -EDGE_PX:
-                    continue
+                if coverage == "msaa4":
+                    d = [bary(i + sx, j + sy).min() * px_per_bary for sx, sy in MSAA4]
+                    inside = any(x > EDGE_PX for x in d)
+                    if not inside and not any(abs(x) <= EDGE_PX for x in d):
+                        continue
+                else:
+                    if w.min() * px_per_bary < -EDGE_PX:
+                        continue
+                    inside = bool(w.min() * px_per_bary > EDGE_PX)
                 z = float(w @ win[:, 2])
                 # the fill rule decides within EDGE_PX of an edge; a sub-pixel vertex snap can move z across a slice
-                certain = bool(w.min() * px_per_bary > EDGE_PX) and abs(z * V - np.rint(z * V)) > z_slack * V + 1e-5
+                certain = inside and abs(z * V - np.rint(z * V)) > z_slack * V + 1e-5
                 if not 0.0 <= z <= 1.0:
                     continue                                    # depth clipping (13.5), glDepthRange default
                 results = []
@@ -327,13 +342,13 @@ def voxel_reference_fragments(sc, u, shadow_d24, dtype, tri_ids=None, jitter=Fal
     return frags
 
 
-def voxel_reference_accumulator(sc, u, shadow_d24, tri_ids=None):
+def voxel_reference_accumulator(sc, u, shadow_d24, tri_ids=None, coverage="center"):
     """Per-voxel fragment counts and byte sums the reference's voxelisation program produces.  A voxel is `certain`
     when every fragment landing in it (a) is interior to its triangle, (b) targets the same voxel in float32 and float64
     execution and under the sub-pixel jitter, and (c) stores bytes that move by at most 1 under either.  Returns (voxel
     index, count, rgb sums, uncertain voxel indices, fragments run)."""
-    f32 = voxel_reference_fragments(sc, u, shadow_d24, np.float32, tri_ids, jitter=True)
-    f64 = voxel_reference_fragments(sc, u, shadow_d24, np.float64, tri_ids)
+    f32 = voxel_reference_fragments(sc, u, shadow_d24, np.float32, tri_ids, jitter=True, coverage=coverage)
+    f64 = voxel_reference_fragments(sc, u, shadow_d24, np.float64, tri_ids, coverage=coverage)
     assert len(f32) == len(f64)
     acc, bad = {}, set()
     for (r32, certain, _), (r64, _, _) in zip(f32, f64):

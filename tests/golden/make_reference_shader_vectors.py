@@ -10,6 +10,8 @@ Contents (scene: tests/glsl_harness.fixture_scene(), centre-sample coverage):
   vox_*      Voxelization.vs -> .gs -> .fs over every triangle at V = 16: per voxel, the number of fragments stored and
              the sum of the RGB bytes imageStore would write, for voxels whose fragments are all `certain`
   shards_*   the same program over forty randomly oriented triangles (tests/glsl_harness.shards_scene())
+  voxm_*, shardsm_*  both again with 4x MSAA coverage (the reference's default framebuffer): a fragment wherever any of the
+             four samples is inside, shaded at the pixel centre
   frame_*    VoxelConeTracing.vs -> .fs for every covered pixel of a 48 x 40 frame at V = 32, given the shadow map, the
              voxel grid and the triangle-per-pixel map stored next to them (the fixed-function inputs of that stage)
   config1_*  the same stage at BASELINE config 1 (Cornell box, 64^3, 256 x 256, 1024^2 shadow map, 4x MSAA voxel coverage)
@@ -47,7 +49,8 @@ def fixed_function_inputs(kind):
     """Shadow map, voxel grid and visibility for the fixture scene.  They are INPUTS of the stages under test (the
     reference's own frame would get them from the GL pipeline); the oracle supplies them here and the tests check that
     whatever they compare was given the same ones."""
-    sc = {"card": gh.card_scene, "shards": gh.shards_scene, "config1": scenes.cornell, "atrium": gh.atrium_scene}.get(kind, gh.fixture_scene)()
+    sc = {"card": gh.card_scene, "shards": gh.shards_scene, "shards_msaa4": gh.shards_scene, "config1": scenes.cornell,
+          "atrium": gh.atrium_scene}.get(kind, gh.fixture_scene)()
     u = gh.scene_uniforms(sc, kind)
     u["FilterMode"] = 0
     o = Oracle(); o.set_uniforms(u); o.load_scene(sc)
@@ -83,6 +86,12 @@ def generate(frame_stride=1, voxel_tris=None, card_stride=1, shard_tris=None, co
     idx, cnt, sums, bad, nf = gh.voxel_reference_accumulator(sc, u, ff["depth"], shard_tris)
     out.update(shards_index=idx, shards_count=cnt, shards_sums=sums, shards_uncertain=bad, shards_fragments=np.int64(nf))
     log(f"shards: {nf} fragments, {len(idx)} certain voxels, {len(bad)} uncertain  [{time.time() - t0:.1f} s]")
+    # the same two scenes under the reference's own default: a 4-sample framebuffer (main.cpp:30)
+    for kind, key, tris in (("voxel_msaa4", "voxm", voxel_tris), ("shards_msaa4", "shardsm", shard_tris)):
+        sc, u, ff = fixed_function_inputs(kind)
+        idx, cnt, sums, bad, nf = gh.voxel_reference_accumulator(sc, u, ff["depth"], tris, coverage="msaa4")
+        out.update({f"{key}_index": idx, f"{key}_count": cnt, f"{key}_sums": sums, f"{key}_uncertain": bad, f"{key}_fragments": np.int64(nf)})
+        log(f"{kind}: {nf} fragments, {len(idx)} certain voxels, {len(bad)} uncertain  [{time.time() - t0:.1f} s]")
     sc, u, ff = fixed_function_inputs("frame")
     W, H = int(u["screen_width"]), int(u["screen_height"])
     pixels = [(i, j) for j in range(H) for i in range(W) if ff["visibility"][j, i] != 0xFFFFFFFF][::frame_stride]

@@ -179,10 +179,11 @@ def test_fixture_is_what_the_reference_shaders_produce(vectors, oracle_mod):
     assert len(common) > 50
     part = dict(zip(again["vox_index"].tolist(), again["vox_count"].tolist()))
     assert all(part[k] <= full[k] for k in common) and any(part[k] == full[k] for k in common)
-    full = dict(zip(vectors["shards_index"].tolist(), vectors["shards_count"].tolist()))
-    part = dict(zip(again["shards_index"].tolist(), again["shards_count"].tolist()))
-    common = [k for k in part if k in full]
-    assert len(common) > 50 and all(part[k] <= full[k] for k in common)
+    for key in ("shards", "shardsm", "voxm"):
+        full = dict(zip(vectors[key + "_index"].tolist(), vectors[key + "_count"].tolist()))
+        part = dict(zip(again[key + "_index"].tolist(), again[key + "_count"].tolist()))
+        common = [k for k in part if k in full]
+        assert len(common) > 50 and all(part[k] <= full[k] for k in common), key
 
 
 # ------------------------------------------------------------------------------------------- comparisons
@@ -257,8 +258,8 @@ def test_oracle_matches_reference_shader_vectors(vectors, oracle_mod, filter_mod
     FilterMode 1 (the B200 texture unit's 8-bit weights, the oracle's default): within 1-2/255."""
     sc = gh.fixture_scene()
     res = {}
-    for kind in ("voxel", "shards", "frame", "card"):
-        sc = {"card": gh.card_scene, "shards": gh.shards_scene}.get(kind, gh.fixture_scene)()
+    for kind in ("voxel", "shards", "voxel_msaa4", "shards_msaa4", "frame", "card"):
+        sc = {"card": gh.card_scene, "shards": gh.shards_scene, "shards_msaa4": gh.shards_scene}.get(kind, gh.fixture_scene)()
         u = gh.scene_uniforms(sc, kind)
         u["FilterMode"] = filter_mode
         o = oracle_mod.Oracle(); o.set_uniforms(u); o.load_scene(sc)
@@ -272,6 +273,8 @@ def test_oracle_matches_reference_shader_vectors(vectors, oracle_mod, filter_mod
     c = res["card"]
     check_card(vectors, c["depth"], c["grid0"], c["vis"], c["frame"], f"oracle FilterMode={filter_mode}", exact=filter_mode == 0)
     check_voxels(vectors, "shards", res["shards"]["counts"], res["shards"]["sums"], f"oracle FilterMode={filter_mode}")
+    for kind, key in (("voxel_msaa4", "voxm"), ("shards_msaa4", "shardsm")):        # the reference's default: 4x MSAA
+        check_voxels(vectors, key, res[kind]["counts"], res[kind]["sums"], f"oracle FilterMode={filter_mode}")
 
 
 def check_sampled_frame(vectors, key, label, depth, grid0, vis, frame, who, exact, frac_bar):
@@ -341,8 +344,8 @@ def test_gpu_matches_reference_shader_vectors(vectors, gpu_ctx):
     """The CUDA path, through the C ABI, against the executed reference shaders (no oracle in between)."""
     sc = gh.fixture_scene()
     res = {}
-    for kind in ("voxel", "shards", "frame", "card"):
-        sc = {"card": gh.card_scene, "shards": gh.shards_scene}.get(kind, gh.fixture_scene)()
+    for kind in ("voxel", "shards", "voxel_msaa4", "shards_msaa4", "frame", "card"):
+        sc = {"card": gh.card_scene, "shards": gh.shards_scene, "shards_msaa4": gh.shards_scene}.get(kind, gh.fixture_scene)()
         u = gh.scene_uniforms(sc, kind)
         gpu_ctx.set_uniforms(u); gpu_ctx.load_scene(sc)
         gpu_ctx.draw_depth(); gpu_ctx.draw_voxels(); gpu_ctx.render(); gpu_ctx.sync()
@@ -354,3 +357,5 @@ def test_gpu_matches_reference_shader_vectors(vectors, gpu_ctx):
     c = res["card"]
     check_card(vectors, c["depth"], c["grid0"], c["vis"], c["frame"], "libvct_b200", exact=False)
     check_voxels(vectors, "shards", res["shards"]["counts"], res["shards"]["sums"], "libvct_b200", per_fragment=2)
+    for kind, key in (("voxel_msaa4", "voxm"), ("shards_msaa4", "shardsm")):
+        check_voxels(vectors, key, res[kind]["counts"], res[kind]["sums"], "libvct_b200", per_fragment=2)
