@@ -62,7 +62,7 @@ def atrium_scene():
 def scene_uniforms(sc, kind):
     if kind.endswith("_msaa4"):
         return uniforms.scene_uniforms(sc, coverage="msaa4", **{"voxel_msaa4": VOXEL, "shards_msaa4": SHARDS}[kind])
-    kw = dict({"frame": FRAME, "voxel": VOXEL, "card": CARD, "shards": SHARDS, "config1": CONFIG1, "atrium": ATRIUM}[kind])
+    kw = dict({"frame": FRAME, "voxel": VOXEL, "card": CARD, "shards": SHARDS, "config1": CONFIG1, "atrium": ATRIUM, "config2": CONFIG2}[kind])
     kw.setdefault("coverage", "center")
     return uniforms.scene_uniforms(sc, **kw)
 
@@ -528,6 +528,8 @@ SHARDS = dict(V=32, width=16, height=16, shadow_map_size=128)
 CONFIG1 = dict(V=64, width=256, height=256, shadow_map_size=1024, coverage="msaa4")     # BASELINE.json configs[0]
 ATRIUM = dict(V=32, width=96, height=54, shadow_map_size=512, coverage="conservative")  # the golden atrium case
 ATRIUM_STRIDE = 3
+CONFIG2 = dict(V=256, width=1920, height=1080, shadow_map_size=4096, coverage="conservative")   # BASELINE.json configs[1], the headline
+CONFIG2_STRIDE = 691                                                                           # ~3000 of the 2 M pixels
 CONFIG1_STRIDE = 13                                                                   # every 13th covered pixel
 
 

@@ -18,6 +18,8 @@ Contents (scene: tests/glsl_harness.fixture_scene(), centre-sample coverage):
              on every 13th covered pixel; the inputs are pinned by CRC-32 instead of being stored
   atrium_*   the same stage on the 6126-triangle atrium (22 materials, minified textures, cut-out cards, conservative voxel
              coverage; the scene of atrium_v32_conservative.npz) on every 3rd covered pixel; inputs pinned by CRC-32
+  config2_*  the same stage at BASELINE config 2, the headline benchmark configuration (259 608 triangles, 256^3, 1920 x 1080,
+             4096^2 shadow map, 512^2 textures), on every 691st covered pixel (3000 pixels); inputs pinned by CRC-32
   card_*     the same stage on an alpha cut-out card in front of a wall WITHOUT a triangle-per-pixel map: the fragment
              shader runs on the covering triangles nearest first and its `discard` decides which one is seen
 The float32 run is the vector; a float64 run, a +-4e-6 gain on the voxel-texture fetches (frame stages) and a 1/256 px
@@ -50,7 +52,7 @@ def fixed_function_inputs(kind):
     reference's own frame would get them from the GL pipeline); the oracle supplies them here and the tests check that
     whatever they compare was given the same ones."""
     sc = {"card": gh.card_scene, "shards": gh.shards_scene, "shards_msaa4": gh.shards_scene, "config1": scenes.cornell,
-          "atrium": gh.atrium_scene}.get(kind, gh.fixture_scene)()
+          "atrium": gh.atrium_scene, "config2": scenes.atrium}.get(kind, gh.fixture_scene)()
     u = gh.scene_uniforms(sc, kind)
     u["FilterMode"] = 0
     o = Oracle(); o.set_uniforms(u); o.load_scene(sc)
@@ -71,7 +73,7 @@ def stable_frame(sc, u, ff, pixels):
     return c32, stable
 
 
-def generate(frame_stride=1, voxel_tris=None, card_stride=1, shard_tris=None, config1_stride=1, atrium_stride=1, log=print):
+def generate(frame_stride=1, voxel_tris=None, card_stride=1, shard_tris=None, config1_stride=1, atrium_stride=1, config2_stride=1, log=print):
     t0 = time.time()
     out = {}
     sc, u, ff = fixed_function_inputs("voxel")
@@ -132,6 +134,17 @@ def generate(frame_stride=1, voxel_tris=None, card_stride=1, shard_tris=None, co
                atrium_tri=ff["visibility"][px[:, 1], px[:, 0]].astype(np.int64),
                atrium_depth_crc=np.uint32(zlib.crc32(ff["depth"].tobytes())), atrium_grid0_crc=np.uint32(zlib.crc32(ff["grid0"].tobytes())))
     log(f"atrium: {len(pixels)} pixels, {int(stable.sum())} stable  [{time.time() - t0:.1f} s]")
+    if config2_stride:
+        # BASELINE config 2, the headline: 259 608 triangles, 256^3, 1920 x 1080, 4096^2 shadow map, 512^2 textures
+        sc, u, ff = fixed_function_inputs("config2")
+        W, H = int(u["screen_width"]), int(u["screen_height"])
+        pixels = [(i, j) for j in range(H) for i in range(W) if ff["visibility"][j, i] != 0xFFFFFFFF][::gh.CONFIG2_STRIDE * config2_stride]
+        c32, stable = stable_frame(sc, u, ff, pixels)
+        px = np.array(pixels, dtype=np.int32)
+        out.update(config2_px=px, config2_rgba=c32.astype(np.float32), config2_stable=stable,
+                   config2_tri=ff["visibility"][px[:, 1], px[:, 0]].astype(np.int64),
+                   config2_depth_crc=np.uint32(zlib.crc32(ff["depth"].tobytes())), config2_grid0_crc=np.uint32(zlib.crc32(ff["grid0"].tobytes())))
+        log(f"config 2: {len(pixels)} pixels, {int(stable.sum())} stable  [{time.time() - t0:.1f} s]")
     return out
 
 
@@ -139,7 +152,7 @@ if __name__ == "__main__":
     if not gh.reference_available():
         sys.exit("the reference's shader files are not at " + gh.SHADER_DIR)
     vectors = generate()
-    meta = dict(shader_sha256=gh.shader_hashes(), frame=gh.FRAME, voxel=gh.VOXEL, card=gh.CARD, shards=gh.SHARDS, config1=gh.CONFIG1, config1_stride=gh.CONFIG1_STRIDE, atrium=gh.ATRIUM, atrium_stride=gh.ATRIUM_STRIDE,
+    meta = dict(shader_sha256=gh.shader_hashes(), frame=gh.FRAME, voxel=gh.VOXEL, card=gh.CARD, shards=gh.SHARDS, config1=gh.CONFIG1, config1_stride=gh.CONFIG1_STRIDE, atrium=gh.ATRIUM, atrium_stride=gh.ATRIUM_STRIDE, config2=gh.CONFIG2, config2_stride=gh.CONFIG2_STRIDE,
                 edge_px=gh.EDGE_PX,
                 note="float32 execution of the reference's GLSL text by tests/glsl_run.py")
     np.savez_compressed(OUT, meta=np.array(json.dumps(meta)), **vectors)

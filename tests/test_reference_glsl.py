@@ -161,7 +161,10 @@ def test_fixture_is_what_the_reference_shaders_produce(vectors, oracle_mod):
     assert meta["frame"] == gh.FRAME and meta["voxel"] == gh.VOXEL and meta["card"] == gh.CARD and meta["shards"] == gh.SHARDS
     tris = list(range(0, 44, 6))
     again = mk.generate(frame_stride=9, voxel_tris=tris, card_stride=11, shard_tris=list(range(0, 40, 5)), config1_stride=40,
-                        atrium_stride=17, log=lambda s: None)
+                        atrium_stride=17, config2_stride=40, log=lambda s: None)
+    assert np.array_equal(again["config2_px"], vectors["config2_px"][::40])
+    assert np.array_equal(again["config2_rgba"], vectors["config2_rgba"][::40])
+    assert again["config2_depth_crc"] == vectors["config2_depth_crc"] and again["config2_grid0_crc"] == vectors["config2_grid0_crc"]
     assert np.array_equal(again["atrium_px"], vectors["atrium_px"][::17])
     assert np.array_equal(again["atrium_rgba"], vectors["atrium_rgba"][::17])
     assert again["atrium_depth_crc"] == vectors["atrium_depth_crc"] and again["atrium_grid0_crc"] == vectors["atrium_grid0_crc"]
@@ -295,22 +298,24 @@ def check_sampled_frame(vectors, key, label, depth, grid0, vis, frame, who, exac
     print(f"[reference-glsl] {who}: {label} {int(use.sum())} pixels, exact {100 * (dd == 0).mean():.2f} %, within 1/255 "
           f"{100 * (dd <= 1).mean():.2f} %, within 2/255 {100 * (dd <= 2).mean():.2f} %, max {dd.max()}, psnr {psnr:.1f} dB")
     if exact:
+        # every byte is the reference shader's float value rounded, give or take 0.05 of an 8-bit step of float32
+        # evaluation-order noise (a byte differs only where that value sits on a rounding boundary)
         x = np.clip(vectors[key + "_rgba"].astype(np.float64)[use], 0, 1) * 255.0
-        tie = (np.abs(x - np.floor(x) - 0.5) < 1e-3).any(1)          # the reference value itself sits on a rounding tie
-        assert (dd[~tie] == 0).all() and (dd <= 1).all() and tie.mean() < 0.02
+        assert np.abs(got - x).max() <= 0.55 and (dd == 0).mean() >= 0.998
     else:
         assert (dd <= 2).mean() >= frac_bar and psnr >= 40.0
 
 
 # north_star: >= 99.9 % within 2/255 and >= 40 dB on the frame.  These are samples of frames (4848 and 1728 pixels, a handful
-# of cone-exit flips each), so the sample bars are 99.8 % for config 1 and -- a V = 32 fixture, see FRAC_MIN_SMALL in
+# of cone-exit flips each; 3000 for config 2), so the sample bars are 99.8 % for configs 1 and 2 and -- a V = 32 fixture, see FRAC_MIN_SMALL in
 # test_gpu_parity.py -- 99 % for the atrium; the full frames are held to their bars against the oracle in test_gpu_parity.py.
-SAMPLED = {"config1": ("config 1 (64^3, 256x256)", 0.998), "atrium": ("atrium (6126 tris, 22 materials, 32^3, 96x54)", 0.99)}
+SAMPLED = {"config1": ("config 1 (64^3, 256x256)", 0.998), "atrium": ("atrium (6126 tris, 22 materials, 32^3, 96x54)", 0.99),
+           "config2": ("config 2, the headline (259 608 tris, 256^3, 1920x1080)", 0.998)}
 
 
 def sampled_scene(key):
     from vct_b200 import scenes
-    return scenes.cornell() if key == "config1" else gh.atrium_scene()
+    return {"config1": scenes.cornell, "atrium": gh.atrium_scene, "config2": scenes.atrium}[key]()
 
 
 @pytest.mark.parametrize("key", sorted(SAMPLED))
