@@ -59,10 +59,21 @@ def atrium_scene():
     return scenes.atrium(detail=0.1, tex_size=32)
 
 
+def config4_scene(step=3):
+    """The 1 048 576-triangle knot of BASELINE config 4 at one time step of bench.py's animation (positions displaced
+    along the base normals by 12 sin(phase + 0.21 step), float32; normals, tangents and uv stay those of the base mesh)."""
+    sc = scenes.dynamic_knot()
+    base, nrm = sc.verts[:, :3].astype(np.float32), sc.verts[:, 3:6].astype(np.float32)
+    phase = (base[:, 0] * np.float32(0.004) + base[:, 2] * np.float32(0.003)).astype(np.float32)
+    amp = (np.float32(12.0) * np.sin(phase + np.float32(0.21 * step)).astype(np.float32)).astype(np.float32)
+    sc.verts[:, :3] = (base + nrm * amp[:, None]).astype(np.float32)
+    return sc
+
+
 def scene_uniforms(sc, kind):
     if kind.endswith("_msaa4"):
         return uniforms.scene_uniforms(sc, coverage="msaa4", **{"voxel_msaa4": VOXEL, "shards_msaa4": SHARDS}[kind])
-    kw = dict({"frame": FRAME, "voxel": VOXEL, "card": CARD, "shards": SHARDS, "config1": CONFIG1, "atrium": ATRIUM, "config2": CONFIG2}[kind])
+    kw = dict({"frame": FRAME, "voxel": VOXEL, "card": CARD, "shards": SHARDS, "config1": CONFIG1, "atrium": ATRIUM, "config2": CONFIG2, "config4": CONFIG4}[kind])
     kw.setdefault("coverage", "center")
     return uniforms.scene_uniforms(sc, **kw)
 
@@ -423,11 +434,12 @@ class FrameStage:
         q = self.linear_bary(ti, px, py) / self.triangle(ti)[1][:, 3]        # GL 4.3 eq. 14.9
         return q / q.sum()
 
-    def shade(self, ti, i, j):
-        """fragment stage at the centre of pixel (i, j) of triangle ti; None when the shader discards"""
+    def shade(self, ti, i, j, ox=0.0, oy=0.0):
+        """fragment stage at the centre of pixel (i, j) of triangle ti (moved by (ox, oy) px: what a sub-pixel vertex snap
+        does to the interpolated inputs); None when the shader discards"""
         rows = self.triangle(ti)[0]
         fs = self.fs
-        w = self.persp(ti, i + 0.5, j + 0.5)
+        w = self.persp(ti, i + 0.5 + ox, j + 0.5 + oy)
         for k, name in enumerate(self.NAMES):
             fs.globals[name] = sum(w[m] * rows[m][1][k] for m in range(3)).astype(self.dtype)
         uv = fs.globals["tex"].astype(np.float64)
@@ -472,7 +484,7 @@ class FrameStage:
         return [ti for _, ti in found]
 
 
-def frame_reference_pixels(sc, u, shadow_d24, grid0, visibility, pixels, dtype, voxel_gain=1.0):
+def frame_reference_pixels(sc, u, shadow_d24, grid0, visibility, pixels, dtype, voxel_gain=1.0, offset=(0.0, 0.0)):
     """Runs VoxelConeTracing.vs on the three vertices of the triangle the visibility pass found at each pixel,
     interpolates the seven varyings perspective-correctly at the pixel centre (fixed function, float64) and runs
     VoxelConeTracing.fs.  Returns float colours [n, 4] (NaN rows for background pixels and discarded fragments)."""
@@ -481,7 +493,7 @@ def frame_reference_pixels(sc, u, shadow_d24, grid0, visibility, pixels, dtype, 
     for n, (i, j) in enumerate(pixels):
         ti = int(visibility[j, i])
         if ti != 0xFFFFFFFF:
-            c = st.shade(ti, i, j)
+            c = st.shade(ti, i, j, *offset)
             if c is not None:
                 out[n] = c
     return out
@@ -529,6 +541,9 @@ CONFIG1 = dict(V=64, width=256, height=256, shadow_map_size=1024, coverage="msaa
 ATRIUM = dict(V=32, width=96, height=54, shadow_map_size=512, coverage="conservative")  # the golden atrium case
 ATRIUM_STRIDE = 3
 CONFIG2 = dict(V=256, width=1920, height=1080, shadow_map_size=4096, coverage="conservative")   # BASELINE.json configs[1], the headline
+CONFIG4 = dict(V=256, width=1920, height=1080, shadow_map_size=4096, coverage="conservative")   # BASELINE.json configs[3]
+CONFIG4_STRIDE = 307
+CONFIG4_STEP = 3                 # = the default of config4_scene()
 CONFIG2_STRIDE = 691                                                                           # ~3000 of the 2 M pixels
 CONFIG1_STRIDE = 13                                                                   # every 13th covered pixel
 

@@ -20,11 +20,15 @@ Contents (scene: tests/glsl_harness.fixture_scene(), centre-sample coverage):
              coverage; the scene of atrium_v32_conservative.npz) on every 3rd covered pixel; inputs pinned by CRC-32
   config2_*  the same stage at BASELINE config 2, the headline benchmark configuration (259 608 triangles, 256^3, 1920 x 1080,
              4096^2 shadow map, 512^2 textures), on every 691st covered pixel (3000 pixels); inputs pinned by CRC-32
+  config4_*  the same stage at BASELINE config 4 (the 1 048 576-triangle knot at time step 3, 256^3, 1920 x 1080) on every
+             307th covered pixel; inputs pinned by CRC-32
   card_*     the same stage on an alpha cut-out card in front of a wall WITHOUT a triangle-per-pixel map: the fragment
              shader runs on the covering triangles nearest first and its `discard` decides which one is seen
 The float32 run is the vector; a float64 run, a +-4e-6 gain on the voxel-texture fetches (frame stages) and a 1/256 px
 jitter (voxel stages) mark the entries that are numerically stable, i.e. whose value does not hinge on a rounding the GL
-specification leaves open (in practice: a cone loop ending with alpha within ~1e-6 of MAX_ALPHA).
+specification leaves open (in practice: a cone loop ending with alpha within ~1e-6 of MAX_ALPHA).  The sampled full-size
+frames also carry *_slack: per pixel, how far the colour moves when the fragment's inputs are interpolated 1/256 px off
+centre (GL's sub-pixel vertex snap) -- a shadow-map tap or texel boundary that close decides by itself.
 """
 import json
 import os
@@ -52,7 +56,7 @@ def fixed_function_inputs(kind):
     reference's own frame would get them from the GL pipeline); the oracle supplies them here and the tests check that
     whatever they compare was given the same ones."""
     sc = {"card": gh.card_scene, "shards": gh.shards_scene, "shards_msaa4": gh.shards_scene, "config1": scenes.cornell,
-          "atrium": gh.atrium_scene, "config2": scenes.atrium}.get(kind, gh.fixture_scene)()
+          "atrium": gh.atrium_scene, "config2": scenes.atrium, "config4": gh.config4_scene}.get(kind, gh.fixture_scene)()
     u = gh.scene_uniforms(sc, kind)
     u["FilterMode"] = 0
     o = Oracle(); o.set_uniforms(u); o.load_scene(sc)
@@ -73,7 +77,18 @@ def stable_frame(sc, u, ff, pixels):
     return c32, stable
 
 
-def generate(frame_stride=1, voxel_tris=None, card_stride=1, shard_tris=None, config1_stride=1, atrium_stride=1, config2_stride=1, log=print):
+def snap_slack(sc, u, ff, pixels, c32):
+    """How far (in 8-bit steps, per pixel) the executed fragment stage moves when its inputs are interpolated 1/256 px
+    off the pixel centre in the four diagonal directions -- the freedom GL's sub-pixel vertex snap leaves to a
+    conforming rasteriser (a PCF tap or a texel boundary crossed by that much)."""
+    slack = np.zeros(len(pixels))
+    for off in gh.JITTER[1:]:
+        c = gh.frame_reference_pixels(sc, u, ff["depth"], ff["grid0"], ff["visibility"], pixels, np.float32, offset=off)
+        slack = np.maximum(slack, np.abs(np.clip(np.nan_to_num(c), 0, 1) - np.clip(np.nan_to_num(c32), 0, 1)).max(1) * 255.0)
+    return slack.astype(np.float32)
+
+
+def generate(frame_stride=1, voxel_tris=None, card_stride=1, shard_tris=None, config1_stride=1, atrium_stride=1, config2_stride=1, config4_stride=1, log=print):
     t0 = time.time()
     out = {}
     sc, u, ff = fixed_function_inputs("voxel")
@@ -120,6 +135,7 @@ def generate(frame_stride=1, voxel_tris=None, card_stride=1, shard_tris=None, co
     pixels = [(i, j) for j in range(H) for i in range(W) if ff["visibility"][j, i] != 0xFFFFFFFF][::gh.CONFIG1_STRIDE * config1_stride]
     c32, stable = stable_frame(sc, u, ff, pixels)
     px = np.array(pixels, dtype=np.int32)
+    out["config1_slack"] = snap_slack(sc, u, ff, pixels, c32)
     out.update(config1_px=px, config1_rgba=c32.astype(np.float32), config1_stable=stable,
                config1_tri=ff["visibility"][px[:, 1], px[:, 0]].astype(np.int64),
                config1_depth_crc=np.uint32(zlib.crc32(ff["depth"].tobytes())), config1_grid0_crc=np.uint32(zlib.crc32(ff["grid0"].tobytes())))
@@ -130,6 +146,7 @@ def generate(frame_stride=1, voxel_tris=None, card_stride=1, shard_tris=None, co
     pixels = [(i, j) for j in range(H) for i in range(W) if ff["visibility"][j, i] != 0xFFFFFFFF][::gh.ATRIUM_STRIDE * atrium_stride]
     c32, stable = stable_frame(sc, u, ff, pixels)
     px = np.array(pixels, dtype=np.int32)
+    out["atrium_slack"] = snap_slack(sc, u, ff, pixels, c32)
     out.update(atrium_px=px, atrium_rgba=c32.astype(np.float32), atrium_stable=stable,
                atrium_tri=ff["visibility"][px[:, 1], px[:, 0]].astype(np.int64),
                atrium_depth_crc=np.uint32(zlib.crc32(ff["depth"].tobytes())), atrium_grid0_crc=np.uint32(zlib.crc32(ff["grid0"].tobytes())))
@@ -141,10 +158,23 @@ def generate(frame_stride=1, voxel_tris=None, card_stride=1, shard_tris=None, co
         pixels = [(i, j) for j in range(H) for i in range(W) if ff["visibility"][j, i] != 0xFFFFFFFF][::gh.CONFIG2_STRIDE * config2_stride]
         c32, stable = stable_frame(sc, u, ff, pixels)
         px = np.array(pixels, dtype=np.int32)
+        out["config2_slack"] = snap_slack(sc, u, ff, pixels, c32)
         out.update(config2_px=px, config2_rgba=c32.astype(np.float32), config2_stable=stable,
                    config2_tri=ff["visibility"][px[:, 1], px[:, 0]].astype(np.int64),
                    config2_depth_crc=np.uint32(zlib.crc32(ff["depth"].tobytes())), config2_grid0_crc=np.uint32(zlib.crc32(ff["grid0"].tobytes())))
         log(f"config 2: {len(pixels)} pixels, {int(stable.sum())} stable  [{time.time() - t0:.1f} s]")
+    if config4_stride:
+        # BASELINE config 4: the 1 048 576-triangle knot (sub-pixel triangles), one time step of the animation
+        sc, u, ff = fixed_function_inputs("config4")
+        W, H = int(u["screen_width"]), int(u["screen_height"])
+        pixels = [(i, j) for j in range(H) for i in range(W) if ff["visibility"][j, i] != 0xFFFFFFFF][::gh.CONFIG4_STRIDE * config4_stride]
+        c32, stable = stable_frame(sc, u, ff, pixels)
+        px = np.array(pixels, dtype=np.int32)
+        out["config4_slack"] = snap_slack(sc, u, ff, pixels, c32)
+        out.update(config4_px=px, config4_rgba=c32.astype(np.float32), config4_stable=stable,
+                   config4_tri=ff["visibility"][px[:, 1], px[:, 0]].astype(np.int64),
+                   config4_depth_crc=np.uint32(zlib.crc32(ff["depth"].tobytes())), config4_grid0_crc=np.uint32(zlib.crc32(ff["grid0"].tobytes())))
+        log(f"config 4: {len(pixels)} pixels, {int(stable.sum())} stable  [{time.time() - t0:.1f} s]")
     return out
 
 
@@ -152,7 +182,8 @@ if __name__ == "__main__":
     if not gh.reference_available():
         sys.exit("the reference's shader files are not at " + gh.SHADER_DIR)
     vectors = generate()
-    meta = dict(shader_sha256=gh.shader_hashes(), frame=gh.FRAME, voxel=gh.VOXEL, card=gh.CARD, shards=gh.SHARDS, config1=gh.CONFIG1, config1_stride=gh.CONFIG1_STRIDE, atrium=gh.ATRIUM, atrium_stride=gh.ATRIUM_STRIDE, config2=gh.CONFIG2, config2_stride=gh.CONFIG2_STRIDE,
+    meta = dict(shader_sha256=gh.shader_hashes(), frame=gh.FRAME, voxel=gh.VOXEL, card=gh.CARD, shards=gh.SHARDS, config1=gh.CONFIG1, config1_stride=gh.CONFIG1_STRIDE, atrium=gh.ATRIUM, atrium_stride=gh.ATRIUM_STRIDE, config2=gh.CONFIG2, config2_stride=gh.CONFIG2_STRIDE, config4=gh.CONFIG4, config4_stride=gh.CONFIG4_STRIDE,
+                config4_step=gh.CONFIG4_STEP,
                 edge_px=gh.EDGE_PX,
                 note="float32 execution of the reference's GLSL text by tests/glsl_run.py")
     np.savez_compressed(OUT, meta=np.array(json.dumps(meta)), **vectors)
