@@ -26,7 +26,7 @@ class OrcParams(C.Structure):
         ("DiffuseTanHalfAngle", C.c_float), ("SpecularTanHalfAngle", C.c_float), ("StepMultiplier", C.c_float),
         ("MaxDistance", C.c_float), ("MaxAlpha", C.c_float), ("PcfRadius", C.c_int32), ("ShadowBias", C.c_float),
         ("CoveragePolicy", C.c_int32), ("VoxelStoreMode", C.c_int32), ("Bounces", C.c_int32),
-        ("FilterMode", C.c_int32), ("GridFormat", C.c_int32),
+        ("FilterMode", C.c_int32), ("GridFormat", C.c_int32), ("RasterOrigin", C.c_int32),
     ]
 
 

@@ -738,6 +738,8 @@ struct HTri {
   HVert c[3];
   HEdge e[3];   /* e[i] is the edge opposite vertex i */
   int i0, i1, j0, j1;
+  float ox, oy; /* origin the edge functions are expressed in: (0,0) = the window's (the defined semantics);
+                 * RasterOrigin = 1 (experiment): a pixel corner next to the triangle */
 };
 
 /* VoxelConeTracing.vs:25 + viewport + back-face cull (main.cpp:57-58) as 2D homogeneous rasterisation
@@ -760,10 +762,20 @@ bool setup_htri(const orc_ctx* o, size_t ti, HTri* t) {
     in_near[k] = (c.z >= -c.w) && (c.w > 0.0f);
   }
   if (!in_near[0] && !in_near[1] && !in_near[2]) return false;
-  t->e[0] = hcross(t->c[1], t->c[2]);
-  t->e[1] = hcross(t->c[2], t->c[0]);
-  t->e[2] = hcross(t->c[0], t->c[1]);
-  float det = (t->c[0].X * t->e[0].A + t->c[0].Y * t->e[0].B) + t->c[0].w * t->e[0].C;
+  t->ox = t->oy = 0.0f;
+  HVert l[3] = {t->c[0], t->c[1], t->c[2]};
+  if (p.RasterOrigin == 1) {
+    /* same edge functions, written in a frame whose origin is the pixel corner below-left of the first vertex in front
+     * of the eye: the products that cancel in hcross / heval are then a few pixels times w instead of the window size
+     * times w, i.e. ~2.5 decimal digits more of the float32 mantissa go to the triangle itself */
+    for (int k = 0; k < 3; ++k)
+      if (t->c[k].w > 0.0f) { t->ox = std::floor(t->c[k].X / t->c[k].w); t->oy = std::floor(t->c[k].Y / t->c[k].w); break; }
+    for (int k = 0; k < 3; ++k) { l[k].X = t->c[k].X - t->ox * t->c[k].w; l[k].Y = t->c[k].Y - t->oy * t->c[k].w; }
+  }
+  t->e[0] = hcross(l[1], l[2]);
+  t->e[1] = hcross(l[2], l[0]);
+  t->e[2] = hcross(l[0], l[1]);
+  float det = (l[0].X * t->e[0].A + l[0].Y * t->e[0].B) + l[0].w * t->e[0].C;
   if (!(det > 0.0f)) return false;  /* back face or degenerate */
 
   /* conservative screen bounding box of the near-clipped polygon */
@@ -798,6 +810,7 @@ bool setup_htri(const orc_ctx* o, size_t ti, HTri* t) {
 
 /* perspective-correct barycentrics at a pixel centre; false if outside */
 inline bool hbary(const HTri& t, float px, float py, float b[3], bool test) {
+  px -= t.ox; py -= t.oy;
   float e0 = heval(t.e[0], px, py), e1 = heval(t.e[1], px, py), e2 = heval(t.e[2], px, py);
   if (test && !(hinside(t.e[0], e0) && hinside(t.e[1], e1) && hinside(t.e[2], e2))) return false;
   float s = (e0 + e1) + e2;
@@ -859,7 +872,8 @@ static void orc_visibility(orc_ctx* o, int y0, int y1) {
         float px = (float)i + 0.5f, py = (float)j + 0.5f;
         /* window depth = z_clip / w_clip at the pixel; both are linear in the (unnormalised) homogeneous edge
          * functions, so the common 1/sum cancels: one division per fragment */
-        float e0 = heval(t.e[0], px, py), e1 = heval(t.e[1], px, py), e2 = heval(t.e[2], px, py);
+        float lx = px - t.ox, ly = py - t.oy;
+        float e0 = heval(t.e[0], lx, ly), e1 = heval(t.e[1], lx, ly), e2 = heval(t.e[2], lx, ly);
         if (!(hinside(t.e[0], e0) && hinside(t.e[1], e1) && hinside(t.e[2], e2))) continue;
         if (!((e0 + e1) + e2 > 0.0f)) continue;
         float zc = (e0 * t.c[0].zc + e1 * t.c[1].zc) + e2 * t.c[2].zc;

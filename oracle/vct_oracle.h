@@ -59,6 +59,8 @@ typedef struct orc_params {
                                         fraction truncated), as measured on B200 texture hardware and as llvmpipe's
                                         RGBA8 path does; 0 = fp32 weights */
   int32_t GridFormat;                /* 0 = RGBA8 (the reference, Voxel_Cone_Tracing.h:119), 1 = RGBA16F (BASELINE config 3) */
+  int32_t RasterOrigin;              /* frame pass edge functions: 0 = window origin (defined semantics, what the CUDA path
+                                        does), 1 = per-triangle local origin (oracle-only experiment) */
 } orc_params;
 
 typedef struct orc_ctx orc_ctx;

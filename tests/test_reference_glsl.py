@@ -346,6 +346,28 @@ def test_oracle_matches_reference_shaders_on_sampled_frames(vectors, oracle_mod,
     o.close()
 
 
+def test_local_raster_origin_removes_the_config4_gap(vectors, oracle_mod):
+    """Evidence for DESIGN.md section 8 item 3 (oracle-only experiment, `RasterOrigin = 1`): the SAME float32 homogeneous
+    edge functions written in a frame whose origin is a pixel corner next to the triangle, instead of the window's,
+    interpolate ~250x more accurately on config 4's small triangles -- and the frame then agrees with the executed
+    reference shaders like the other configurations do (every pixel within 1/255, > 99.5 % byte-exact).  Coverage
+    decisions at triangle edges move with it (the noise that decided them is gone), which is why the product path,
+    the oracle default and the fixtures would have to change together."""
+    sc = sampled_scene("config4")
+    u = gh.scene_uniforms(sc, "config4")
+    u["FilterMode"], u["RasterOrigin"] = 0, 1
+    o = oracle_mod.Oracle(); o.set_uniforms(u); o.load_scene(sc)
+    o.draw_depth(); o.draw_voxels(); o.render()
+    px, tri, stable = vectors["config4_px"], vectors["config4_tri"], vectors["config4_stable"]
+    use = stable & (o.visibility()[px[:, 1], px[:, 0]].astype(np.int64) == tri)
+    want = gh.to_unorm8(vectors["config4_rgba"].astype(np.float64))[use]
+    dd = np.abs(o.frame()[px[use, 1], px[use, 0]].astype(np.int32) - want).max(1)
+    print(f"[reference-glsl] oracle, RasterOrigin=1: config 4 {int(use.sum())} pixels (same visible triangle on {100 * use.mean():.2f} %), "
+          f"exact {100 * (dd == 0).mean():.2f} %, within 1/255 {100 * (dd <= 1).mean():.2f} %, max {dd.max()}")
+    o.close()
+    assert use.mean() >= 0.97 and (dd <= 1).all() and (dd == 0).mean() >= 0.995
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("key", sorted(SAMPLED))
 def test_gpu_matches_reference_shaders_on_sampled_frames(vectors, gpu_ctx, key):
