@@ -119,6 +119,52 @@ def test_interpreter_float32_rounding_and_builtins():
     assert float(g64["a"]) == 0.1 + 0.2
 
 
+def test_interpreter_more_expression_forms():
+    """Matrix products (ProjectionMatrix * ModelViewMatrix * v associates left to right), compound assignment through a
+    swizzle, array element stores, nested calls to functions defined later in the file, ivec arithmetic, unary minus on
+    vectors, comparison chains in a ternary cascade (the shape of Voxelization.gs:34-41)."""
+    src = """
+        uniform mat4 A; uniform mat4 B;
+        out vec4 p; out vec4 q; out vec3 v; out ivec3 iv; out float s; out int axis; out vec3 neg;
+        vec3 palette[3] = vec3[](vec3(1, 0, 0), vec3(0, 1, 0), vec3(0, 0, 1));
+        float quad(float x) { return twice(twice(x)); }      // defined below: definitions may come in any order
+        float twice(float x) { return x + x; }
+        void main() {
+            p = A * B * vec4(1, 2, 3, 1);
+            q = A * (B * vec4(1, 2, 3, 1));
+            v = vec3(1.0, 2.0, 3.0); v.xz += vec2(10.0, 20.0); v.y *= 0.5f; v /= 2.0;
+            palette[1] = palette[0] + palette[2];
+            s = quad(1.5) + palette[1].z + palette[1].x;
+            iv = ivec3(7, 8, 9); iv.z = 16 - 1 - iv.x; iv = iv + ivec3(1);
+            vec3 n = vec3(0.3, 0.3, 0.2);
+            if (n.x >= n.y && n.x >= n.z) axis = 1; else if (n.y >= n.x && n.y >= n.z) axis = 2; else axis = 3;
+            mat4 m = axis == 1 ? A : axis == 2 ? B : A * B;
+            neg = -(m * vec4(1, 0, 0, 0)).xyz;
+        }"""
+    A = np.array([[2, 0, 0, 1], [0, 1, 0, 2], [0, 0, 1, 3], [0, 0, 0, 1]], dtype=np.float64)      # maths form
+    B = np.array([[0, -1, 0, 0], [1, 0, 0, 0], [0, 0, 1, 5], [0, 0, 0, 1]], dtype=np.float64)
+    g = run_snippet(src, A=A.T.reshape(-1), B=B.T.reshape(-1)).globals      # uniforms arrive column-major
+    want = A @ B @ np.array([1, 2, 3, 1.0])
+    assert g["p"].tolist() == want.tolist() == g["q"].tolist()
+    assert g["v"].tolist() == [5.5, 0.5, 11.5] and float(g["s"]) == 8.0 and g["iv"].tolist() == [8, 9, 9]
+    assert g["axis"] == 1 and g["neg"].tolist() == (-A[:3, 0]).tolist()
+
+
+def test_interpreter_refuses_what_it_does_not_implement():
+    """Outside the subset the interpreter stops instead of guessing."""
+    for bad in ("void main() { vec3 a = vec3(1.0); bool b = a == a; }",          # vector comparison
+                "void main() { float a[2]; }",                                     # local arrays
+                "void main() { vec3 v = vec3(1.0); v.xx = vec2(1.0); }",           # repeated component in a store
+                "void main() { undefined_function(1.0); }",
+                "void main() { float x = 1.0; x = y; }",                           # undeclared identifier
+                "void main() { mat3 m = mat3(1.0); }",                             # diagonal constructor form
+                "void main() { int i = 3 % 2.0; }"):
+        with pytest.raises(glsl_run.GlslError):
+            run_snippet(bad)
+    with pytest.raises(glsl_run.GlslError):
+        glsl_run.Program("void main() { float x = 1.0 @ 2.0; }")
+
+
 def test_interpreter_interface_blocks_and_geometry_stage():
     src = """
         layout (triangles) in;
