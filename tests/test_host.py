@@ -140,3 +140,18 @@ def test_interleaved_row_strips_partition_the_frame(height, world):
             owner[b:e] = r
             assert (b // 8) % world == r
     assert (owner >= 0).all() and max(counts) - min(counts) <= 1
+
+
+def test_flythrough_script_drives_the_fly_camera():
+    """tools/flythrough.py: the reference's event loop (main.cpp:97-149) as a script; --dry-run needs no device."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("flythrough", os.path.join(ROOT, "tools", "flythrough.py"))
+    fly = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fly)
+    ev = fly.parse_script("W*3 M(900,0) E*2 S(10) S")
+    assert len(ev) == 8 and ev[0] == ("key", 0) and ev[3] == ("mouse", 900.0, 0.0) and ev[6] == ("scroll", 10.0) and ev[7] == ("key", 1)
+    with np.testing.assert_raises(ValueError):
+        fly.parse_script("X*3")
+    cam = fly.main(["--script", "W*3 M(900,0) E*2 S(10)", "--dt", "0.5", "--dry-run"])
+    np.testing.assert_allclose(cam.position, [0.0, 2.6, 205.0 - 3.9], atol=1e-4)     # Cornell camera (0, 0, 205): 3 x 1.3 forward, 2 x 1.3 up
+    assert cam.Yaw == 0.0 and cam.Zoom == 35.0

@@ -390,3 +390,9 @@ def test_obj_asset_textures_are_what_the_reference_would_upload(tmp_path):
         want = ref_stb.load(str(tmp_path / name))
         assert np.array_equal(sc.textures[tex], want), name
     assert sc.textures[d].shape == (48, 64, 3) and np.abs(sc.textures[d].astype(int) - rgb).mean() < 40     # lossy (noisy chroma at 4:2:0), but that picture
+
+
+def test_pnm_writer_round_trips_through_the_reference_decoder():
+    for c in (1, 3):
+        img = picture(9, 14, c, 40 + c)
+        assert np.array_equal(assert_same(images.encode_pnm(img), "own PNM writer"), img)

@@ -188,3 +188,31 @@ def test_interpreter_reads_every_reference_shader():
         for n in names[f] - {"DiffuseTexture", "SpecularTexture", "MaskTexture", "HeightTexture", "HeightTextureSize", "ShadowMap", "VoxelTexture",
                              "Shininess", "Opacity", "ShowDiffuse", "ShowIndirectDiffuse", "ShowSpecular", "ShowIndirectSpecular"}:
             assert n in u, (f, n)
+
+
+def test_fly_camera_mirrors_camera_h():
+    """Camera.h:21-25, 80-144: the constants and the movement rules of the fly camera, Python mirror and C++ facade."""
+    from vct_b200 import renderer
+    c = text("Camera.h")
+    speed, sens = floats(r"const float SPEED = " + NUM, c, 1)[0], floats(r"const float SENSITIVITY = " + NUM, c, 1)[0]
+    assert "MovementSpeed = SPEED;" in c and "MouseSensitivity = SENSITIVITY;" in c
+    assert re.findall(r"^\t(\w+),?$", section(c, "enum Camera_Direction", "};"), flags=re.M) == ["FORWARD", "BACKWARD", "LEFT", "RIGHT", "UP", "DOWN"]
+    cam = renderer.Camera()
+    assert (cam.MovementSpeed, cam.MouseSensitivity) == (speed, sens) == (2.6, 0.1)
+    assert [renderer.FORWARD, renderer.BACKWARD, renderer.LEFT, renderer.RIGHT, renderer.UP, renderer.DOWN] == list(range(6))
+    np.testing.assert_allclose(cam.Front, [0, 0, -1], atol=1e-6)                       # Yaw = -90 looks down -z
+    np.testing.assert_allclose(cam.Right, [1, 0, 0], atol=1e-6)
+    p0 = cam.position.copy()
+    cam.ProcessKeyBoard(renderer.FORWARD, 0.5); np.testing.assert_allclose(cam.position - p0, [0, 0, -1.3], atol=1e-6)
+    cam.ProcessKeyBoard(renderer.RIGHT, 1.0); np.testing.assert_allclose(cam.position - p0, [2.6, 0, -1.3], atol=1e-6)
+    cam.ProcessKeyBoard(renderer.DOWN, 1.0); np.testing.assert_allclose(cam.position - p0, [2.6, -2.6, -1.3], atol=1e-6)
+    cam.ProcessMouseMovement(900.0, 2000.0)                                             # 90 degrees right, pitch clamps at 89
+    assert cam.Yaw == 0.0 and cam.Pitch == 89.0 and "if (Pitch > 89.0f)" in c and "if (Pitch < -89.0f)" in c
+    np.testing.assert_allclose(cam.Front, [np.cos(np.radians(89)), np.sin(np.radians(89)), 0], atol=1e-6)
+    cam.ProcessMouseScroll(50.0); assert cam.Zoom == 1.0
+    cam.ProcessMouseScroll(-100.0); assert cam.Zoom == 45.0 and "if (Zoom > 45.0f)" in c
+    np.testing.assert_allclose(cam.GetViewMatrix() @ np.append(cam.position + cam.Front, 1.0), [0, 0, -1, 1], atol=1e-5)
+    mine = open(os.path.join(ROOT, "voxel-cone-tracing_b200", "host", "Voxel_Cone_Tracing.h")).read()
+    assert "MovementSpeed = 2.6f, MouseSensitivity = 0.1f" in mine
+    for m in ("ProcessKeyBoard", "ProcessMouseMovement", "ProcessMouseScroll", "UpdateCamera", "GetViewMatrix"):
+        assert re.search(rf"\b{m}\(", c) and re.search(rf"\b{m}\(", mine), m

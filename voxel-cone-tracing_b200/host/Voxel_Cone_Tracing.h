@@ -20,17 +20,48 @@
 using vctm::mat4;
 using vctm::vec3;
 
-// Camera.h: position, Yaw = -90, Pitch = 0, Zoom = 45 (Camera.h:21-25); GetViewMatrix (Camera.h:75-78)
+// Camera.h: the fly camera -- position, Yaw = -90, Pitch = 0, Zoom = 45, MovementSpeed = 2.6, MouseSensitivity = 0.1
+// (Camera.h:21-25, 50-60); GetViewMatrix (:75-78), ProcessKeyBoard (:80-101), ProcessMouseMovement (:103-119),
+// ProcessMouseScroll (:121-129), UpdateCamera (:131-144)
+enum Camera_Direction { FORWARD, BACKWARD, LEFT, RIGHT, UP, DOWN };
 struct Camera {
   vec3 position;
+  vec3 Front = vec3(0.0f, 0.0f, -1.0f), Up = vec3(0.0f, 1.0f, 0.0f), Right = vec3(1.0f, 0.0f, 0.0f), WorldUp = vec3(0.0f, 1.0f, 0.0f);
   float Yaw = -90.0f, Pitch = 0.0f, Zoom = 45.0f;
-  explicit Camera(vec3 p = vec3(0.0f, 4.0f, 0.0f)) : position(p) {}
+  float MovementSpeed = 2.6f, MouseSensitivity = 0.1f;
+  explicit Camera(vec3 p = vec3(0.0f, 4.0f, 0.0f)) : position(p) { UpdateCamera(); }
+  void UpdateCamera() {
+    float y = vctm::radians(Yaw), p = vctm::radians(Pitch);
+    Front = vctm::normalize(vec3(std::cos(y) * std::cos(p), std::sin(p), std::sin(y) * std::cos(p)));
+    Right = vctm::normalize(vctm::cross(Front, WorldUp));
+    Up = vctm::normalize(vctm::cross(Right, Front));
+  }
   mat4 GetViewMatrix() const {
     float y = vctm::radians(Yaw), p = vctm::radians(Pitch);
     vec3 front = vctm::normalize(vec3(std::cos(y) * std::cos(p), std::sin(p), std::sin(y) * std::cos(p)));
     vec3 right = vctm::normalize(vctm::cross(front, vec3(0.0f, 1.0f, 0.0f)));
     vec3 up = vctm::normalize(vctm::cross(right, front));
     return vctm::lookAt(position, position + front, up);
+  }
+  void ProcessKeyBoard(Camera_Direction direction, float deltaTime) {
+    float velocity = MovementSpeed * deltaTime;
+    if (direction == FORWARD) position = position + Front * velocity;
+    if (direction == BACKWARD) position = position - Front * velocity;
+    if (direction == LEFT) position = position - Right * velocity;
+    if (direction == RIGHT) position = position + Right * velocity;
+    if (direction == UP) position = position + WorldUp * velocity;
+    if (direction == DOWN) position = position - WorldUp * velocity;
+  }
+  void ProcessMouseMovement(float xOffset, float yOffset, bool constrainPitch = true) {
+    Yaw += xOffset * MouseSensitivity;
+    Pitch += yOffset * MouseSensitivity;
+    if (constrainPitch) { if (Pitch > 89.0f) Pitch = 89.0f; if (Pitch < -89.0f) Pitch = -89.0f; }
+    UpdateCamera();
+  }
+  void ProcessMouseScroll(float yOffset) {
+    Zoom -= yOffset;
+    if (Zoom < 1.0f) Zoom = 1.0f;
+    if (Zoom > 45.0f) Zoom = 45.0f;
   }
 };
 

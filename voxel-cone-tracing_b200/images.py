@@ -880,6 +880,22 @@ def load_image(path: str, native_channels: bool = False) -> np.ndarray:
     return decode(data, path, native_channels)
 
 
+def encode_pnm(img: np.ndarray) -> bytes:
+    """uint8 (h, w) / (h, w, 1) -> binary PGM, (h, w, 3) -> binary PPM"""
+    a = np.ascontiguousarray(img, dtype=np.uint8)
+    if a.ndim == 2:
+        a = a[..., None]
+    h, w, c = a.shape
+    if c not in (1, 3):
+        raise ValueError("PNM holds one or three channels")
+    return (b"P5" if c == 1 else b"P6") + f"\n{w} {h}\n255\n".encode() + a.tobytes()
+
+
+def save_pnm(img: np.ndarray, path: str) -> None:
+    with open(path, "wb") as f:
+        f.write(encode_pnm(img))
+
+
 def save_png(img: np.ndarray, path: str) -> None:
     with open(path, "wb") as f:
         f.write(encode_png(img))

@@ -11,15 +11,51 @@ from . import uniforms as un
 from .capi import Context
 
 
+FORWARD, BACKWARD, LEFT, RIGHT, UP, DOWN = range(6)     # enum Camera_Direction, Camera.h:11-19
+
+
 class Camera:
-    """Camera.h: position, Yaw = -90, Pitch = 0, Zoom = 45 (Camera.h:21-25)."""
+    """Camera.h: the LearnOpenGL fly camera the reference steers with W/A/S/D + mouse (main.cpp:97-149).  position,
+    Yaw = -90, Pitch = 0, Zoom = 45, MovementSpeed = SPEED = 2.6, MouseSensitivity = SENSITIVITY = 0.1 (Camera.h:21-25,
+    50-60); Front / Right / Up from yaw and pitch (UpdateCamera, :131-144)."""
 
     def __init__(self, position=(0.0, 4.0, 0.0), yaw=-90.0, pitch=0.0, zoom=45.0):
         self.position = np.asarray(position, dtype=np.float32)
+        self.WorldUp = np.array([0.0, 1.0, 0.0], dtype=np.float32)
         self.Yaw, self.Pitch, self.Zoom = float(yaw), float(pitch), float(zoom)
+        self.MovementSpeed, self.MouseSensitivity = 2.6, 0.1
+        self.UpdateCamera()
+
+    def UpdateCamera(self):
+        y, p = np.radians(np.float32(self.Yaw)), np.radians(np.float32(self.Pitch))
+        front = np.array([np.cos(y) * np.cos(p), np.sin(p), np.sin(y) * np.cos(p)], dtype=np.float32)
+        self.Front = front / np.linalg.norm(front)
+        right = np.cross(self.Front, self.WorldUp)
+        self.Right = (right / np.linalg.norm(right)).astype(np.float32)
+        up = np.cross(self.Right, self.Front)
+        self.Up = (up / np.linalg.norm(up)).astype(np.float32)
 
     def GetViewMatrix(self):
         return gm.view_matrix(self.position, self.Yaw, self.Pitch)
+
+    def ProcessKeyBoard(self, direction, deltaTime):
+        """Camera.h:80-101 (W/S/A/D/E/Q in main.cpp:104-121): move by MovementSpeed * deltaTime"""
+        step = np.float32(self.MovementSpeed * deltaTime)
+        axis, sign = {FORWARD: (self.Front, 1), BACKWARD: (self.Front, -1), LEFT: (self.Right, -1), RIGHT: (self.Right, 1),
+                      UP: (self.WorldUp, 1), DOWN: (self.WorldUp, -1)}[direction]
+        self.position = (self.position + sign * step * axis).astype(np.float32)
+
+    def ProcessMouseMovement(self, xOffset, yOffset, constrainPitch=True):
+        """Camera.h:103-119: offsets scaled by MouseSensitivity; pitch kept inside +-89 degrees"""
+        self.Yaw += xOffset * self.MouseSensitivity
+        self.Pitch += yOffset * self.MouseSensitivity
+        if constrainPitch:
+            self.Pitch = min(max(self.Pitch, -89.0), 89.0)
+        self.UpdateCamera()
+
+    def ProcessMouseScroll(self, yOffset):
+        """Camera.h:121-129: Zoom (the field of view, in degrees) kept inside [1, 45]"""
+        self.Zoom = min(max(self.Zoom - float(yOffset), 1.0), 45.0)
 
 
 class Voxel_Cone_Tracing:
