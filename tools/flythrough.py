@@ -1,13 +1,14 @@
 #!/usr/bin/env python
 """The reference's render loop with its fly camera, headless: a script of key presses and mouse moves instead of GLFW
-events (main.cpp:77-149), one PNG / PPM per frame instead of glfwSwapBuffers.
+events (main.cpp:77-150), one PNG / PPM per frame instead of glfwSwapBuffers.
 
     python tools/flythrough.py --scene atrium --grid 256 --size 1280x720 --script "W*30 D*10 M(120,0) W*20 S(-10)" --out fly_%04d.png
     python tools/flythrough.py --script "W*3 M(90,0) E*2" --dry-run        # camera path only, no device needed
 
-Script tokens (each yields one frame; `*n` repeats): W S A D = forward / back / left / right, E Q = up / down
-(ProcessKeyBoard with deltaTime = --dt), M(dx,dy) = mouse move in pixels (ProcessMouseMovement), S(dy) with an
-argument = scroll (ProcessMouseScroll, changes the field of view)."""
+Script tokens (each yields one frame; `*n` repeats): W S A D = forward / back / left / right as main.cpp:136-143 binds
+them, E Q = the enum's UP / DOWN (Camera.h:16-17; the reference binds no key to them) -- ProcessKeyBoard with
+deltaTime = --dt; M(dx,dy) = mouse move in pixels (mouse_callback -> ProcessMouseMovement), S(dy) with an argument =
+scroll (scroll_callback -> ProcessMouseScroll, changes the field of view)."""
 import argparse
 import os
 import re

@@ -15,7 +15,7 @@ FORWARD, BACKWARD, LEFT, RIGHT, UP, DOWN = range(6)     # enum Camera_Direction,
 
 
 class Camera:
-    """Camera.h: the LearnOpenGL fly camera the reference steers with W/A/S/D + mouse (main.cpp:97-149).  position,
+    """Camera.h: the LearnOpenGL fly camera the reference steers with W/A/S/D + mouse (main.cpp:100-150).  position,
     Yaw = -90, Pitch = 0, Zoom = 45, MovementSpeed = SPEED = 2.6, MouseSensitivity = SENSITIVITY = 0.1 (Camera.h:21-25,
     50-60); Front / Right / Up from yaw and pitch (UpdateCamera, :131-144)."""
 
@@ -39,7 +39,8 @@ class Camera:
         return gm.view_matrix(self.position, self.Yaw, self.Pitch)
 
     def ProcessKeyBoard(self, direction, deltaTime):
-        """Camera.h:80-101 (W/S/A/D/E/Q in main.cpp:104-121): move by MovementSpeed * deltaTime"""
+        """Camera.h:80-101 (W / S / A / D in main.cpp:136-143; UP and DOWN exist in the enum but no key is bound to them):
+        move by MovementSpeed * deltaTime"""
         step = np.float32(self.MovementSpeed * deltaTime)
         axis, sign = {FORWARD: (self.Front, 1), BACKWARD: (self.Front, -1), LEFT: (self.Right, -1), RIGHT: (self.Right, 1),
                       UP: (self.WorldUp, 1), DOWN: (self.WorldUp, -1)}[direction]
